@@ -1,0 +1,61 @@
+// Host-side plumbing shared by all launchers of libfmc_b200: error reporting for the C ABI and
+// TMA tensor-map construction (driver entry point resolved at run time so the library loads,
+// and its symbols can be inspected, on a machine without a GPU driver).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/fmc_b200.h"
+
+namespace fmc {
+
+// Error codes returned through the C ABI (0 = success).
+enum : int {
+  FMC_OK = 0,
+  FMC_ERR_SHAPE = -1,    // unsupported shape / alignment for the kernel
+  FMC_ERR_CUDA = -2,     // CUDA runtime error at launch
+  FMC_ERR_DRIVER = -3,   // driver entry point / tensor-map encode failure
+  FMC_ERR_ARG = -4,      // null pointer or inconsistent arguments
+};
+
+void set_error(const char* fmt, ...);
+
+#define FMC_REQUIRE(cond, code, ...) \
+  do {                               \
+    if (!(cond)) {                   \
+      ::fmc::set_error(__VA_ARGS__); \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+#define FMC_CUDA_OK(expr)                                                               \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::fmc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                       \
+      return ::fmc::FMC_ERR_CUDA;                                                       \
+    }                                                                                   \
+  } while (0)
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+    return FMC_ERR_CUDA;
+  }
+  return FMC_OK;
+}
+
+int device_sm_count();
+
+// bf16 tensor map, up to 4 dims; dims[0]/box[0] innermost (elements), strides[i] in BYTES for dim i+1.
+// swizzle128: CU_TENSOR_MAP_SWIZZLE_128B (inner box must then be <= 64 bf16).
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, bool swizzle128);
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace fmc

@@ -1,0 +1,373 @@
+// Linear-layer GEMM for the FMC denoising step:  C[M,N] = epilogue(A[M,K] * W[N,K]^T)
+//
+// This one kernel carries every `nn.Linear` / 1x1-conv on the hot path once Domain-LoRA has been
+// folded into W (reference: fmc/models/attention_processor.py:138-157 q/k/v/out projections,
+// fmc/models/motion_module.py:219,228 proj_in/proj_out, diffusers FeedForward GEGLU,
+// PoseAdaptorAttnProcessor.qkv_merge attention_processor.py:257).
+//
+// sm_100a design: persistent CTAs (one per SM), warp-specialised
+//   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, BK = 64 bf16 per stage)
+//   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16 per instruction)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue       (tcgen05.ld -> bias / GEGLU / row-bias / residual -> global)
+// The fp32 accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fmc {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmParams {
+  int M, N, K;
+  void* C;
+  long long ldc;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  const float* rowbias;
+  int rows_per_group;
+  long long ldrb;
+  int flags;
+  int tiles_m, tiles_n;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN <= 128) ? 6 : (BN <= 160 ? 5 : 4);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "SW128 tiles must stay 1024-byte aligned");
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t acc_full_bar[2];
+  __shared__ uint64_t acc_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int kblocks = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full_bar[a], 1);
+      mbar_init(&acc_empty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_slot, Cfg::TMEM_COLS);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n;
+        const int n_blk = tile % p.tiles_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+              ::"r"(sa), "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&full_bar[stage])),
+              "r"(kb * GEMM_BK), "r"(m_blk * GEMM_BM)
+              : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+              ::"r"(sb), "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar[stage])),
+              "r"(kb * GEMM_BK), "r"(n_blk * BN)
+              : "memory");
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // +32 bytes per 16-element K step inside the 128-byte swizzle span (start address is in 16 B units)
+            umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&acc_full_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const bool geglu = (p.flags & FMC_GEMM_GEGLU) != 0;
+    const bool out_f32 = (p.flags & FMC_GEMM_OUT_F32) != 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.tiles_n;
+      const int n_blk = tile % p.tiles_n;
+      mbar_wait(&acc_full_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const int row = m_blk * GEMM_BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const float* rb = nullptr;
+      if (p.rowbias != nullptr && row_ok) rb = p.rowbias + static_cast<long long>(row / p.rows_per_group) * p.ldrb;
+
+      if (!geglu) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 16; ++c) {
+          const int col0 = n_blk * BN + c * 16;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r[16];
+          tmem_ld_x16(taddr + static_cast<uint32_t>(c * 16), r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (row_ok) {
+            if (rb != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb + col0 + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            }
+            if (p.residual != nullptr) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(row) * p.ldr + col0);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint4 u = __ldg(rp + h);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  v[h * 8 + 2 * j] += bf16_lo(w[j]);
+                  v[h * 8 + 2 * j + 1] += bf16_hi(w[j]);
+                }
+              }
+            }
+            if (out_f32) {
+              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + col0);
+              op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                 pack_bf16x2(v[6], v[7]));
+              op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                 pack_bf16x2(v[14], v[15]));
+            }
+          }
+        }
+      } else {
+        // GEGLU: W rows are interleaved in blocks of 16 (value block, gate block); out = value * gelu(gate).
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n_blk * BN + c * 32;  // column of the value block in the interleaved N space
+          if (col0 >= p.N) break;
+          uint32_t ra[16], rg[16];
+          tmem_ld_x16(taddr + static_cast<uint32_t>(c * 32), ra);
+          tmem_ld_x16(taddr + static_cast<uint32_t>(c * 32 + 16), rg);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(ra[j]);
+            float g = __uint_as_float(rg[j]);
+            if (p.bias != nullptr) {
+              a += __ldg(p.bias + col0 + j);
+              g += __ldg(p.bias + col0 + 16 + j);
+            }
+            v[j] = a * gelu_erf(g);
+          }
+          const int ocol0 = col0 >> 1;
+          if (row_ok) {
+            if (p.residual != nullptr) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(row) * p.ldr + ocol0);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint4 u = __ldg(rp + h);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  v[h * 8 + 2 * j] += bf16_lo(w[j]);
+                  v[h * 8 + 2 * j + 1] += bf16_hi(w[j]);
+                }
+              }
+            }
+            if (out_f32) {
+              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + ocol0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + ocol0);
+              op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                 pack_bf16x2(v[6], v[7]));
+              op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                 pack_bf16x2(v[14], v[15]));
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FMC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  p.tiles_m = ceil_div(p.M, GEMM_BM);
+  p.tiles_n = ceil_div(p.N, BN);
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  return check_launch("gemm_bf16_kernel");
+}
+
+}  // namespace fmc
+
+using namespace fmc;
+
+extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
+                             int N, int K, const float* bias, const void* residual, long long ldr,
+                             const float* rowbias, int rows_per_group, long long ldrb, int flags, int tile_n,
+                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FMC_REQUIRE(A && W && C, FMC_ERR_ARG, "fmc_gemm_bf16: null operand");
+  FMC_REQUIRE(M > 0 && N > 0 && K > 0, FMC_ERR_SHAPE, "fmc_gemm_bf16: empty problem %dx%dx%d", M, N, K);
+  FMC_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, FMC_ERR_SHAPE,
+              "fmc_gemm_bf16: K=%d, lda=%lld, ldw=%lld must be multiples of 8 (16-byte TMA rows)", K, lda, ldw);
+  const bool geglu = (flags & FMC_GEMM_GEGLU) != 0;
+  FMC_REQUIRE(N % (geglu ? 32 : 16) == 0, FMC_ERR_SHAPE, "fmc_gemm_bf16: N=%d must be a multiple of %d", N,
+              geglu ? 32 : 16);
+  const int align_out = (flags & FMC_GEMM_OUT_F32) ? 4 : 8;
+  FMC_REQUIRE(ldc % align_out == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, FMC_ERR_SHAPE,
+              "fmc_gemm_bf16: output must be 16-byte aligned per row (ldc=%lld)", ldc);
+  FMC_REQUIRE(residual == nullptr || (ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0),
+              FMC_ERR_SHAPE, "fmc_gemm_bf16: residual must be 16-byte aligned per row (ldr=%lld)", ldr);
+  FMC_REQUIRE(rowbias == nullptr || (rows_per_group > 0 && ldrb % 4 == 0), FMC_ERR_ARG,
+              "fmc_gemm_bf16: rowbias needs rows_per_group > 0 and ldrb %% 4 == 0");
+
+  int bn = tile_n;
+  if (bn == 0) bn = (N % 160 == 0) ? 160 : ((N % 128 == 0 || N > 128) ? 128 : 64);
+  FMC_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, FMC_ERR_SHAPE, "fmc_gemm_bf16: unsupported tile_n %d", bn);
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint32_t box[2] = {GEMM_BK, GEMM_BM};
+    int rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box, true);
+    if (rc != FMC_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(bn)};
+    int rc = make_tmap_bf16(&tmB, W, 2, dims, strides, box, true);
+    if (rc != FMC_OK) return rc;
+  }
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.C = C; p.ldc = ldc;
+  p.bias = bias;
+  p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
+  p.rowbias = rowbias; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; p.ldrb = ldrb;
+  p.flags = flags;
+  switch (bn) {
+    case 64: return launch_gemm<64>(tmA, tmB, p, stream);
+    case 128: return launch_gemm<128>(tmA, tmB, p, stream);
+    case 160: return launch_gemm<160>(tmA, tmB, p, stream);
+    default: return launch_gemm<256>(tmA, tmB, p, stream);
+  }
+}
