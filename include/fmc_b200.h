@@ -41,6 +41,97 @@ int fmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, vo
                   int K, const float* bias, const void* residual, long long ldr, const float* rowbias,
                   int rows_per_group, long long ldrb, int flags, int tile_n, void* stream);
 
+/* O[i] = softmax(Q[i] K[kv(i)]^T * scale) V[kv(i)] per head, flash-style on tcgen05 (scores never leave the SM).
+ * Replaces head_to_batch_dim + get_attention_scores (baddbmm, softmax) + bmm + batch_to_head_dim of the spatial
+ * processors: fmc/models/attention_processor.py:148-154 (LoRAAttnProcessor, attn1 self / attn2 text cross).
+ * Q rows: image i owns rows [i*nq, (i+1)*nq); kv group g = i / kv_div owns K/V rows [g*kv_stride, g*kv_stride + nk).
+ * Head h of Q / K starts at column q_col0 / k_col0 + h*head_stride (head_stride = 48 with zero padding when
+ * head_dim = 40); head h of V at column v_col0 + h*head_dim.  Q, K, V may alias one fused [token, q|k|v] buffer. */
+int fmc_spatial_attn_bf16(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K, long long ldk,
+                          int k_col0, const void* V, long long ldv, int v_col0, long long kv_rows, int head_stride,
+                          void* O, long long ldo, int images, int heads, int head_dim, int nq, int nk, int kv_div,
+                          int kv_stride, float scale, void* stream);
+
+/* Temporal self-attention core over the f frames of every latent position, directly on channels-last activations
+ * (row of token (b, frame, hw) = (b*F + frame)*HW + hw; QKV row = [q | k | v] column blocks).
+ * Replaces fmc/models/attention_processor.py:61-67 and :271-281 as reached from
+ * fmc/models/motion_module.py:349-389 (TemporalSelfAttention), incl. the '(b h w) f c' rearranges of :218,:230. */
+int fmc_temporal_attn_bf16(const void* QKV, long long ld, int q_col0, int k_col0, int v_col0, int head_stride,
+                           void* O, long long ldo, int B, int F, int HW, int heads, int head_dim, float scale,
+                           void* stream);
+
+/* out = LayerNorm(x) * gamma + beta (+ pe[frame(row)]) in bf16; optionally out2 = that (in fp32) + add.
+ * frame(row) = (row / HW) % F for channels-last [B, F, HW, C] rows.  One warp per row, fp32 statistics.
+ * Replaces nn.LayerNorm at fmc/models/motion_module.py:289,297 and diffusers BasicTransformerBlock norm1-3,
+ * PositionalEncoding.forward motion_module.py:319-321 (x + pe[:, :f]) and the `hidden_states + pose_feature`
+ * operand of qkv_merge, fmc/models/attention_processor.py:257. */
+int fmc_layernorm_bf16(const void* x, long long ldx, const float* gamma, const float* beta, float eps, void* out,
+                       long long ldo, const float* pe, int F, int HW, const void* add, long long ldadd, void* out2,
+                       long long ldo2, long long rows, int C, void* stream);
+
+/* Per-image GroupNorm on channels-last x[images, HW, C] (+ channel bias rowbias[image / rowbias_div] added first)
+ * (+ SiLU).
+ * stats_ws: fp32 workspace of 2*groups*images floats.  Replaces InflatedGroupNorm fmc/models/resnet.py:27-37
+ * (motion_module.py:217), diffusers ResnetBlock2D.norm1/norm2 + SiLU (+ the time-embedding add between them),
+ * Transformer2DModel.norm, and conv_norm_out + conv_act fmc/models/unet.py:1288-1292. */
+int fmc_groupnorm_bf16(const void* x, long long ldx, const float* gamma, const float* beta, float eps, void* out,
+                       long long ldo, float* stats_ws, int images, int HW, int C, int groups, int silu,
+                       const float* rowbias, long long ldrb, int rowbias_div, void* stream);
+
+/* out = a (+ b) (+ rowbias[row / rows_per_group]) (ReLU optional).  Residual adds, the ObjectEncoder feature
+ * injection fmc/modified_modules.py:115-117, time-embedding broadcast, nn.ReLU of fmc/adapter.py:93. */
+int fmc_add_bf16(const void* a, long long lda, const void* b, long long ldb, const float* rowbias, int rows_per_group,
+                 long long ldrb, void* out, long long ldo, long long rows, int C, int relu, void* stream);
+
+/* torch 'nearest' resize of channels-last [N, h, w, C] -> [N, oh, ow, C] (diffusers Upsample2D, called at
+ * fmc/models/unet_blocks.py:701-704). */
+int fmc_resize_nearest_bf16(const void* x, void* out, int N, int h, int w, int oh, int ow, int C, void* stream);
+
+/* AvgPool2d(2) on channels-last (Downsample with use_conv=False, fmc/models/pose_adaptor.py:95, fmc/adapter.py:57). */
+int fmc_avgpool2_bf16(const void* x, void* out, int N, int h, int w, int C, void* stream);
+
+/* dst[r, 0:cols] = src[r, 0:cols] with row strides: the skip-connection channel concat torch.cat(dim=1) of
+ * fmc/models/unet_blocks.py:660,786 written straight into the concatenated buffer. */
+int fmc_copy2d_bf16(const void* src, long long lds, void* dst, long long ldd, long long rows, int cols, void* stream);
+
+/* Layout / dtype conversion between the reference tensor layout [B, C, F, H, W] fp32 and channels-last bf16
+ * [B, F, H, W, Cpad] (replaces the einops rearranges around every op, e.g. unet_blocks.py:402-409). */
+int fmc_ncfhw_f32_to_cl_bf16(const float* x, void* out, int B, int C, int F, long long HW, int Cpad, void* stream);
+int fmc_cl_bf16_to_ncfhw_f32(const void* x, long long ldc, float* out, int B, int C, int F, long long HW, void* stream);
+
+/* fp32 -> bf16 (optional SiLU): `nonlinearity(temb)` of diffusers ResnetBlock2D, TimestepEmbedding.act. */
+int fmc_cast_act_bf16(const float* x, void* out, long long n, int silu, void* stream);
+
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0) (fmc/models/unet.py:1090): [cos | sin] in bf16. */
+int fmc_timestep_embedding_bf16(const float* t, void* out, int B, int dim, void* stream);
+
+/* Pluecker-ray embedding (o x d, d): ray_condition fmc/data/dataset.py:930-972 via to_plucker_embedding
+ * train_cam_ctrl.py:77-90.  K[BF,4] = (fx,fy,cx,cy), c2w[BF,3,4].  _f32: out[BF,H,W,6] (the reference's return
+ * layout).  _unshuffle_bf16: out[BF,H/8,W/8,384], channel comp*64 + dy*8 + dx = PixelUnshuffle(8) of
+ * fmc/models/pose_adaptor.py:227-228 fused in (write-only, HBM bound). */
+int fmc_plucker_f32(const float* K, const float* c2w, float* out, int BF, int H, int W, void* stream);
+int fmc_plucker_unshuffle_bf16(const float* K, const float* c2w, void* out, int BF, int H, int W, void* stream);
+
+/* ObjectEncoder input build, get_traj_features_v2 fmc/util.py:147-203: last object with mask > 0 wins per pixel;
+ * channels = (info*m)*m (12) and m*m (1).  info[BF,n_obj,12], masks[BF,n_obj,H,W] fp32.
+ * _f32: feat[BF,13,H,W] + mask[BF,H,W] in the reference layout (bit-exact).  _unshuffle_bf16: feat
+ * [BF,H/8,W/8,832] with channel c*64 + dy*8 + dx (PixelUnshuffle(8) of fmc/adapter.py:163 fused) + mask[BF,H,W]. */
+int fmc_traj_scatter_f32(const float* info, const float* masks, float* feat, float* mask_out, int BF, int n_obj, int H,
+                         int W, void* stream);
+int fmc_traj_scatter_unshuffle_bf16(const float* info, const float* masks, void* feat, float* mask_out, int BF,
+                                    int n_obj, int H, int W, void* stream);
+
+/* x * nearest-resized mask, fmc/adapter.py:175-177.  row_index[h] / col_index[w] map a level pixel to the
+ * full-resolution mask pixel (composition of the iterated F.interpolate(mode='nearest') calls). */
+int fmc_mask_modulate_bf16(const void* x, const float* mask, const int* row_index, const int* col_index, void* out,
+                           int N, int h, int w, int C, int H, int W, void* stream);
+
+/* CFG combine + DDIM(eta=0) update on fp32 latents: fmc/pipelines/pipeline_animation_cm_om.py:711-720 and
+ * diffusers DDIMScheduler.step.  eps_cond = NULL disables guidance.  eps_out (optional) receives the combined eps. */
+int fmc_cfg_ddim_step_f32(const float* eps_uncond, const float* eps_cond, float guidance_scale, const float* latents,
+                          float* latents_out, float* eps_out, float alpha_t, float alpha_prev, long long n,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,67 @@
+"""ctypes binding of libfmc_b200.so (include/fmc_b200.h).  The library is the product: if it is missing or an
+entry point is absent the import of any op fails loudly -- there is no fallback path."""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfmc_b200.so")
+
+P, I, L, F = c_void_p, c_int, c_longlong, c_float
+
+# name -> argtypes, in the order of include/fmc_b200.h
+SIGNATURES = {
+    "fmc_gemm_bf16": [P, L, P, L, P, L, I, I, I, P, P, L, P, I, L, I, I, P],
+    "fmc_spatial_attn_bf16": [P, L, I, L, P, L, I, P, L, I, L, I, P, L, I, I, I, I, I, I, I, F, P],
+    "fmc_temporal_attn_bf16": [P, L, I, I, I, I, P, L, I, I, I, I, I, F, P],
+    "fmc_layernorm_bf16": [P, L, P, P, F, P, L, P, I, I, P, L, P, L, L, I, P],
+    "fmc_groupnorm_bf16": [P, L, P, P, F, P, L, P, I, I, I, I, I, P, L, I, P],
+    "fmc_add_bf16": [P, L, P, L, P, I, L, P, L, L, I, I, P],
+    "fmc_resize_nearest_bf16": [P, P, I, I, I, I, I, I, P],
+    "fmc_avgpool2_bf16": [P, P, I, I, I, I, P],
+    "fmc_copy2d_bf16": [P, L, P, L, L, I, P],
+    "fmc_ncfhw_f32_to_cl_bf16": [P, P, I, I, I, L, I, P],
+    "fmc_cl_bf16_to_ncfhw_f32": [P, L, P, I, I, I, L, P],
+    "fmc_cast_act_bf16": [P, P, L, I, P],
+    "fmc_timestep_embedding_bf16": [P, P, I, I, P],
+    "fmc_plucker_f32": [P, P, P, I, I, I, P],
+    "fmc_plucker_unshuffle_bf16": [P, P, P, I, I, I, P],
+    "fmc_traj_scatter_f32": [P, P, P, P, I, I, I, I, P],
+    "fmc_traj_scatter_unshuffle_bf16": [P, P, P, P, I, I, I, I, P],
+    "fmc_mask_modulate_bf16": [P, P, P, P, P, I, I, I, I, I, I, P],
+    "fmc_cfg_ddim_step_f32": [P, P, F, P, P, P, F, F, L, P],
+}
+
+_lib = None
+
+
+class FmcError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the CUDA library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FmcError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(make -C synfmc_b200/csrc). There is no CPU or PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        handle.fmc_last_error_string.restype = c_char_p
+        handle.fmc_last_error_string.argtypes = []
+        handle.fmc_abi_version.restype = c_int
+        handle.fmc_abi_version.argtypes = []
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the .so does not export what the header declares
+            fn.restype = c_int
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def call(name, *args):
+    """Invoke an entry point; a non-zero return code becomes an exception carrying the library's message."""
+    handle = lib()
+    rc = getattr(handle, name)(*args)
+    if rc != 0:
+        raise FmcError(f"{name} failed (rc={rc}): {handle.fmc_last_error_string().decode()}")

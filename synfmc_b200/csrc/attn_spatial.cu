@@ -1,0 +1,406 @@
+// Spatial attention core (self over N_l latent tokens, cross over 77 text tokens):
+//     O[i, :, h] = softmax(Q[i, :, h] K[kv(i), :, h]^T * scale) V[kv(i), :, h]
+// Replaces the materialised baddbmm -> softmax -> bmm of the reference
+// (fmc/models/attention_processor.py:148-154, diffusers Attention.get_attention_scores): the score matrix
+// ([256, 2560, 2560] fp32 = 6.7 GB at level 0) never leaves the SM.
+//
+// sm_100a design, one CTA per SM, persistent over (image, head, 128-query block) work items:
+//   warp 0     TMA producer: Q tile once per item, K / V^T tiles through a ring of smem stages
+//   warp 1     MMA issuer  : S = Q K^T (tcgen05, fp32 in TMEM, two S buffers), O += P V (P staged as bf16 in smem)
+//   warp 2     TMEM allocator
+//   warps 4-7  softmax     : one query row per thread (TMEM lane == row, no shuffles), exp2 with the scale folded in,
+//                            lazy rescaling of the TMEM-resident O accumulator (only when the row max grows by > 2^8),
+//                            epilogue O / l -> bf16 -> global
+// Q, K and V are read exactly as the fused projection GEMM wrote them ([token, q | k | v] rows): Q and K are K-major
+// SWIZZLE_128B operands of S = Q K^T, V is the MN-major B operand of O += P V -- no transposes anywhere.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fmc {
+
+constexpr int FA_BM = 128;  // query rows per item
+constexpr int FA_BN = 128;  // keys per KV tile
+constexpr int FA_THREADS = 256;
+constexpr float FA_RESCALE_THRESHOLD = 8.0f;  // log2 units
+
+struct FaParams {
+  int heads;
+  int nq;             // query tokens per image
+  int nk;             // valid keys per kv group
+  int kv_div;         // kv group of image i = i / kv_div   (1 for self-attention, f for text cross-attention)
+  int kv_stride;      // rows between kv groups in K (and columns in V^T)
+  int head_stride;    // elements between heads inside a Q / K row (48 for d = 40: zero padded by the projection)
+  int q_col0;         // column of head 0 inside the Q rows
+  int k_col0;         // column of head 0 inside the K rows
+  int v_col0;         // column of head 0 inside the V rows (V heads are never padded)
+  int images;
+  int q_blocks;       // ceil(nq / 128)
+  int kv_tiles;       // ceil(nk / 128)
+  float scale_log2e;  // softmax scale * log2(e)
+  __nv_bfloat16* O;
+  long long ldo;
+};
+
+template <int D>
+struct FaCfg {
+  static constexpr int DK = (D + 15) / 16 * 16;      // 48 / 80 / 160 : K extent of QK^T, N extent of PV
+  static constexpr int QCH = (DK + 63) / 64;         // 64-element (128 B) chunks per Q / K row
+  static constexpr int Q_BYTES = QCH * FA_BM * 128;
+  static constexpr int K_BYTES = QCH * FA_BN * 128;
+  // V tile: QCH 64-channel chunks of 128 key rows exactly as the projection wrote them (MN-major B operand of PV)
+  static constexpr int V_BYTES = QCH * FA_BN * 128;
+  static constexpr int P_BYTES = 2 * FA_BM * 128;
+  static constexpr int KV_BYTES = K_BYTES + V_BYTES;
+  static constexpr int STAGES = (D <= 48) ? 4 : (D <= 80 ? 2 : 1);
+  static constexpr int SMEM_BYTES = Q_BYTES + P_BYTES + STAGES * KV_BYTES + 1024;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int O_COL = 256;                  // S buffers at columns 0 and 128
+  static_assert(V_BYTES % 1024 == 0 && K_BYTES % 1024 == 0, "tiles must stay 1024-byte aligned");
+  static_assert(DK % 16 == 0 && DK <= 256, "UMMA N constraint");
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int D>
+__global__ void __launch_bounds__(FA_THREADS, 1)
+spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, FaParams p) {
+  using Cfg = FaCfg<D>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int DK = Cfg::DK;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t q_full, q_empty, p_ready, p_free, o_final, o_free;
+  __shared__ uint64_t kv_full[STAGES], kv_empty[STAGES];
+  __shared__ uint64_t s_full[2], s_free[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;
+  const uint32_t sP = sQ + Cfg::Q_BYTES;
+  const uint32_t sKV = sP + Cfg::P_BYTES;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_items = p.images * p.heads * p.q_blocks;
+  const int T = p.kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&q_full, 1);
+    mbar_init(&q_empty, 1);
+    mbar_init(&p_ready, 4);
+    mbar_init(&p_free, 1);
+    mbar_init(&o_final, 1);
+    mbar_init(&o_free, 4);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_free[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_slot, Cfg::TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (lane == 0) {
+      uint32_t t = 0;   // global KV tile counter of this CTA
+      uint32_t it = 0;  // item counter of this CTA
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int qb = item % p.q_blocks;
+        const int head = (item / p.q_blocks) % p.heads;
+        const int img = item / (p.q_blocks * p.heads);
+        const int q_row0 = img * p.nq + qb * FA_BM;
+        const int kv_row0 = (img / p.kv_div) * p.kv_stride;
+        mbar_wait(&q_empty, (it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&q_full, Cfg::Q_BYTES);
+#pragma unroll
+        for (int c = 0; c < Cfg::QCH; ++c)
+          tma_load_2d_a(sQ + c * (FA_BM * 128), &tmQ, &q_full, p.q_col0 + head * p.head_stride + c * 64, q_row0);
+        for (int j = 0; j < T; ++j, ++t) {
+          const int st = t % STAGES;
+          const uint32_t ph = (t / STAGES) & 1u;
+          mbar_wait(&kv_empty[st], ph ^ 1u);
+          mbar_arrive_expect_tx(&kv_full[st], Cfg::KV_BYTES);
+          const uint32_t sK = sKV + st * Cfg::KV_BYTES;
+          const uint32_t sV = sK + Cfg::K_BYTES;
+#pragma unroll
+          for (int c = 0; c < Cfg::QCH; ++c)
+            tma_load_2d_a(sK + c * (FA_BN * 128), &tmK, &kv_full[st], p.k_col0 + head * p.head_stride + c * 64,
+                          kv_row0 + j * FA_BN);
+#pragma unroll
+          for (int c = 0; c < Cfg::QCH; ++c)
+            tma_load_2d_a(sV + c * (FA_BN * 128), &tmV, &kv_full[st], p.v_col0 + head * D + c * 64,
+                          kv_row0 + j * FA_BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------ MMA issuer ------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(FA_BM, FA_BN);
+      constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(FA_BM, DK);
+      uint32_t t = 0, it = 0;
+      auto issue_pv = [&](uint32_t u, bool first_of_item) {
+        mbar_wait(&p_ready, u & 1u);
+        tc_fence_after_sync();
+        const int st = u % STAGES;
+        const uint32_t sV = sKV + st * Cfg::KV_BYTES + Cfg::K_BYTES;
+#pragma unroll
+        for (int k = 0; k < FA_BN / 16; ++k) {
+          const uint64_t da = umma_desc_k_sw128(sP + (k >> 2) * (FA_BM * 128) + (k & 3) * 32);
+          const uint64_t db = umma_desc_mn_sw128(sV + k * (16 * 128), FA_BN * 128, 1024);
+          umma_bf16_ss(tmem_base + Cfg::O_COL, da, db, idesc_o, (!first_of_item || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(&p_free);
+      };
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        mbar_wait(&q_full, it & 1u);
+        mbar_wait(&o_free, (it & 1u) ^ 1u);
+        tc_fence_after_sync();
+        for (int j = 0; j < T; ++j, ++t) {
+          const int st = t % STAGES;
+          const uint32_t ph = (t / STAGES) & 1u;
+          const uint32_t sb = t & 1u;
+          const uint32_t sph = (t >> 1) & 1u;
+          // with a single KV stage the previous PV must be issued first: its commit is what frees the stage
+          if constexpr (STAGES == 1) {
+            if (j >= 1) issue_pv(t - 1, j == 1);
+          }
+          mbar_wait(&kv_full[st], ph);
+          mbar_wait(&s_free[sb], sph ^ 1u);
+          tc_fence_after_sync();
+          const uint32_t sK = sKV + st * Cfg::KV_BYTES;
+#pragma unroll
+          for (int k = 0; k < DK / 16; ++k) {
+            const uint64_t da = umma_desc_k_sw128(sQ + (k >> 2) * (FA_BM * 128) + (k & 3) * 32);
+            const uint64_t db = umma_desc_k_sw128(sK + (k >> 2) * (FA_BN * 128) + (k & 3) * 32);
+            umma_bf16_ss(tmem_base + sb * 128u, da, db, idesc_s, k > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[sb]);
+          if (j == T - 1) umma_commit(&q_empty);
+          if constexpr (STAGES > 1) {
+            if (j >= 1) issue_pv(t - 1, j == 1);
+          }
+        }
+        issue_pv(t - 1, T == 1);
+        umma_commit(&o_final);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------ softmax + epilogue ------------------------------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row inside the 128-query tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float c = p.scale_log2e;
+    uint32_t t = 0, it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int qb = item % p.q_blocks;
+      const int head = (item / p.q_blocks) % p.heads;
+      const int img = item / (p.q_blocks * p.heads);
+      float m_used = -INFINITY;
+      float l = 0.f;
+      for (int j = 0; j < T; ++j, ++t) {
+        const uint32_t sb = t & 1u;
+        const uint32_t sph = (t >> 1) & 1u;
+        const int valid = p.nk - j * FA_BN;  // keys of this tile with index < valid are real
+        mbar_wait(&s_full[sb], sph);
+        tc_fence_after_sync();
+        const uint32_t s_addr = lane_addr + sb * 128u;
+        // pass A: row maximum (scaled to log2 units)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t v[32];
+          tmem_ld_x32(s_addr + c4 * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float s = (c4 * 32 + i < valid) ? __uint_as_float(v[i]) * c : -INFINITY;
+            mx = fmaxf(mx, s);
+          }
+        }
+        const bool need = mx > m_used + FA_RESCALE_THRESHOLD;
+        const float m_new = need ? mx : m_used;
+        const float alpha = fast_exp2(m_used - m_new);  // 1 when unchanged, 0 on the first tile
+        // PV of the previous tile must have finished: O is stable and the P buffer is free
+        mbar_wait(&p_free, (t & 1u) ^ 1u);
+        tc_fence_after_sync();
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+#pragma unroll 1
+          for (int cc = 0; cc < DK / 16; ++cc) {
+            uint32_t o[16];
+            tmem_ld_x16(lane_addr + Cfg::O_COL + cc * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x16(lane_addr + Cfg::O_COL + cc * 16, o);
+          }
+          tmem_st_wait();
+        }
+        l *= alpha;
+        m_used = m_new;
+        // pass B: P = exp2(S * c - m) -> bf16 -> smem (SWIZZLE_128B K-major: row r, 16-byte piece j at (j ^ (r & 7)))
+        const uint32_t p_row = sP + r * 128;
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t v[32];
+          tmem_ld_x32(s_addr + c4 * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c4 * 32 + i < valid) ? fast_exp2(fmaf(__uint_as_float(v[i]), c, -m_used)) : 0.f;
+            const float p1 = (c4 * 32 + i + 1 < valid) ? fast_exp2(fmaf(__uint_as_float(v[i + 1]), c, -m_used)) : 0.f;
+            l += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int piece = c4 * 4 + g;  // 16-byte piece index inside the 256-byte P row
+            const uint32_t addr = p_row + (piece >> 3) * (FA_BM * 128) + (((piece & 7) ^ (r & 7)) << 4);
+            st_shared_v4(addr, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
+        }
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s_free[sb]);
+          mbar_arrive(&p_ready);
+        }
+      }
+      // epilogue: O / l -> bf16 -> global
+      mbar_wait(&o_final, it & 1u);
+      tc_fence_after_sync();
+      const float inv = 1.0f / l;
+      const int q_in_img = qb * FA_BM + r;
+      const bool row_ok = q_in_img < p.nq;
+      __nv_bfloat16* orow = p.O + (static_cast<long long>(img) * p.nq + q_in_img) * p.ldo + head * D;
+#pragma unroll 1
+      for (int cc = 0; cc < DK / 16; ++cc) {
+        uint32_t o[16];
+        tmem_ld_x16(lane_addr + Cfg::O_COL + cc * 16, o);
+        tmem_ld_wait();
+        if (row_ok) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            pk[i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+          uint4* dst = reinterpret_cast<uint4*>(orow + cc * 16);
+          if (cc * 16 + 8 <= D) dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if (cc * 16 + 16 <= D) dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int D>
+static int launch_fa(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FaParams& p,
+                     cudaStream_t stream) {
+  using Cfg = FaCfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FMC_CUDA_OK(cudaFuncSetAttribute(spatial_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int items = p.images * p.heads * p.q_blocks;
+  const int grid = items < device_sm_count() ? items : device_sm_count();
+  spatial_attn_kernel<D><<<grid, FA_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  return check_launch("spatial_attn_kernel");
+}
+
+}  // namespace fmc
+
+using namespace fmc;
+
+extern "C" int fmc_spatial_attn_bf16(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K,
+                                     long long ldk, int k_col0, const void* V, long long ldv, int v_col0,
+                                     long long kv_rows, int head_stride, void* O, long long ldo, int images, int heads,
+                                     int head_dim, int nq, int nk, int kv_div, int kv_stride, float scale,
+                                     void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FMC_REQUIRE(Q && K && V && O, FMC_ERR_ARG, "fmc_spatial_attn_bf16: null operand");
+  FMC_REQUIRE(head_dim == 40 || head_dim == 80 || head_dim == 160, FMC_ERR_SHAPE,
+              "fmc_spatial_attn_bf16: head_dim %d not in {40, 80, 160}", head_dim);
+  const int dk = (head_dim + 15) / 16 * 16;
+  FMC_REQUIRE(head_stride >= dk, FMC_ERR_SHAPE,
+              "fmc_spatial_attn_bf16: head_stride %d must cover the zero-padded head width %d", head_stride, dk);
+  FMC_REQUIRE(images > 0 && heads > 0 && nq > 0 && nk > 0 && kv_div > 0, FMC_ERR_SHAPE,
+              "fmc_spatial_attn_bf16: empty problem");
+  FMC_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 &&
+                  v_col0 % 8 == 0,
+              FMC_ERR_SHAPE, "fmc_spatial_attn_bf16: strides / column offsets must be multiples of 8 elements");
+  FMC_REQUIRE((reinterpret_cast<uintptr_t>(O) & 15) == 0, FMC_ERR_SHAPE, "fmc_spatial_attn_bf16: O not 16-byte aligned");
+
+  CUtensorMap tmQ, tmK, tmV;
+  const uint32_t box[2] = {64, 128};
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(ldq), static_cast<uint64_t>(q_rows)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ldq) * 2};
+    int rc = make_tmap_bf16(&tmQ, Q, 2, dims, strides, box, true);
+    if (rc != FMC_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(ldk), static_cast<uint64_t>(kv_rows)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ldk) * 2};
+    int rc = make_tmap_bf16(&tmK, K, 2, dims, strides, box, true);
+    if (rc != FMC_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(ldv), static_cast<uint64_t>(kv_rows)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ldv) * 2};
+    int rc = make_tmap_bf16(&tmV, V, 2, dims, strides, box, true);
+    if (rc != FMC_OK) return rc;
+  }
+  FaParams p{};
+  p.heads = heads;
+  p.nq = nq;
+  p.nk = nk;
+  p.kv_div = kv_div;
+  p.kv_stride = kv_stride;
+  p.head_stride = head_stride;
+  p.q_col0 = q_col0;
+  p.k_col0 = k_col0;
+  p.v_col0 = v_col0;
+  p.images = images;
+  p.q_blocks = ceil_div(nq, FA_BM);
+  p.kv_tiles = ceil_div(nk, FA_BN);
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.O = static_cast<__nv_bfloat16*>(O);
+  p.ldo = ldo;
+  switch (head_dim) {
+    case 40: return launch_fa<40>(tmQ, tmK, tmV, p, stream);
+    case 80: return launch_fa<80>(tmQ, tmK, tmV, p, stream);
+    default: return launch_fa<160>(tmQ, tmK, tmV, p, stream);
+  }
+}

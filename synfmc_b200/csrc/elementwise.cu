@@ -1,0 +1,507 @@
+// HBM-bound glue kernels of the denoising step on channels-last bf16 activations: vectorised (16-byte) loads and
+// stores, one pass over the data each.  Reference lines are cited per entry point in include/fmc_b200.h.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fmc {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = bf16_lo(w[j]);
+    v[2 * j + 1] = bf16_hi(w[j]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+// out[r, c] = a[r, c] (+ b[r, c]) (+ rowbias[r / rows_per_group, c]), optional ReLU.  Strided rows, C % 8 == 0.
+__global__ void __launch_bounds__(256)
+add_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const __nv_bfloat16* __restrict__ b, long long ldb,
+           const float* __restrict__ rowbias, int rows_per_group, long long ldrb, __nv_bfloat16* __restrict__ out,
+           long long ldo, long long rows, int C, int relu) {
+  const int nvec = C >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= rows * nvec) return;
+  const long long r = idx / nvec;
+  const int vi = static_cast<int>(idx % nvec);
+  float v[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a + r * lda) + vi), v);
+  if (b != nullptr) {
+    float w[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + r * ldb) + vi), w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += w[j];
+  }
+  if (rowbias != nullptr) {
+    const float* rb = rowbias + (r / rows_per_group) * ldrb + vi * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += __ldg(rb + j);
+  }
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  *(reinterpret_cast<uint4*>(out + r * ldo) + vi) = pack8(v);
+}
+
+// Nearest-neighbour resize of [N, h, w, C] to [N, oh, ow, C] (torch 'nearest': src = floor(dst * in / out)).
+__global__ void __launch_bounds__(256)
+resize_nearest_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int h, int w, int oh,
+                      int ow, int C, float sh, float sw) {
+  const int nvec = C >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(N) * oh * ow * nvec;
+  if (idx >= total) return;
+  const int vi = static_cast<int>(idx % nvec);
+  long long t = idx / nvec;
+  const int ox = static_cast<int>(t % ow);
+  t /= ow;
+  const int oy = static_cast<int>(t % oh);
+  const int n = static_cast<int>(t / oh);
+  const int iy = min(static_cast<int>(floorf(oy * sh)), h - 1);
+  const int ix = min(static_cast<int>(floorf(ox * sw)), w - 1);
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<long long>(n) * h + iy) * w + ix) * C) + vi);
+  *(reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * oh + oy) * ow + ox) * C) + vi) = u;
+}
+
+// 2x2 average pooling (AvgPool2d(2), floor) of [N, h, w, C].
+__global__ void __launch_bounds__(256)
+avgpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int h, int w, int C) {
+  const int oh = h >> 1, ow = w >> 1, nvec = C >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(N) * oh * ow * nvec;
+  if (idx >= total) return;
+  const int vi = static_cast<int>(idx % nvec);
+  long long t = idx / nvec;
+  const int ox = static_cast<int>(t % ow);
+  t /= ow;
+  const int oy = static_cast<int>(t % oh);
+  const int n = static_cast<int>(t / oh);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(
+                        x + ((static_cast<long long>(n) * h + 2 * oy + dy) * w + 2 * ox + dx) * C) + vi), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
+  *(reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * oh + oy) * ow + ox) * C) + vi) = pack8(acc);
+}
+
+// Strided 2-D copy (channel concat of skip connections): dst[r, 0:cols] = src[r, 0:cols].
+__global__ void __launch_bounds__(256)
+copy2d_kernel(const __nv_bfloat16* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd,
+              long long rows, int cols) {
+  const int nvec = cols >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= rows * nvec) return;
+  const long long r = idx / nvec;
+  const int vi = static_cast<int>(idx % nvec);
+  *(reinterpret_cast<uint4*>(dst + r * ldd) + vi) = __ldg(reinterpret_cast<const uint4*>(src + r * lds) + vi);
+}
+
+// [B, C, F, H, W] fp32 (reference layout) -> [B, F, H, W, Cpad] bf16 (channels-last, zero padded channels).
+__global__ void __launch_bounds__(256)
+ncfhw_to_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int F, long long HW,
+                   int Cpad) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * F * HW * Cpad;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % Cpad);
+  long long t = idx / Cpad;
+  const long long hw = t % HW;
+  t /= HW;
+  const int f = static_cast<int>(t % F);
+  const int b = static_cast<int>(t / F);
+  const float v = c < C ? __ldg(x + ((static_cast<long long>(b) * C + c) * F + f) * HW + hw) : 0.f;
+  out[idx] = __float2bfloat16(v);
+}
+
+// [B, F, H, W, ldc] bf16 -> [B, C, F, H, W] fp32.
+__global__ void __launch_bounds__(256)
+cl_to_ncfhw_kernel(const __nv_bfloat16* __restrict__ x, long long ldc, float* __restrict__ out, int B, int C, int F,
+                   long long HW) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * C * F * HW;
+  if (idx >= total) return;
+  const long long hw = idx % HW;
+  long long t = idx / HW;
+  const int f = static_cast<int>(t % F);
+  t /= F;
+  const int c = static_cast<int>(t % C);
+  const int b = static_cast<int>(t / C);
+  out[idx] = __bfloat162float(x[((static_cast<long long>(b) * F + f) * HW + hw) * ldc + c]);
+}
+
+// fp32 -> bf16 with optional SiLU (time-embedding activations feeding the projection GEMMs).
+__global__ void __launch_bounds__(256)
+cast_act_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n, int silu) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= n) return;
+  float v = x[idx];
+  if (silu) v = v / (1.0f + __expf(-v));
+  out[idx] = __float2bfloat16(v);
+}
+
+// diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): out[b] = [cos(t e_i) | sin(t e_i)], e_i = 1e4^(-i/half).
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int B, int dim) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (idx >= B * half) return;
+  const int b = idx / half, i = idx % half;
+  const float e = expf(-logf(10000.0f) * static_cast<float>(i) / static_cast<float>(half));
+  const float a = t[b] * e;
+  out[b * dim + i] = __float2bfloat16(cosf(a));
+  out[b * dim + half + i] = __float2bfloat16(sinf(a));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pluecker rays (a9): K[b*f, 4] = (fx, fy, cx, cy), c2w[b*f, 3, 4].  For pixel centre (i + .5, j + .5):
+//   dir = normalize((i - cx) / fx, (j - cy) / fy, 1);  d = dir * R^T;  o = t;  out = (o x d, d)
+// plain: out[b*f, H, W, 6] fp32.  unshuffled: out[b*f, H/8, W/8, 6*64] bf16 with channel comp*64 + dy*8 + dx
+// (the PixelUnshuffle(8) of CameraPoseEncoder.forward, fmc/models/pose_adaptor.py:227-228, fused away).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void plucker_pixel(const float* __restrict__ K, const float* __restrict__ M, int px, int py,
+                                              float (&out)[6]) {
+  const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+  const float x = ((static_cast<float>(px) + 0.5f) - cx) / fx;
+  const float y = ((static_cast<float>(py) + 0.5f) - cy) / fy;
+  const float z = 1.0f;
+  const float n = sqrtf(x * x + y * y + z * z);
+  const float dx = x / n, dy = y / n, dz = z / n;
+  // rays_d = dir @ R^T  ->  d_k = sum_m dir_m R[k][m]
+  const float d0 = dx * M[0] + dy * M[1] + dz * M[2];
+  const float d1 = dx * M[4] + dy * M[5] + dz * M[6];
+  const float d2 = dx * M[8] + dy * M[9] + dz * M[10];
+  const float o0 = M[3], o1 = M[7], o2 = M[11];
+  out[0] = o1 * d2 - o2 * d1;
+  out[1] = o2 * d0 - o0 * d2;
+  out[2] = o0 * d1 - o1 * d0;
+  out[3] = d0;
+  out[4] = d1;
+  out[5] = d2;
+}
+
+__global__ void __launch_bounds__(256)
+plucker_plain_kernel(const float* __restrict__ K, const float* __restrict__ c2w, float* __restrict__ out, int BF, int H,
+                     int W) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(BF) * H * W;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % W);
+  const int py = static_cast<int>((idx / W) % H);
+  const int n = static_cast<int>(idx / (static_cast<long long>(W) * H));
+  float v[6];
+  plucker_pixel(K + n * 4, c2w + n * 12, px, py, v);
+  float* o = out + idx * 6;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) o[j] = v[j];
+}
+
+// one thread per (frame, cell y, cell x, comp, dy): writes 8 consecutive channels (dx = 0..7) = one 16-byte store
+__global__ void __launch_bounds__(256)
+plucker_unshuffle_kernel(const float* __restrict__ K, const float* __restrict__ c2w, __nv_bfloat16* __restrict__ out,
+                         int BF, int H, int W) {
+  const int h8 = H >> 3, w8 = W >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(BF) * h8 * w8 * 8;  // x 8 dy; the 6 comps are produced together
+  if (idx >= total) return;
+  const int dy = static_cast<int>(idx & 7);
+  long long t = idx >> 3;
+  const int cx = static_cast<int>(t % w8);
+  t /= w8;
+  const int cy = static_cast<int>(t % h8);
+  const int n = static_cast<int>(t / h8);
+  float v[8][6];
+#pragma unroll
+  for (int dx = 0; dx < 8; ++dx) plucker_pixel(K + n * 4, c2w + n * 12, cx * 8 + dx, cy * 8 + dy, v[dx]);
+  __nv_bfloat16* cell = out + ((static_cast<long long>(n) * h8 + cy) * w8 + cx) * 384;
+#pragma unroll
+  for (int comp = 0; comp < 6; ++comp) {
+    float r[8];
+#pragma unroll
+    for (int dx = 0; dx < 8; ++dx) r[dx] = v[dx][comp];
+    *reinterpret_cast<uint4*>(cell + comp * 64 + dy * 8) = pack8(r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ObjectEncoder input (a10), fmc/util.py:147-203: per pixel the LAST object with mask > 0 wins;
+//   traj = (info * m) * m   (12 channels),   maskf = m * m ... exactly: features = cat(info*m, m) * m.
+// plain:      feat[bf, 13, H, W] fp32 + mask[bf, H, W] fp32 (reference layout, bit-exact scatter)
+// unshuffled: feat[bf, H/8, W/8, 13*64] bf16 (channel c*64 + dy*8 + dx) + mask[bf, H, W] fp32
+// info[bf, n_obj, 12] fp32, masks[bf, n_obj, H, W] fp32.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void traj_pixel(const float* __restrict__ info, const float* __restrict__ masks, int n_obj,
+                                           long long hw_stride, long long pix, float (&feat)[13], float& mval) {
+  int sel = -1;
+  float m = 0.f;
+  for (int o = 0; o < n_obj; ++o) {
+    const float mo = __ldg(masks + o * hw_stride + pix);
+    if (mo > 0.f) {
+      sel = o;
+      m = mo;
+    }
+  }
+  mval = m;
+  if (sel < 0) {
+#pragma unroll
+    for (int c = 0; c < 13; ++c) feat[c] = 0.f;
+    return;
+  }
+#pragma unroll
+  for (int c = 0; c < 12; ++c) {
+    const float masked = __fmul_rn(__ldg(info + sel * 12 + c), m);  // expanded_obj_info * obj_mask   (util.py:176)
+    feat[c] = __fmul_rn(masked, m);                                 // features * mask_features       (util.py:200)
+  }
+  feat[12] = __fmul_rn(m, m);
+}
+
+__global__ void __launch_bounds__(256)
+traj_plain_kernel(const float* __restrict__ info, const float* __restrict__ masks, float* __restrict__ feat,
+                  float* __restrict__ mask_out, int BF, int n_obj, int H, int W) {
+  const long long HW = static_cast<long long>(H) * W;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= BF * HW) return;
+  const long long pix = idx % HW;
+  const int n = static_cast<int>(idx / HW);
+  float f[13], m;
+  traj_pixel(info + static_cast<long long>(n) * n_obj * 12, masks + static_cast<long long>(n) * n_obj * HW, n_obj, HW, pix, f, m);
+#pragma unroll
+  for (int c = 0; c < 13; ++c) feat[(static_cast<long long>(n) * 13 + c) * HW + pix] = f[c];
+  mask_out[idx] = m;
+}
+
+__global__ void __launch_bounds__(256)
+traj_unshuffle_kernel(const float* __restrict__ info, const float* __restrict__ masks, __nv_bfloat16* __restrict__ feat,
+                      float* __restrict__ mask_out, int BF, int n_obj, int H, int W) {
+  const int h8 = H >> 3, w8 = W >> 3;
+  const long long HW = static_cast<long long>(H) * W;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(BF) * h8 * w8 * 8;
+  if (idx >= total) return;
+  const int dy = static_cast<int>(idx & 7);
+  long long t = idx >> 3;
+  const int cx = static_cast<int>(t % w8);
+  t /= w8;
+  const int cy = static_cast<int>(t % h8);
+  const int n = static_cast<int>(t / h8);
+  float v[8][13];
+  const int py = cy * 8 + dy;
+#pragma unroll
+  for (int dx = 0; dx < 8; ++dx) {
+    const long long pix = static_cast<long long>(py) * W + cx * 8 + dx;
+    float m;
+    traj_pixel(info + static_cast<long long>(n) * n_obj * 12, masks + static_cast<long long>(n) * n_obj * HW, n_obj, HW, pix,
+               v[dx], m);
+    mask_out[static_cast<long long>(n) * HW + pix] = m;
+  }
+  __nv_bfloat16* cell = feat + ((static_cast<long long>(n) * h8 + cy) * w8 + cx) * 832;
+#pragma unroll
+  for (int c = 0; c < 13; ++c) {
+    float r[8];
+#pragma unroll
+    for (int dx = 0; dx < 8; ++dx) r[dx] = v[dx][c];
+    *reinterpret_cast<uint4*>(cell + c * 64 + dy * 8) = pack8(r);
+  }
+}
+
+// Mask modulation of an ObjectEncoder level (fmc/adapter.py:175-177): out[n, y, x, :] = x[n, y, x, :] * mask[n, ry[y], rx[x]]
+// where ry / rx compose the iterated nearest-neighbour resizes down to this level (built on the host).
+__global__ void __launch_bounds__(256)
+mask_modulate_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mask, const int* __restrict__ ry,
+                     const int* __restrict__ rx, __nv_bfloat16* __restrict__ out, int N, int h, int w, int C, int H, int W) {
+  const int nvec = C >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(N) * h * w * nvec;
+  if (idx >= total) return;
+  const int vi = static_cast<int>(idx % nvec);
+  long long t = idx / nvec;
+  const int xx = static_cast<int>(t % w);
+  t /= w;
+  const int yy = static_cast<int>(t % h);
+  const int n = static_cast<int>(t / h);
+  const float m = __ldg(mask + (static_cast<long long>(n) * H + __ldg(ry + yy)) * W + __ldg(rx + xx));
+  const long long off = ((static_cast<long long>(n) * h + yy) * w + xx) * C;
+  float v[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(x + off) + vi), v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= m;
+  *(reinterpret_cast<uint4*>(out + off) + vi) = pack8(v);
+}
+
+// CFG combine + DDIM (eta = 0) update on fp32 latents in the reference layout (pipeline_animation_cm_om.py:711-720,
+// diffusers DDIMScheduler.step): eps = e_u + g (e_c - e_u); x0 = (x - sqrt(1-a_t) eps) / sqrt(a_t);
+// x' = sqrt(a_prev) x0 + sqrt(1-a_prev) eps.   eps_c == nullptr: no guidance (eps = e_u).
+__global__ void __launch_bounds__(256)
+cfg_ddim_kernel(const float* __restrict__ eps_u, const float* __restrict__ eps_c, float guidance,
+                const float* __restrict__ x, float* __restrict__ x_out, float* __restrict__ eps_out, float sqrt_a_t,
+                float sqrt_1m_a_t, float sqrt_a_prev, float sqrt_1m_a_prev, long long n) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= n) return;
+  const float eu = eps_u[idx];
+  const float eps = eps_c != nullptr ? eu + guidance * (eps_c[idx] - eu) : eu;
+  const float x0 = (x[idx] - sqrt_1m_a_t * eps) / sqrt_a_t;
+  x_out[idx] = sqrt_a_prev * x0 + sqrt_1m_a_prev * eps;
+  if (eps_out != nullptr) eps_out[idx] = eps;
+}
+
+static inline unsigned blocks_for(long long n) { return static_cast<unsigned>((n + 255) / 256); }
+
+}  // namespace fmc
+
+using namespace fmc;
+
+extern "C" int fmc_add_bf16(const void* a, long long lda, const void* b, long long ldb, const float* rowbias,
+                            int rows_per_group, long long ldrb, void* out, long long ldo, long long rows, int C,
+                            int relu, void* stream) {
+  FMC_REQUIRE(a && out, FMC_ERR_ARG, "fmc_add_bf16: null operand");
+  FMC_REQUIRE(C % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0 && (b == nullptr || ldb % 8 == 0), FMC_ERR_SHAPE,
+              "fmc_add_bf16: C and strides must be multiples of 8");
+  FMC_REQUIRE(rowbias == nullptr || rows_per_group > 0, FMC_ERR_ARG, "fmc_add_bf16: rows_per_group must be positive");
+  if (rows == 0) return FMC_OK;
+  add_kernel<<<blocks_for(rows * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), lda, static_cast<const __nv_bfloat16*>(b), ldb, rowbias,
+      rows_per_group > 0 ? rows_per_group : 1, ldrb, static_cast<__nv_bfloat16*>(out), ldo, rows, C, relu);
+  return check_launch("add_kernel");
+}
+
+extern "C" int fmc_resize_nearest_bf16(const void* x, void* out, int N, int h, int w, int oh, int ow, int C,
+                                       void* stream) {
+  FMC_REQUIRE(x && out, FMC_ERR_ARG, "fmc_resize_nearest_bf16: null operand");
+  FMC_REQUIRE(C % 8 == 0, FMC_ERR_SHAPE, "fmc_resize_nearest_bf16: C must be a multiple of 8");
+  const long long total = static_cast<long long>(N) * oh * ow * (C / 8);
+  if (total == 0) return FMC_OK;
+  resize_nearest_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, h, w, oh, ow, C,
+      static_cast<float>(h) / oh, static_cast<float>(w) / ow);
+  return check_launch("resize_nearest_kernel");
+}
+
+extern "C" int fmc_avgpool2_bf16(const void* x, void* out, int N, int h, int w, int C, void* stream) {
+  FMC_REQUIRE(x && out, FMC_ERR_ARG, "fmc_avgpool2_bf16: null operand");
+  FMC_REQUIRE(C % 8 == 0, FMC_ERR_SHAPE, "fmc_avgpool2_bf16: C must be a multiple of 8");
+  const long long total = static_cast<long long>(N) * (h / 2) * (w / 2) * (C / 8);
+  if (total == 0) return FMC_OK;
+  avgpool2_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, h, w, C);
+  return check_launch("avgpool2_kernel");
+}
+
+extern "C" int fmc_copy2d_bf16(const void* src, long long lds, void* dst, long long ldd, long long rows, int cols,
+                               void* stream) {
+  FMC_REQUIRE(src && dst, FMC_ERR_ARG, "fmc_copy2d_bf16: null operand");
+  FMC_REQUIRE(cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, FMC_ERR_SHAPE, "fmc_copy2d_bf16: cols/strides must be multiples of 8");
+  if (rows == 0 || cols == 0) return FMC_OK;
+  copy2d_kernel<<<blocks_for(rows * (cols / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
+  return check_launch("copy2d_kernel");
+}
+
+extern "C" int fmc_ncfhw_f32_to_cl_bf16(const float* x, void* out, int B, int C, int F, long long HW, int Cpad,
+                                        void* stream) {
+  FMC_REQUIRE(x && out && Cpad >= C, FMC_ERR_ARG, "fmc_ncfhw_f32_to_cl_bf16: bad arguments");
+  const long long total = static_cast<long long>(B) * F * HW * Cpad;
+  if (total == 0) return FMC_OK;
+  ncfhw_to_cl_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(out), B, C, F, HW, Cpad);
+  return check_launch("ncfhw_to_cl_kernel");
+}
+
+extern "C" int fmc_cl_bf16_to_ncfhw_f32(const void* x, long long ldc, float* out, int B, int C, int F, long long HW,
+                                        void* stream) {
+  FMC_REQUIRE(x && out && ldc >= C, FMC_ERR_ARG, "fmc_cl_bf16_to_ncfhw_f32: bad arguments");
+  const long long total = static_cast<long long>(B) * C * F * HW;
+  if (total == 0) return FMC_OK;
+  cl_to_ncfhw_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldc, out, B, C, F, HW);
+  return check_launch("cl_to_ncfhw_kernel");
+}
+
+extern "C" int fmc_cast_act_bf16(const float* x, void* out, long long n, int silu, void* stream) {
+  FMC_REQUIRE(x && out, FMC_ERR_ARG, "fmc_cast_act_bf16: null operand");
+  if (n == 0) return FMC_OK;
+  cast_act_kernel<<<blocks_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(out), n, silu);
+  return check_launch("cast_act_kernel");
+}
+
+extern "C" int fmc_timestep_embedding_bf16(const float* t, void* out, int B, int dim, void* stream) {
+  FMC_REQUIRE(t && out && dim % 2 == 0, FMC_ERR_ARG, "fmc_timestep_embedding_bf16: bad arguments");
+  if (B == 0) return FMC_OK;
+  timestep_embedding_kernel<<<(B * dim / 2 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      t, static_cast<__nv_bfloat16*>(out), B, dim);
+  return check_launch("timestep_embedding_kernel");
+}
+
+extern "C" int fmc_plucker_f32(const float* K, const float* c2w, float* out, int BF, int H, int W, void* stream) {
+  FMC_REQUIRE(K && c2w && out, FMC_ERR_ARG, "fmc_plucker_f32: null operand");
+  const long long total = static_cast<long long>(BF) * H * W;
+  if (total == 0) return FMC_OK;
+  plucker_plain_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(K, c2w, out, BF, H, W);
+  return check_launch("plucker_plain_kernel");
+}
+
+extern "C" int fmc_plucker_unshuffle_bf16(const float* K, const float* c2w, void* out, int BF, int H, int W,
+                                          void* stream) {
+  FMC_REQUIRE(K && c2w && out, FMC_ERR_ARG, "fmc_plucker_unshuffle_bf16: null operand");
+  FMC_REQUIRE(H % 8 == 0 && W % 8 == 0, FMC_ERR_SHAPE, "fmc_plucker_unshuffle_bf16: H=%d W=%d must be multiples of 8", H, W);
+  const long long total = static_cast<long long>(BF) * (H / 8) * (W / 8) * 8;
+  if (total == 0) return FMC_OK;
+  plucker_unshuffle_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      K, c2w, static_cast<__nv_bfloat16*>(out), BF, H, W);
+  return check_launch("plucker_unshuffle_kernel");
+}
+
+extern "C" int fmc_traj_scatter_f32(const float* info, const float* masks, float* feat, float* mask_out, int BF,
+                                    int n_obj, int H, int W, void* stream) {
+  FMC_REQUIRE(info && masks && feat && mask_out, FMC_ERR_ARG, "fmc_traj_scatter_f32: null operand");
+  const long long total = static_cast<long long>(BF) * H * W;
+  if (total == 0) return FMC_OK;
+  traj_plain_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(info, masks, feat, mask_out, BF, n_obj, H, W);
+  return check_launch("traj_plain_kernel");
+}
+
+extern "C" int fmc_traj_scatter_unshuffle_bf16(const float* info, const float* masks, void* feat, float* mask_out,
+                                               int BF, int n_obj, int H, int W, void* stream) {
+  FMC_REQUIRE(info && masks && feat && mask_out, FMC_ERR_ARG, "fmc_traj_scatter_unshuffle_bf16: null operand");
+  FMC_REQUIRE(H % 8 == 0 && W % 8 == 0, FMC_ERR_SHAPE, "fmc_traj_scatter_unshuffle_bf16: H=%d W=%d must be multiples of 8", H, W);
+  const long long total = static_cast<long long>(BF) * (H / 8) * (W / 8) * 8;
+  if (total == 0) return FMC_OK;
+  traj_unshuffle_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      info, masks, static_cast<__nv_bfloat16*>(feat), mask_out, BF, n_obj, H, W);
+  return check_launch("traj_unshuffle_kernel");
+}
+
+extern "C" int fmc_mask_modulate_bf16(const void* x, const float* mask, const int* row_index, const int* col_index,
+                                      void* out, int N, int h, int w, int C, int H, int W, void* stream) {
+  FMC_REQUIRE(x && mask && row_index && col_index && out, FMC_ERR_ARG, "fmc_mask_modulate_bf16: null operand");
+  FMC_REQUIRE(C % 8 == 0, FMC_ERR_SHAPE, "fmc_mask_modulate_bf16: C must be a multiple of 8");
+  const long long total = static_cast<long long>(N) * h * w * (C / 8);
+  if (total == 0) return FMC_OK;
+  mask_modulate_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), mask, row_index, col_index, static_cast<__nv_bfloat16*>(out), N, h, w, C, H, W);
+  return check_launch("mask_modulate_kernel");
+}
+
+extern "C" int fmc_cfg_ddim_step_f32(const float* eps_uncond, const float* eps_cond, float guidance_scale,
+                                     const float* latents, float* latents_out, float* eps_out, float alpha_t,
+                                     float alpha_prev, long long n, void* stream) {
+  FMC_REQUIRE(eps_uncond && latents && latents_out, FMC_ERR_ARG, "fmc_cfg_ddim_step_f32: null operand");
+  FMC_REQUIRE(alpha_t > 0.f && alpha_t <= 1.f && alpha_prev > 0.f && alpha_prev <= 1.f, FMC_ERR_ARG,
+              "fmc_cfg_ddim_step_f32: alphas must be in (0, 1]");
+  if (n == 0) return FMC_OK;
+  cfg_ddim_kernel<<<blocks_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      eps_uncond, eps_cond, guidance_scale, latents, latents_out, eps_out, sqrtf(alpha_t), sqrtf(1.f - alpha_t),
+      sqrtf(alpha_prev), sqrtf(1.f - alpha_prev), n);
+  return check_launch("cfg_ddim_kernel");
+}

@@ -85,6 +85,24 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* map, uin
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// Variants taking a shared-window address (u32) for the destination.
+__device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const void* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_a(uint32_t smem_dst, const void* map, uint64_t* bar, int c0, int c1,
+                                              int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
@@ -142,6 +160,23 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          | (1u << 10)                            // B format  = BF16
          | (static_cast<uint32_t>(N >> 3) << 17) // N / 8
          | (static_cast<uint32_t>(M >> 4) << 24);// M / 16
+}
+
+// MN-major operand tile staged by TMA with SWIZZLE_128B: each K index is one 128-byte row holding 64 consecutive
+// M/N elements; eight K rows form a 1024-byte group (SBO); 64-element M/N blocks are `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::f16 instruction descriptor with B taken MN-major (A stays K-major).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the CTA.

@@ -1,0 +1,410 @@
+"""Execution engine of the B200-native FMC denoising step.
+
+Activations are channels-last bf16 `[B, f, h, w, C]` for the whole step, so the spatial token view `[(B f), (h w), C]`
+and the temporal one `[(B h w), f, C]` (frame stride h*w rows) are both free: none of the reference's einops
+rearranges (fmc/models/unet_blocks.py:402-409, fmc/models/motion_module.py:218,230) exist here.
+
+`*Plan` objects hold device-ready weights derived once from the fp32 parameters of the `fmc.models` mirror modules:
+Domain-LoRA folded into the projections (exact while LoRA is frozen), q|k|v fused into one GEMM with the
+q/k heads zero-padded to a multiple of 16 columns, GEGLU rows interleaved for the fused epilogue, the CameraAdapter
+scale folded into qkv_merge.  The `run_*` functions issue the kernels of include/fmc_b200.h in order.
+"""
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+# --------------------------------------------------------------------------------------------------------------
+# channels-last activation wrapper passed between the mirror modules
+# --------------------------------------------------------------------------------------------------------------
+class CL:
+    """A `[B, C, f, h, w]` activation stored channels-last as bf16 `[B, f, h, w, C]`.
+
+    `.shape` reports the reference layout so code written against `fmc.models` (e.g. the trainer-bound
+    Adapted_*_forward functions reading `hidden_states.shape[2]`) keeps working."""
+
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        assert t.dtype == BF16 and t.ndim == 5 and t.is_contiguous()
+        self.t = t
+
+    @staticmethod
+    def from_reference(x):
+        return x if isinstance(x, CL) else CL(ops.to_channels_last(x))
+
+    def to_reference(self):
+        return ops.from_channels_last(self.t)
+
+    @property
+    def shape(self):
+        B, F, H, W, C = self.t.shape
+        return torch.Size((B, C, F, H, W))
+
+    @property
+    def dims(self):
+        return tuple(self.t.shape)  # B, F, H, W, C
+
+    def rows(self):
+        return self.t.view(-1, self.t.shape[-1])
+
+    def images(self):
+        B, F, H, W, C = self.t.shape
+        return self.t.view(B * F, H, W, C)
+
+    def __add__(self, other):
+        other = CL.from_reference(other)
+        assert other.t.shape == self.t.shape
+        return CL(ops.add(self.rows(), other.rows()).view(self.t.shape))
+
+
+def as_cl_feature(x):
+    """Pose / object features arrive either as CL or in the reference layout [B, C, f, h, w]."""
+    return CL.from_reference(x)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# plans
+# --------------------------------------------------------------------------------------------------------------
+def _dev_bf16(w, device):
+    return w.detach().to(device=device, dtype=torch.float32).to(BF16).contiguous()
+
+
+def _dev_f32(w, device):
+    return None if w is None else w.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class LinearPlan:
+    def __init__(self, weight, bias, device, geglu=False):
+        """weight [N, K] fp32 (already folded / fused), bias [N] or None."""
+        if geglu:
+            weight, bias = _interleave_geglu(weight, bias)
+        self.w = _dev_bf16(weight, device)
+        self.b = _dev_f32(bias, device)
+        self.geglu = geglu
+        self.N, self.K = self.w.shape
+
+    def __call__(self, a, residual=None, out=None, rowbias=None, rows_per_group=0):
+        return ops.gemm(a, self.w, bias=self.b, residual=residual, out=out, geglu=self.geglu, rowbias=rowbias,
+                        rows_per_group=rows_per_group)
+
+
+def _interleave_geglu(weight, bias):
+    """diffusers GEGLU: proj -> chunk(2) = (value | gate).  Reorder rows into blocks of 16 value rows followed by their
+    16 gate rows so the GEMM epilogue can form value * gelu(gate) from adjacent TMEM column chunks."""
+    n2 = weight.shape[0]
+    half = n2 // 2
+    assert half % 16 == 0
+    idx = torch.arange(half).view(-1, 16)
+    order = torch.cat([idx, idx + half], dim=1).reshape(-1)
+    weight = weight[order]
+    bias = bias[order] if bias is not None else None
+    return weight, bias
+
+
+def _fold_lora(linear_w, lora, scale):
+    """W' = W + scale * (alpha/rank) * up @ down  (diffusers LoRALinearLayer; fmc attention_processor.py:138)."""
+    if lora is None:
+        return linear_w.detach().float()
+    up, down = lora.up.weight.detach().float(), lora.down.weight.detach().float()
+    s = scale
+    if getattr(lora, "network_alpha", None) is not None:
+        s = s * lora.network_alpha / lora.rank
+    return linear_w.detach().float() + s * (up @ down)
+
+
+def _pad_heads(w, heads, d, hs):
+    """[heads*d, K] -> [heads*hs, K] with zero rows after each head (hs = d rounded up to 16)."""
+    if hs == d:
+        return w
+    K = w.shape[1]
+    out = w.new_zeros(heads, hs, K)
+    out[:, :d] = w.view(heads, d, K)
+    return out.view(heads * hs, K)
+
+
+class AttnPlan:
+    """One attention (spatial self, spatial text-cross, or temporal self) with everything foldable folded."""
+
+    def __init__(self, attn, device, lora_scale_override=None):
+        from .fmc.models.attention_processor import (LoRAAttnProcessor, LORAPoseAdaptorAttnProcessor,
+                                                     PoseAdaptorAttnProcessor)
+        proc = attn.processor
+        heads = attn.heads
+        C = attn.to_q.weight.shape[0]
+        d = C // heads
+        hs = (d + 15) // 16 * 16
+        self.heads, self.d, self.hs, self.C = heads, d, hs, C
+        self.scale = attn.scale
+        self.rescale = float(getattr(attn, "rescale_output_factor", 1.0))
+        has_lora = isinstance(proc, (LoRAAttnProcessor, LORAPoseAdaptorAttnProcessor))
+        ls = 0.0
+        if has_lora:
+            ls = proc.lora_scale if lora_scale_override is None else lora_scale_override
+
+        def folded(name):
+            lin = getattr(attn, name) if name != "to_out" else attn.to_out[0]
+            lora = getattr(proc, f"{name}_lora") if has_lora else None
+            return _fold_lora(lin.weight, lora, ls)
+
+        wq = _pad_heads(folded("to_q"), heads, d, hs)
+        wk = _pad_heads(folded("to_k"), heads, d, hs)
+        wv = folded("to_v")
+        self.is_cross = bool(getattr(attn, "is_cross_attention", False))
+        if self.is_cross:
+            self.q = LinearPlan(wq, None, device)
+            self.kv = LinearPlan(torch.cat([wk, wv], dim=0), None, device)
+        else:
+            self.qkv = LinearPlan(torch.cat([wq, wk, wv], dim=0), None, device)
+        wo = folded("to_out") / self.rescale
+        bo = attn.to_out[0].bias.detach().float() / self.rescale if attn.to_out[0].bias is not None else None
+        self.out = LinearPlan(wo, bo, device)
+        # CameraAdapter: m = qkv_merge(x + pose) * scale + x  (attention_processor.py:257); scale folded into W, b
+        self.merge = None
+        if isinstance(proc, (PoseAdaptorAttnProcessor, LORAPoseAdaptorAttnProcessor)):
+            if not (proc.query_condition and proc.key_value_condition):
+                raise NotImplementedError("only query_condition and key_value_condition (qkv_merge) is configured by the "
+                                          "shipped FMC configs (configs/cam.yaml:121-129)")
+            s = float(proc.scale)
+            self.merge = LinearPlan(proc.qkv_merge.weight.detach().float() * s,
+                                    proc.qkv_merge.bias.detach().float() * s, device)
+        self.q_col0 = 0
+        self.k_col0 = heads * hs
+        self.v_col0 = 2 * heads * hs
+
+
+class NormPlan:
+    def __init__(self, norm, device):
+        self.g = _dev_f32(norm.weight, device)
+        self.b = _dev_f32(norm.bias, device)
+        self.eps = float(norm.eps)
+        self.groups = getattr(norm, "num_groups", None)
+
+
+class ConvPlan:
+    def __init__(self, conv, device):
+        self.w = conv.weight.detach().to(device=device, dtype=BF16).contiguous(memory_format=torch.channels_last)
+        self.b = conv.bias.detach().to(device=device, dtype=BF16) if conv.bias is not None else None
+        self.stride = conv.stride
+        self.padding = conv.padding
+        self.cin, self.cout = conv.in_channels, conv.out_channels
+        self.ksize = conv.kernel_size[0]
+        # 1x1 convolutions are plain GEMMs over channels-last rows
+        self.linear = LinearPlan(conv.weight.detach().float().view(self.cout, self.cin), conv.bias, device) \
+            if self.ksize == 1 and self.cin % 8 == 0 and self.cout % 16 == 0 else None
+
+    def __call__(self, x_img, relu=False):
+        """x_img [N, h, w, Cin] -> [N, oh, ow, Cout]."""
+        if self.linear is not None:
+            N, h, w, _ = x_img.shape
+            y = self.linear(x_img.reshape(-1, self.cin)).view(N, h, w, self.cout)
+        else:
+            y = ops.conv2d_cl(x_img, self.w, self.b, stride=self.stride, padding=self.padding)
+        if relu:
+            y2 = y.view(-1, self.cout)
+            ops.add(y2, relu=True, out=y2)
+        return y
+
+
+# --------------------------------------------------------------------------------------------------------------
+# executors
+# --------------------------------------------------------------------------------------------------------------
+def run_spatial_self_attention(plan, x_norm, residual, images, n_tokens):
+    """attn1 of a BasicTransformerBlock on rows [(images n_tokens), C]; returns to_out(attn) + residual."""
+    qkv = plan.qkv(x_norm)
+    ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=BF16)
+    ops.spatial_attn(qkv, plan.q_col0, qkv, plan.k_col0, qkv, plan.v_col0, plan.hs, ctx, images, plan.heads, plan.d,
+                     n_tokens, n_tokens, 1, n_tokens, plan.scale)
+    return plan.out(ctx, residual=residual)
+
+
+TEXT_PAD = 80  # text keys per batch item, 77 padded to a multiple of 8 rows (TMA row-stride alignment)
+
+
+def prepare_text(text, device):
+    """[B, 77, 768] fp32 -> zero-padded bf16 rows [B * 80, 768] shared by every cross-attention of the step."""
+    B, n, c = text.shape
+    buf = torch.zeros((B, TEXT_PAD, c), device=device, dtype=BF16)
+    buf[:, :n] = text.to(device=device, dtype=BF16)
+    return buf.view(B * TEXT_PAD, c), n
+
+
+def run_spatial_cross_attention(plan, x_norm, residual, images, n_tokens, text_rows, text_len, frames):
+    """attn2: queries from the latent tokens, keys / values from the text of the clip the frame belongs to.  The
+    reference repeats the text f times ('b n c -> (b f) n c', unet.py:1110); here K/V are projected once per clip
+    and image i reads kv group i // frames."""
+    q = plan.q(x_norm)
+    kv = plan.kv(text_rows)
+    ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=BF16)
+    ops.spatial_attn(q, 0, kv, 0, kv, plan.heads * plan.hs, plan.hs, ctx, images, plan.heads, plan.d, n_tokens, text_len,
+                     frames, TEXT_PAD, plan.scale)
+    return plan.out(ctx, residual=residual)
+
+
+def run_temporal_attention(plan, x_norm, x_plus_pose, residual, B, F, HW):
+    """TemporalSelfAttention on channels-last rows.  x_norm = LN(h) + PE; x_plus_pose = x_norm + pose (block 0 only)."""
+    src = x_norm
+    if plan.merge is not None:
+        src = plan.merge(x_plus_pose, residual=x_norm)  # m = qkv_merge(x + pose) * s + x
+    qkv = plan.qkv(src)
+    ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=BF16)
+    ops.temporal_attn(qkv, plan.q_col0, plan.k_col0, plan.v_col0, plan.hs, ctx, B, F, HW, plan.heads, plan.d, plan.scale)
+    return plan.out(ctx, residual=residual)
+
+
+def nearest_index_chain(sizes):
+    """Index map of iterated F.interpolate(mode='nearest') calls: sizes = [full, level0, level1, ...].  Returns, per
+    level, the int32 index into the FULL-resolution axis (torch: src = min(floor(dst * in/out), in - 1), float32)."""
+    maps = []
+    cur = torch.arange(sizes[0], dtype=torch.int64)
+    for prev, nxt in zip(sizes[:-1], sizes[1:]):
+        scale = torch.tensor(prev / nxt, dtype=torch.float32)
+        src = torch.clamp(torch.floor(torch.arange(nxt, dtype=torch.float32) * scale).to(torch.int64), max=prev - 1)
+        cur = cur[src]
+        maps.append(cur.to(torch.int32))
+    return maps
+
+
+# --------------------------------------------------------------------------------------------------------------
+# text context shared by every cross-attention of one U-Net call
+# --------------------------------------------------------------------------------------------------------------
+class TextCtx:
+    """encoder_hidden_states [B, 77, 768] -> zero-padded bf16 rows [B * 80, 768]."""
+
+    def __init__(self, text, device):
+        self.rows, self.length = prepare_text(text, device)
+        self.batch = text.shape[0]
+
+    @staticmethod
+    def of(x, batch, frames, device):
+        if isinstance(x, TextCtx):
+            return x
+        if x.shape[0] == batch * frames and frames > 1:
+            x = x[::frames]  # the reference's 'b n c -> (b f) n c' repeat (unet.py:1110): every f-th row is distinct
+        assert x.shape[0] == batch, (x.shape, batch)
+        return TextCtx(x, device)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Transformer2DModel / ResnetBlock2D / resamplers on channels-last activations
+# --------------------------------------------------------------------------------------------------------------
+def plan_transformer2d(mod, device):
+    if getattr(mod, "_plan", None) is None or mod._plan["device"] != device:
+        blocks = []
+        for blk in mod.transformer_blocks:
+            blocks.append({
+                "norm1": NormPlan(blk.norm1, device), "attn1": AttnPlan(blk.attn1, device),
+                "norm2": NormPlan(blk.norm2, device), "attn2": AttnPlan(blk.attn2, device),
+                "norm3": NormPlan(blk.norm3, device),
+                "ff1": LinearPlan(blk.ff.net[0].proj.weight.detach().float(), blk.ff.net[0].proj.bias.detach().float(),
+                                  device, geglu=True),
+                "ff2": LinearPlan(blk.ff.net[2].weight.detach().float(), blk.ff.net[2].bias.detach().float(), device),
+            })
+        c_in = mod.proj_in.weight.shape[1]
+        inner = mod.proj_in.weight.shape[0]
+        mod._plan = {
+            "device": device, "norm": NormPlan(mod.norm, device), "blocks": blocks,
+            "proj_in": LinearPlan(mod.proj_in.weight.detach().float().view(inner, c_in), mod.proj_in.bias.detach().float(), device),
+            "proj_out": LinearPlan(mod.proj_out.weight.detach().float().view(c_in, inner), mod.proj_out.bias.detach().float(), device),
+        }
+    return mod._plan
+
+
+def run_transformer2d(mod, x, text):
+    """diffusers Transformer2DModel as called at fmc/models/unet_blocks.py:407: GN -> 1x1 conv -> [self-attn, text
+    cross-attn, GEGLU FF] -> 1x1 conv -> + input."""
+    B, F, H, W, C = x.dims
+    images, N = B * F, H * W
+    rows = x.rows()
+    p = plan_transformer2d(mod, rows.device)
+    text = TextCtx.of(text, B, F, rows.device)
+    n = ops.groupnorm(rows, p["norm"].g, p["norm"].b, p["norm"].eps, images, N, groups=p["norm"].groups)
+    h = p["proj_in"](n)
+    for bp in p["blocks"]:
+        n1 = ops.layernorm(h, bp["norm1"].g, bp["norm1"].b, bp["norm1"].eps)
+        h = run_spatial_self_attention(bp["attn1"], n1, h, images, N)
+        n2 = ops.layernorm(h, bp["norm2"].g, bp["norm2"].b, bp["norm2"].eps)
+        h = run_spatial_cross_attention(bp["attn2"], n2, h, images, N, text.rows, text.length, F)
+        n3 = ops.layernorm(h, bp["norm3"].g, bp["norm3"].b, bp["norm3"].eps)
+        h = bp["ff2"](bp["ff1"](n3), residual=h)
+    out = p["proj_out"](h, residual=rows)
+    return CL(out.view(B, F, H, W, C))
+
+
+def plan_resnet(mod, device):
+    if getattr(mod, "_plan", None) is None or mod._plan["device"] != device:
+        mod._plan = {
+            "device": device,
+            "norm1": NormPlan(mod.norm1, device), "conv1": ConvPlan(mod.conv1, device),
+            "temb": LinearPlan(mod.time_emb_proj.weight.detach().float(), mod.time_emb_proj.bias.detach().float(), device),
+            "norm2": NormPlan(mod.norm2, device), "conv2": ConvPlan(mod.conv2, device),
+            "shortcut": ConvPlan(mod.conv_shortcut, device) if mod.conv_shortcut is not None else None,
+            "scale": float(mod.output_scale_factor),
+        }
+        assert mod._plan["scale"] == 1.0, "output_scale_factor != 1 is not used by SD1.5 / FMC"
+    return mod._plan
+
+
+class Temb:
+    """Time embedding `emb` [B, 1280] fp32 plus its cached silu(emb) in bf16 (the operand of every time_emb_proj)."""
+
+    def __init__(self, emb):
+        self.emb = emb
+        self.act = ops.cast_act(emb, silu=True)
+
+    @staticmethod
+    def of(x):
+        return x if isinstance(x, Temb) else Temb(x.float())
+
+
+def run_resnet(mod, x, temb):
+    """diffusers ResnetBlock2D per frame (unet_blocks.py:402-404)."""
+    temb_act = Temb.of(temb).act
+    B, F, H, W, C = x.dims
+    images, HW = B * F, H * W
+    rows = x.rows()
+    p = plan_resnet(mod, rows.device)
+    n1 = ops.groupnorm(rows, p["norm1"].g, p["norm1"].b, p["norm1"].eps, images, HW, groups=p["norm1"].groups, silu=True)
+    h = p["conv1"](n1.view(images, H, W, C))
+    cout = h.shape[-1]
+    tproj = ops.gemm(temb_act, p["temb"].w, bias=p["temb"].b, out_f32=True)  # [B, Cout] fp32, broadcast over frames
+    # the time-embedding add happens inside the second GroupNorm (before its statistics), saving a pass over h
+    n2 = ops.groupnorm(h.view(-1, cout), p["norm2"].g, p["norm2"].b, p["norm2"].eps, images, HW, groups=p["norm2"].groups,
+                       silu=True, rowbias=tproj, rowbias_div=F)
+    h2 = p["conv2"](n2.view(images, H, W, cout)).view(-1, cout)
+    if p["shortcut"] is not None:
+        out = p["shortcut"].linear(rows, residual=h2)
+    else:
+        out = ops.add(rows, h2)
+    return CL(out.view(B, F, H, W, cout))
+
+
+def run_downsample(mod, x):
+    B, F, H, W, C = x.dims
+    if getattr(mod, "_plan", None) is None or mod._plan.w.device != x.t.device:
+        mod._plan = ConvPlan(mod.conv, x.t.device)
+    y = mod._plan(x.images())
+    return CL(y.view(B, F, *y.shape[1:]))
+
+
+def run_upsample(mod, x, output_size=None):
+    B, F, H, W, C = x.dims
+    if getattr(mod, "_plan", None) is None or mod._plan.w.device != x.t.device:
+        mod._plan = ConvPlan(mod.conv, x.t.device)
+    oh, ow = (2 * H, 2 * W) if output_size is None else (int(output_size[-2]), int(output_size[-1]))
+    up = ops.resize_nearest(x.images(), oh, ow)
+    y = mod._plan(up)
+    return CL(y.view(B, F, *y.shape[1:]))
+
+
+def concat_channels(a, b):
+    """torch.cat([a, b], dim=1) of the reference layout = channel concat of channels-last rows."""
+    B, F, H, W, Ca = a.dims
+    Cb = b.dims[-1]
+    out = torch.empty((B, F, H, W, Ca + Cb), device=a.t.device, dtype=BF16)
+    rows = out.view(-1, Ca + Cb)
+    ops.copy2d(a.rows(), rows[:, :Ca])
+    ops.copy2d(b.rows(), rows[:, Ca:])
+    return CL(out)

@@ -1,0 +1,19 @@
+"""Mirror of the one hot-path function of fmc/data/dataset.py: `ray_condition` (:930-972), the Pluecker-ray embedding,
+computed on the GPU by fmc_plucker_f32 instead of on the CPU (train_cam_ctrl.py:87 passes device='cpu')."""
+import torch
+
+from ... import ops
+
+
+def ray_condition(K, c2w, H, W, device, flip_flag=None):
+    """K [B, V, 4] = (fx, fy, cx, cy); c2w [B, V, 4, 4] -> [B, V, H, W, 6] = (o x d, d), fp32 on `device`.
+    (The reference's default-dim torch.cross misbehaves when B == 3 or V == 3; dim=-1 is implemented)"""
+    if flip_flag is not None and int(torch.as_tensor(flip_flag).sum().item()) > 0:
+        raise NotImplementedError("horizontal flip is never enabled by the trainers (flip_flag = zeros)")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("synfmc_b200.fmc.data.dataset.ray_condition runs on CUDA only (no CPU fallback)")
+    B, V = K.shape[:2]
+    Kd = K.to(dev, torch.float32).reshape(B * V, 4)
+    M = c2w.to(dev, torch.float32)[..., :3, :].reshape(B * V, 3, 4)
+    return ops.plucker(Kd, M, H, W).view(B, V, H, W, 6)

@@ -1,0 +1,175 @@
+"""Mirror of fmc/pipelines/pipeline_animation.py: `CameraCtrlPipeline` (:442-719).  The denoising loop (:661-707) --
+CFG batch doubling, per-window U-Net, CFG combine, multidiff window averaging, DDIM update -- runs on the libfmc_b200
+kernels; prompt encoding (CLIP) and VAE decode are frozen third-party networks outside the hot path (SURVEY.md
+section 2, rows 13) and are used as passed in (or skipped: pass `prompt_embeds`, read `.latents`)."""
+from types import SimpleNamespace
+
+import torch
+
+from ... import ops
+from ...engine import CL
+from ..models.pose_adaptor import unshuffle8_to_cl
+
+
+class AnimationPipelineOutput(SimpleNamespace):
+    pass
+
+
+def _slice_frames(feat, start, length):
+    t = feat.t[:, start:start + length]
+    return feat if t.shape[1] == feat.t.shape[1] else CL(t.contiguous())
+
+
+class CameraCtrlPipeline:
+    _accepts_traj = False
+
+    def __init__(self, vae, text_encoder, tokenizer, unet, scheduler, pose_encoder):
+        self.vae, self.text_encoder, self.tokenizer = vae, text_encoder, tokenizer
+        self.unet, self.scheduler, self.pose_encoder = unet, scheduler, pose_encoder
+        self.vae_scale_factor = 8
+
+    def enable_vae_slicing(self):
+        if self.vae is not None and hasattr(self.vae, "enable_slicing"):
+            self.vae.enable_slicing()
+
+    def to(self, device):
+        for m in (self.vae, self.text_encoder, self.unet, self.pose_encoder):
+            if m is not None and hasattr(m, "to"):
+                m.to(device)
+        return self
+
+    # ---- frozen third-party stages (outside the hot path) ----
+    def _encode_prompt(self, prompt, device, do_cfg, negative_prompt):
+        if self.text_encoder is None or self.tokenizer is None:
+            raise RuntimeError("no text encoder attached: pass prompt_embeds=[(2)b, 77, 768]")
+        def enc(texts):
+            ids = self.tokenizer(texts, padding="max_length", max_length=self.tokenizer.model_max_length,
+                                 truncation=True, return_tensors="pt").input_ids
+            return self.text_encoder(ids.to(device))[0]
+        cond = enc(prompt)
+        if not do_cfg:
+            return cond
+        neg = negative_prompt if negative_prompt is not None else [""] * len(prompt)
+        return torch.cat([enc(neg), cond])
+
+    def decode_latents(self, latents):
+        if self.vae is None:
+            raise RuntimeError("no VAE attached: read `.latents` from the output instead of `.videos`")
+        f = latents.shape[2]
+        latents = (1 / 0.18215 * latents).permute(0, 2, 1, 3, 4).flatten(0, 1)
+        frames = [self.vae.decode(latents[i:i + 1]).sample for i in range(latents.shape[0])]
+        video = torch.cat(frames)
+        video = video.reshape(-1, f, *video.shape[1:]).permute(0, 2, 1, 3, 4)
+        return (video / 2 + 0.5).clamp(0, 1).cpu().float()
+
+    def prepare_latents(self, batch_size, channels, video_length, height, width, dtype, device, generator, latents=None):
+        shape = (batch_size, channels, video_length, height // self.vae_scale_factor, width // self.vae_scale_factor)
+        if latents is None:
+            rand_device = "cpu" if generator is not None and generator.device.type == "cpu" else device
+            latents = torch.randn(shape, generator=generator, device=rand_device, dtype=dtype).to(device)
+        else:
+            if latents.shape != shape:
+                raise ValueError(f"Unexpected latents shape, got {latents.shape}, expected {shape}")
+            latents = latents.to(device)
+        return latents * self.scheduler.init_noise_sigma
+
+    # ---- the hot loop ----
+    @torch.no_grad()
+    def denoise(self, latents, text_embeddings, pose_features, video_length, traj_features=None,
+                num_inference_steps=25, guidance_scale=8.0, multidiff_total_steps=1, multidiff_overlaps=12,
+                omcm_min_step=None, max_steps=None, callback=None, callback_steps=1):
+        """latents [b, 4, F, h, w] fp32 (device); text_embeddings [(2)b, 77, 768]; pose_features: 4 CL features over all
+        F frames (already duplicated for CFG); traj_features: 4 CL features (CFG: zeros ++ features) or None."""
+        do_cfg = guidance_scale > 1.0
+        self.scheduler.set_timesteps(num_inference_steps)
+        L = video_length
+        b = latents.shape[0]
+        latents = latents.float().contiguous()
+        for i, t in enumerate(self.scheduler.timesteps.tolist()):
+            if max_steps is not None and i >= max_steps:
+                break
+            step_traj = traj_features
+            if omcm_min_step is not None and traj_features is not None and omcm_min_step > 0 and t < omcm_min_step:
+                step_traj = None
+            a_t, a_prev = self.scheduler.alphas_for(t)
+            window_eps = []
+            for k in range(multidiff_total_steps):
+                s = k * (L - multidiff_overlaps)
+                part = latents[:, :, s:s + L].contiguous()
+                x_in = torch.cat([part] * 2) if do_cfg else part
+                feats = [_slice_frames(f, s, L) for f in pose_features]
+                kw = {"traj_features": step_traj} if self._accepts_traj else {}
+                eps = self.unet(x_in, t, encoder_hidden_states=text_embeddings, pose_embedding_features=feats,
+                                **kw).sample
+                window_eps.append((s, eps))
+            if multidiff_total_steps == 1:
+                s, eps = window_eps[0]
+                e_u, e_c = (eps[:b], eps[b:]) if do_cfg else (eps, None)
+                latents = ops.cfg_ddim_step(e_u, e_c, guidance_scale, latents, a_t, a_prev)
+            else:
+                # overlapping windows: average the guided predictions per frame (:673-699), then one DDIM update
+                noise = torch.zeros_like(latents)
+                count = torch.zeros_like(latents)
+                for s, eps in window_eps:
+                    count[:, :, s:s + L] += 1
+                for s, eps in window_eps:
+                    e = eps[:b] + guidance_scale * (eps[b:] - eps[:b]) if do_cfg else eps
+                    noise[:, :, s:s + L] += e / count[:, :, s:s + L]
+                latents = ops.cfg_ddim_step(noise, None, 1.0, latents, a_t, a_prev)
+            if callback is not None and i % callback_steps == 0:
+                callback(i, t, latents)
+        return latents
+
+    def _pose_features(self, pose_embedding, do_cfg):
+        if isinstance(pose_embedding, list):
+            raise NotImplementedError("per-window pose-embedding lists: pass one embedding covering all frames")
+        assert pose_embedding.ndim == 5
+        feats = self.pose_encoder.encode_cl(unshuffle8_to_cl(pose_embedding.float()))
+        if do_cfg:
+            feats = [CL(torch.cat([f.t, f.t], dim=0)) for f in feats]
+        return feats
+
+    def _traj_features(self, traj_features, do_cfg):
+        if traj_features is None:
+            return None
+        feats = [CL.from_reference(f) for f in traj_features]
+        if do_cfg:
+            feats = [CL(torch.cat([torch.zeros_like(f.t), f.t], dim=0)) for f in feats]  # uncond half gets zeros (:671-676)
+        return feats
+
+    @torch.no_grad()
+    def __call__(self, prompt, pose_embedding, video_length, traj_features=None, height=None, width=None,
+                 num_inference_steps=50, guidance_scale=7.5, negative_prompt=None, num_videos_per_prompt=1, eta=0.0,
+                 generator=None, latents=None, output_type="tensor", return_dict=True, callback=None,
+                 callback_steps=1, multidiff_total_steps=1, multidiff_overlaps=12, prompt_embeds=None, **kwargs):
+        assert eta == 0.0 and num_videos_per_prompt == 1
+        if traj_features is not None and not self._accepts_traj:
+            raise TypeError("traj_features needs CameraObjCtrlPipeline")
+        device = pose_embedding.device
+        height = height or self.unet.config.sample_size * self.vae_scale_factor
+        width = width or self.unet.config.sample_size * self.vae_scale_factor
+        batch_size = latents.shape[0] if latents is not None else 1
+        if isinstance(prompt, list):
+            batch_size = len(prompt)
+        do_cfg = guidance_scale > 1.0
+        if prompt_embeds is None:
+            prompt = prompt if isinstance(prompt, list) else [prompt] * batch_size
+            if negative_prompt is not None and not isinstance(negative_prompt, list):
+                negative_prompt = [negative_prompt] * batch_size
+            prompt_embeds = self._encode_prompt(prompt, device, do_cfg, negative_prompt)
+        single_len = video_length
+        total_len = multidiff_total_steps * (video_length - multidiff_overlaps) + multidiff_overlaps
+        latents = self.prepare_latents(batch_size, self.unet.in_channels, total_len, height, width, torch.float32,
+                                       device, generator, latents)
+        pose_features = self._pose_features(pose_embedding, do_cfg)
+        traj = self._traj_features(traj_features, do_cfg)
+        if traj is not None:
+            assert multidiff_total_steps == 1  # pipeline_animation_cm_om.py:690
+        latents = self.denoise(latents, prompt_embeds.to(device), pose_features, single_len, traj_features=traj,
+                               num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
+                               multidiff_total_steps=multidiff_total_steps, multidiff_overlaps=multidiff_overlaps,
+                               omcm_min_step=kwargs.get("omcm_min_step"), callback=callback,
+                               callback_steps=callback_steps)
+        videos = self.decode_latents(latents) if self.vae is not None else None
+        out = AnimationPipelineOutput(videos=videos, latents=latents)
+        return out if return_dict else (videos if videos is not None else latents)

@@ -1,0 +1,52 @@
+"""Mirror of fmc/util.py:147-213 `get_traj_features_v2`: builds the ObjectEncoder input (6-D object pose broadcast x
+Gaussian-mask scatter) and runs the ObjectEncoder.  The reference's Python triple loop with boolean-mask indexing
+(:161-182) is one kernel here (fmc_traj_scatter_unshuffle_bf16): last object with mask > 0 wins per pixel, channels
+(info*m)*m and m*m, written directly in the PixelUnshuffle(8) channels-last layout the Adapter consumes."""
+import random
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..engine import CL
+
+
+def pack_objects(obj_info_list_list, obj_mask_list_list, device):
+    """Nested lists (clip -> frame -> [n_obj, 12] numpy / [n_obj, 1, H, W] tensor) -> dense fp32 device tensors
+    info [B, F, n_max, 12], masks [B, F, n_max, H, W]; missing objects are zero masks (never selected)."""
+    assert len(obj_info_list_list) == len(obj_mask_list_list)
+    B, Fn = len(obj_info_list_list), len(obj_info_list_list[0])
+    H, W = obj_mask_list_list[0][0].shape[-2:]
+    n_max = max(int(np.asarray(i).shape[0]) for clip in obj_info_list_list for i in clip)
+    info = torch.zeros(B, Fn, n_max, 12, dtype=torch.float32)
+    masks = torch.zeros(B, Fn, n_max, H, W, dtype=torch.float32)
+    for b, (infos, ms) in enumerate(zip(obj_info_list_list, obj_mask_list_list)):
+        for f, (obj_info, obj_mask) in enumerate(zip(infos, ms)):
+            oi = torch.from_numpy(np.asarray(obj_info)).to(torch.float32)
+            om = torch.as_tensor(obj_mask).to(torch.float32)
+            info[b, f, :oi.shape[0]] = oi
+            masks[b, f, :om.shape[0]] = om[:, 0]
+    return info.to(device), masks.to(device)
+
+
+def traj_features_cl(info, masks, omcm, null_clips=None):
+    """info [B, F, n, 12], masks [B, F, n, H, W] (device fp32) -> 4 CL features [B, F, h_l, w_l, C_l]."""
+    B, Fn, n, H, W = masks.shape
+    feat, mask = ops.traj_scatter_unshuffle(info.view(B * Fn, n, 12), masks.view(B * Fn, n, H, W))
+    if null_clips:
+        fv = feat.view(B, Fn, *feat.shape[1:])
+        for i in null_clips:
+            fv[i].zero_()
+    outs = omcm.encode_cl(feat, mask)
+    return [CL(o.view(B, Fn, *o.shape[1:])) for o in outs]
+
+
+def get_traj_features_v2(obj_info_list_list, obj_mask_list_list, omcm, cfg_random_null_om, cfg_random_null_om_ratio,
+                         is_cm_condition_null_list, local_rank, dtype):
+    """Reference signature; returns 4 tensors [b, C_l, f, h_l, w_l] (fp32, reference layout)."""
+    device = torch.device("cuda", local_rank) if isinstance(local_rank, int) else torch.device(local_rank)
+    info, masks = pack_objects(obj_info_list_list, obj_mask_list_list, device)
+    null = []
+    if cfg_random_null_om:
+        null = [i for i in range(info.shape[0]) if not (random.random() > cfg_random_null_om_ratio)]
+    return [f.to_reference() for f in traj_features_cl(info, masks, omcm, null)]

@@ -1,0 +1,275 @@
+"""Tensor-level wrappers over the C ABI (include/fmc_b200.h).  torch is used for device memory and the current
+stream only; every function launches hand-written sm_100a kernels through ctypes and raises if the library or a
+CUDA device is missing (no CPU / eager fallback)."""
+import torch
+
+from . import _cabi
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _check_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _cabi.FmcError("synfmc_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _rows2d(t, dtype=BF16):
+    assert t.dtype == dtype and t.ndim == 2 and t.stride(1) == 1, (t.dtype, t.shape, t.stride())
+    return t
+
+
+def gemm(a, w, bias=None, residual=None, out=None, geglu=False, out_f32=False, rowbias=None, rows_per_group=0,
+         tile_n=0):
+    """out[M, N(/2)] = epilogue(a[M, K] @ w[N, K]^T); see fmc_gemm_bf16."""
+    _check_cuda(a, w)
+    _rows2d(a)
+    _rows2d(w)
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_f32 else BF16)
+    assert out.shape == (M, n_out) and out.stride(1) == 1
+    flags = (1 if geglu else 0) | (2 if out_f32 else 0)
+    if residual is not None:
+        _rows2d(residual)
+        assert residual.shape == (M, n_out)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+    if rowbias is not None:
+        assert rowbias.dtype == torch.float32 and rowbias.stride(1) == 1 and rowbias.shape[1] == N
+    _cabi.call("fmc_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), M, N,
+               K, _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, _ptr(rowbias),
+               rows_per_group, rowbias.stride(0) if rowbias is not None else 0, flags, tile_n, _stream())
+    return out
+
+
+def spatial_attn(q, q_col0, k, k_col0, v, v_col0, head_stride, out, images, heads, head_dim, nq, nk, kv_div, kv_stride,
+                 scale):
+    _check_cuda(q, k, v, out)
+    for t in (q, k, v, out):
+        _rows2d(t)
+    assert k.shape[0] == v.shape[0]
+    _cabi.call("fmc_spatial_attn_bf16", q.data_ptr(), q.stride(0), q_col0, q.shape[0], k.data_ptr(), k.stride(0), k_col0,
+               v.data_ptr(), v.stride(0), v_col0, k.shape[0], head_stride, out.data_ptr(), out.stride(0), images, heads,
+               head_dim, nq, nk, kv_div, kv_stride, float(scale), _stream())
+    return out
+
+
+def temporal_attn(qkv, q_col0, k_col0, v_col0, head_stride, out, B, F, HW, heads, head_dim, scale):
+    _check_cuda(qkv, out)
+    _rows2d(qkv)
+    _rows2d(out)
+    assert qkv.shape[0] == B * F * HW == out.shape[0]
+    _cabi.call("fmc_temporal_attn_bf16", qkv.data_ptr(), qkv.stride(0), q_col0, k_col0, v_col0, head_stride,
+               out.data_ptr(), out.stride(0), B, F, HW, heads, head_dim, float(scale), _stream())
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None, pe=None, F=0, HW=0, add=None, out2=None):
+    _check_cuda(x)
+    _rows2d(x)
+    rows, C = x.shape
+    if out is None:
+        out = torch.empty((rows, C), device=x.device, dtype=BF16)
+    if add is not None and out2 is None:
+        out2 = torch.empty((rows, C), device=x.device, dtype=BF16)
+    _cabi.call("fmc_layernorm_bf16", x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps),
+               out.data_ptr(), out.stride(0), _ptr(pe), F, HW, _ptr(add), add.stride(0) if add is not None else 0,
+               _ptr(out2), out2.stride(0) if out2 is not None else 0, rows, C, _stream())
+    return (out, out2) if add is not None else out
+
+
+def groupnorm(x, gamma, beta, eps, images, HW, groups=32, silu=False, rowbias=None, rowbias_div=1, out=None):
+    """x: [images*HW, C] rows (channels-last); statistics per (image, group)."""
+    _check_cuda(x)
+    _rows2d(x)
+    rows, C = x.shape
+    assert rows == images * HW
+    if out is None:
+        out = torch.empty((rows, C), device=x.device, dtype=BF16)
+    stats = torch.empty((images, groups, 2), device=x.device, dtype=torch.float32)
+    if rowbias is not None:
+        assert rowbias.dtype == torch.float32 and rowbias.shape == (images // rowbias_div, C) and rowbias.stride(1) == 1
+    _cabi.call("fmc_groupnorm_bf16", x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps),
+               out.data_ptr(), out.stride(0), stats.data_ptr(), images, HW, C, groups, 1 if silu else 0, _ptr(rowbias),
+               rowbias.stride(0) if rowbias is not None else 0, rowbias_div, _stream())
+    return out
+
+
+def add(a, b=None, rowbias=None, rows_per_group=0, relu=False, out=None):
+    _check_cuda(a)
+    _rows2d(a)
+    rows, C = a.shape
+    if out is None:
+        out = torch.empty((rows, C), device=a.device, dtype=BF16)
+    if b is not None:
+        _rows2d(b)
+        assert b.shape == a.shape
+    _cabi.call("fmc_add_bf16", a.data_ptr(), a.stride(0), _ptr(b), b.stride(0) if b is not None else 0, _ptr(rowbias),
+               rows_per_group, rowbias.stride(0) if rowbias is not None else 0, out.data_ptr(), out.stride(0), rows, C,
+               1 if relu else 0, _stream())
+    return out
+
+
+def resize_nearest(x, oh, ow):
+    """x: [N, h, w, C] contiguous bf16."""
+    _check_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    N, h, w, C = x.shape
+    out = torch.empty((N, oh, ow, C), device=x.device, dtype=BF16)
+    _cabi.call("fmc_resize_nearest_bf16", x.data_ptr(), out.data_ptr(), N, h, w, oh, ow, C, _stream())
+    return out
+
+
+def avgpool2(x):
+    _check_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    N, h, w, C = x.shape
+    out = torch.empty((N, h // 2, w // 2, C), device=x.device, dtype=BF16)
+    _cabi.call("fmc_avgpool2_bf16", x.data_ptr(), out.data_ptr(), N, h, w, C, _stream())
+    return out
+
+
+def copy2d(src, dst):
+    """dst[:, :cols] = src (both row-strided 2-D bf16 views)."""
+    _check_cuda(src, dst)
+    _rows2d(src)
+    _rows2d(dst)
+    assert src.shape == dst.shape
+    _cabi.call("fmc_copy2d_bf16", src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), src.shape[0],
+               src.shape[1], _stream())
+    return dst
+
+
+def to_channels_last(x, c_pad=None):
+    """[B, C, F, H, W] fp32 -> [B, F, H, W, Cpad] bf16."""
+    _check_cuda(x)
+    x = x.contiguous().float()
+    B, C, F, H, W = x.shape
+    c_pad = c_pad or C
+    out = torch.empty((B, F, H, W, c_pad), device=x.device, dtype=BF16)
+    _cabi.call("fmc_ncfhw_f32_to_cl_bf16", x.data_ptr(), out.data_ptr(), B, C, F, H * W, c_pad, _stream())
+    return out
+
+
+def from_channels_last(x, C=None):
+    """[B, F, H, W, ld] bf16 -> [B, C, F, H, W] fp32."""
+    _check_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    B, F, H, W, ld = x.shape
+    C = C or ld
+    out = torch.empty((B, C, F, H, W), device=x.device, dtype=torch.float32)
+    _cabi.call("fmc_cl_bf16_to_ncfhw_f32", x.data_ptr(), ld, out.data_ptr(), B, C, F, H * W, _stream())
+    return out
+
+
+def cast_act(x, silu=False):
+    _check_cuda(x)
+    x = x.contiguous()
+    assert x.dtype == torch.float32
+    out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _cabi.call("fmc_cast_act_bf16", x.data_ptr(), out.data_ptr(), x.numel(), 1 if silu else 0, _stream())
+    return out
+
+
+def timestep_embedding(t, dim):
+    _check_cuda(t)
+    t = t.contiguous().float()
+    out = torch.empty((t.numel(), dim), device=t.device, dtype=BF16)
+    _cabi.call("fmc_timestep_embedding_bf16", t.data_ptr(), out.data_ptr(), t.numel(), dim, _stream())
+    return out
+
+
+def plucker(K, c2w, H, W):
+    """K [BF, 4], c2w [BF, 3, 4] fp32 -> [BF, H, W, 6] fp32."""
+    _check_cuda(K, c2w)
+    K = K.contiguous().float()
+    c2w = c2w.contiguous().float()
+    BF = K.shape[0]
+    out = torch.empty((BF, H, W, 6), device=K.device, dtype=torch.float32)
+    _cabi.call("fmc_plucker_f32", K.data_ptr(), c2w.data_ptr(), out.data_ptr(), BF, H, W, _stream())
+    return out
+
+
+def plucker_unshuffle(K, c2w, H, W):
+    """-> [BF, H/8, W/8, 384] bf16 (PixelUnshuffle(8) fused)."""
+    _check_cuda(K, c2w)
+    K = K.contiguous().float()
+    c2w = c2w.contiguous().float()
+    BF = K.shape[0]
+    out = torch.empty((BF, H // 8, W // 8, 384), device=K.device, dtype=BF16)
+    _cabi.call("fmc_plucker_unshuffle_bf16", K.data_ptr(), c2w.data_ptr(), out.data_ptr(), BF, H, W, _stream())
+    return out
+
+
+def traj_scatter(info, masks):
+    """info [BF, n_obj, 12], masks [BF, n_obj, H, W] fp32 -> (feat [BF, 13, H, W] fp32, mask [BF, H, W] fp32)."""
+    _check_cuda(info, masks)
+    info = info.contiguous().float()
+    masks = masks.contiguous().float()
+    BF, n_obj, H, W = masks.shape
+    feat = torch.empty((BF, 13, H, W), device=masks.device, dtype=torch.float32)
+    mask = torch.empty((BF, H, W), device=masks.device, dtype=torch.float32)
+    _cabi.call("fmc_traj_scatter_f32", info.data_ptr(), masks.data_ptr(), feat.data_ptr(), mask.data_ptr(), BF, n_obj, H, W,
+               _stream())
+    return feat, mask
+
+
+def traj_scatter_unshuffle(info, masks):
+    """-> (feat [BF, H/8, W/8, 832] bf16, mask [BF, H, W] fp32)."""
+    _check_cuda(info, masks)
+    info = info.contiguous().float()
+    masks = masks.contiguous().float()
+    BF, n_obj, H, W = masks.shape
+    feat = torch.empty((BF, H // 8, W // 8, 832), device=masks.device, dtype=BF16)
+    mask = torch.empty((BF, H, W), device=masks.device, dtype=torch.float32)
+    _cabi.call("fmc_traj_scatter_unshuffle_bf16", info.data_ptr(), masks.data_ptr(), feat.data_ptr(), mask.data_ptr(), BF,
+               n_obj, H, W, _stream())
+    return feat, mask
+
+
+def mask_modulate(x, mask, row_index, col_index):
+    """x [N, h, w, C] bf16, mask [N, H, W] fp32, index maps int32 [h], [w]."""
+    _check_cuda(x, mask)
+    assert x.dtype == BF16 and x.is_contiguous() and mask.is_contiguous()
+    N, h, w, C = x.shape
+    out = torch.empty_like(x)
+    _cabi.call("fmc_mask_modulate_bf16", x.data_ptr(), mask.data_ptr(), row_index.data_ptr(), col_index.data_ptr(),
+               out.data_ptr(), N, h, w, C, mask.shape[1], mask.shape[2], _stream())
+    return out
+
+
+def cfg_ddim_step(eps_uncond, eps_cond, guidance_scale, latents, alpha_t, alpha_prev, return_eps=False):
+    _check_cuda(eps_uncond, latents)
+    assert eps_uncond.dtype == torch.float32 and latents.dtype == torch.float32
+    eps_uncond = eps_uncond.contiguous()
+    latents = latents.contiguous()
+    if eps_cond is not None:
+        eps_cond = eps_cond.contiguous()
+    out = torch.empty_like(latents)
+    eps_out = torch.empty_like(latents) if return_eps else None
+    _cabi.call("fmc_cfg_ddim_step_f32", eps_uncond.data_ptr(), _ptr(eps_cond), float(guidance_scale), latents.data_ptr(),
+               out.data_ptr(), _ptr(eps_out), float(alpha_t), float(alpha_prev), latents.numel(), _stream())
+    return (out, eps_out) if return_eps else out
+
+
+def conv2d_cl(x, weight, bias, stride=1, padding=1):
+    """3x3 / strided convolutions on channels-last bf16 [N, h, w, Cin] -> [N, oh, ow, Cout].
+
+    Round 1: cuDNN through torch (library call, like cuBLAS); the implicit-GEMM tcgen05 conv is SURVEY 8(f) row 1.
+    `weight` must already be bf16 in torch.channels_last memory format."""
+    _check_cuda(x)
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), weight, bias, stride=stride, padding=padding)
+    y = y.permute(0, 2, 3, 1)
+    return y if y.is_contiguous() else y.contiguous()
