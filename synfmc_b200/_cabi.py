@@ -8,6 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfmc_b200.so")
 
 P, I, L, F = c_void_p, c_int, c_longlong, c_float
+ABI_VERSION = 1  # FMC_B200_ABI_VERSION of include/fmc_b200.h
 
 # name -> argtypes, in the order of include/fmc_b200.h
 SIGNATURES = {
@@ -59,9 +60,26 @@ def lib():
     return _lib
 
 
+# kernels launched by one call of each entry point (groupnorm = statistics + apply); everything else launches one
+KERNELS_PER_CALL = {"fmc_groupnorm_bf16": 2}
+launch_count = 0  # kernels of this library launched by this process (bench.py reports it as gpu_launches)
+trace = None      # when set to a list by bench.py: (name, args, start_event, end_event) per call, CUDA events on the
+                  # launching stream -- the per-kernel timing behind the roofline figures
+
+
 def call(name, *args):
     """Invoke an entry point; a non-zero return code becomes an exception carrying the library's message."""
+    global launch_count
     handle = lib()
-    rc = getattr(handle, name)(*args)
+    if trace is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(handle, name)(*args)
+        e1.record()
+        trace.append((name, args, e0, e1))
+    else:
+        rc = getattr(handle, name)(*args)
     if rc != 0:
         raise FmcError(f"{name} failed (rc={rc}): {handle.fmc_last_error_string().decode()}")
+    launch_count += KERNELS_PER_CALL.get(name, 1)

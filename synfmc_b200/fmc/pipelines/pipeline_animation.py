@@ -80,10 +80,8 @@ class CameraCtrlPipeline:
                 omcm_min_step=None, max_steps=None, callback=None, callback_steps=1):
         """latents [b, 4, F, h, w] fp32 (device); text_embeddings [(2)b, 77, 768]; pose_features: 4 CL features over all
         F frames (already duplicated for CFG); traj_features: 4 CL features (CFG: zeros ++ features) or None."""
-        do_cfg = guidance_scale > 1.0
         self.scheduler.set_timesteps(num_inference_steps)
         L = video_length
-        b = latents.shape[0]
         latents = latents.float().contiguous()
         for i, t in enumerate(self.scheduler.timesteps.tolist()):
             if max_steps is not None and i >= max_steps:
@@ -91,34 +89,45 @@ class CameraCtrlPipeline:
             step_traj = traj_features
             if omcm_min_step is not None and traj_features is not None and omcm_min_step > 0 and t < omcm_min_step:
                 step_traj = None
-            a_t, a_prev = self.scheduler.alphas_for(t)
-            window_eps = []
-            for k in range(multidiff_total_steps):
-                s = k * (L - multidiff_overlaps)
-                part = latents[:, :, s:s + L].contiguous()
-                x_in = torch.cat([part] * 2) if do_cfg else part
-                feats = [_slice_frames(f, s, L) for f in pose_features]
-                kw = {"traj_features": step_traj} if self._accepts_traj else {}
-                eps = self.unet(x_in, t, encoder_hidden_states=text_embeddings, pose_embedding_features=feats,
-                                **kw).sample
-                window_eps.append((s, eps))
-            if multidiff_total_steps == 1:
-                s, eps = window_eps[0]
-                e_u, e_c = (eps[:b], eps[b:]) if do_cfg else (eps, None)
-                latents = ops.cfg_ddim_step(e_u, e_c, guidance_scale, latents, a_t, a_prev)
-            else:
-                # overlapping windows: average the guided predictions per frame (:673-699), then one DDIM update
-                noise = torch.zeros_like(latents)
-                count = torch.zeros_like(latents)
-                for s, eps in window_eps:
-                    count[:, :, s:s + L] += 1
-                for s, eps in window_eps:
-                    e = eps[:b] + guidance_scale * (eps[b:] - eps[:b]) if do_cfg else eps
-                    noise[:, :, s:s + L] += e / count[:, :, s:s + L]
-                latents = ops.cfg_ddim_step(noise, None, 1.0, latents, a_t, a_prev)
+            latents = self.denoise_step(latents, t, text_embeddings, pose_features, L, traj_features=step_traj,
+                                        guidance_scale=guidance_scale, multidiff_total_steps=multidiff_total_steps,
+                                        multidiff_overlaps=multidiff_overlaps)
             if callback is not None and i % callback_steps == 0:
                 callback(i, t, latents)
         return latents
+
+    @torch.no_grad()
+    def denoise_step(self, latents, t, text_embeddings, pose_features, video_length, traj_features=None,
+                     guidance_scale=8.0, multidiff_total_steps=1, multidiff_overlaps=12):
+        """One iteration of the loop at pipeline_animation.py:669-707 / pipeline_animation_cm_om.py:678-726: per-window
+        U-Net on the CFG-doubled latents, CFG combine, window averaging, DDIM update.  `t` is a Python int taken from
+        `scheduler.timesteps` after `set_timesteps`; returns the new fp32 latents."""
+        do_cfg = guidance_scale > 1.0
+        L = video_length
+        b = latents.shape[0]
+        a_t, a_prev = self.scheduler.alphas_for(t)
+        window_eps = []
+        for k in range(multidiff_total_steps):
+            s = k * (L - multidiff_overlaps)
+            part = latents if multidiff_total_steps == 1 else latents[:, :, s:s + L].contiguous()
+            x_in = torch.cat([part] * 2) if do_cfg else part
+            feats = [_slice_frames(f, s, L) for f in pose_features]
+            kw = {"traj_features": traj_features} if self._accepts_traj else {}
+            eps = self.unet(x_in, t, encoder_hidden_states=text_embeddings, pose_embedding_features=feats, **kw).sample
+            window_eps.append((s, eps))
+        if multidiff_total_steps == 1:
+            s, eps = window_eps[0]
+            e_u, e_c = (eps[:b], eps[b:]) if do_cfg else (eps, None)
+            return ops.cfg_ddim_step(e_u, e_c, guidance_scale, latents, a_t, a_prev)
+        # overlapping windows: average the guided predictions per frame (:673-699), then one DDIM update
+        noise = torch.zeros_like(latents)
+        count = torch.zeros_like(latents)
+        for s, eps in window_eps:
+            count[:, :, s:s + L] += 1
+        for s, eps in window_eps:
+            e = eps[:b] + guidance_scale * (eps[b:] - eps[:b]) if do_cfg else eps
+            noise[:, :, s:s + L] += e / count[:, :, s:s + L]
+        return ops.cfg_ddim_step(noise, None, 1.0, latents, a_t, a_prev)
 
     def _pose_features(self, pose_embedding, do_cfg):
         if isinstance(pose_embedding, list):
@@ -168,7 +177,8 @@ class CameraCtrlPipeline:
         latents = self.denoise(latents, prompt_embeds.to(device), pose_features, single_len, traj_features=traj,
                                num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
                                multidiff_total_steps=multidiff_total_steps, multidiff_overlaps=multidiff_overlaps,
-                               omcm_min_step=kwargs.get("omcm_min_step"), callback=callback,
+                               omcm_min_step=kwargs.get("omcm_min_step"), max_steps=kwargs.get("max_steps"),
+                               callback=callback,
                                callback_steps=callback_steps)
         videos = self.decode_latents(latents) if self.vae is not None else None
         out = AnimationPipelineOutput(videos=videos, latents=latents)

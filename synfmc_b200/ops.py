@@ -270,6 +270,13 @@ def conv2d_cl(x, weight, bias, stride=1, padding=1):
     Round 1: cuDNN through torch (library call, like cuBLAS); the implicit-GEMM tcgen05 conv is SURVEY 8(f) row 1.
     `weight` must already be bf16 in torch.channels_last memory format."""
     _check_cuda(x)
+    if _cabi.trace is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), weight, bias, stride=stride, padding=padding)
+    if _cabi.trace is not None:
+        e1.record()
+        _cabi.trace.append(("cudnn_conv2d", (x.shape[0] * y.shape[2] * y.shape[3], weight.shape[0],
+                                             weight.shape[1] * weight.shape[2] * weight.shape[3]), e0, e1))
     y = y.permute(0, 2, 3, 1)
     return y if y.is_contiguous() else y.contiguous()
