@@ -170,6 +170,18 @@ def summarise_trace(trace, steps, peaks):
         a["flops"] += fl
         a["bytes"] += by
     total = sum(a["ms"] for a in agg.values()) or 1.0
+    dump = os.environ.get("FMC_BENCH_TRACE")
+    if dump:  # per-shape breakdown for kernel work (not part of the JSON line)
+        shapes = {}
+        for name, args, e0, e1 in trace:
+            key = (name,) + tuple(a for a in args if isinstance(a, int) and abs(a) < (1 << 31))
+            rec = shapes.setdefault(key, [0, 0.0, 0.0])
+            rec[0] += 1
+            rec[1] += e0.elapsed_time(e1)
+            rec[2] += flops_of(name, args)[0]
+        with open(dump, "w") as fh:
+            for key, (n, ms, fl) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+                fh.write(f"{ms / steps:9.3f} ms/step  {n / steps:6.1f} calls/step  {fl / (ms * 1e-3) / 1e12 if ms else 0:8.1f} TF/s  {key}\n")
     table = {}
     for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
         row = {"launches_per_step": round(a["launches"] / steps, 1), "ms_per_step": round(a["ms"] / steps, 3),

@@ -85,12 +85,13 @@ def test_tiny_unet_forward(cuda_device, obj):
         assert rel_l2(got0, want) > 5 * UNET_TOL
 
 
-def test_tiny_unet_odd_size_and_timestep_forms(cuda_device):
-    """Latent sizes that are not multiples of the up-factor take the `upsample_size` path (unet.py:1057-1063,1240);
-    int, 0-d and [B] tensor timesteps are equivalent (unet.py:1075-1090)."""
+def test_tiny_unet_timestep_forms(cuda_device):
+    """int, 0-d and [B] tensor timesteps are equivalent (unet.py:1075-1090).  (Latent sizes that are not multiples of
+    the up-factor make the reference pass a 3-element `upsample_size` (unet.py:1240, shape[2:] of a 5-D tensor) into
+    a 2-D interpolate, which raises -- so odd sizes are outside the reference's domain and carry no parity case.)"""
     o_unet = helpers.build_oracle_unet(tiny=True)
     p_unet = helpers.build_product_unet(o_unet, tiny=True, device=cuda_device)
-    sample, text, feats, _ = _unet_inputs(1, 4, 9, 11, (320, 640), seed=2)
+    sample, text, feats, _ = _unet_inputs(1, 4, 8, 12, (320, 640), seed=2)
     with torch.no_grad():
         want = o_unet(sample, 41, text, pose_embedding_features=feats).sample
     d = [x.to(cuda_device) for x in feats]
