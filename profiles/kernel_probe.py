@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Launch ONE hot-path kernel at its BASELINE config-2 shape a few times (for `ncu --set full -k regex:... -s 2 -c 1`).
+usage: python profiles/kernel_probe.py <case> [reps]      cases: see CASES"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from synfmc_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda", 0)
+BF = torch.bfloat16
+
+
+def rnd(*shape, scale=1.0, dtype=BF):
+    return (torch.randn(*shape, device=dev) * scale).to(dtype)
+
+
+def gemm_case(M, N, K, res=False, geglu=False):
+    a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    bias = rnd(N, dtype=torch.float32)
+    r = rnd(M, N // 2 if geglu else N) if res else None
+    return lambda: ops.gemm(a, w, bias=bias, residual=r, geglu=geglu)
+
+
+def spatial_case(images, d, n):
+    heads, hs = 8, (d + 15) // 16 * 16
+    qkv = rnd(images * n, 2 * heads * hs + heads * d)
+    out = torch.empty(images * n, heads * d, device=dev, dtype=BF)
+    return lambda: ops.spatial_attn(qkv, 0, qkv, heads * hs, qkv, 2 * heads * hs, hs, out, images, heads, d, n, n, 1, n,
+                                    d ** -0.5)
+
+
+def temporal_case(B, F, HW, d):
+    heads, hs = 8, (d + 15) // 16 * 16
+    qkv = rnd(B * F * HW, 2 * heads * hs + heads * d)
+    out = torch.empty(B * F * HW, heads * d, device=dev, dtype=BF)
+    return lambda: ops.temporal_attn(qkv, 0, heads * hs, 2 * heads * hs, hs, out, B, F, HW, heads, d, d ** -0.5)
+
+
+def groupnorm_case(images, HW, C):
+    x, g, b = rnd(images * HW, C), rnd(C, dtype=torch.float32), rnd(C, dtype=torch.float32)
+    return lambda: ops.groupnorm(x, g, b, 1e-6, images, HW, silu=True)
+
+
+def layernorm_case(rows, C):
+    x, g, b = rnd(rows, C), rnd(C, dtype=torch.float32), rnd(C, dtype=torch.float32)
+    return lambda: ops.layernorm(x, g, b, 1e-5)
+
+
+CASES = {
+    "gemm_l0_out": lambda: gemm_case(81920, 320, 320, res=True),        # to_out / proj_out + residual at level 0
+    "gemm_l0_qkv": lambda: gemm_case(81920, 1088, 320),                 # fused q|k|v (heads padded 40 -> 48)
+    "gemm_l0_geglu": lambda: gemm_case(81920, 2560, 320, geglu=True),   # FeedForward GEGLU at level 0
+    "gemm_l0_ff2": lambda: gemm_case(81920, 320, 1280, res=True),
+    "gemm_l1_geglu": lambda: gemm_case(20480, 5120, 640, geglu=True),
+    "gemm_l2_qkv": lambda: gemm_case(5120, 3840, 1280),
+    "spatial_l0": lambda: spatial_case(32, 40, 2560),
+    "spatial_l1": lambda: spatial_case(32, 80, 640),
+    "temporal_l0": lambda: temporal_case(2, 16, 2560, 40),
+    "groupnorm_l0": lambda: groupnorm_case(32, 2560, 320),
+    "layernorm_l0": lambda: layernorm_case(81920, 320),
+}
+
+if __name__ == "__main__":
+    fn = CASES[sys.argv[1]]()
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    print(f"{sys.argv[1]}: {s.elapsed_time(e) / reps * 1e3:.1f} us per call")

@@ -46,6 +46,11 @@ static EncodeTiledFn get_encode_fn() {
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, bool swizzle128) {
+  return make_tmap_bf16_sw(out, base, rank, dims, strides_bytes, box, swizzle128 ? 128 : 0);
+}
+
+int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   FMC_REQUIRE(fn != nullptr, FMC_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   FMC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, FMC_ERR_SHAPE, "TMA base %p not 16-byte aligned", base);
@@ -65,7 +70,9 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
                   gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FMC_REQUIRE(r == CUDA_SUCCESS, FMC_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return FMC_OK;

@@ -56,6 +56,10 @@ int device_sm_count();
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, bool swizzle128);
 
+// same with an explicit swizzle span in bytes (0, 32, 64 or 128)
+int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, int swizzle_bytes);
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace fmc

@@ -298,6 +298,343 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+
+// =====================================================================================================================
+// bf16-output GEMM with a shared-memory / TMA epilogue  (the workhorse: every bf16 linear of the step)
+//
+//   warp 0      TMA producer of the A / W k-slices           (SWIZZLE_128B, BK = 64)
+//   warp 1      tcgen05.mma issuer                           (128 x BN x 16 per instruction, fp32 accumulators in TMEM)
+//   warp 2      TMEM allocator
+//   warp 3      output mover: TMA-loads the residual tile into the staging buffer ahead of time, TMA-stores finished
+//               tiles (coalesced 128-byte lines instead of one 32-byte sector per thread)
+//   warps 4-11  epilogue: two warps per TMEM lane quadrant, each owning half of the 32-column sub-tiles:
+//               tcgen05.ld -> + bias (+ row bias) (+ residual from smem) | value * gelu(gate) -> bf16 -> staging smem
+// Accumulators and staging buffers are double-buffered, so MMA of tile i+1, epilogue of tile i and the store of tile
+// i-1 overlap.  The staging buffer is a row of [128 x 32] bf16 sub-tiles in SWIZZLE_64B layout (conflict-free for one
+// row per thread).
+// =====================================================================================================================
+constexpr int GEMM2_THREADS = 384;
+constexpr int SUB_COLS = 32;                      // output columns per staging sub-tile
+constexpr int SUB_BYTES = GEMM_BM * SUB_COLS * 2;  // 8 KB
+
+template <int BN, bool GEGLU>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
+  static constexpr int NSUB = OUT_COLS / SUB_COLS;
+  static constexpr int OUT_BYTES = NSUB * SUB_BYTES;
+  static constexpr int AVAIL = 227 * 1024 - 1024 - 2 * OUT_BYTES - 512;
+  static constexpr int STAGES_RAW = AVAIL / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * OUT_BYTES + 1024;
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N constraint for M=128");
+  static_assert(OUT_COLS % SUB_COLS == 0 && NSUB >= 1, "whole sub-tiles");
+  static_assert(STAGES >= 3, "not enough shared memory for the k pipeline");
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0 && OUT_BYTES % 1024 == 0, "1024-byte aligned tiles");
+};
+
+// erf-GELU with erf from Abramowitz & Stegun 7.1.28 (|err| <= 3e-7): 1 - erf(x) = (1 + a1 x + ... + a6 x^6)^-16, x >= 0.
+// 1 + erf(-x) = 1 - erf(x) is formed directly, so the negative tail has no cancellation.  One MUFU (rcp) per value.
+__device__ __forceinline__ float gelu_fast(float g) {
+  const float x = fabsf(g) * 0.70710678118654752440f;
+  float p = fmaf(x, 0.0000430638f, 0.0002765672f);
+  p = fmaf(x, p, 0.0001520143f);
+  p = fmaf(x, p, 0.0092705272f);
+  p = fmaf(x, p, 0.0422820123f);
+  p = fmaf(x, p, 0.0705230784f);
+  p = fmaf(x, p, 1.0f);
+  float r = __frcp_rn(p);
+  r *= r; r *= r; r *= r; r *= r;            // (1/p)^16 = 1 - erf(x)
+  const float one_plus_erf = g >= 0.f ? 2.0f - r : r;
+  return 0.5f * g * one_plus_erf;
+}
+
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t (&v)[4]) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void epi_bar_arrive_warp(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+template <int BN, bool GEGLU>
+__global__ void __launch_bounds__(GEMM2_THREADS, 1)
+gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmParams p) {
+  using Cfg = Gemm2Cfg<BN, GEGLU>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int NSUB = Cfg::NSUB;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t acc_full_bar[2];
+  __shared__ uint64_t acc_empty_bar[2];
+  __shared__ uint64_t buf_ready_bar[2];  // staging buffer b holds the residual (or is simply free) for its next tile
+  __shared__ uint64_t out_ready_bar[2];  // staging buffer b holds a finished output tile
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t out_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int kblocks = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const bool has_res = p.residual != nullptr;
+  const int n_out = GEGLU ? p.N / 2 : p.N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (has_res) tma_prefetch_desc(&tmR);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full_bar[a], 1);
+      mbar_init(&acc_empty_bar[a], 8);
+      mbar_init(&buf_ready_bar[a], 1);
+      mbar_init(&out_ready_bar[a], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_slot, Cfg::TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (A, W) ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n;
+        const int n_blk = tile % p.tiles_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          tma_load_2d_a(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d_a(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&acc_full_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------ output mover ------------------------------
+    if (lane == 0) {
+      // arm staging buffer `b` for tile `tile`: residual tile lands there (complete_tx) or it is simply marked free
+      auto arm = [&](int b, int tile) {
+        if (has_res) {
+          const int m_blk = tile / p.tiles_n;
+          const int n_blk = tile % p.tiles_n;
+          int nsub_ok = 0;
+          for (int s = 0; s < NSUB; ++s) nsub_ok += (n_blk * Cfg::OUT_COLS + s * SUB_COLS < n_out) ? 1 : 0;
+          mbar_arrive_expect_tx(&buf_ready_bar[b], static_cast<uint32_t>(nsub_ok * SUB_BYTES));
+          for (int s = 0; s < nsub_ok; ++s) {
+            tma_load_2d_a(out_base + b * Cfg::OUT_BYTES + s * SUB_BYTES, &tmR, &buf_ready_bar[b],
+                          n_blk * Cfg::OUT_COLS + s * SUB_COLS, m_blk * GEMM_BM);
+          }
+        } else {
+          mbar_arrive(&buf_ready_bar[b]);
+        }
+      };
+      int tile = blockIdx.x;
+      if (tile < num_tiles) arm(0, tile);
+      if (tile + static_cast<int>(gridDim.x) < num_tiles) arm(1, tile + gridDim.x);
+      int it = 0;
+      for (; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t ph = static_cast<uint32_t>(it >> 1) & 1u;
+        const int m_blk = tile / p.tiles_n;
+        const int n_blk = tile % p.tiles_n;
+        mbar_wait(&out_ready_bar[b], ph);
+        for (int s = 0; s < NSUB; ++s) {
+          const int col = n_blk * Cfg::OUT_COLS + s * SUB_COLS;
+          if (col < n_out) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmC)),
+                         "r"(out_base + b * Cfg::OUT_BYTES + s * SUB_BYTES), "r"(col), "r"(m_blk * GEMM_BM)
+                         : "memory");
+          }
+        }
+        tma_store_commit();
+        const int next2 = tile + 2 * static_cast<int>(gridDim.x);
+        if (next2 < num_tiles) {
+          tma_store_wait_read<0>();  // the store has drained buffer b: reuse it for the tile after next
+          arm(b, next2);
+        }
+      }
+      tma_store_wait<0>();
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;                   // TMEM lane quadrant of this warp
+    const int half = (warp - 4) >> 2;         // which half of the sub-tiles
+    constexpr int S_SPLIT = (NSUB + 1) / 2;
+    const int s_begin = half == 0 ? 0 : S_SPLIT;
+    const int s_end = half == 0 ? S_SPLIT : NSUB;
+    const int r_in_tile = q * 32 + lane;
+    const uint32_t row_off = static_cast<uint32_t>(r_in_tile) * 64u;
+    const uint32_t sw = static_cast<uint32_t>((r_in_tile >> 1) & 3);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t ph = static_cast<uint32_t>(it >> 1) & 1u;
+      const int m_blk = tile / p.tiles_n;
+      const int n_blk = tile % p.tiles_n;
+      const int row = m_blk * GEMM_BM + r_in_tile;
+      const float* rb = nullptr;
+      if (p.rowbias != nullptr && row < p.M) rb = p.rowbias + static_cast<long long>(row / p.rows_per_group) * p.ldrb;
+      mbar_wait(&acc_full_bar[b], ph);
+      mbar_wait(&buf_ready_bar[b], ph);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(b * BN);
+      const uint32_t buf = out_base + b * Cfg::OUT_BYTES + row_off;
+#pragma unroll 1
+      for (int s = s_begin; s < s_end; ++s) {
+        const int ocol0 = n_blk * Cfg::OUT_COLS + s * SUB_COLS;  // first output column of this sub-tile
+        if (ocol0 >= n_out) break;                                // warp-uniform
+        float v[32];
+        if constexpr (!GEGLU) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr + static_cast<uint32_t>(s * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ocol0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (rb != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb + ocol0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+        } else {
+          // interleaved N space: [16 value | 16 gate] blocks; 64 accumulator columns -> 32 outputs
+          uint32_t r0[32], r1[32];
+          tmem_ld_x32(taddr + static_cast<uint32_t>(s * 64), r0);
+          tmem_ld_x32(taddr + static_cast<uint32_t>(s * 64 + 32), r1);
+          tmem_ld_wait();
+          const int ncol0 = n_blk * BN + s * 64;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a0 = __uint_as_float(r0[j]), g0 = __uint_as_float(r0[16 + j]);
+            float a1 = __uint_as_float(r1[j]), g1 = __uint_as_float(r1[16 + j]);
+            if (p.bias != nullptr) {
+              a0 += __ldg(p.bias + ncol0 + j);
+              g0 += __ldg(p.bias + ncol0 + 16 + j);
+              a1 += __ldg(p.bias + ncol0 + 32 + j);
+              g1 += __ldg(p.bias + ncol0 + 48 + j);
+            }
+            v[j] = a0 * gelu_fast(g0);
+            v[16 + j] = a1 * gelu_fast(g1);
+          }
+        }
+        const uint32_t sub = buf + static_cast<uint32_t>(s * SUB_BYTES);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t addr = sub + ((static_cast<uint32_t>(c) ^ sw) << 4);
+          if (has_res) {
+            uint32_t w[4];
+            ld_shared_v4(addr, w);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[c * 8 + 2 * j] += bf16_lo(w[j]);
+              v[c * 8 + 2 * j + 1] += bf16_hi(w[j]);
+            }
+          }
+          st_shared_v4(addr, pack_bf16x2(v[c * 8], v[c * 8 + 1]), pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
+                       pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();  // staging writes -> visible to the TMA store
+      epi_bar_arrive_warp(&acc_empty_bar[b], lane);
+      if (lane == 0) mbar_arrive(&out_ready_bar[b]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, bool GEGLU>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                        GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN, GEGLU>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FMC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tma_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  p.tiles_m = ceil_div(p.M, GEMM_BM);
+  p.tiles_n = ceil_div(p.N, BN);
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  gemm_bf16_tma_kernel<BN, GEGLU><<<grid, GEMM2_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
+  return check_launch("gemm_bf16_tma_kernel");
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -338,9 +675,21 @@ extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long l
   FMC_REQUIRE(rowbias == nullptr || (rows_per_group > 0 && ldrb % 4 == 0), FMC_ERR_ARG,
               "fmc_gemm_bf16: rowbias needs rows_per_group > 0 and ldrb %% 4 == 0");
 
+  const bool out_f32 = (flags & FMC_GEMM_OUT_F32) != 0;
+  const int n_out = geglu ? N / 2 : N;
+  const bool tma_epilogue = !out_f32 && n_out % SUB_COLS == 0 && (!geglu || N % 64 == 0);
+
   int bn = tile_n;
-  if (bn == 0) bn = (N % 160 == 0) ? 160 : ((N % 128 == 0 || N > 128) ? 128 : 64);
-  FMC_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, FMC_ERR_SHAPE, "fmc_gemm_bf16: unsupported tile_n %d", bn);
+  if (tma_epilogue) {
+    if (geglu) {
+      if (bn != 128 && bn != 256) bn = (N % 256 == 0 || N > 1024) ? 256 : 128;
+    } else if (bn != 64 && bn != 128 && bn != 160) {
+      bn = N <= 64 ? 64 : (N <= 128 ? 128 : 160);
+    }
+  } else {
+    if (bn == 0) bn = (N % 160 == 0) ? 160 : ((N % 128 == 0 || N > 128) ? 128 : 64);
+    FMC_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, FMC_ERR_SHAPE, "fmc_gemm_bf16: unsupported tile_n %d", bn);
+  }
 
   CUtensorMap tmA, tmB;
   {
@@ -364,6 +713,33 @@ extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long l
   p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
   p.rowbias = rowbias; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; p.ldrb = ldrb;
   p.flags = flags;
+  if (tma_epilogue) {
+    CUtensorMap tmC, tmR;
+    const uint32_t box[2] = {SUB_COLS, GEMM_BM};
+    {
+      const uint64_t dims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(M)};
+      const uint64_t strides[1] = {static_cast<uint64_t>(ldc) * 2};
+      int rc = make_tmap_bf16_sw(&tmC, C, 2, dims, strides, box, 64);
+      if (rc != FMC_OK) return rc;
+    }
+    if (residual != nullptr) {
+      const uint64_t dims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(M)};
+      const uint64_t strides[1] = {static_cast<uint64_t>(ldr) * 2};
+      int rc = make_tmap_bf16_sw(&tmR, residual, 2, dims, strides, box, 64);
+      if (rc != FMC_OK) return rc;
+    } else {
+      tmR = tmC;
+    }
+    if (geglu) {
+      if (bn == 256) return launch_gemm2<256, true>(tmA, tmB, tmC, tmR, p, stream);
+      return launch_gemm2<128, true>(tmA, tmB, tmC, tmR, p, stream);
+    }
+    switch (bn) {
+      case 64: return launch_gemm2<64, false>(tmA, tmB, tmC, tmR, p, stream);
+      case 128: return launch_gemm2<128, false>(tmA, tmB, tmC, tmR, p, stream);
+      default: return launch_gemm2<160, false>(tmA, tmB, tmC, tmR, p, stream);
+    }
+  }
   switch (bn) {
     case 64: return launch_gemm<64>(tmA, tmB, p, stream);
     case 128: return launch_gemm<128>(tmA, tmB, p, stream);

@@ -11,194 +11,266 @@
 namespace fmc {
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, the row lives in registers (C <= 1280 -> at most 5 x 8 values per lane).
+// LayerNorm: one warp per row, R rows in flight per warp (all loads issued before the first reduction), the rows live
+// in registers (NV vectors of 8 channels per lane, C <= NV * 256).
 // out  = LN(x) * gamma + beta (+ pe[frame])            (bf16)
 // out2 = out_fp32 + add                                 (bf16, optional: CameraAdapter input x + pose)
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_MAX_VEC = 5;  // per lane: 5 vectors of 8 channels -> C <= 1280
+constexpr int LN_WARPS = 8;
 
-__global__ void __launch_bounds__(256)
+template <int NV, int R, bool HAS_ADD>
+__global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out, long long ldo,
                  const float* __restrict__ pe, int F, int HW, const __nv_bfloat16* __restrict__ add, long long ldadd,
                  __nv_bfloat16* __restrict__ out2, long long ldo2, long long rows, int C) {
   const int lane = threadIdx.x & 31;
-  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long long row0 = (blockIdx.x * static_cast<long long>(LN_WARPS) + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
   const int nvec = C >> 3;
-  float v[LN_MAX_VEC][8];
-  float sum = 0.f;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+  const float inv_c = 1.0f / static_cast<float>(C);
+  uint4 raw[R][NV];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      const uint4 u = __ldg(xr + vi);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r < rows ? row0 + r : rows - 1;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[i][2 * j] = bf16_lo(w[j]);
-        v[i][2 * j + 1] = bf16_hi(w[j]);
-        sum += v[i][2 * j] + v[i][2 * j + 1];
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      raw[r][i] = vi < nvec ? __ldg(xr + vi) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  uint4 addraw[HAS_ADD ? R : 1][HAS_ADD ? NV : 1];
+  if constexpr (HAS_ADD) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r < rows ? row0 + r : rows - 1;
+      const uint4* ar = reinterpret_cast<const uint4*>(add + row * ldadd);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + i * 32;
+        addraw[r][i] = vi < nvec ? __ldg(ar + vi) : make_uint4(0u, 0u, 0u, 0u);
       }
     }
   }
+  float mean[R], rstd[R];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / C;
-  float sq = 0.f;
+  for (int r = 0; r < R; ++r) {
+    float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
-    if (lane + i * 32 < nvec) {
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mean;
-        sq += d * d;
+      for (int j = 0; j < 4; ++j) sum += bf16_lo(w[j]) + bf16_hi(w[j]);  // padding vectors are zero
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mean[r] = sum * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nvec) {
+        const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float d0 = bf16_lo(w[j]) - mean[r], d1 = bf16_hi(w[j]) - mean[r];
+          sq += d0 * d0 + d1 * d1;
+        }
       }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    rstd[r] = rsqrtf(sq * inv_c + eps);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / C + eps);
-  const float* per = pe != nullptr ? pe + static_cast<long long>((row / HW) % F) * C : nullptr;
-#pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) {
       const int c0 = vi * 8;
-      float y[8];
+      float g[8], bb[8];
 #pragma unroll
       for (int j = 0; j < 8; j += 4) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0 + j));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c0 + j));
-        y[j] = (v[i][j] - mean) * rstd * g.x + b.x;
-        y[j + 1] = (v[i][j + 1] - mean) * rstd * g.y + b.y;
-        y[j + 2] = (v[i][j + 2] - mean) * rstd * g.z + b.z;
-        y[j + 3] = (v[i][j + 3] - mean) * rstd * g.w + b.w;
-        if (per != nullptr) {
-          const float4 e = __ldg(reinterpret_cast<const float4*>(per + c0 + j));
-          y[j] += e.x; y[j + 1] += e.y; y[j + 2] += e.z; y[j + 3] += e.w;
-        }
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + j));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c0 + j));
+        g[j] = g4.x; g[j + 1] = g4.y; g[j + 2] = g4.z; g[j + 3] = g4.w;
+        bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
       }
-      *reinterpret_cast<uint4*>(out + row * ldo + c0) =
-          make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-      if (out2 != nullptr) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(add + row * ldadd + c0));
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          y[2 * j] += bf16_lo(w[j]);
-          y[2 * j + 1] += bf16_hi(w[j]);
+      for (int r = 0; r < R; ++r) {
+        const long long row = row0 + r;
+        if (row < rows) {
+          const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            y[2 * j] = (bf16_lo(w[j]) - mean[r]) * rstd[r] * g[2 * j] + bb[2 * j];
+            y[2 * j + 1] = (bf16_hi(w[j]) - mean[r]) * rstd[r] * g[2 * j + 1] + bb[2 * j + 1];
+          }
+          if (pe != nullptr) {
+            const float* per = pe + static_cast<long long>((row / HW) % F) * C + c0;
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+              const float4 e = __ldg(reinterpret_cast<const float4*>(per + j));
+              y[j] += e.x; y[j + 1] += e.y; y[j + 2] += e.z; y[j + 3] += e.w;
+            }
+          }
+          *reinterpret_cast<uint4*>(out + row * ldo + c0) = make_uint4(
+              pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+          if constexpr (HAS_ADD) {
+            const uint32_t aw[4] = {addraw[r][i].x, addraw[r][i].y, addraw[r][i].z, addraw[r][i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              y[2 * j] += bf16_lo(aw[j]);
+              y[2 * j + 1] += bf16_hi(aw[j]);
+            }
+            *reinterpret_cast<uint4*>(out2 + row * ldo2 + c0) = make_uint4(
+                pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+          }
         }
-        *reinterpret_cast<uint4*>(out2 + row * ldo2 + c0) =
-            make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm statistics: x [images, HW, C] -> stats[images, G, 2] = (sum, sum of squares), accumulated with atomics.
-// Each thread owns one 8-channel vector position and walks rows; per-channel partials go to shared per-group sums.
+// GroupNorm, deterministic two-kernel form (no atomics: a fixed reduction order, so two runs are bit-identical).
+//   partial: grid (chunks, images); a block reduces GN_ROWS rows of one image to (sum, sum of squares) per group and
+//            writes partial[img][chunk][g][2].
+//   apply  : grid (chunks, images); a block folds the partials of its image in chunk order into mean / rstd, turns
+//            gamma / beta (and the optional per-image channel bias) into one scale / shift pair per channel, then
+//            streams its rows: y = x * a + b (optional SiLU).
+// Thread layout in both: `nvec = C / 8` lanes per row (one 16-byte vector each), blockDim / nvec rows in flight.
 // ------------------------------------------------------------------------------------------------
-constexpr int GN_ROWS_PER_BLOCK = 64;
+constexpr int GN_ROWS = 64;       // rows per block, partial kernel
+constexpr int GN_APPLY_ROWS = 32;  // rows per block, apply kernel
+constexpr int GN_MAX_GROUPS = 64;
 
 __global__ void __launch_bounds__(1024)
-groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float* __restrict__ stats, int HW, int C,
-                       int G, const float* __restrict__ rowbias, long long ldrb, int rb_div) {
-  __shared__ float s_sum[64], s_sq[64];
+groupnorm_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float* __restrict__ partial, int HW, int C,
+                         int G, int chunks, const float* __restrict__ rowbias, long long ldrb, int rb_div) {
+  extern __shared__ float gn_smem[];  // [rows_par][C] sums, then [rows_par][C] squares
   const int img = blockIdx.y;
-  const int row0 = blockIdx.x * GN_ROWS_PER_BLOCK;
+  const int row0 = blockIdx.x * GN_ROWS;
   const int nvec = C >> 3;
-  const int cpg = C / G;
-  if (threadIdx.x < 64) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
-  __syncthreads();
-  const int lanes_per_row = nvec;                       // threads cooperating on one row
-  const int rows_par = blockDim.x / lanes_per_row;      // rows processed concurrently (>= 1 when C <= 2048)
-  if (rows_par > 0) {
-    const int vi = threadIdx.x % lanes_per_row;
-    const int rsub = threadIdx.x / lanes_per_row;
-    if (rsub < rows_par) {
-      float a[8], b[8];
+  const int rows_par = blockDim.x / nvec;
+  const int vi = threadIdx.x % nvec;
+  const int rsub = threadIdx.x / nvec;
+  float a[8], b[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
-      float rb[8];
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  if (rsub < rows_par) {
+    float rb[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) rb[j] = rowbias != nullptr ? __ldg(rowbias + (img / rb_div) * ldrb + vi * 8 + j) : 0.f;
-      const int rend = min(row0 + GN_ROWS_PER_BLOCK, HW);
-      for (int r = row0 + rsub; r < rend; r += rows_par) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<long long>(img) * HW + r) * ldx) + vi);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int j = 0; j < 8; ++j) rb[j] = rowbias != nullptr ? __ldg(rowbias + (img / rb_div) * ldrb + vi * 8 + j) : 0.f;
+    const int rend = min(row0 + GN_ROWS, HW);
+    for (int r = row0 + rsub; r < rend; r += rows_par) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<long long>(img) * HW + r) * ldx) + vi);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float lo = bf16_lo(w[j]) + rb[2 * j], hi = bf16_hi(w[j]) + rb[2 * j + 1];
-          a[2 * j] += lo; b[2 * j] += lo * lo;
-          a[2 * j + 1] += hi; b[2 * j + 1] += hi * hi;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float lo = bf16_lo(w[j]) + rb[2 * j], hi = bf16_hi(w[j]) + rb[2 * j + 1];
+        a[2 * j] += lo; b[2 * j] = fmaf(lo, lo, b[2 * j]);
+        a[2 * j + 1] += hi; b[2 * j + 1] = fmaf(hi, hi, b[2 * j + 1]);
       }
-      // fold the 8 channels into (at most two) groups
-      int g_prev = (vi * 8) / cpg;
-      float sa = 0.f, sb = 0.f;
+    }
+    float* ssum = gn_smem + static_cast<size_t>(rsub) * C + vi * 8;
+    float* ssq = gn_smem + static_cast<size_t>(rows_par + rsub) * C + vi * 8;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int g = (vi * 8 + j) / cpg;
-        if (g != g_prev) {
-          atomicAdd(&s_sum[g_prev], sa);
-          atomicAdd(&s_sq[g_prev], sb);
-          sa = sb = 0.f;
-          g_prev = g;
-        }
-        sa += a[j];
-        sb += b[j];
-      }
-      atomicAdd(&s_sum[g_prev], sa);
-      atomicAdd(&s_sq[g_prev], sb);
+    for (int j = 0; j < 8; ++j) {
+      ssum[j] = a[j];
+      ssq[j] = b[j];
     }
   }
   __syncthreads();
-  if (threadIdx.x < G) {
-    atomicAdd(&stats[(static_cast<long long>(img) * G + threadIdx.x) * 2], s_sum[threadIdx.x]);
-    atomicAdd(&stats[(static_cast<long long>(img) * G + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+  // 2*G threads: thread (g, which) folds rows_par x cpg values in a fixed order
+  if (threadIdx.x < 2 * G) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    const int cpg = C / G;
+    float acc = 0.f;
+    for (int r = 0; r < rows_par; ++r) {
+      const float* src = gn_smem + static_cast<size_t>(which * rows_par + r) * C + g * cpg;
+      for (int c = 0; c < cpg; ++c) acc += src[c];
+    }
+    partial[((static_cast<long long>(img) * chunks + blockIdx.x) * G + g) * 2 + which] = acc;
   }
 }
 
-// y = (x (+ rowbias) - mean) * rstd * gamma + beta, optional SiLU.  One thread per 8-channel vector.
-__global__ void __launch_bounds__(256)
-groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ stats,
+__global__ void __launch_bounds__(1024)
+groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ partial,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                       __nv_bfloat16* __restrict__ out, long long ldo, long long rows, int HW, int C, int G, int silu,
+                       __nv_bfloat16* __restrict__ out, long long ldo, int HW, int C, int G, int chunks, int silu,
                        const float* __restrict__ rowbias, long long ldrb, int rb_div) {
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  const int img = blockIdx.y;
+  const int row0 = blockIdx.x * GN_APPLY_ROWS;
   const int nvec = C >> 3;
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (idx >= rows * nvec) return;
-  const long long row = idx / nvec;
-  const int vi = static_cast<int>(idx % nvec);
-  const int img = static_cast<int>(row / HW);
   const int cpg = C / G;
-  const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * ldx) + vi);
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-  float y[8];
+  if (threadIdx.x < G) {
+    float s = 0.f, ss = 0.f;
+    const float* pp = partial + (static_cast<long long>(img) * chunks * G + threadIdx.x) * 2;
+    for (int c = 0; c < chunks; ++c) {
+      s += pp[static_cast<long long>(c) * G * 2];
+      ss += pp[static_cast<long long>(c) * G * 2 + 1];
+    }
+    const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
+    const float mean = s * inv_n;
+    const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int rows_par = blockDim.x / nvec;
+  const int vi = threadIdx.x % nvec;
+  const int rsub = threadIdx.x / nvec;
+  if (rsub >= rows_par) return;
+  float sa[8], sb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = vi * 8 + j;
     const int g = c / cpg;
-    const float s = __ldg(stats + (static_cast<long long>(img) * G + g) * 2);
-    const float ss = __ldg(stats + (static_cast<long long>(img) * G + g) * 2 + 1);
-    const float mean = s * inv_n;
-    const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    float xv = (j & 1) ? bf16_hi(w[j >> 1]) : bf16_lo(w[j >> 1]);
-    if (rowbias != nullptr) xv += __ldg(rowbias + (img / rb_div) * ldrb + c);
-    float t = (xv - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-    if (silu) t = t / (1.0f + __expf(-t));
-    y[j] = t;
+    const float sc = s_rstd[g] * __ldg(gamma + c);
+    const float rbv = rowbias != nullptr ? __ldg(rowbias + (img / rb_div) * ldrb + c) : 0.f;
+    sa[j] = sc;
+    sb[j] = fmaf(rbv - s_mean[g], sc, __ldg(beta + c));
   }
-  *reinterpret_cast<uint4*>(out + row * ldo + vi * 8) =
-      make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+  const int rend = min(row0 + GN_APPLY_ROWS, HW);
+  for (int r = row0 + rsub; r < rend; r += rows_par) {
+    const long long row = static_cast<long long>(img) * HW + r;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * ldx) + vi);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      y[2 * j] = fmaf(bf16_lo(w[j]), sa[2 * j], sb[2 * j]);
+      y[2 * j + 1] = fmaf(bf16_hi(w[j]), sa[2 * j + 1], sb[2 * j + 1]);
+    }
+    if (silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = y[j] * __frcp_rn(1.0f + __expf(-y[j]));
+    }
+    *reinterpret_cast<uint4*>(out + row * ldo + vi * 8) =
+        make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+  }
+}
+
+template <int NV, int R>
+static int launch_layernorm(const void* x, long long ldx, const float* gamma, const float* beta, float eps, void* out,
+                            long long ldo, const float* pe, int F, int HW, const void* add, long long ldadd, void* out2,
+                            long long ldo2, long long rows, int C, cudaStream_t stream) {
+  const long long per_block = static_cast<long long>(LN_WARPS) * R;
+  const unsigned grid = static_cast<unsigned>((rows + per_block - 1) / per_block);
+  if (out2 != nullptr) {
+    layernorm_kernel<NV, R, true><<<grid, LN_WARPS * 32, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo, pe,
+        F > 0 ? F : 1, HW > 0 ? HW : 1, static_cast<const __nv_bfloat16*>(add), ldadd,
+        static_cast<__nv_bfloat16*>(out2), ldo2, rows, C);
+  } else {
+    layernorm_kernel<NV, R, false><<<grid, LN_WARPS * 32, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo, pe,
+        F > 0 ? F : 1, HW > 0 ? HW : 1, nullptr, 0, nullptr, 0, rows, C);
+  }
+  return check_launch("layernorm_kernel");
 }
 
 }  // namespace fmc
@@ -216,12 +288,16 @@ extern "C" int fmc_layernorm_bf16(const void* x, long long ldx, const float* gam
   FMC_REQUIRE((out2 == nullptr) == (add == nullptr), FMC_ERR_ARG, "fmc_layernorm_bf16: add and out2 go together");
   FMC_REQUIRE(pe == nullptr || (F > 0 && HW > 0), FMC_ERR_ARG, "fmc_layernorm_bf16: pe needs F and HW");
   if (rows == 0) return FMC_OK;
-  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  layernorm_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps,
-                                             static_cast<__nv_bfloat16*>(out), ldo, pe, F > 0 ? F : 1, HW > 0 ? HW : 1,
-                                             static_cast<const __nv_bfloat16*>(add), ldadd,
-                                             static_cast<__nv_bfloat16*>(out2), ldo2, rows, C);
-  return check_launch("layernorm_kernel");
+  const int nv = (C / 8 + 31) / 32;
+#define FMC_LN_ARGS x, ldx, gamma, beta, eps, out, ldo, pe, F, HW, add, ldadd, out2, ldo2, rows, C, stream
+  switch (nv) {
+    case 1: return launch_layernorm<1, 4>(FMC_LN_ARGS);
+    case 2: return launch_layernorm<2, 4>(FMC_LN_ARGS);
+    case 3: return launch_layernorm<3, 2>(FMC_LN_ARGS);
+    case 4: return launch_layernorm<4, 2>(FMC_LN_ARGS);
+    default: return launch_layernorm<5, 2>(FMC_LN_ARGS);
+  }
+#undef FMC_LN_ARGS
 }
 
 extern "C" int fmc_groupnorm_bf16(const void* x, long long ldx, const float* gamma, const float* beta, float eps,
@@ -233,18 +309,25 @@ extern "C" int fmc_groupnorm_bf16(const void* x, long long ldx, const float* gam
               "fmc_groupnorm_bf16: unsupported C=%d groups=%d", C, groups);
   FMC_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0, FMC_ERR_SHAPE, "fmc_groupnorm_bf16: row strides must be multiples of 8");
   if (images == 0 || HW == 0) return FMC_OK;
-  FMC_CUDA_OK(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * groups * images, stream));
-  dim3 grid(ceil_div(HW, GN_ROWS_PER_BLOCK), images);
+  // stats_ws holds the per-chunk partial sums: 2 * groups * images * ceil(HW / 64) floats
+  const int chunks = ceil_div(HW, GN_ROWS);
   const int nvec = C / 8;
-  const int stat_threads = nvec * (nvec >= 512 ? 1 : 512 / nvec);  // whole rows per pass, <= 1024 threads
-  groupnorm_stats_kernel<<<grid, stat_threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, stats_ws, HW, C, groups,
-                                                   rowbias, ldrb, rowbias_div > 0 ? rowbias_div : 1);
-  int rc = check_launch("groupnorm_stats_kernel");
+  const int threads = nvec * (nvec >= 512 ? 1 : 512 / nvec);  // whole rows per pass, <= 1024 threads
+  const int rows_par = threads / nvec;
+  const size_t smem = static_cast<size_t>(2) * rows_par * C * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    FMC_CUDA_OK(cudaFuncSetAttribute(groupnorm_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+    smem_set = smem;
+  }
+  const int rb_div = rowbias_div > 0 ? rowbias_div : 1;
+  groupnorm_partial_kernel<<<dim3(chunks, images), threads, smem, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, stats_ws, HW, C, groups, chunks, rowbias, ldrb, rb_div);
+  int rc = check_launch("groupnorm_partial_kernel");
   if (rc != FMC_OK) return rc;
-  const long long rows = static_cast<long long>(images) * HW;
-  const long long n = rows * (C / 8);
-  groupnorm_apply_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, stats_ws, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo, rows,
-      HW, C, groups, silu, rowbias, ldrb, rowbias_div > 0 ? rowbias_div : 1);
+  groupnorm_apply_kernel<<<dim3(ceil_div(HW, GN_APPLY_ROWS), images), threads, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, stats_ws, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo, HW, C,
+      groups, chunks, silu, rowbias, ldrb, rb_div);
   return check_launch("groupnorm_apply_kernel");
 }
