@@ -71,8 +71,8 @@ int fmc_layernorm_bf16(const void* x, long long ldx, const float* gamma, const f
 
 /* Per-image GroupNorm on channels-last x[images, HW, C] (+ channel bias rowbias[image / rowbias_div] added first)
  * (+ SiLU).
- * stats_ws: fp32 workspace of 2*groups*images*ceil(HW/64) floats (per-chunk partial sums, folded in a fixed order:
- * deterministic, no atomics).  Replaces InflatedGroupNorm fmc/models/resnet.py:27-37
+ * stats_ws: fp32 workspace of 2*images*(groups*ceil(HW/64) + C) floats (per-chunk partial sums, folded in a fixed
+ * order -- deterministic, no atomics -- then one scale/shift pair per image and channel).  Replaces InflatedGroupNorm fmc/models/resnet.py:27-37
  * (motion_module.py:217), diffusers ResnetBlock2D.norm1/norm2 + SiLU (+ the time-embedding add between them),
  * Transformer2DModel.norm, and conv_norm_out + conv_act fmc/models/unet.py:1288-1292. */
 int fmc_groupnorm_bf16(const void* x, long long ldx, const float* gamma, const float* beta, float eps, void* out,

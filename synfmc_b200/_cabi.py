@@ -60,8 +60,8 @@ def lib():
     return _lib
 
 
-# kernels launched by one call of each entry point (groupnorm = statistics + apply); everything else launches one
-KERNELS_PER_CALL = {"fmc_groupnorm_bf16": 2}
+# kernels launched by one call of each entry point (groupnorm = partial sums + finalize + apply); everything else launches one
+KERNELS_PER_CALL = {"fmc_groupnorm_bf16": 3}
 launch_count = 0  # kernels of this library launched by this process (bench.py reports it as gpu_launches)
 trace = None      # when set to a list by bench.py: (name, args, start_event, end_event) per call, CUDA events on the
                   # launching stream -- the per-kernel timing behind the roofline figures

@@ -346,7 +346,7 @@ __device__ __forceinline__ float gelu_fast(float g) {
   p = fmaf(x, p, 0.0422820123f);
   p = fmaf(x, p, 0.0705230784f);
   p = fmaf(x, p, 1.0f);
-  float r = __frcp_rn(p);
+  float r = rcp_fast(p);
   r *= r; r *= r; r *= r; r *= r;            // (1/p)^16 = 1 - erf(x)
   const float one_plus_erf = g >= 0.f ? 2.0f - r : r;
   return 0.5f * g * one_plus_erf;
@@ -572,17 +572,25 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tmem_ld_wait();
           const int ncol0 = n_blk * BN + s * 64;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a0 = __uint_as_float(r0[j]), g0 = __uint_as_float(r0[16 + j]);
-            float a1 = __uint_as_float(r1[j]), g1 = __uint_as_float(r1[16 + j]);
+          for (int hblk = 0; hblk < 2; ++hblk) {
+            const uint32_t(&rr)[32] = hblk == 0 ? r0 : r1;
+            float bv[32];
             if (p.bias != nullptr) {
-              a0 += __ldg(p.bias + ncol0 + j);
-              g0 += __ldg(p.bias + ncol0 + 16 + j);
-              a1 += __ldg(p.bias + ncol0 + 32 + j);
-              g1 += __ldg(p.bias + ncol0 + 48 + j);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + hblk * 32 + j));
+                bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) bv[j] = 0.f;
             }
-            v[j] = a0 * gelu_fast(g0);
-            v[16 + j] = a1 * gelu_fast(g1);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = __uint_as_float(rr[j]) + bv[j];
+              const float g = __uint_as_float(rr[16 + j]) + bv[16 + j];
+              v[hblk * 16 + j] = a * gelu_fast(g);
+            }
           }
         }
         const uint32_t sub = buf + static_cast<uint32_t>(s * SUB_BYTES);

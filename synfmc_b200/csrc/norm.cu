@@ -134,6 +134,136 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float
 }
 
 // ------------------------------------------------------------------------------------------------
+// LayerNorm for C = 40 * LPR (the U-Net widths 320 / 640 / 1280): LPR lanes share a row (5 vectors of 8 channels per
+// lane, every lane busy), 32 / LPR rows per warp pass, R passes in flight.  Same arithmetic as above.
+// ------------------------------------------------------------------------------------------------
+template <int LPR, int R, bool HAS_ADD>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm40_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out, long long ldo,
+                   const float* __restrict__ pe, int F, int HW, const __nv_bfloat16* __restrict__ add, long long ldadd,
+                   __nv_bfloat16* __restrict__ out2, long long ldo2, long long rows) {
+  constexpr int C = 40 * LPR;
+  constexpr int RPW = 32 / LPR;  // rows per warp pass
+  constexpr int NV = 5;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;    // lane inside the row group
+  const int rw = lane / LPR;     // row inside the warp pass
+  const long long row0 = (blockIdx.x * static_cast<long long>(LN_WARPS) + (threadIdx.x >> 5)) * (RPW * R) + rw;
+  if (row0 - rw >= rows) return;
+  constexpr float inv_c = 1.0f / static_cast<float>(C);
+  uint4 raw[R][NV];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r * RPW < rows ? row0 + r * RPW : rows - 1;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) raw[r][i] = __ldg(xr + sub + i * LPR);
+  }
+  uint4 addraw[HAS_ADD ? R : 1][HAS_ADD ? NV : 1];
+  if constexpr (HAS_ADD) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r * RPW < rows ? row0 + r * RPW : rows - 1;
+      const uint4* ar = reinterpret_cast<const uint4*>(add + row * ldadd);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) addraw[r][i] = __ldg(ar + sub + i * LPR);
+    }
+  }
+  float mean[R], rstd[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sum += bf16_lo(w[j]) + bf16_hi(w[j]);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mean[r] = sum * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d0 = bf16_lo(w[j]) - mean[r], d1 = bf16_hi(w[j]) - mean[r];
+        sq += d0 * d0 + d1 * d1;
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    rstd[r] = rsqrtf(sq * inv_c + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (sub + i * LPR) * 8;
+    float g[8], bb[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + j));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c0 + j));
+      g[j] = g4.x; g[j + 1] = g4.y; g[j + 2] = g4.z; g[j + 3] = g4.w;
+      bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r * RPW;
+      if (row < rows) {
+        const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          y[2 * j] = (bf16_lo(w[j]) - mean[r]) * rstd[r] * g[2 * j] + bb[2 * j];
+          y[2 * j + 1] = (bf16_hi(w[j]) - mean[r]) * rstd[r] * g[2 * j + 1] + bb[2 * j + 1];
+        }
+        if (pe != nullptr) {
+          const float* per = pe + static_cast<long long>((row / HW) % F) * C + c0;
+#pragma unroll
+          for (int j = 0; j < 8; j += 4) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(per + j));
+            y[j] += e.x; y[j + 1] += e.y; y[j + 2] += e.z; y[j + 3] += e.w;
+          }
+        }
+        *reinterpret_cast<uint4*>(out + row * ldo + c0) = make_uint4(
+            pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        if constexpr (HAS_ADD) {
+          const uint32_t aw[4] = {addraw[r][i].x, addraw[r][i].y, addraw[r][i].z, addraw[r][i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            y[2 * j] += bf16_lo(aw[j]);
+            y[2 * j + 1] += bf16_hi(aw[j]);
+          }
+          *reinterpret_cast<uint4*>(out2 + row * ldo2 + c0) = make_uint4(
+              pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+      }
+    }
+  }
+}
+
+template <int LPR, int R>
+static int launch_layernorm40(const void* x, long long ldx, const float* gamma, const float* beta, float eps, void* out,
+                              long long ldo, const float* pe, int F, int HW, const void* add, long long ldadd,
+                              void* out2, long long ldo2, long long rows, cudaStream_t stream) {
+  const long long per_block = static_cast<long long>(LN_WARPS) * (32 / LPR) * R;
+  const unsigned grid = static_cast<unsigned>((rows + per_block - 1) / per_block);
+  if (out2 != nullptr) {
+    layernorm40_kernel<LPR, R, true><<<grid, LN_WARPS * 32, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo, pe,
+        F > 0 ? F : 1, HW > 0 ? HW : 1, static_cast<const __nv_bfloat16*>(add), ldadd,
+        static_cast<__nv_bfloat16*>(out2), ldo2, rows);
+  } else {
+    layernorm40_kernel<LPR, R, false><<<grid, LN_WARPS * 32, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo, pe,
+        F > 0 ? F : 1, HW > 0 ? HW : 1, nullptr, 0, nullptr, 0, rows);
+  }
+  return check_launch("layernorm40_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
 // GroupNorm, deterministic two-kernel form (no atomics: a fixed reduction order, so two runs are bit-identical).
 //   partial: grid (chunks, images); a block reduces GN_ROWS rows of one image to (sum, sum of squares) per group and
 //            writes partial[img][chunk][g][2].
@@ -183,28 +313,32 @@ groupnorm_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, flo
     }
   }
   __syncthreads();
-  // 2*G threads: thread (g, which) folds rows_par x cpg values in a fixed order
+  // fold rows first (2*C column sums over rows_par rows), then channels into groups -- both in a fixed order
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int which = i / C, c = i - which * C;
+    float acc = 0.f;
+    for (int r = 0; r < rows_par; ++r) acc += gn_smem[static_cast<size_t>(which * rows_par + r) * C + c];
+    gn_smem[static_cast<size_t>(which * rows_par) * C + c] = acc;  // row 0 of each half now holds the column sums
+  }
+  __syncthreads();
   if (threadIdx.x < 2 * G) {
     const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
     const int cpg = C / G;
+    const float* src = gn_smem + static_cast<size_t>(which * rows_par) * C + g * cpg;
     float acc = 0.f;
-    for (int r = 0; r < rows_par; ++r) {
-      const float* src = gn_smem + static_cast<size_t>(which * rows_par + r) * C + g * cpg;
-      for (int c = 0; c < cpg; ++c) acc += src[c];
-    }
+    for (int c = 0; c < cpg; ++c) acc += src[c];
     partial[((static_cast<long long>(img) * chunks + blockIdx.x) * G + g) * 2 + which] = acc;
   }
 }
 
-__global__ void __launch_bounds__(1024)
-groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ partial,
-                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                       __nv_bfloat16* __restrict__ out, long long ldo, int HW, int C, int G, int chunks, int silu,
-                       const float* __restrict__ rowbias, long long ldrb, int rb_div) {
+// scale / shift per (image, channel): y = x * a + b with a = rstd * gamma, b = beta + (rowbias - mean) * a.
+// grid = images; the partial sums are folded in chunk order (deterministic).
+__global__ void __launch_bounds__(256)
+groupnorm_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float eps, float2* __restrict__ ab, int HW, int C, int G,
+                          int chunks, const float* __restrict__ rowbias, long long ldrb, int rb_div) {
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
-  const int img = blockIdx.y;
-  const int row0 = blockIdx.x * GN_APPLY_ROWS;
-  const int nvec = C >> 3;
+  const int img = blockIdx.x;
   const int cpg = C / G;
   if (threadIdx.x < G) {
     float s = 0.f, ss = 0.f;
@@ -220,37 +354,59 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const
     s_rstd[threadIdx.x] = rsqrtf(var + eps);
   }
   __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float a = s_rstd[g] * __ldg(gamma + c);
+    const float rbv = rowbias != nullptr ? __ldg(rowbias + (img / rb_div) * ldrb + c) : 0.f;
+    ab[static_cast<long long>(img) * C + c] = make_float2(a, fmaf(rbv - s_mean[g], a, __ldg(beta + c)));
+  }
+}
+
+constexpr int GN_UNROLL = 4;
+
+__global__ void __launch_bounds__(1024)
+groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float2* __restrict__ ab,
+                       __nv_bfloat16* __restrict__ out, long long ldo, int HW, int C, int silu) {
+  const int img = blockIdx.y;
+  const int nvec = C >> 3;
   const int rows_par = blockDim.x / nvec;
   const int vi = threadIdx.x % nvec;
   const int rsub = threadIdx.x / nvec;
   if (rsub >= rows_par) return;
   float sa[8], sb[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = vi * 8 + j;
-    const int g = c / cpg;
-    const float sc = s_rstd[g] * __ldg(gamma + c);
-    const float rbv = rowbias != nullptr ? __ldg(rowbias + (img / rb_div) * ldrb + c) : 0.f;
-    sa[j] = sc;
-    sb[j] = fmaf(rbv - s_mean[g], sc, __ldg(beta + c));
-  }
-  const int rend = min(row0 + GN_APPLY_ROWS, HW);
-  for (int r = row0 + rsub; r < rend; r += rows_par) {
-    const long long row = static_cast<long long>(img) * HW + r;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * ldx) + vi);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    float y[8];
+  {
+    const float4* p4 = reinterpret_cast<const float4*>(ab + static_cast<long long>(img) * C + vi * 8);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      y[2 * j] = fmaf(bf16_lo(w[j]), sa[2 * j], sb[2 * j]);
-      y[2 * j + 1] = fmaf(bf16_hi(w[j]), sa[2 * j + 1], sb[2 * j + 1]);
+      const float4 v = __ldg(p4 + j);
+      sa[2 * j] = v.x; sb[2 * j] = v.y; sa[2 * j + 1] = v.z; sb[2 * j + 1] = v.w;
     }
-    if (silu) {
+  }
+  const int row0 = blockIdx.x * (rows_par * GN_UNROLL) + rsub;
+  uint4 u[GN_UNROLL];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = y[j] * __frcp_rn(1.0f + __expf(-y[j]));
+  for (int k = 0; k < GN_UNROLL; ++k) {
+    const int r = row0 + k * rows_par;
+    if (r < HW) u[k] = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<long long>(img) * HW + r) * ldx) + vi);
+  }
+#pragma unroll
+  for (int k = 0; k < GN_UNROLL; ++k) {
+    const int r = row0 + k * rows_par;
+    if (r < HW) {
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        y[2 * j] = fmaf(bf16_lo(w[j]), sa[2 * j], sb[2 * j]);
+        y[2 * j + 1] = fmaf(bf16_hi(w[j]), sa[2 * j + 1], sb[2 * j + 1]);
+      }
+      if (silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = y[j] * rcp_fast(1.0f + __expf(-y[j]));
+      }
+      *reinterpret_cast<uint4*>(out + (static_cast<long long>(img) * HW + r) * ldo + vi * 8) = make_uint4(
+          pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
     }
-    *reinterpret_cast<uint4*>(out + row * ldo + vi * 8) =
-        make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
   }
 }
 
@@ -288,6 +444,9 @@ extern "C" int fmc_layernorm_bf16(const void* x, long long ldx, const float* gam
   FMC_REQUIRE((out2 == nullptr) == (add == nullptr), FMC_ERR_ARG, "fmc_layernorm_bf16: add and out2 go together");
   FMC_REQUIRE(pe == nullptr || (F > 0 && HW > 0), FMC_ERR_ARG, "fmc_layernorm_bf16: pe needs F and HW");
   if (rows == 0) return FMC_OK;
+  if (C == 320) return launch_layernorm40<8, 2>(x, ldx, gamma, beta, eps, out, ldo, pe, F, HW, add, ldadd, out2, ldo2, rows, stream);
+  if (C == 640) return launch_layernorm40<16, 2>(x, ldx, gamma, beta, eps, out, ldo, pe, F, HW, add, ldadd, out2, ldo2, rows, stream);
+  if (C == 1280) return launch_layernorm40<32, 2>(x, ldx, gamma, beta, eps, out, ldo, pe, F, HW, add, ldadd, out2, ldo2, rows, stream);
   const int nv = (C / 8 + 31) / 32;
 #define FMC_LN_ARGS x, ldx, gamma, beta, eps, out, ldo, pe, F, HW, add, ldadd, out2, ldo2, rows, C, stream
   switch (nv) {
@@ -309,7 +468,7 @@ extern "C" int fmc_groupnorm_bf16(const void* x, long long ldx, const float* gam
               "fmc_groupnorm_bf16: unsupported C=%d groups=%d", C, groups);
   FMC_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0, FMC_ERR_SHAPE, "fmc_groupnorm_bf16: row strides must be multiples of 8");
   if (images == 0 || HW == 0) return FMC_OK;
-  // stats_ws holds the per-chunk partial sums: 2 * groups * images * ceil(HW / 64) floats
+  // stats_ws: [images][chunks][groups][2] partial sums, then [images][C] (scale, shift) pairs
   const int chunks = ceil_div(HW, GN_ROWS);
   const int nvec = C / 8;
   const int threads = nvec * (nvec >= 512 ? 1 : 512 / nvec);  // whole rows per pass, <= 1024 threads
@@ -322,12 +481,16 @@ extern "C" int fmc_groupnorm_bf16(const void* x, long long ldx, const float* gam
     smem_set = smem;
   }
   const int rb_div = rowbias_div > 0 ? rowbias_div : 1;
+  float2* ab = reinterpret_cast<float2*>(stats_ws + static_cast<size_t>(2) * groups * images * chunks);
   groupnorm_partial_kernel<<<dim3(chunks, images), threads, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, stats_ws, HW, C, groups, chunks, rowbias, ldrb, rb_div);
   int rc = check_launch("groupnorm_partial_kernel");
   if (rc != FMC_OK) return rc;
-  groupnorm_apply_kernel<<<dim3(ceil_div(HW, GN_APPLY_ROWS), images), threads, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, stats_ws, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo, HW, C,
-      groups, chunks, silu, rowbias, ldrb, rb_div);
+  groupnorm_finalize_kernel<<<images, 256, 0, stream>>>(stats_ws, gamma, beta, eps, ab, HW, C, groups, chunks, rowbias,
+                                                        ldrb, rb_div);
+  rc = check_launch("groupnorm_finalize_kernel");
+  if (rc != FMC_OK) return rc;
+  groupnorm_apply_kernel<<<dim3(ceil_div(HW, rows_par * GN_UNROLL), images), threads, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, ab, static_cast<__nv_bfloat16*>(out), ldo, HW, C, silu);
   return check_launch("groupnorm_apply_kernel");
 }

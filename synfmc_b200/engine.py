@@ -184,9 +184,10 @@ class NormPlan:
 
 
 class ConvPlan:
-    def __init__(self, conv, device):
+    def __init__(self, conv, device, use_bias=True):
+        """use_bias=False: the caller folds conv.bias into the next kernel (saves the separate bias pass)."""
         self.w = conv.weight.detach().to(device=device, dtype=BF16).contiguous(memory_format=torch.channels_last)
-        self.b = conv.bias.detach().to(device=device, dtype=BF16) if conv.bias is not None else None
+        self.b = conv.bias.detach().to(device=device, dtype=BF16) if (conv.bias is not None and use_bias) else None
         self.stride = conv.stride
         self.padding = conv.padding
         self.cin, self.cout = conv.in_channels, conv.out_channels
@@ -335,12 +336,22 @@ def run_transformer2d(mod, x, text):
 
 def plan_resnet(mod, device):
     if getattr(mod, "_plan", None) is None or mod._plan["device"] != device:
+        # conv1.bias rides on the time-embedding projection (both are per-channel adds in front of norm2), conv2.bias
+        # on the shortcut GEMM bias or the residual add: the 3x3 convolutions themselves run bias-free
+        b1 = mod.conv1.bias.detach().float()
+        b2 = mod.conv2.bias.detach().float()
+        shortcut = None
+        if mod.conv_shortcut is not None:
+            sc = mod.conv_shortcut
+            shortcut = LinearPlan(sc.weight.detach().float().view(sc.out_channels, sc.in_channels),
+                                  sc.bias.detach().float() + b2, device)
         mod._plan = {
             "device": device,
-            "norm1": NormPlan(mod.norm1, device), "conv1": ConvPlan(mod.conv1, device),
-            "temb": LinearPlan(mod.time_emb_proj.weight.detach().float(), mod.time_emb_proj.bias.detach().float(), device),
-            "norm2": NormPlan(mod.norm2, device), "conv2": ConvPlan(mod.conv2, device),
-            "shortcut": ConvPlan(mod.conv_shortcut, device) if mod.conv_shortcut is not None else None,
+            "norm1": NormPlan(mod.norm1, device), "conv1": ConvPlan(mod.conv1, device, use_bias=False),
+            "temb": LinearPlan(mod.time_emb_proj.weight.detach().float(), mod.time_emb_proj.bias.detach().float() + b1,
+                               device),
+            "norm2": NormPlan(mod.norm2, device), "conv2": ConvPlan(mod.conv2, device, use_bias=False),
+            "shortcut": shortcut, "bias2": _dev_f32(b2, device).view(1, -1),
             "scale": float(mod.output_scale_factor),
         }
         assert mod._plan["scale"] == 1.0, "output_scale_factor != 1 is not used by SD1.5 / FMC"
@@ -375,9 +386,9 @@ def run_resnet(mod, x, temb):
                        silu=True, rowbias=tproj, rowbias_div=F)
     h2 = p["conv2"](n2.view(images, H, W, cout)).view(-1, cout)
     if p["shortcut"] is not None:
-        out = p["shortcut"].linear(rows, residual=h2)
+        out = p["shortcut"](rows, residual=h2)
     else:
-        out = ops.add(rows, h2)
+        out = ops.add(rows, h2, rowbias=p["bias2"], rows_per_group=rows.shape[0])
     return CL(out.view(B, F, H, W, cout))
 
 

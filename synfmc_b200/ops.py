@@ -98,7 +98,7 @@ def groupnorm(x, gamma, beta, eps, images, HW, groups=32, silu=False, rowbias=No
     assert rows == images * HW
     if out is None:
         out = torch.empty((rows, C), device=x.device, dtype=BF16)
-    stats = torch.empty((images, (HW + 63) // 64, groups, 2), device=x.device, dtype=torch.float32)
+    stats = torch.empty((2 * images * (groups * ((HW + 63) // 64) + C),), device=x.device, dtype=torch.float32)
     if rowbias is not None:
         assert rowbias.dtype == torch.float32 and rowbias.shape == (images // rowbias_div, C) and rowbias.stride(1) == 1
     _cabi.call("fmc_groupnorm_bf16", x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps),

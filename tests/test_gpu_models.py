@@ -193,3 +193,21 @@ def test_config1_full_unet(cuda_device):
     got = PoseAdaptor(p_unet, p_enc)(latents.to(cuda_device), torch.tensor([961], device=cuda_device),
                                      text.to(cuda_device), plucker.to(cuda_device))
     assert rel_l2(got, want) < UNET_TOL
+
+
+def test_product_against_reference_golden_vectors(cuda_device):
+    """CUDA path vs the committed vectors that the reference's own fmc/* code produced (tests/golden/make_golden.py):
+    tiny U-Net cam / cam+obj forwards and the CameraAdapter motion module."""
+    import os
+    from tests.golden.make_golden import golden_inputs
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fmc_reference_vectors.pt"),
+                      weights_only=False)
+    inp = golden_inputs()
+    dev = cuda_device
+    for obj, key in ((False, "unet_cam"), (True, "unet_obj")):
+        o_unet = helpers.build_oracle_unet(tiny=True, obj=obj)  # weights only (name-seeded, same as the reference run)
+        p_unet = helpers.build_product_unet(o_unet, tiny=True, obj=obj, device=dev)
+        kw = {"traj_features": [t.to(dev) for t in inp["traj_feats"]]} if obj else {}
+        got = p_unet(inp["sample"].to(dev), 961, inp["text"].to(dev),
+                     pose_embedding_features=[x.to(dev) for x in inp["pose_feats"]], **kw).sample
+        assert rel_l2(got, gold[key]) < UNET_TOL, key
