@@ -275,7 +275,7 @@ def run_reference(args):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from synfmc_b200 import _cabi, ops
+    from synfmc_b200 import _cabi, ops, shard
     from synfmc_b200.engine import CL
     from synfmc_b200.fmc.util import pack_objects, traj_features_cl
 
@@ -287,8 +287,7 @@ def run_b200(args):
                          "CPU oracle)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    shard.init(backend="nccl", device=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
     peaks = load_peaks()
     _cabi.lib()
@@ -296,10 +295,7 @@ def run_b200(args):
     pipe, omcm = build_product(dev)
     K, c2w, infos, masks, latents_h, text_h = synth_clip(rank)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = shard.barrier
 
     # --- once per clip: CameraEncoder + ObjectEncoder (outside the step, like pipeline_animation_cm_om.py:657-676)
     def encoders():
@@ -333,10 +329,7 @@ def run_b200(args):
         fn(n)
         e.record()
         barrier()
-        ms = torch.tensor([s.elapsed_time(e)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
+        return shard.max_over_ranks(s.elapsed_time(e), device=dev)
 
     # --- device-resident loop
     state = {"lat": latents_h.to(dev)}
