@@ -324,6 +324,345 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+
+// =====================================================================================================================
+// Two-query-tile variant (head_dim 40): 256 query rows per work item, one softmax warpgroup per 128-row tile.
+//   warp 0      TMA producer (both Q tiles once per item; K / V tiles through a 3-stage ring)
+//   warp 1      MMA issuer: per KV tile  PV_A(j-1), S_A = Q_A K^T(j), PV_B(j-1), S_B = Q_B K^T(j)
+//   warp 2      TMEM allocator
+//   warps 4-7   softmax warpgroup A (rows 0-127),  warps 8-11  softmax warpgroup B (rows 128-255)
+// While warpgroup A turns S_A(j) into P_A(j), the tensor pipe computes S_B(j) and warpgroup B is still busy with the
+// previous tile, so MUFU / TMEM reads of one group hide the MMA round trip of the other.
+// The softmax is single pass for every tile after the first: P = exp2(S c - m) with the running reference m; the row
+// maximum is tracked on the side and a growth of more than 2^8 schedules a rescale of (O, l) for the NEXT tile, when
+// PV of this tile has certainly finished (S_full(j+1) is committed after PV(j) in the same in-order MMA stream).  A
+// growth beyond 2^64 (overflow territory) falls back to an immediate rescale + second pass.  O / l is exact for any
+// reference m, so a pending rescale at the end of the row is simply dropped.
+// =====================================================================================================================
+constexpr int FA2_THREADS = 384;
+constexpr float FA2_REDO_THRESHOLD = 64.0f;
+
+template <int D>
+struct Fa2Cfg {
+  static constexpr int DK = (D + 15) / 16 * 16;
+  static constexpr int QCH = (DK + 63) / 64;
+  static constexpr int Q_BYTES = QCH * FA_BM * 128;     // one 128-row Q tile
+  static constexpr int K_BYTES = QCH * FA_BN * 128;
+  static constexpr int V_BYTES = QCH * FA_BN * 128;
+  static constexpr int P_BYTES = 2 * FA_BM * 128;       // one 128 x 128 bf16 P tile
+  static constexpr int KV_BYTES = K_BYTES + V_BYTES;
+  static constexpr int STAGES = 3;
+  static constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * P_BYTES + STAGES * KV_BYTES + 1024;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int O_COL = 256;                      // S_A at 0, S_B at 128, O_A at 256, O_B at 256 + DK
+  static_assert(QCH == 1, "two-tile variant is built for head_dim <= 64");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int D>
+__global__ void __launch_bounds__(FA2_THREADS, 1)
+spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, FaParams p) {
+  using Cfg = Fa2Cfg<D>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int DK = Cfg::DK;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t q_full, q_empty;
+  __shared__ uint64_t kv_full[STAGES], kv_empty[STAGES];
+  __shared__ uint64_t s_full[2], p_ready[2], o_final[2], o_free[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;                        // two Q tiles
+  const uint32_t sP = sQ + 2 * Cfg::Q_BYTES;            // two P tiles
+  const uint32_t sKV = sP + 2 * Cfg::P_BYTES;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_pairs = (p.nq + 2 * FA_BM - 1) / (2 * FA_BM);
+  const int num_items = p.images * p.heads * q_pairs;
+  const int T = p.kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&q_full, 1);
+    mbar_init(&q_empty, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(&s_full[w], 1);
+      mbar_init(&p_ready[w], 4);
+      mbar_init(&o_final[w], 1);
+      mbar_init(&o_free[w], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_slot, Cfg::TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (lane == 0) {
+      uint32_t t = 0, it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int qp = item % q_pairs;
+        const int head = (item / q_pairs) % p.heads;
+        const int img = item / (q_pairs * p.heads);
+        const int q_row0 = img * p.nq + qp * 2 * FA_BM;
+        const int kv_row0 = (img / p.kv_div) * p.kv_stride;
+        mbar_wait(&q_empty, (it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&q_full, 2 * Cfg::Q_BYTES);
+        tma_load_2d_a(sQ, &tmQ, &q_full, p.q_col0 + head * p.head_stride, q_row0);
+        tma_load_2d_a(sQ + Cfg::Q_BYTES, &tmQ, &q_full, p.q_col0 + head * p.head_stride, q_row0 + FA_BM);
+        for (int j = 0; j < T; ++j, ++t) {
+          const int st = t % STAGES;
+          const uint32_t ph = (t / STAGES) & 1u;
+          mbar_wait(&kv_empty[st], ph ^ 1u);
+          mbar_arrive_expect_tx(&kv_full[st], Cfg::KV_BYTES);
+          const uint32_t sK = sKV + st * Cfg::KV_BYTES;
+          tma_load_2d_a(sK, &tmK, &kv_full[st], p.k_col0 + head * p.head_stride, kv_row0 + j * FA_BN);
+          tma_load_2d_a(sK + Cfg::K_BYTES, &tmV, &kv_full[st], p.v_col0 + head * D, kv_row0 + j * FA_BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------ MMA issuer ------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(FA_BM, FA_BN);
+      constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(FA_BM, DK);
+      uint32_t t = 0, it = 0;
+      // O_w += P_w(tile u) V(tile u)
+      auto issue_pv = [&](int w, uint32_t u, bool first_of_item) {
+        mbar_wait(&p_ready[w], u & 1u);
+        if (first_of_item) mbar_wait(&o_free[w], (it & 1u) ^ 1u);  // previous item's epilogue has read O_w
+        tc_fence_after_sync();
+        const uint32_t sV = sKV + (u % STAGES) * Cfg::KV_BYTES + Cfg::K_BYTES;
+        const uint32_t sPw = sP + w * Cfg::P_BYTES;
+#pragma unroll
+        for (int k = 0; k < FA_BN / 16; ++k) {
+          const uint64_t da = umma_desc_k_sw128(sPw + (k >> 2) * (FA_BM * 128) + (k & 3) * 32);
+          const uint64_t db = umma_desc_mn_sw128(sV + k * (16 * 128), FA_BN * 128, 1024);
+          umma_bf16_ss(tmem_base + Cfg::O_COL + w * DK, da, db, idesc_o, (!first_of_item || k > 0) ? 1u : 0u);
+        }
+      };
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        mbar_wait(&q_full, it & 1u);
+        tc_fence_after_sync();
+        for (int j = 0; j < T; ++j, ++t) {
+          const int st = t % STAGES;
+          const uint32_t ph = (t / STAGES) & 1u;
+          mbar_wait(&kv_full[st], ph);
+          tc_fence_after_sync();
+          const uint32_t sK = sKV + st * Cfg::KV_BYTES;
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            if (j >= 1) {
+              issue_pv(w, t - 1, j == 1);
+              if (w == 1) umma_commit(&kv_empty[(t - 1) % STAGES]);
+            }
+            // S_w is free: P_w(j-1) ready means group w has finished reading S_w(j-1) (for j = 0 the wait happened
+            // when the last PV of the previous item was issued)
+#pragma unroll
+            for (int k = 0; k < DK / 16; ++k) {
+              const uint64_t da = umma_desc_k_sw128(sQ + w * Cfg::Q_BYTES + k * 32);
+              const uint64_t db = umma_desc_k_sw128(sK + k * 32);
+              umma_bf16_ss(tmem_base + w * 128u, da, db, idesc_s, k > 0 ? 1u : 0u);
+            }
+            umma_commit(&s_full[w]);
+          }
+          if (j == T - 1) umma_commit(&q_empty);
+        }
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          issue_pv(w, t - 1, T == 1);
+          umma_commit(&o_final[w]);
+        }
+        umma_commit(&kv_empty[(t - 1) % STAGES]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------ softmax warpgroups + epilogue ------------------------------------
+    const int w = (warp - 4) >> 2;  // 0: rows 0-127 (A), 1: rows 128-255 (B)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;    // row inside this group's 128-row tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t s_addr = lane_addr + static_cast<uint32_t>(w) * 128u;
+    const uint32_t o_addr = lane_addr + Cfg::O_COL + static_cast<uint32_t>(w) * DK;
+    const uint32_t p_row = sP + w * Cfg::P_BYTES + r * 128;
+    const float c = p.scale_log2e;
+    uint32_t t = 0, it = 0;
+
+    // P = exp2(S c - m) for the 128 keys of the tile -> bf16 -> smem; returns the row sum, tracks the scaled row max
+    auto exp_pass = [&](float m, int valid, float& mx) -> float {
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t v[32];
+        tmem_ld_x32(s_addr + c4 * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+        if (valid >= FA_BN) {
+          float mr = -INFINITY;  // raw (unscaled) maximum: c > 0, so max commutes with the scale
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float v0 = __uint_as_float(v[i]), v1 = __uint_as_float(v[i + 1]);
+            mr = fmaxf(mr, fmaxf(v0, v1));
+            const float p0 = fast_exp2(fmaf(v0, c, -m)), p1 = fast_exp2(fmaf(v1, c, -m));
+            lsum += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          mx = fmaxf(mx, mr * c);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const bool ok0 = c4 * 32 + i < valid, ok1 = c4 * 32 + i + 1 < valid;
+            const float s0 = ok0 ? __uint_as_float(v[i]) * c : -INFINITY;
+            const float s1 = ok1 ? __uint_as_float(v[i + 1]) * c : -INFINITY;
+            mx = fmaxf(mx, fmaxf(s0, s1));
+            const float p0 = ok0 ? fast_exp2(s0 - m) : 0.f, p1 = ok1 ? fast_exp2(s1 - m) : 0.f;
+            lsum += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int piece = c4 * 4 + g;
+          const uint32_t addr = p_row + (piece >> 3) * (FA_BM * 128) + (((piece & 7) ^ (r & 7)) << 4);
+          st_shared_v4(addr, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+      }
+      return lsum;
+    };
+    auto rescale_o = [&](float alpha) {
+#pragma unroll 1
+      for (int cc = 0; cc < DK / 16; ++cc) {
+        uint32_t o[16];
+        tmem_ld_x16(o_addr + cc * 16, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_x16(o_addr + cc * 16, o);
+      }
+      tmem_st_wait();
+    };
+
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int qp = item % q_pairs;
+      const int head = (item / q_pairs) % p.heads;
+      const int img = item / (q_pairs * p.heads);
+      float m_used = -INFINITY, l = 0.f;
+      float pend_alpha = 1.0f, pend_m = 0.f;
+      bool pend = false;
+      for (int j = 0; j < T; ++j, ++t) {
+        const int valid = p.nk - j * FA_BN;
+        mbar_wait(&s_full[w], t & 1u);  // S_w(j) complete, hence PV_w(j-1) complete as well (in-order MMA stream)
+        tc_fence_after_sync();
+        if (j == 0) {
+          // first tile: exact row maximum first
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint32_t v[32];
+            tmem_ld_x32(s_addr + c4 * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              mx = fmaxf(mx, (c4 * 32 + i < valid) ? __uint_as_float(v[i]) * c : -INFINITY);
+          }
+          m_used = mx;
+          float dummy = -INFINITY;
+          l = exp_pass(m_used, valid, dummy);
+        } else {
+          if (__any_sync(0xffffffffu, pend)) {
+            rescale_o(pend_alpha);  // alpha = 1 for rows without a pending change
+            l *= pend_alpha;
+            if (pend) m_used = pend_m;
+            pend = false;
+            pend_alpha = 1.0f;
+          }
+          float mx = -INFINITY;
+          float lt = exp_pass(m_used, valid, mx);
+          if (__any_sync(0xffffffffu, mx > m_used + FA2_REDO_THRESHOLD)) {
+            // overflow territory: rescale now (PV(j-1) is complete) and redo the tile against the new maximum
+            const float m_new = fmaxf(m_used, mx);
+            const float alpha = fast_exp2(m_used - m_new);
+            rescale_o(alpha);
+            l *= alpha;
+            m_used = m_new;
+            float dummy = -INFINITY;
+            lt = exp_pass(m_used, valid, dummy);
+          } else if (mx > m_used + FA_RESCALE_THRESHOLD) {
+            pend = true;
+            pend_m = mx;
+            pend_alpha = fast_exp2(m_used - mx);
+          }
+          l += lt;
+        }
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[w]);
+      }
+      // epilogue: O_w / l -> bf16 -> global  (O and l share the reference m_used; a pending rescale is irrelevant)
+      mbar_wait(&o_final[w], it & 1u);
+      tc_fence_after_sync();
+      const float inv = 1.0f / l;
+      const int q_in_img = qp * 2 * FA_BM + w * FA_BM + r;
+      const bool row_ok = q_in_img < p.nq;
+      __nv_bfloat16* orow = p.O + (static_cast<long long>(img) * p.nq + q_in_img) * p.ldo + head * D;
+#pragma unroll 1
+      for (int cc = 0; cc < DK / 16; ++cc) {
+        uint32_t o[16];
+        tmem_ld_x16(o_addr + cc * 16, o);
+        tmem_ld_wait();
+        if (row_ok) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            pk[i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+          uint4* dst = reinterpret_cast<uint4*>(orow + cc * 16);
+          if (cc * 16 + 8 <= D) dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if (cc * 16 + 16 <= D) dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[w]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int D>
+static int launch_fa2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FaParams& p,
+                      cudaStream_t stream) {
+  using Cfg = Fa2Cfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FMC_CUDA_OK(cudaFuncSetAttribute(spatial_attn2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int items = p.images * p.heads * ((p.nq + 2 * FA_BM - 1) / (2 * FA_BM));
+  const int grid = items < device_sm_count() ? items : device_sm_count();
+  spatial_attn2_kernel<D><<<grid, FA2_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  return check_launch("spatial_attn2_kernel");
+}
+
 template <int D>
 static int launch_fa(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FaParams& p,
                      cudaStream_t stream) {
@@ -399,7 +738,7 @@ extern "C" int fmc_spatial_attn_bf16(const void* Q, long long ldq, int q_col0, l
   p.O = static_cast<__nv_bfloat16*>(O);
   p.ldo = ldo;
   switch (head_dim) {
-    case 40: return launch_fa<40>(tmQ, tmK, tmV, p, stream);
+    case 40: return launch_fa2<40>(tmQ, tmK, tmV, p, stream);
     case 80: return launch_fa<80>(tmQ, tmK, tmV, p, stream);
     default: return launch_fa<160>(tmQ, tmK, tmV, p, stream);
   }
