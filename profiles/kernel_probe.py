@@ -39,6 +39,13 @@ def temporal_case(B, F, HW, d):
     return lambda: ops.temporal_attn(qkv, 0, heads * hs, 2 * heads * hs, hs, out, B, F, HW, heads, d, d ** -0.5)
 
 
+def temporal_fused_case(B, F, HW):
+    x = rnd(B * F * HW, 320)
+    w = rnd(8 * 144, 320, scale=320 ** -0.5)
+    out = torch.empty(B * F * HW, 320, device=dev, dtype=BF)
+    return lambda: ops.temporal_qkv_attn(x, w, out, B, F, HW, 8, 40 ** -0.5)
+
+
 def groupnorm_case(images, HW, C):
     x, g, b = rnd(images * HW, C), rnd(C, dtype=torch.float32), rnd(C, dtype=torch.float32)
     return lambda: ops.groupnorm(x, g, b, 1e-6, images, HW, silu=True)
@@ -58,6 +65,7 @@ CASES = {
     "gemm_l2_qkv": lambda: gemm_case(5120, 3840, 1280),
     "spatial_l0": lambda: spatial_case(32, 40, 2560),
     "spatial_l1": lambda: spatial_case(32, 80, 640),
+    "temporal_fused_l0": lambda: temporal_fused_case(2, 16, 2560),
     "temporal_l0": lambda: temporal_case(2, 16, 2560, 40),
     "groupnorm_l0": lambda: groupnorm_case(32, 2560, 320),
     "layernorm_l0": lambda: layernorm_case(81920, 320),

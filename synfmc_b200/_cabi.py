@@ -15,6 +15,8 @@ SIGNATURES = {
     "fmc_gemm_bf16": [P, L, P, L, P, L, I, I, I, P, P, L, P, I, L, I, I, P],
     "fmc_spatial_attn_bf16": [P, L, I, L, P, L, I, P, L, I, L, I, P, L, I, I, I, I, I, I, I, F, P],
     "fmc_temporal_attn_bf16": [P, L, I, I, I, I, P, L, I, I, I, I, I, F, P],
+    "fmc_temporal_qkv_attn_bf16": [P, L, P, L, P, L, I, I, I, I, I, F, P],
+    "fmc_debug_set_timeline": [P],
     "fmc_layernorm_bf16": [P, L, P, P, F, P, L, P, I, I, P, L, P, L, L, I, P],
     "fmc_groupnorm_bf16": [P, L, P, P, F, P, L, P, I, I, I, I, I, P, L, I, P],
     "fmc_add_bf16": [P, L, P, L, P, I, L, P, L, L, I, I, P],

@@ -120,7 +120,7 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t t = 0;   // global KV tile counter of this CTA
       uint32_t it = 0;  // item counter of this CTA
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
@@ -154,7 +154,7 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer ------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(FA_BM, FA_BN);
       constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(FA_BM, DK);
       uint32_t t = 0, it = 0;
@@ -411,7 +411,7 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t t = 0, it = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int qp = item % q_pairs;
@@ -436,7 +436,7 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer ------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(FA_BM, FA_BN);
       constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(FA_BM, DK);
       uint32_t t = 0, it = 0;

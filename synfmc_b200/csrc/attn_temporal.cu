@@ -108,7 +108,7 @@ temporal_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, TaParams p) {
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t n = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
         int b, hw0, head;
@@ -138,7 +138,7 @@ temporal_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, TaParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer ------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
       constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, DK);
       auto issue_s = [&](uint32_t n) {

@@ -94,7 +94,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -124,7 +124,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -413,7 +413,7 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   if (warp == 0) {
     // ------------------------------ TMA producer (A, W) ------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -434,7 +434,7 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -470,7 +470,7 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp == 3) {
     // ------------------------------ output mover ------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       // arm staging buffer `b` for tile `tile`: residual tile lands there (complete_tx) or it is simply marked free
       auto arm = [&](int b, int tile) {
         if (has_res) {

@@ -14,6 +14,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp, chosen by `elect.sync`.  Single-thread roles (TMA producer, tcgen05.mma issuer) must be
+// entered this way from warp-uniform control flow: behind a divergent `if (lane == 0)` the compiler cannot prove the
+// uniform-datapath instructions (UTCHMMA / UTMALDG / UTCBAR) are warp-uniform and wraps EACH of them in an
+// ELECT / BRA.U.ANY loop -- measured ~100 cycles per tcgen05.mma instead of the N/2-cycle floor
+// (profiles/microbench/mma_bench.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------

@@ -9,11 +9,15 @@ Domain-LoRA folded into the projections (exact while LoRA is frozen),
 q/k heads zero-padded to a multiple of 16 columns, GEGLU rows interleaved for the fused epilogue, the CameraAdapter
 scale folded into qkv_merge.  The `run_*` functions issue the kernels of include/fmc_b200.h in order.
 """
+import os
+
 import torch
 
 from . import ops
 
 BF16 = torch.bfloat16
+# debugging switch: FMC_UNFUSED_TEMPORAL=1 runs the temporal attention as GEMM + attention kernels instead of the fused one
+FUSED_TEMPORAL = not os.environ.get("FMC_UNFUSED_TEMPORAL")
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -128,7 +132,7 @@ def _pad_heads(w, heads, d, hs):
 class AttnPlan:
     """One attention (spatial self, spatial text-cross, or temporal self) with everything foldable folded."""
 
-    def __init__(self, attn, device, lora_scale_override=None):
+    def __init__(self, attn, device, lora_scale_override=None, fused_temporal=False):
         from .fmc.models.attention_processor import (LoRAAttnProcessor, LORAPoseAdaptorAttnProcessor,
                                                      PoseAdaptorAttnProcessor)
         proc = attn.processor
@@ -173,6 +177,12 @@ class AttnPlan:
         self.q_col0 = 0
         self.k_col0 = heads * hs
         self.v_col0 = 2 * heads * hs
+        # fused projection + temporal attention kernel (fmc_temporal_qkv_attn_bf16): per head [q | k | v] row blocks,
+        # each zero-padded 40 -> 48
+        self.w_head_major = None
+        if FUSED_TEMPORAL and fused_temporal and not self.is_cross and C == 320 and heads == 8:
+            blocks = [_pad_heads(w, heads, d, hs).view(heads, hs, C) for w in (folded("to_q"), folded("to_k"), wv)]
+            self.w_head_major = _dev_bf16(torch.cat(blocks, dim=1).reshape(heads * 3 * hs, C), device)
 
 
 class NormPlan:
@@ -249,8 +259,11 @@ def run_temporal_attention(plan, x_norm, x_plus_pose, residual, B, F, HW):
     src = x_norm
     if plan.merge is not None:
         src = plan.merge(x_plus_pose, residual=x_norm)  # m = qkv_merge(x + pose) * s + x
-    qkv = plan.qkv(src)
     ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=BF16)
+    if plan.w_head_major is not None and F in (4, 8, 16, 32):
+        ops.temporal_qkv_attn(src, plan.w_head_major, ctx, B, F, HW, plan.heads, plan.scale)
+        return plan.out(ctx, residual=residual)
+    qkv = plan.qkv(src)
     ops.temporal_attn(qkv, plan.q_col0, plan.k_col0, plan.v_col0, plan.hs, ctx, B, F, HW, plan.heads, plan.d, plan.scale)
     return plan.out(ctx, residual=residual)
 

@@ -66,7 +66,7 @@ class TemporalTransformerBlock(nn.Module):
         if self._plan is None or self._plan["device"] != device:
             p = {"device": device, "attn": [], "norms": [], "pe": []}
             for attn, norm in zip(self.attention_blocks, self.norms):
-                p["attn"].append(engine.AttnPlan(attn, device))
+                p["attn"].append(engine.AttnPlan(attn, device, fused_temporal=True))
                 p["norms"].append(engine.NormPlan(norm, device))
                 p["pe"].append(attn.pos_encoder.pe[0].detach().to(device=device, dtype=torch.float32).contiguous()
                                if attn.pos_encoder is not None else None)

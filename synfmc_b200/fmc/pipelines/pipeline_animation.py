@@ -6,8 +6,8 @@ from types import SimpleNamespace
 
 import torch
 
-from ... import ops
-from ...engine import CL
+from ... import _cabi, ops
+from ...engine import CL, TextCtx
 from ..models.pose_adaptor import unshuffle8_to_cl
 
 
@@ -20,13 +20,88 @@ def _slice_frames(feat, start, length):
     return feat if t.shape[1] == feat.t.shape[1] else CL(t.contiguous())
 
 
+class _StepGraph:
+    """The CFG-doubled U-Net forward of one denoising step, captured once into a CUDA graph for fixed shapes.
+
+    A step is ~830 launches of 5-200 us kernels; issued one by one from Python the deep (small-token) levels are
+    launch-bound.  The graph owns static input buffers (latents, timestep, text, pose / object features); `run` copies
+    the caller's tensors in (device-to-device, < 0.3 % of a step), replays, and returns the static noise prediction.
+    Tensor maps and scalar kernel arguments are frozen at capture time, which is why everything that changes per step
+    lives in device memory."""
+
+    def __init__(self, unet, latents, text, feats, traj, do_cfg, accepts_traj):
+        dev = latents.device
+        self.unet, self.do_cfg, self.accepts_traj = unet, do_cfg, accepts_traj
+        self.lat = torch.empty_like(latents)
+        self.text = torch.empty(text.shape, device=dev, dtype=torch.float32)
+        self.t = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.feats = [CL(torch.empty_like(f.t)) for f in feats]
+        self.traj = None if traj is None else [CL(torch.empty_like(f.t)) for f in traj]
+        self._load(latents, text, feats, traj)
+        self.t.fill_(1.0)
+        # eager warm-up on a side stream: builds the weight plans, sets kernel attributes, lets cuDNN pick algorithms
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._forward()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        n0 = _cabi.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.eps = self._forward()
+        self.launches = _cabi.launch_count - n0
+        _cabi.launch_count = n0  # capture launched nothing; replays are counted in run()
+
+    def _forward(self):
+        x_in = torch.cat([self.lat] * 2) if self.do_cfg else self.lat
+        kw = {"traj_features": self.traj} if self.accepts_traj else {}
+        text = TextCtx(self.text, self.text.device)
+        return self.unet(x_in, self.t, encoder_hidden_states=text, pose_embedding_features=self.feats, **kw).sample
+
+    def _load(self, latents, text, feats, traj):
+        self.lat.copy_(latents)
+        self.text.copy_(text)
+        for dst, src in zip(self.feats, feats):
+            if dst.t.data_ptr() != src.t.data_ptr():
+                dst.t.copy_(src.t)
+        if self.traj is not None:
+            for dst, src in zip(self.traj, traj):
+                if dst.t.data_ptr() != src.t.data_ptr():
+                    dst.t.copy_(src.t)
+
+    def run(self, latents, t, text, feats, traj):
+        self._load(latents, text, feats, traj)
+        self.t.fill_(float(t))
+        self.graph.replay()
+        _cabi.launch_count += self.launches
+        return self.eps
+
+
 class CameraCtrlPipeline:
     _accepts_traj = False
+    use_cuda_graph = True   # single-window steps replay a captured graph (see _StepGraph); False = launch kernel by kernel
+    max_graphs = 4
 
     def __init__(self, vae, text_encoder, tokenizer, unet, scheduler, pose_encoder):
         self.vae, self.text_encoder, self.tokenizer = vae, text_encoder, tokenizer
         self.unet, self.scheduler, self.pose_encoder = unet, scheduler, pose_encoder
         self.vae_scale_factor = 8
+        self._graphs = {}
+
+    def _step_graph(self, latents, text, feats, traj, do_cfg):
+        key = (tuple(latents.shape), tuple(text.shape), do_cfg, tuple(f.dims for f in feats),
+               None if traj is None else tuple(f.dims for f in traj), latents.device)
+        g = self._graphs.get(key)
+        if g is None:
+            while len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+            g = self._graphs[key] = _StepGraph(self.unet, latents, text, feats, traj, do_cfg, self._accepts_traj)
+        return g
+
+    def reset_graphs(self):
+        """Drop captured graphs (call after changing weights / processors: plans and graphs freeze them)."""
+        self._graphs.clear()
 
     def enable_vae_slicing(self):
         if self.vae is not None and hasattr(self.vae, "enable_slicing"):
@@ -106,6 +181,16 @@ class CameraCtrlPipeline:
         L = video_length
         b = latents.shape[0]
         a_t, a_prev = self.scheduler.alphas_for(t)
+        if (self.use_cuda_graph and multidiff_total_steps == 1 and _cabi.trace is None and not torch.is_tensor(t)
+                and torch.is_tensor(text_embeddings) and latents.dtype == torch.float32):
+            feats = [CL.from_reference(f) for f in pose_features]
+            traj = traj_features if self._accepts_traj else None
+            if traj is not None:
+                traj = [CL.from_reference(f) for f in traj]
+            eps = self._step_graph(latents, text_embeddings, feats, traj, do_cfg).run(latents, t, text_embeddings, feats,
+                                                                                     traj)
+            e_u, e_c = (eps[:b], eps[b:]) if do_cfg else (eps, None)
+            return ops.cfg_ddim_step(e_u, e_c, guidance_scale, latents, a_t, a_prev)
         window_eps = []
         for k in range(multidiff_total_steps):
             s = k * (L - multidiff_overlaps)

@@ -76,6 +76,18 @@ def temporal_attn(qkv, q_col0, k_col0, v_col0, head_stride, out, B, F, HW, heads
     return out
 
 
+def temporal_qkv_attn(x, w_qkv, out, B, F, HW, heads, scale):
+    """Fused per-head q|k|v projection + attention over frames (fmc_temporal_qkv_attn_bf16); x, out: [(B F HW), 320]."""
+    _check_cuda(x, w_qkv, out)
+    _rows2d(x)
+    _rows2d(w_qkv)
+    _rows2d(out)
+    assert x.shape[0] == B * F * HW == out.shape[0] and x.shape[1] == out.shape[1] == w_qkv.shape[1]
+    _cabi.call("fmc_temporal_qkv_attn_bf16", x.data_ptr(), x.stride(0), w_qkv.data_ptr(), w_qkv.stride(0), out.data_ptr(),
+               out.stride(0), B, F, HW, x.shape[1], heads, float(scale), _stream())
+    return out
+
+
 def layernorm(x, gamma, beta, eps=1e-5, out=None, pe=None, F=0, HW=0, add=None, out2=None):
     _check_cuda(x)
     _rows2d(x)

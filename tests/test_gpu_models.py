@@ -171,6 +171,36 @@ def test_cfg_denoise_loop(cuda_device):
     assert rel_l2(out.latents, want) < UNET_TOL
 
 
+def test_cuda_graph_step_is_bit_identical_to_eager(cuda_device):
+    """The captured-graph step (default) replays exactly the kernels of the kernel-by-kernel step: same latents bit for
+    bit over 3 steps that cross the omcm_min_step boundary (two graphs: with / without object features), and again on
+    replay with new inputs in the same buffers."""
+    from oracle.rays import to_plucker_embedding
+    from synfmc_b200 import synth
+    from synfmc_b200.fmc._blocks import DDIMScheduler
+    from synfmc_b200.fmc.pipelines.pipeline_animation_cm_om import CameraObjCtrlPipeline
+    channels = (320, 640)
+    o_unet = helpers.build_oracle_unet(tiny=True, obj=True)
+    p_unet = helpers.build_product_unet(o_unet, tiny=True, obj=True, device=cuda_device)
+    p_enc = helpers.build_product_pose_encoder(helpers.build_oracle_pose_encoder(channels), channels, device=cuda_device)
+    b, f, H, W = 1, 8, 64, 96
+    K, c2w = synth.synth_camera(b, f, H, W, seed=6)
+    plucker = to_plucker_embedding(c2w, K, (H, W)).permute(0, 2, 1, 3, 4).contiguous().to(cuda_device)
+    _, _, _, trajs = _unet_inputs(b, f, H // 8, W // 8, channels, seed=7, traj=True)
+    trajs = [t.to(cuda_device) for t in trajs]
+    pipe = CameraObjCtrlPipeline(None, None, None, p_unet, DDIMScheduler(), p_enc)
+    outs = {}
+    for seed in (6, 9):
+        latents, text = synth.synth_step_inputs(b, f, H // 8, W // 8, cfg=True, seed=seed)
+        for graph in (False, True):
+            pipe.use_cuda_graph = graph
+            outs[graph] = pipe(None, plucker, f, traj_features=trajs, height=H, width=W, num_inference_steps=25,
+                               guidance_scale=8.0, latents=latents.to(cuda_device), prompt_embeds=text.to(cuda_device),
+                               omcm_min_step=900, max_steps=3).latents.clone()
+        assert torch.equal(outs[False], outs[True]), seed
+    assert len(pipe._graphs) == 2
+
+
 @pytest.mark.timeout(1500)
 def test_config1_full_unet(cuda_device):
     """BASELINE config 1: 1 clip 256x256x16f (latent 32x32), full SD1.5-shaped 4-level U-Net, 1 DDIM step (t = 961),

@@ -134,6 +134,30 @@ def test_temporal_attention(ops, cuda_device, B, F, HW, d):
     assert rel(out, want) < BF16_TOL
 
 
+@pytest.mark.parametrize("B,F,HW", [(1, 16, 8), (1, 16, 64), (2, 16, 100), (1, 4, 70), (1, 8, 33), (1, 32, 10),
+                                    (2, 16, 2560)])
+def test_temporal_qkv_attention_fused(ops, cuda_device, B, F, HW):
+    """Fused q|k|v projection + attention over frames (C = 320, 8 x 40) against fp32 torch on the same bf16 inputs:
+    to_q/to_k/to_v + attention core of attention_processor.py:46-67 / :259-281."""
+    heads, d, hs, C = 8, 40, 48, 320
+    rows = B * F * HW
+    x = randn(rows, C, seed=1)
+    wq, wk, wv = (randn(C, C, seed=s, scale=C ** -0.5) for s in (2, 3, 4))
+    blocks = [_pad_heads(w.t(), heads, d, hs).t().reshape(heads, hs, C) for w in (wq, wk, wv)]
+    w_head_major = torch.cat(blocks, dim=1).reshape(heads * 3 * hs, C)
+    out = torch.empty(rows, C, dtype=torch.bfloat16, device=cuda_device)
+    ops.temporal_qkv_attn(bf(x).to(cuda_device), bf(w_head_major).to(cuda_device), out, B, F, HW, heads, d ** -0.5)
+
+    def seq(t):  # [(B F HW), C] -> [(B HW), heads, F, d]
+        return t.view(B, F, HW, heads, d).permute(0, 2, 3, 1, 4).reshape(B * HW, heads, F, d)
+    # the kernel rounds q, k, v to bf16 between the projection and the attention, like the un-fused chain
+    q, k, v = (bf(x @ w.t()).float() for w in (wq, wk, wv))
+    o = Fn.scaled_dot_product_attention(seq(q), seq(k), seq(v))
+    want = o.view(B, HW, heads, F, d).permute(0, 3, 1, 2, 4).reshape(rows, C)
+    assert rel(out, want) < BF16_TOL
+    torch.cuda.synchronize()
+
+
 # ---------------------------------------------------------------- norms / elementwise
 @pytest.mark.parametrize("rows,C", [(1000, 320), (77, 640), (4096, 1280)])
 def test_layernorm_plain(ops, cuda_device, rows, C):
