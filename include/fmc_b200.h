@@ -62,15 +62,15 @@ int fmc_temporal_attn_bf16(const void* QKV, long long ld, int q_col0, int k_col0
 
 /* Fused q|k|v projection + temporal attention (channels = 320, 8 heads x 40): O = softmax((X Wq^T)(X Wk^T)^T * scale)
  * (X Wv^T) over the f frames of every latent position, one kernel, the [token, q|k|v] tensor never reaches HBM.
- * X, O: channels-last rows as for fmc_temporal_attn_bf16.  Wqkv: bf16 [8 * 144, 320], per head h the rows
- * [to_q rows of h (40) | 8 zero rows | to_k rows of h (40) | 8 zero rows | to_v rows of h (40) | 8 zero rows].
+ * X, O: channels-last rows as for fmc_temporal_attn_bf16.  Wqkv: bf16 [8 * 128, 320], per head h the rows
+ * [to_q rows of h (40) | to_k rows of h (40) | to_v rows of h (40) | 8 zero rows].
  * Replaces attn.to_q / to_k / to_v (bias-free) + the attention core of fmc/models/attention_processor.py:46-67
  * (AttnProcessor) and :259-281 (PoseAdaptorAttnProcessor, where X is the merged tensor of :257) as reached from
  * TemporalSelfAttention.forward, fmc/models/motion_module.py:349-389.  Other widths: error (use the un-fused pair). */
 int fmc_temporal_qkv_attn_bf16(const void* X, long long ldx, const void* Wqkv, long long ldw, void* O, long long ldo,
                                int B, int F, int HW, int channels, int heads, float scale, void* stream);
 
-/* Diagnostics for fmc_temporal_qkv_attn_bf16: `device_buffer` (6 * 64 * 8 int64, or NULL to switch off) receives
+/* Diagnostics for fmc_temporal_qkv_attn_bf16: `device_buffer` (4 * 64 * 8 int64, or NULL to switch off) receives
  * clock64() stamps of the pipeline events of CTA 0 -- [role][item][event], see csrc/temporal_fused.cu. */
 int fmc_debug_set_timeline(void* device_buffer);
 

@@ -9,18 +9,6 @@
 
 using namespace fmc;
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "elect.sync _|P1, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -65,6 +53,15 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(int N, int mode, int chai
         umma_bf16_ss(d1, da + 2, db + 2, idesc, 1);
         umma_bf16_ss(tmem, da + 4, db + 4, idesc, 1);
         umma_bf16_ss(d1, da + 6, db + 6, idesc, 1);
+      }
+    } else if (mode == 2) {
+      const uint32_t idesc_mn = umma_idesc_bf16_bmn(128, N);
+#pragma unroll 1
+      for (int i = 0; i < reps; i += 4) {
+        umma_bf16_ts(tmem, ta, umma_desc_mn_sw128(sB, 16384, 1024), idesc_mn, 1);
+        umma_bf16_ts(d1, ta + 8, umma_desc_mn_sw128(sB + 2048, 16384, 1024), idesc_mn, 1);
+        umma_bf16_ts(tmem, ta + 16, umma_desc_mn_sw128(sB + 4096, 16384, 1024), idesc_mn, 1);
+        umma_bf16_ts(d1, ta + 24, umma_desc_mn_sw128(sB + 6144, 16384, 1024), idesc_mn, 1);
       }
     } else {
 #pragma unroll 1
@@ -144,15 +141,16 @@ int main() {
   cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 51200);
   cudaFuncSetAttribute(ts_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 20480);
   const int reps = 256;
-  for (int mode = 0; mode < 2; ++mode)
+  for (int mode = 0; mode < 3; ++mode)
     for (int chains = 1; chains <= 2; ++chains)
-      for (int N : {48, 96, 128, 144, 192, 256}) {
+      for (int N : {48, 64, 128, 256}) {
         if (chains == 2 && N > 192) continue;  // second D tile at column 256, TS A operand at 448..479
+        if (mode == 2 && N > 64) continue;      // MN-major B: one 64-element N block
         bench_kernel<<<1, 128, 51200>>>(N, mode, chains, reps, out);
         long long h[2];
         cudaError_t e = cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { printf("mode %d N %d: %s\n", mode, N, cudaGetErrorString(e)); return 1; }
-        printf("%s chains=%d N=%3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (ideal %d)\n", mode ? "TS" : "SS", chains, N,
+        printf("%s chains=%d N=%3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (ideal %d)\n", mode == 0 ? "SS" : (mode == 1 ? "TS" : "TS/B-MN"), chains, N,
                double(h[0]) / reps, double(h[1]) / reps, N / 2);
       }
   // TS layout check

@@ -5,7 +5,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfmc_b200.so")
+# FMC_B200_LIB: A/B kernel experiments load another build of the same library (profiles/variants/*.so)
+LIB_PATH = os.environ.get("FMC_B200_LIB") or os.path.join(_HERE, "libfmc_b200.so")
 
 P, I, L, F = c_void_p, c_int, c_longlong, c_float
 ABI_VERSION = 1  # FMC_B200_ABI_VERSION of include/fmc_b200.h

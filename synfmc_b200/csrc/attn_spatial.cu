@@ -501,45 +501,60 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float c = p.scale_log2e;
     uint32_t t = 0, it = 0;
 
-    // P = exp2(S c - m) for the 128 keys of the tile -> bf16 -> smem; returns the row sum, tracks the scaled row max
-    auto exp_pass = [&](float m, int valid, float& mx) -> float {
-      float lsum = 0.f;
-#pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t v[32];
-        tmem_ld_x32(s_addr + c4 * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        if (valid >= FA_BN) {
-          float mr = -INFINITY;  // raw (unscaled) maximum: c > 0, so max commutes with the scale
+    // P = exp2(S c - m) for the 128 keys of the tile -> bf16 -> smem; returns the row sum, tracks the scaled row max.
+    // The four 32-column TMEM loads are software-pipelined: chunk c4 + 1 is in flight while chunk c4 is exponentiated
+    // (-10 % at level 0).  Measured dead ends, kept out of the code (profiles/r01_spatial_attention_experiments.md):
+    // splitting max / sum into independent chains (+6 %: more instructions, the warps are MUFU / issue bound), 64-key
+    // half tiles that ping-pong inside a group (+11 %) and serving the two groups on demand instead of A, B (+14 %):
+    // the two warps sharing a scheduler overlap best -- one in its FFMA phase, one in its MUFU phase -- when the
+    // groups stay in step.
+    auto exp_chunk = [&](const uint32_t (&v)[32], int c4, float m, int valid, float& mx, float& lsum) {
+      uint32_t pk[16];
+      if (valid >= FA_BN) {
+        float mr = -INFINITY;  // raw (unscaled) maximum: c > 0, so max commutes with the scale
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float v0 = __uint_as_float(v[i]), v1 = __uint_as_float(v[i + 1]);
-            mr = fmaxf(mr, fmaxf(v0, v1));
-            const float p0 = fast_exp2(fmaf(v0, c, -m)), p1 = fast_exp2(fmaf(v1, c, -m));
-            lsum += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-          }
-          mx = fmaxf(mx, mr * c);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const bool ok0 = c4 * 32 + i < valid, ok1 = c4 * 32 + i + 1 < valid;
-            const float s0 = ok0 ? __uint_as_float(v[i]) * c : -INFINITY;
-            const float s1 = ok1 ? __uint_as_float(v[i + 1]) * c : -INFINITY;
-            mx = fmaxf(mx, fmaxf(s0, s1));
-            const float p0 = ok0 ? fast_exp2(s0 - m) : 0.f, p1 = ok1 ? fast_exp2(s1 - m) : 0.f;
-            lsum += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-          }
+        for (int i = 0; i < 32; i += 2) {
+          const float v0 = __uint_as_float(v[i]), v1 = __uint_as_float(v[i + 1]);
+          mr = fmaxf(mr, fmaxf(v0, v1));
+          const float p0 = fast_exp2(fmaf(v0, c, -m)), p1 = fast_exp2(fmaf(v1, c, -m));
+          lsum += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
         }
+        mx = fmaxf(mx, mr * c);
+      } else {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int piece = c4 * 4 + g;
-          const uint32_t addr = p_row + (piece >> 3) * (FA_BM * 128) + (((piece & 7) ^ (r & 7)) << 4);
-          st_shared_v4(addr, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        for (int i = 0; i < 32; i += 2) {
+          const bool ok0 = c4 * 32 + i < valid, ok1 = c4 * 32 + i + 1 < valid;
+          const float s0 = ok0 ? __uint_as_float(v[i]) * c : -INFINITY;
+          const float s1 = ok1 ? __uint_as_float(v[i + 1]) * c : -INFINITY;
+          mx = fmaxf(mx, fmaxf(s0, s1));
+          const float p0 = ok0 ? fast_exp2(s0 - m) : 0.f, p1 = ok1 ? fast_exp2(s1 - m) : 0.f;
+          lsum += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
         }
       }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int piece = c4 * 4 + g;
+        const uint32_t addr = p_row + (piece >> 3) * (FA_BM * 128) + (((piece & 7) ^ (r & 7)) << 4);
+        st_shared_v4(addr, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      }
+    };
+    auto exp_pass = [&](float m, int valid, float& mx) -> float {
+      float lsum = 0.f;
+      uint32_t va[32], vb[32];
+      tmem_ld_x32(s_addr, va);
+      tmem_ld_wait();
+      tmem_ld_x32(s_addr + 32, vb);
+      exp_chunk(va, 0, m, valid, mx, lsum);
+      tmem_ld_wait();
+      tmem_ld_x32(s_addr + 64, va);
+      exp_chunk(vb, 1, m, valid, mx, lsum);
+      tmem_ld_wait();
+      tmem_ld_x32(s_addr + 96, vb);
+      exp_chunk(va, 2, m, valid, mx, lsum);
+      tmem_ld_wait();
+      exp_chunk(vb, 3, m, valid, mx, lsum);
       return lsum;
     };
     auto rescale_o = [&](float alpha) {

@@ -1,25 +1,30 @@
 // Fused temporal self-attention for the CameraAdapter motion module (C = 320, 8 heads x 40):
-//     [q | k | v] = m W_qkv^T            per head, on tcgen05 (M = 128 tokens = 128/f sequences, N = 144, K = 320)
+//     [q | k | v] = m W_qkv^T            per head, on tcgen05 (M = 128 tokens = 128/f sequences, N = 128, K = 320)
 //     o = softmax(q k^T * scale) v        over the f frames of each latent position (block-diagonal 128 x 128 tile)
 // in ONE kernel: the [token, 1088] q|k|v tensor of the un-fused chain (fmc_gemm_bf16 -> fmc_temporal_attn_bf16) never
-// exists -- per (token tile, head) the projection lands in tensor memory, is converted to bf16 straight into the
-// shared-memory operand tiles of the score / PV MMAs, and only o[token, 320] goes back to HBM.
+// exists -- per (token tile, head) the projection lands in tensor memory and is turned into MMA operands on chip;
+// only o[token, 320] goes back to HBM.
 //
 // Replaces to_q / to_k / to_v + head_to_batch_dim + baddbmm + softmax + bmm + batch_to_head_dim of the temporal
 // processors (fmc/models/attention_processor.py:46-67 AttnProcessor, :259-281 PoseAdaptorAttnProcessor) as reached
 // from TemporalSelfAttention.forward (fmc/models/motion_module.py:349-389).
 //
 // Work decomposition: persistent CTAs (one per SM) walk token tiles; the tile's input rows [128, 320] stay resident in
-// shared memory (SWIZZLE_128B, five 64-column k-blocks) for all eight heads while the per-head weight slices
-// [144, 320] stream through a 3-stage TMA ring.
+// shared memory (SWIZZLE_128B, five 64-column k-blocks, reloaded k-block by k-block behind the last head) while the
+// per-head weight slices [128, 320] stream through a 6-stage TMA ring (one head = 5 stages, so the next head's weights
+// are always in flight).  q and the probabilities P never touch shared memory: they are written back to TENSOR MEMORY
+// as packed bf16 and consumed as the A operand of the score / PV MMAs (tcgen05.mma with A in TMEM), q in place over
+// its fp32 accumulator columns, P in place over the scores (lane = row, column c = elements 2c, 2c+1; checked by
+// profiles/microbench/mma_bench.cu).  Only k and v (B operands) are staged in shared memory.
 //   warp 0       TMA producer (input tile, weight ring)
-//   warp 1       tcgen05.mma issuer: G(m) projection, S(m) scores, PV(m); software-pipelined so that the projection
-//                of head m+2 fills the tensor pipe while head m is in its softmax
+//   warp 1       tcgen05.mma issuer: per item m = (tile, head):  S(m), G(m+2), PV(m)  -- the projection of head m+2
+//                keeps the tensor pipe busy while head m is in its softmax; one issuing thread = in-order execution,
+//                which is what makes the in-place q / P operands safe against the next accumulator write
 //   warp 2       TMEM allocator
-//   warps 4-7    WG-A: q, k  TMEM -> bf16 -> smem operand tiles; block-diagonal softmax; P -> smem
-//   warps 8-11   WG-B: v     TMEM -> bf16 -> smem (plus a ones column so the PV MMA also yields the softmax row sum);
+//   warps 4-7    WG-A: q -> bf16 -> TMEM, k -> bf16 -> smem; block-diagonal softmax; P -> bf16 -> TMEM
+//   warps 8-11   WG-B: v -> bf16 -> smem (plus a ones column so the PV MMA also yields the softmax row sum);
 //                o epilogue (normalise, bf16, store)
-// TMEM (512 columns): projection accumulators 2 x 144 | S 128 | O 2 x 48.
+// TMEM (512 columns): projection accumulators 2 x 128 | S / P 128 | O 2 x 48.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -32,21 +37,19 @@ constexpr int TF_C = 320;                 // channels
 constexpr int TF_D = 40;                  // head width
 constexpr int TF_DK = 48;                 // head width padded to the MMA K granularity
 constexpr int TF_HEADS = 8;
-constexpr int TF_HEAD_ROWS = 3 * TF_DK;   // weight rows per head: q(48) | k(48) | v(48), pads are zero rows
+constexpr int TF_HEAD_ROWS = 128;         // weight rows per head: q(40) | k(40) | v(40) | 8 zero rows
 constexpr int TF_KB = TF_C / 64;          // k-blocks of the resident input tile
 constexpr int TF_KBLK_BYTES = 128 * 128;  // [128 rows x 64 bf16] SWIZZLE_128B block
 constexpr int TF_A_BYTES = TF_KB * TF_KBLK_BYTES;
-constexpr int TF_W_STAGE_BYTES = TF_HEAD_ROWS * 128;  // [144 rows x 64 bf16]
-constexpr int TF_W_STAGES = 3;
-constexpr int TF_OFF_Q = TF_A_BYTES;
-constexpr int TF_OFF_K = TF_OFF_Q + TF_KBLK_BYTES;
+constexpr int TF_W_STAGE_BYTES = TF_HEAD_ROWS * 128;  // [128 rows x 64 bf16]
+constexpr int TF_W_STAGES = 6;
+constexpr int TF_OFF_K = TF_A_BYTES;
 constexpr int TF_OFF_V = TF_OFF_K + TF_KBLK_BYTES;
-constexpr int TF_OFF_P = TF_OFF_V + TF_KBLK_BYTES;
-constexpr int TF_OFF_W = TF_OFF_P + 2 * TF_KBLK_BYTES;
+constexpr int TF_OFF_W = TF_OFF_V + TF_KBLK_BYTES;
 constexpr int TF_SMEM_BYTES = TF_OFF_W + TF_W_STAGES * TF_W_STAGE_BYTES + 1024;
-constexpr uint32_t TF_COL_G = 0;     // 2 x 144 projection accumulators
-constexpr uint32_t TF_COL_S = 288;   // 128 score columns
-constexpr uint32_t TF_COL_O = 416;   // 2 x 48 output accumulators
+constexpr uint32_t TF_COL_G = 0;     // 2 x 128 projection accumulators (q bf16 is rewritten in place over columns 0..23)
+constexpr uint32_t TF_COL_S = 256;   // 128 score columns (P bf16 is rewritten in place over columns 0..63)
+constexpr uint32_t TF_COL_O = 384;   // 2 x 48 output accumulators
 static_assert(TF_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(TF_W_STAGE_BYTES % 1024 == 0, "SW128 tiles stay 1024-byte aligned");
 
@@ -60,8 +63,7 @@ struct TfParams {
   long long* timeline;  // diagnostics (fmc_debug_set_timeline): clock64() of pipeline events of CTA 0, or nullptr
 };
 
-// timeline[role][item][event], role 0 = MMA issuer, 1 = WG-A (warp 4), 2 = WG-B (warp 8), 3 = TMA producer (W chunk
-// issue times), 4 / 5 = MMA issuer before / after the w_full wait of each W chunk
+// timeline[role][item][event], role 0 = MMA issuer, 1 = WG-A (warp 4), 2 = WG-B (warp 8), 3 = TMA producer
 constexpr int TF_TL_ITEMS = 64, TF_TL_EVENTS = 8;
 static long long* g_tf_timeline = nullptr;
 #define TF_MARK(role, item, ev)                                                                              \
@@ -76,36 +78,54 @@ __device__ __forceinline__ float tf_exp2(float x) {
   return y;
 }
 
-// fp32 accumulator columns [col0, col0 + 48) of this thread's TMEM lane -> bf16 -> row `r` of a [128 x 64] SW128 tile
-__device__ __forceinline__ void tf_convert48(uint32_t taddr, uint32_t tile, int r) {
-  uint32_t a[32], b[16];
-  tmem_ld_x32(taddr, a);
-  tmem_ld_x16(taddr + 32, b);
-  tmem_ld_wait();
+// D[tmem] (+)= A[tmem, packed bf16] * B[smem]^T
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// 40 fp32 values (a[0..31], b[0..7]) -> bf16 -> row `r` of a [128 x 64] SW128 smem tile; columns 40..47 (the padding of
+// the head width to the MMA K granularity) become zero, or (1, 0, ..., 0) with `ones_col40`
+__device__ __forceinline__ void tf_store40(const uint32_t (&a)[32], const uint32_t (&b)[8], uint32_t tile, int r,
+                                           bool ones_col40) {
   const uint32_t row = tile + static_cast<uint32_t>(r) * 128u;
   const uint32_t sw = static_cast<uint32_t>(r & 7);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 4; ++j)
     st_shared_v4(row + ((static_cast<uint32_t>(j) ^ sw) << 4),
                  pack_bf16x2(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1])),
                  pack_bf16x2(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3])),
                  pack_bf16x2(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5])),
                  pack_bf16x2(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7])));
-  }
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    st_shared_v4(row + ((static_cast<uint32_t>(4 + j) ^ sw) << 4),
-                 pack_bf16x2(__uint_as_float(b[8 * j]), __uint_as_float(b[8 * j + 1])),
-                 pack_bf16x2(__uint_as_float(b[8 * j + 2]), __uint_as_float(b[8 * j + 3])),
-                 pack_bf16x2(__uint_as_float(b[8 * j + 4]), __uint_as_float(b[8 * j + 5])),
-                 pack_bf16x2(__uint_as_float(b[8 * j + 6]), __uint_as_float(b[8 * j + 7])));
-  }
+  st_shared_v4(row + ((4u ^ sw) << 4), pack_bf16x2(__uint_as_float(b[0]), __uint_as_float(b[1])),
+               pack_bf16x2(__uint_as_float(b[2]), __uint_as_float(b[3])),
+               pack_bf16x2(__uint_as_float(b[4]), __uint_as_float(b[5])),
+               pack_bf16x2(__uint_as_float(b[6]), __uint_as_float(b[7])));
+  st_shared_v4(row + ((5u ^ sw) << 4), ones_col40 ? 0x00003F80u : 0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 
 __global__ void __launch_bounds__(TF_THREADS, 1)
 temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, TfParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t a_full, a_free;
+  __shared__ uint64_t a_full[TF_KB], a_free[TF_KB];
   __shared__ uint64_t w_full[TF_W_STAGES], w_empty[TF_W_STAGES];
   __shared__ uint64_t g_full[2], g_free[2];
   __shared__ uint64_t qk_ready, s_full, p_ready, v_ready;
@@ -114,29 +134,30 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
-  const uint32_t sQ = smem_base + TF_OFF_Q;
   const uint32_t sK = smem_base + TF_OFF_K;
   const uint32_t sV = smem_base + TF_OFF_V;
-  const uint32_t sP = smem_base + TF_OFF_P;
   const uint32_t sW = smem_base + TF_OFF_W;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.B * p.tiles_per_b;
-  const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int my_items = my_tiles * TF_HEADS;
-
-  // P is block diagonal: only the 32-column block of each warp's rows is ever rewritten, the rest stays zero
-  for (uint32_t off = threadIdx.x * 16; off < 2 * TF_KBLK_BYTES; off += TF_THREADS * 16)
-    st_shared_v4(sP + off, 0u, 0u, 0u, 0u);
-  fence_proxy_async_smem();
+  // Work items are (tile, head) pairs in tile-major order; every CTA takes one contiguous range, so the load is even
+  // to 1 / heads of a tile (640 tiles on 148 SMs would otherwise cost 5 rounds for 4.3 rounds of work).  A range may
+  // start or end in the middle of a tile: two CTAs then load the same input tile and write different heads of it.
+  const int total_items = p.B * p.tiles_per_b * TF_HEADS;
+  const int per_cta = (total_items + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int g0 = static_cast<int>(blockIdx.x) * per_cta;
+  const int my_items = max(0, min(per_cta, total_items - g0));
+  const int tile0 = g0 / TF_HEADS;
+  const int my_tiles = my_items > 0 ? (g0 + my_items - 1) / TF_HEADS - tile0 + 1 : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(&a_full, 1);
-    mbar_init(&a_free, 1);
+    for (int s = 0; s < TF_KB; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_free[s], 1);
+    }
     for (int s = 0; s < TF_W_STAGES; ++s) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
@@ -159,14 +180,13 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
 
-  // every CTA walks the same 8 heads x 5 k-chunks of W per tile; rotating the order per CTA keeps the 148 CTAs from
-  // all pulling the same 18 KB chunk (the same L2 slices) at the same moment
-  const int head_rot = static_cast<int>(blockIdx.x) & (TF_HEADS - 1);
-  const int kb_rot = static_cast<int>(blockIdx.x) % TF_KB;
-  auto head_of = [&](uint32_t m) -> int { return static_cast<int>((m + head_rot) & (TF_HEADS - 1)); };
-  auto kb_of = [&](int i) -> int { const int k = i + kb_rot; return k >= TF_KB ? k - TF_KB : k; };
+  // local item m -> global item g0 + m = (tile, head); `it` = index of the tile among this CTA's tiles
+  auto head_of = [&](uint32_t m) -> int { return (g0 + static_cast<int>(m)) & (TF_HEADS - 1); };
+  auto it_of = [&](uint32_t m) -> int { return (g0 + static_cast<int>(m)) / TF_HEADS - tile0; };
+  auto first_of_tile = [&](uint32_t m) -> bool { return m == 0 || head_of(m) == 0; };
+  auto last_of_tile = [&](uint32_t m) -> bool { return static_cast<int>(m) == my_items - 1 || head_of(m) == TF_HEADS - 1; };
   auto tile_coords = [&](int it, int& b, int& hw0) {
-    const int tile = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+    const int tile = tile0 + it;
     b = tile / p.tiles_per_b;
     hw0 = (tile % p.tiles_per_b) * p.seqs_per_tile;
   };
@@ -178,28 +198,29 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       for (int it = 0; it < my_tiles; ++it) {
         int b, hw0;
         tile_coords(it, b, hw0);
-        mbar_wait(&a_free, (static_cast<uint32_t>(it) & 1u) ^ 1u);
-        TF_MARK(3, it * TF_HEADS, 0);
-        mbar_arrive_expect_tx(&a_full, TF_A_BYTES);
         for (int kb = 0; kb < TF_KB; ++kb) {
+          // k-block kb of the previous tile is free once the projection of its last head has read it
+          mbar_wait(&a_free[kb], (static_cast<uint32_t>(it) & 1u) ^ 1u);
+          if (kb == 0) TF_MARK(3, it * TF_HEADS, 0);
+          mbar_arrive_expect_tx(&a_full[kb], TF_KBLK_BYTES);
           for (int g = 0; g < p.seqs_per_tile; ++g) {
             // box = (64 columns, 1 position, F frames): the F rows of sequence (b, hw0 + g); positions past HW are
             // zero-filled by TMA
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                 ::"r"(sA + kb * TF_KBLK_BYTES + g * p.F * 128), "l"(reinterpret_cast<uint64_t>(&tmX)),
-                "r"(smem_u32(&a_full)), "r"(kb * 64), "r"(hw0 + g), "r"(b * p.F)
+                "r"(smem_u32(&a_full[kb])), "r"(kb * 64), "r"(hw0 + g), "r"(b * p.F)
                 : "memory");
           }
         }
-        for (int h = 0; h < TF_HEADS; ++h) {
+        const int h_begin = it == 0 ? (g0 & (TF_HEADS - 1)) : 0;
+        const int h_end = it == my_tiles - 1 ? ((g0 + my_items - 1) & (TF_HEADS - 1)) + 1 : TF_HEADS;
+        for (int h = h_begin; h < h_end; ++h) {
           for (int kb = 0; kb < TF_KB; ++kb, ++nw) {
             const uint32_t st = nw % TF_W_STAGES;
             mbar_wait(&w_empty[st], ((nw / TF_W_STAGES) & 1u) ^ 1u);
-            TF_MARK(3, it * TF_HEADS + h, 1 + kb);
             mbar_arrive_expect_tx(&w_full[st], TF_W_STAGE_BYTES);
-            tma_load_2d_a(sW + st * TF_W_STAGE_BYTES, &tmW, &w_full[st], kb_of(kb) * 64,
-                          head_of(static_cast<uint32_t>(h)) * TF_HEAD_ROWS);
+            tma_load_2d_a(sW + st * TF_W_STAGE_BYTES, &tmW, &w_full[st], kb * 64, h * TF_HEAD_ROWS);
           }
         }
       }
@@ -211,61 +232,57 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
       constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, TF_DK);
       uint32_t nw = 0;
-      // projection of item m (tile m / 8, head m % 8) into accumulator buffer m & 1
+      // projection of item m into accumulator buffer m & 1
       auto issue_g = [&](uint32_t m) {
         const uint32_t buf = m & 1u;
-        const uint32_t head = m % TF_HEADS;
-        const uint32_t it = m / TF_HEADS;
+        const bool first = first_of_tile(m), last = last_of_tile(m);
+        const uint32_t it = static_cast<uint32_t>(it_of(m));
         TF_MARK(0, m, 0);
-        if (head == 0) mbar_wait(&a_full, it & 1u);
         mbar_wait(&g_free[buf], ((m >> 1) & 1u) ^ 1u);
-        TF_MARK(0, m, 1);
         tc_fence_after_sync();
         for (int kb = 0; kb < TF_KB; ++kb, ++nw) {
           const uint32_t st = nw % TF_W_STAGES;
-          TF_MARK(4, m, kb);
+          if (first) mbar_wait(&a_full[kb], it & 1u);
           mbar_wait(&w_full[st], (nw / TF_W_STAGES) & 1u);
-          TF_MARK(5, m, kb);
           tc_fence_after_sync();
-          const uint64_t da = umma_desc_k_sw128(sA + kb_of(kb) * TF_KBLK_BYTES);
+          const uint64_t da = umma_desc_k_sw128(sA + kb * TF_KBLK_BYTES);
           const uint64_t db = umma_desc_k_sw128(sW + st * TF_W_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_ss(tmem_base + TF_COL_G + buf * TF_HEAD_ROWS, da + static_cast<uint64_t>(2 * k),
                          db + static_cast<uint64_t>(2 * k), idesc_g, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&w_empty[st]);
+          if (last) umma_commit(&a_free[kb]);  // last head of the tile (for this CTA): k-block kb may be reloaded
         }
         umma_commit(&g_full[buf]);
-        TF_MARK(0, m, 2);
-        if (head == TF_HEADS - 1) umma_commit(&a_free);  // every read of the resident input tile has been issued
+        TF_MARK(0, m, 1);
       };
+      // S(m) = q k^T: A = packed bf16 q in TMEM (in place over the first 24 accumulator columns), B = k in smem
       auto issue_s = [&](uint32_t m) {
-        TF_MARK(0, m, 3);
+        TF_MARK(0, m, 2);
         mbar_wait(&qk_ready, m & 1u);
-        TF_MARK(0, m, 4);
         tc_fence_after_sync();
+        const uint32_t tq = tmem_base + TF_COL_G + (m & 1u) * TF_HEAD_ROWS;
 #pragma unroll
         for (int k = 0; k < TF_DK / 16; ++k)
-          umma_bf16_ss(tmem_base + TF_COL_S, umma_desc_k_sw128(sQ + k * 32), umma_desc_k_sw128(sK + k * 32), idesc_s,
-                       k > 0 ? 1u : 0u);
+          umma_bf16_ts(tmem_base + TF_COL_S, tq + 8 * k, umma_desc_k_sw128(sK + k * 32), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(&s_full);
+        TF_MARK(0, m, 3);
       };
+      // O(m) = P v: A = packed bf16 P in TMEM (in place over the first 64 score columns), B = v in smem (MN-major)
       auto issue_pv = [&](uint32_t m) {
         const uint32_t buf = m & 1u;
-        TF_MARK(0, m, 5);
+        TF_MARK(0, m, 4);
         mbar_wait(&p_ready, m & 1u);
-        TF_MARK(0, m, 6);
         mbar_wait(&v_ready, m & 1u);
         mbar_wait(&o_free[buf], ((m >> 1) & 1u) ^ 1u);
-        TF_MARK(0, m, 7);
         tc_fence_after_sync();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t da = umma_desc_k_sw128(sP + (k >> 2) * TF_KBLK_BYTES + (k & 3) * 32);
-          const uint64_t db = umma_desc_mn_sw128(sV + k * (16 * 128), TF_KBLK_BYTES, 1024);
-          umma_bf16_ss(tmem_base + TF_COL_O + buf * TF_DK, da, db, idesc_o, k > 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < 8; ++k)
+          umma_bf16_ts(tmem_base + TF_COL_O + buf * TF_DK, tmem_base + TF_COL_S + 8 * k,
+                       umma_desc_mn_sw128(sV + k * (16 * 128), TF_KBLK_BYTES, 1024), idesc_o, k > 0 ? 1u : 0u);
         umma_commit(&o_full[buf]);
+        TF_MARK(0, m, 5);
       };
       const uint32_t items = static_cast<uint32_t>(my_items);
       if (items > 0) issue_g(0);
@@ -283,21 +300,45 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float c = p.scale_log2e;
     const int my_group = lane >> p.F_log2;  // sequence of this row inside the warp's 32-row block
+    const uint32_t zeros[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (uint32_t m = 0; m < static_cast<uint32_t>(my_items); ++m) {
       const uint32_t buf = m & 1u;
       const bool mark = warp == 4 && lane == 0;
+      const uint32_t tg = lane_addr + TF_COL_G + buf * TF_HEAD_ROWS;
       if (mark) TF_MARK(1, m, 0);
       mbar_wait(&g_full[buf], (m >> 1) & 1u);
       if (mark) TF_MARK(1, m, 1);
       tc_fence_after_sync();
-      // S(m-1) has completed (this warp consumed it), so the Q / K operand tiles are free
-      tf_convert48(lane_addr + TF_COL_G + buf * TF_HEAD_ROWS, sQ, r);
-      tf_convert48(lane_addr + TF_COL_G + buf * TF_HEAD_ROWS + TF_DK, sK, r);
+      {
+        // q: 40 fp32 columns -> 20 packed bf16 columns (+ 4 zero columns: K padded to 48), in place
+        uint32_t a[32], b[8];
+        tmem_ld_x32(tg, a);
+        tmem_ld_x8(tg + 32, b);
+        tmem_ld_wait();
+        uint32_t lo[16], hi[8];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) lo[i] = pack_bf16x2(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hi[i] = pack_bf16x2(__uint_as_float(b[2 * i]), __uint_as_float(b[2 * i + 1]));
+#pragma unroll
+        for (int i = 4; i < 8; ++i) hi[i] = 0u;
+        tmem_st_x16(tg, lo);
+        tmem_st_x8(tg + 16, hi);
+      }
+      {
+        // k -> smem operand tile; S(m-1) has completed (this warp consumed it), so the tile is free
+        uint32_t a[32], b[8];
+        tmem_ld_x32(tg + TF_D, a);
+        tmem_ld_x8(tg + TF_D + 32, b);
+        tmem_ld_wait();
+        tf_store40(a, b, sK, r, false);
+      }
+      tmem_st_wait();
       tc_fence_before_sync();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&g_free[buf]);
+        mbar_arrive(&g_free[buf]);  // G(m+2) is issued behind S(m) by the same thread, so q (in place) is safe
         mbar_arrive(&qk_ready);
       }
       if (mark) TF_MARK(1, m, 2);
@@ -318,22 +359,17 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 #pragma unroll
       for (int i = 0; i < 32; i += 2)
         pk[i >> 1] = pack_bf16x2(tf_exp2(__uint_as_float(v[i]) - mx), tf_exp2(__uint_as_float(v[i + 1]) - mx));
-      // the P tile is free once PV(m-1) has completed
-      if (mark) TF_MARK(1, m, 4);
-      if (m > 0) mbar_wait(&o_full[(m - 1) & 1u], ((m - 1) >> 1) & 1u);
-      if (mark) TF_MARK(1, m, 5);
-      const uint32_t p_row = sP + r * 128;
+      // P (bf16, 64 packed columns) over the scores: this warp's rows are non-zero only in its own 32-key block
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int piece = q * 4 + g;
-        const uint32_t addr = p_row + (piece >> 3) * TF_KBLK_BYTES + (((piece & 7) ^ (r & 7)) << 4);
-        st_shared_v4(addr, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      for (int j = 0; j < 4; ++j) {
+        if (j == q) tmem_st_x16(lane_addr + TF_COL_S + 16 * j, pk);
+        else tmem_st_x16(lane_addr + TF_COL_S + 16 * j, zeros);
       }
+      tmem_st_wait();
       tc_fence_before_sync();
-      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready);
-      if (mark) TF_MARK(1, m, 6);
+      if (mark) TF_MARK(1, m, 4);
     }
   } else if (warp >= 8) {
     // ------------------------------------ WG-B: v conversion + output epilogue ------------------------------------
@@ -345,8 +381,8 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       // o_full[m & 1] has been observed by the caller
       const uint32_t buf = m & 1u;
       int b, hw0;
-      tile_coords(static_cast<int>(m / TF_HEADS), b, hw0);
-      const int head = head_of(m % TF_HEADS);
+      tile_coords(it_of(m), b, hw0);
+      const int head = head_of(m);
       const int hw = hw0 + seq;
       uint32_t o[32], o2[16];
       tmem_ld_x32(lane_addr + TF_COL_O + buf * TF_DK, o);
@@ -378,41 +414,27 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       mbar_wait(&g_full[buf], (m >> 1) & 1u);
       if (mark) TF_MARK(2, m, 1);
       tc_fence_after_sync();
-      uint32_t a[32], b2[16];
-      tmem_ld_x32(lane_addr + TF_COL_G + buf * TF_HEAD_ROWS + 2 * TF_DK, a);
-      tmem_ld_x16(lane_addr + TF_COL_G + buf * TF_HEAD_ROWS + 2 * TF_DK + 32, b2);
+      uint32_t a[32], b2[8];
+      tmem_ld_x32(lane_addr + TF_COL_G + buf * TF_HEAD_ROWS + 2 * TF_D, a);
+      tmem_ld_x8(lane_addr + TF_COL_G + buf * TF_HEAD_ROWS + 2 * TF_D + 32, b2);
       tmem_ld_wait();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&g_free[buf]);
       // the V tile is free (and O(m-1) is complete) once PV(m-1) has completed
-      if (mark) TF_MARK(2, m, 2);
       if (m > 0) {
         mbar_wait(&o_full[(m - 1) & 1u], ((m - 1) >> 1) & 1u);
         tc_fence_after_sync();
       }
-      if (mark) TF_MARK(2, m, 3);
-      const uint32_t row = sV + static_cast<uint32_t>(r) * 128u;
-      const uint32_t sw = static_cast<uint32_t>(r & 7);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        st_shared_v4(row + ((static_cast<uint32_t>(j) ^ sw) << 4),
-                     pack_bf16x2(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1])),
-                     pack_bf16x2(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3])),
-                     pack_bf16x2(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5])),
-                     pack_bf16x2(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7])));
-      st_shared_v4(row + ((4u ^ sw) << 4), pack_bf16x2(__uint_as_float(b2[0]), __uint_as_float(b2[1])),
-                   pack_bf16x2(__uint_as_float(b2[2]), __uint_as_float(b2[3])),
-                   pack_bf16x2(__uint_as_float(b2[4]), __uint_as_float(b2[5])),
-                   pack_bf16x2(__uint_as_float(b2[6]), __uint_as_float(b2[7])));
-      // columns 40..47 of v are zero padding: column 40 carries 1.0 so that O[:, 40] = sum_j P_ij
-      st_shared_v4(row + ((5u ^ sw) << 4), 0x00003F80u, 0u, 0u, 0u);
+      if (mark) TF_MARK(2, m, 2);
+      // columns 40..47 of the V tile are padding: column 40 carries 1.0 so that O[:, 40] = sum_j P_ij
+      tf_store40(a, b2, sV, r, true);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&v_ready);
-      if (mark) TF_MARK(2, m, 4);
+      if (mark) TF_MARK(2, m, 3);
       if (m > 0) epilogue(m - 1);
-      if (mark) TF_MARK(2, m, 5);
+      if (mark) TF_MARK(2, m, 4);
     }
     if (my_items > 0) {
       const uint32_t m = static_cast<uint32_t>(my_items) - 1;
@@ -434,7 +456,7 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 
 using namespace fmc;
 
-// Diagnostics: device buffer of 6 * 64 * 8 int64 receiving clock64() stamps of CTA 0's pipeline events (nullptr = off).
+// Diagnostics: device buffer of 4 * 64 * 8 int64 receiving clock64() stamps of CTA 0's pipeline events (nullptr = off).
 extern "C" int fmc_debug_set_timeline(void* device_buffer) {
   g_tf_timeline = static_cast<long long*>(device_buffer);
   return FMC_OK;
@@ -484,8 +506,8 @@ extern "C" int fmc_temporal_qkv_attn_bf16(const void* X, long long ldx, const vo
     FMC_CUDA_OK(cudaFuncSetAttribute(temporal_qkv_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = B * p.tiles_per_b;
-  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  const int items = B * p.tiles_per_b * TF_HEADS;
+  const int grid = items < device_sm_count() ? items : device_sm_count();
   temporal_qkv_attn_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(tmX, tmW, p);
   return check_launch("temporal_qkv_attn_kernel");
 }

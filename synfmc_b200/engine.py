@@ -177,12 +177,13 @@ class AttnPlan:
         self.q_col0 = 0
         self.k_col0 = heads * hs
         self.v_col0 = 2 * heads * hs
-        # fused projection + temporal attention kernel (fmc_temporal_qkv_attn_bf16): per head [q | k | v] row blocks,
-        # each zero-padded 40 -> 48
+        # fused projection + temporal attention kernel (fmc_temporal_qkv_attn_bf16): per head the rows
+        # [q (40) | k (40) | v (40) | 8 zero rows]
         self.w_head_major = None
         if FUSED_TEMPORAL and fused_temporal and not self.is_cross and C == 320 and heads == 8:
-            blocks = [_pad_heads(w, heads, d, hs).view(heads, hs, C) for w in (folded("to_q"), folded("to_k"), wv)]
-            self.w_head_major = _dev_bf16(torch.cat(blocks, dim=1).reshape(heads * 3 * hs, C), device)
+            blocks = [w.view(heads, d, C) for w in (folded("to_q"), folded("to_k"), wv)]
+            blocks.append(torch.zeros(heads, 128 - 3 * d, C))
+            self.w_head_major = _dev_bf16(torch.cat(blocks, dim=1).reshape(heads * 128, C), device)
 
 
 class NormPlan:

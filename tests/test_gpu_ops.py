@@ -143,8 +143,8 @@ def test_temporal_qkv_attention_fused(ops, cuda_device, B, F, HW):
     rows = B * F * HW
     x = randn(rows, C, seed=1)
     wq, wk, wv = (randn(C, C, seed=s, scale=C ** -0.5) for s in (2, 3, 4))
-    blocks = [_pad_heads(w.t(), heads, d, hs).t().reshape(heads, hs, C) for w in (wq, wk, wv)]
-    w_head_major = torch.cat(blocks, dim=1).reshape(heads * 3 * hs, C)
+    blocks = [w.view(heads, d, C) for w in (wq, wk, wv)] + [torch.zeros(heads, 128 - 3 * d, C)]
+    w_head_major = torch.cat(blocks, dim=1).reshape(heads * 128, C)
     out = torch.empty(rows, C, dtype=torch.bfloat16, device=cuda_device)
     ops.temporal_qkv_attn(bf(x).to(cuda_device), bf(w_head_major).to(cuda_device), out, B, F, HW, heads, d ** -0.5)
 
