@@ -9,22 +9,22 @@
 // processors (fmc/models/attention_processor.py:46-67 AttnProcessor, :259-281 PoseAdaptorAttnProcessor) as reached
 // from TemporalSelfAttention.forward (fmc/models/motion_module.py:349-389).
 //
-// Every A operand lives in TENSOR MEMORY (tcgen05.mma with A in TMEM: lane = row, 32-bit column c = elements 2c, 2c+1;
-// checked by profiles/microbench/mma_bench.cu): shared memory only carries B operands.  With both operands in shared
-// memory this kernel was shared-memory-bandwidth bound (~125 B/clk: the 80 KB input tile re-read for each of the 8
-// heads on top of the weight stream); see profiles/r01_timeline_temporal_fused_*.txt.
-//   * the tile's input rows [128, 320] land in smem by TMA (prefetched one tile ahead) and are copied ONCE into 160
-//     TMEM columns as packed bf16; the 8 per-head projections read them from there
-//   * q is written back as packed bf16 next to the output accumulator, P in place over the scores
-//   * k, v (B operands) are staged in smem; the per-head weight slices [128, 320] stream through a 6-stage TMA ring
+// Work decomposition: persistent CTAs (one per SM) walk token tiles; the tile's input rows [128, 320] stay resident in
+// shared memory (SWIZZLE_128B, five 64-column k-blocks, reloaded k-block by k-block behind the last head) while the
+// per-head weight slices [128, 320] stream through a 6-stage TMA ring (one head = 5 stages, so the next head's weights
+// are always in flight).  q and the probabilities P never touch shared memory: they are written back to TENSOR MEMORY
+// as packed bf16 and consumed as the A operand of the score / PV MMAs (tcgen05.mma with A in TMEM), q in place over
+// its fp32 accumulator columns, P in place over the scores (lane = row, column c = elements 2c, 2c+1; checked by
+// profiles/microbench/mma_bench.cu).  Only k and v (B operands) are staged in shared memory.
 //   warp 0       TMA producer (input tile, weight ring)
-//   warp 1       tcgen05.mma issuer, per item m = (tile, head):  PV(m-1), S(m), G(m+1); one issuing thread = in-order
-//                execution, which is what makes the in-place P / shared q+O columns safe
+//   warp 1       tcgen05.mma issuer: per item m = (tile, head):  S(m), G(m+2), PV(m)  -- the projection of head m+2
+//                keeps the tensor pipe busy while head m is in its softmax; one issuing thread = in-order execution,
+//                which is what makes the in-place q / P operands safe against the next accumulator write
 //   warp 2       TMEM allocator
 //   warps 4-7    WG-A: q -> bf16 -> TMEM, k -> bf16 -> smem; block-diagonal softmax; P -> bf16 -> TMEM
 //   warps 8-11   WG-B: v -> bf16 -> smem (plus a ones column so the PV MMA also yields the softmax row sum);
-//                o epilogue (normalise, bf16, store); input tile smem -> TMEM at tile boundaries
-// TMEM (512 columns): X 160 | projection accumulator 128 | S / P 128 | (q | O) 2 x 48.
+//                o epilogue (normalise, bf16, store)
+// TMEM (512 columns): projection accumulators 2 x 128 | S / P 128 | O 2 x 48.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -38,7 +38,7 @@ constexpr int TF_D = 40;                  // head width
 constexpr int TF_DK = 48;                 // head width padded to the MMA K granularity
 constexpr int TF_HEADS = 8;
 constexpr int TF_HEAD_ROWS = 128;         // weight rows per head: q(40) | k(40) | v(40) | 8 zero rows
-constexpr int TF_KB = TF_C / 64;          // k-blocks of the input tile
+constexpr int TF_KB = TF_C / 64;          // k-blocks of the resident input tile
 constexpr int TF_KBLK_BYTES = 128 * 128;  // [128 rows x 64 bf16] SWIZZLE_128B block
 constexpr int TF_A_BYTES = TF_KB * TF_KBLK_BYTES;
 constexpr int TF_W_STAGE_BYTES = TF_HEAD_ROWS * 128;  // [128 rows x 64 bf16]
@@ -47,10 +47,9 @@ constexpr int TF_OFF_K = TF_A_BYTES;
 constexpr int TF_OFF_V = TF_OFF_K + TF_KBLK_BYTES;
 constexpr int TF_OFF_W = TF_OFF_V + TF_KBLK_BYTES;
 constexpr int TF_SMEM_BYTES = TF_OFF_W + TF_W_STAGES * TF_W_STAGE_BYTES + 1024;
-constexpr uint32_t TF_COL_X = 0;     // input tile, packed bf16: k-block kb at columns 32 kb .. 32 kb + 31
-constexpr uint32_t TF_COL_G = 160;   // 128 projection accumulator columns: q 0..39 | k 40..79 | v 80..119
-constexpr uint32_t TF_COL_S = 288;   // 128 score columns (P bf16 is rewritten in place over columns 0..63)
-constexpr uint32_t TF_COL_O = 416;   // 2 x 48: packed bf16 q of item m in columns 0..23 until S(m), then O(m)
+constexpr uint32_t TF_COL_G = 0;     // 2 x 128 projection accumulators (q bf16 is rewritten in place over columns 0..23)
+constexpr uint32_t TF_COL_S = 256;   // 128 score columns (P bf16 is rewritten in place over columns 0..63)
+constexpr uint32_t TF_COL_O = 384;   // 2 x 48 output accumulators
 static_assert(TF_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(TF_W_STAGE_BYTES % 1024 == 0, "SW128 tiles stay 1024-byte aligned");
 
@@ -96,15 +95,6 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tf_ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
-}
 
 // 40 fp32 values (a[0..31], b[0..7]) -> bf16 -> row `r` of a [128 x 64] SW128 smem tile; columns 40..47 (the padding of
 // the head width to the MMA K granularity) become zero, or (1, 0, ..., 0) with `ones_col40`
@@ -125,19 +115,25 @@ __device__ __forceinline__ void tf_store40(const uint32_t (&a)[32], const uint32
                pack_bf16x2(__uint_as_float(b[6]), __uint_as_float(b[7])));
   st_shared_v4(row + ((5u ^ sw) << 4), ones_col40 ? 0x00003F80u : 0u, 0u, 0u, 0u);
 }
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 
 __global__ void __launch_bounds__(TF_THREADS, 1)
 temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, TfParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t xs_full, xs_free, x_ready, x_free;
+  __shared__ uint64_t a_full[TF_KB], a_free[TF_KB];
   __shared__ uint64_t w_full[TF_W_STAGES], w_empty[TF_W_STAGES];
-  __shared__ uint64_t g_full, g_free;
+  __shared__ uint64_t g_full[2], g_free[2];
   __shared__ uint64_t qk_ready, s_full, p_ready, v_ready;
   __shared__ uint64_t o_full[2], o_free[2];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sX = smem_base;
+  const uint32_t sA = smem_base;
   const uint32_t sK = smem_base + TF_OFF_K;
   const uint32_t sV = smem_base + TF_OFF_V;
   const uint32_t sW = smem_base + TF_OFF_W;
@@ -158,17 +154,17 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     tma_prefetch_desc(&tmW);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(&xs_full, 1);
-    mbar_init(&xs_free, 4);
-    mbar_init(&x_ready, 4);
-    mbar_init(&x_free, 1);
+    for (int s = 0; s < TF_KB; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_free[s], 1);
+    }
     for (int s = 0; s < TF_W_STAGES; ++s) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
     }
-    mbar_init(&g_full, 1);
-    mbar_init(&g_free, 8);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&g_full[s], 1);
+      mbar_init(&g_free[s], 8);
       mbar_init(&o_full[s], 1);
       mbar_init(&o_free[s], 4);
     }
@@ -199,27 +195,24 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     // ------------------------------------ TMA producer ------------------------------------
     if (elect_one()) {
       uint32_t nw = 0;
-      // tile `it` -> landing buffer (free once tile it-1 has been copied to tensor memory)
-      auto load_tile = [&](int it) {
+      for (int it = 0; it < my_tiles; ++it) {
         int b, hw0;
         tile_coords(it, b, hw0);
-        mbar_wait(&xs_free, (static_cast<uint32_t>(it) & 1u) ^ 1u);
-        TF_MARK(3, it * TF_HEADS, 0);
-        mbar_arrive_expect_tx(&xs_full, TF_A_BYTES);
         for (int kb = 0; kb < TF_KB; ++kb) {
+          // k-block kb of the previous tile is free once the projection of its last head has read it
+          mbar_wait(&a_free[kb], (static_cast<uint32_t>(it) & 1u) ^ 1u);
+          if (kb == 0) TF_MARK(3, it * TF_HEADS, 0);
+          mbar_arrive_expect_tx(&a_full[kb], TF_KBLK_BYTES);
           for (int g = 0; g < p.seqs_per_tile; ++g) {
             // box = (64 columns, 1 position, F frames): the F rows of sequence (b, hw0 + g); positions past HW are
             // zero-filled by TMA
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                ::"r"(sX + kb * TF_KBLK_BYTES + g * p.F * 128), "l"(reinterpret_cast<uint64_t>(&tmX)),
-                "r"(smem_u32(&xs_full)), "r"(kb * 64), "r"(hw0 + g), "r"(b * p.F)
+                ::"r"(sA + kb * TF_KBLK_BYTES + g * p.F * 128), "l"(reinterpret_cast<uint64_t>(&tmX)),
+                "r"(smem_u32(&a_full[kb])), "r"(kb * 64), "r"(hw0 + g), "r"(b * p.F)
                 : "memory");
           }
         }
-      };
-      if (my_tiles > 0) load_tile(0);
-      for (int it = 0; it < my_tiles; ++it) {
         const int h_begin = it == 0 ? (g0 & (TF_HEADS - 1)) : 0;
         const int h_end = it == my_tiles - 1 ? ((g0 + my_items - 1) & (TF_HEADS - 1)) + 1 : TF_HEADS;
         for (int h = h_begin; h < h_end; ++h) {
@@ -229,8 +222,6 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
             mbar_arrive_expect_tx(&w_full[st], TF_W_STAGE_BYTES);
             tma_load_2d_a(sW + st * TF_W_STAGE_BYTES, &tmW, &w_full[st], kb * 64, h * TF_HEAD_ROWS);
           }
-          // prefetch the next tile's rows one tile ahead, behind the first head's weights of this tile
-          if (h == h_begin && it + 1 < my_tiles) load_tile(it + 1);
         }
       }
     }
@@ -241,46 +232,50 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
       constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, TF_DK);
       uint32_t nw = 0;
-      // projection of item m: A = the input tile in TMEM, B = weight k-chunks from the ring
+      // projection of item m into accumulator buffer m & 1
       auto issue_g = [&](uint32_t m) {
+        const uint32_t buf = m & 1u;
+        const bool first = first_of_tile(m), last = last_of_tile(m);
+        const uint32_t it = static_cast<uint32_t>(it_of(m));
         TF_MARK(0, m, 0);
-        mbar_wait(&g_free, (m & 1u) ^ 1u);  // q, k, v of item m-1 have been read out of the accumulator
-        if (first_of_tile(m)) mbar_wait(&x_ready, static_cast<uint32_t>(it_of(m)) & 1u);
+        mbar_wait(&g_free[buf], ((m >> 1) & 1u) ^ 1u);
         tc_fence_after_sync();
         for (int kb = 0; kb < TF_KB; ++kb, ++nw) {
           const uint32_t st = nw % TF_W_STAGES;
+          if (first) mbar_wait(&a_full[kb], it & 1u);
           mbar_wait(&w_full[st], (nw / TF_W_STAGES) & 1u);
           tc_fence_after_sync();
+          const uint64_t da = umma_desc_k_sw128(sA + kb * TF_KBLK_BYTES);
           const uint64_t db = umma_desc_k_sw128(sW + st * TF_W_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_ts(tmem_base + TF_COL_G, tmem_base + TF_COL_X + kb * 32 + k * 8, db + static_cast<uint64_t>(2 * k),
-                         idesc_g, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_ss(tmem_base + TF_COL_G + buf * TF_HEAD_ROWS, da + static_cast<uint64_t>(2 * k),
+                         db + static_cast<uint64_t>(2 * k), idesc_g, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&w_empty[st]);
+          if (last) umma_commit(&a_free[kb]);  // last head of the tile (for this CTA): k-block kb may be reloaded
         }
-        umma_commit(&g_full);
-        if (last_of_tile(m)) umma_commit(&x_free);  // every read of the TMEM-resident input tile has been issued
+        umma_commit(&g_full[buf]);
         TF_MARK(0, m, 1);
       };
-      // S(m) = q k^T: A = packed bf16 q in TMEM (first 24 columns of the item's O buffer), B = k in smem
+      // S(m) = q k^T: A = packed bf16 q in TMEM (in place over the first 24 accumulator columns), B = k in smem
       auto issue_s = [&](uint32_t m) {
         TF_MARK(0, m, 2);
         mbar_wait(&qk_ready, m & 1u);
         tc_fence_after_sync();
-        const uint32_t tq = tmem_base + TF_COL_O + (m & 1u) * TF_DK;
+        const uint32_t tq = tmem_base + TF_COL_G + (m & 1u) * TF_HEAD_ROWS;
 #pragma unroll
         for (int k = 0; k < TF_DK / 16; ++k)
           umma_bf16_ts(tmem_base + TF_COL_S, tq + 8 * k, umma_desc_k_sw128(sK + k * 32), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(&s_full);
         TF_MARK(0, m, 3);
       };
-      // O(m) = P v: A = packed bf16 P in TMEM (in place over the first 64 score columns), B = v in smem (MN-major).
-      // The O buffer was free when WG-A stored q into it (o_free), and S(m) -- the reader of q -- precedes this MMA.
+      // O(m) = P v: A = packed bf16 P in TMEM (in place over the first 64 score columns), B = v in smem (MN-major)
       auto issue_pv = [&](uint32_t m) {
         const uint32_t buf = m & 1u;
         TF_MARK(0, m, 4);
         mbar_wait(&p_ready, m & 1u);
         mbar_wait(&v_ready, m & 1u);
+        mbar_wait(&o_free[buf], ((m >> 1) & 1u) ^ 1u);
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -291,12 +286,12 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       };
       const uint32_t items = static_cast<uint32_t>(my_items);
       if (items > 0) issue_g(0);
+      if (items > 1) issue_g(1);
       for (uint32_t m = 0; m < items; ++m) {
-        if (m > 0) issue_pv(m - 1);
         issue_s(m);
-        if (m + 1 < items) issue_g(m + 1);
+        if (m + 2 < items) issue_g(m + 2);
+        issue_pv(m);
       }
-      if (items > 0) issue_pv(items - 1);
     }
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------ WG-A: q, k conversion + softmax ------------------------------------
@@ -309,14 +304,13 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     for (uint32_t m = 0; m < static_cast<uint32_t>(my_items); ++m) {
       const uint32_t buf = m & 1u;
       const bool mark = warp == 4 && lane == 0;
-      const uint32_t tg = lane_addr + TF_COL_G;
+      const uint32_t tg = lane_addr + TF_COL_G + buf * TF_HEAD_ROWS;
       if (mark) TF_MARK(1, m, 0);
-      mbar_wait(&g_full, m & 1u);
-      mbar_wait(&o_free[buf], ((m >> 1) & 1u) ^ 1u);  // O(m-2) has been read: its columns may take q(m)
+      mbar_wait(&g_full[buf], (m >> 1) & 1u);
       if (mark) TF_MARK(1, m, 1);
       tc_fence_after_sync();
       {
-        // q: 40 fp32 columns -> 20 packed bf16 columns (+ 4 zero columns: K padded to 48)
+        // q: 40 fp32 columns -> 20 packed bf16 columns (+ 4 zero columns: K padded to 48), in place
         uint32_t a[32], b[8];
         tmem_ld_x32(tg, a);
         tmem_ld_x8(tg + 32, b);
@@ -328,8 +322,8 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         for (int i = 0; i < 4; ++i) hi[i] = pack_bf16x2(__uint_as_float(b[2 * i]), __uint_as_float(b[2 * i + 1]));
 #pragma unroll
         for (int i = 4; i < 8; ++i) hi[i] = 0u;
-        tmem_st_x16(lane_addr + TF_COL_O + buf * TF_DK, lo);
-        tmem_st_x8(lane_addr + TF_COL_O + buf * TF_DK + 16, hi);
+        tmem_st_x16(tg, lo);
+        tmem_st_x8(tg + 16, hi);
       }
       {
         // k -> smem operand tile; S(m-1) has completed (this warp consumed it), so the tile is free
@@ -344,7 +338,7 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&g_free);
+        mbar_arrive(&g_free[buf]);  // G(m+2) is issued behind S(m) by the same thread, so q (in place) is safe
         mbar_arrive(&qk_ready);
       }
       if (mark) TF_MARK(1, m, 2);
@@ -378,38 +372,11 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       if (mark) TF_MARK(1, m, 4);
     }
   } else if (warp >= 8) {
-    // ---------------------- WG-B: input tile -> TMEM, v conversion, output epilogue ----------------------
+    // ------------------------------------ WG-B: v conversion + output epilogue ------------------------------------
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int seq = r >> p.F_log2, frame = r & (p.F - 1);
-    // row r of the landed tile (5 k-blocks of 64 bf16) -> 160 packed TMEM columns
-    auto load_x = [&](int it) {
-      mbar_wait(&xs_full, static_cast<uint32_t>(it) & 1u);          // TMA has landed tile `it`
-      mbar_wait(&x_free, (static_cast<uint32_t>(it) & 1u) ^ 1u);    // the projections of tile it-1 have completed
-      tc_fence_after_sync();
-      const uint32_t row = sX + static_cast<uint32_t>(r) * 128u;
-      const uint32_t sw = static_cast<uint32_t>(r & 7);
-#pragma unroll
-      for (int kb = 0; kb < TF_KB; ++kb) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t w[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            tf_ld_shared_v4(row + kb * TF_KBLK_BYTES + ((static_cast<uint32_t>(half * 4 + j) ^ sw) << 4), w[4 * j],
-                            w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-          tmem_st_x16(lane_addr + TF_COL_X + kb * 32 + half * 16, w);
-        }
-      }
-      tmem_st_wait();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&x_ready);
-        mbar_arrive(&xs_free);
-      }
-    };
     auto epilogue = [&](uint32_t m) {
       // o_full[m & 1] has been observed by the caller
       const uint32_t buf = m & 1u;
@@ -440,22 +407,20 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                             pack_bf16x2(__uint_as_float(o2[6]) * inv, __uint_as_float(o2[7]) * inv));
       }
     };
-    if (my_items > 0) load_x(0);
     for (uint32_t m = 0; m < static_cast<uint32_t>(my_items); ++m) {
+      const uint32_t buf = m & 1u;
       const bool mark = warp == 8 && lane == 0;
       if (mark) TF_MARK(2, m, 0);
-      mbar_wait(&g_full, m & 1u);
+      mbar_wait(&g_full[buf], (m >> 1) & 1u);
       if (mark) TF_MARK(2, m, 1);
       tc_fence_after_sync();
       uint32_t a[32], b2[8];
-      tmem_ld_x32(lane_addr + TF_COL_G + 2 * TF_D, a);
-      tmem_ld_x8(lane_addr + TF_COL_G + 2 * TF_D + 32, b2);
+      tmem_ld_x32(lane_addr + TF_COL_G + buf * TF_HEAD_ROWS + 2 * TF_D, a);
+      tmem_ld_x8(lane_addr + TF_COL_G + buf * TF_HEAD_ROWS + 2 * TF_D + 32, b2);
       tmem_ld_wait();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&g_free);
-      // tile boundary: G(m) was the last projection of its tile, the next tile's rows go to tensor memory now
-      if (last_of_tile(m) && static_cast<int>(m) + 1 < my_items) load_x(it_of(m) + 1);
+      if (lane == 0) mbar_arrive(&g_free[buf]);
       // the V tile is free (and O(m-1) is complete) once PV(m-1) has completed
       if (m > 0) {
         mbar_wait(&o_full[(m - 1) & 1u], ((m - 1) >> 1) & 1u);
