@@ -63,6 +63,12 @@ CASES = {
     "gemm_l0_ff2": lambda: gemm_case(81920, 320, 1280, res=True),
     "gemm_l1_geglu": lambda: gemm_case(20480, 5120, 640, geglu=True),
     "gemm_l2_qkv": lambda: gemm_case(5120, 3840, 1280),
+    "gemm_l1_qkv": lambda: gemm_case(20480, 1920, 640),
+    "gemm_l1_out": lambda: gemm_case(20480, 640, 640, res=True),
+    "gemm_l2_out": lambda: gemm_case(5120, 1280, 1280, res=True),
+    "gemm_l2_geglu": lambda: gemm_case(5120, 10240, 1280, geglu=True),
+    "gemm_l2_ff2": lambda: gemm_case(5120, 1280, 5120, res=True),
+    "gemm_l1_ff2": lambda: gemm_case(20480, 640, 2560, res=True),
     "spatial_l0": lambda: spatial_case(32, 40, 2560),
     "spatial_l1": lambda: spatial_case(32, 80, 640),
     "temporal_fused_l0": lambda: temporal_fused_case(2, 16, 2560),

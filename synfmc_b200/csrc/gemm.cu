@@ -12,6 +12,7 @@
 //   warps 4-7   epilogue       (tcgen05.ld -> bias / GEGLU / row-bias / residual -> global)
 // The fp32 accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -360,11 +361,19 @@ __device__ __forceinline__ void epi_bar_arrive_warp(uint64_t* bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
-template <int BN, bool GEGLU>
+// CL = 2: the kernel runs as clusters of two CTAs that work on vertically adjacent output tiles (m_blk = 2 i + rank,
+// same n_blk).  They need the same W k-slices at the same time, so each CTA fetches HALF of every W slice and
+// multicasts it into both CTAs' stages: L2 -> SM traffic per tile drops from (128 + BN) to (128 + BN / 2) rows per
+// k-block.  These GEMMs sit on the L2 -> SM delivery cap (14.6 TB/s measured: 128 x 256 tiles top out at 1245 TFLOP/s,
+// 128 x 160 at 1040), not on the tensor pipe.  A stage is handed back only when BOTH CTAs' MMAs have read it (commit
+// multicast to both empty barriers, count 2).
+template <int BN, bool GEGLU, int CL>
 __global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmParams p) {
   using Cfg = Gemm2Cfg<BN, GEGLU>;
+  static_assert(CL == 1 || CL == 2, "cluster size");
+  static_assert(((BN / 2) * 128) % 1024 == 0, "half W slices must stay 1024-byte aligned");
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NSUB = Cfg::NSUB;
 
@@ -381,10 +390,16 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t out_base = smem_base + STAGES * Cfg::STAGE_BYTES;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
   const int kblocks = (p.K + GEMM_BK - 1) / GEMM_BK;
   const bool has_res = p.residual != nullptr;
   const int n_out = GEGLU ? p.N / 2 : p.N;
+  // work units: CL == 1: output tiles; CL == 2: pairs of vertically adjacent tiles, one per CTA of the cluster
+  const int rank = CL == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int unit0 = static_cast<int>(blockIdx.x) / CL;
+  const int unit_step = static_cast<int>(gridDim.x) / CL;
+  const int num_tiles = ((p.tiles_m + CL - 1) / CL) * p.tiles_n;
+  // unit -> (m_blk, n_blk) of THIS CTA; an odd last row of tiles is computed by both CTAs (identical stores)
+  auto m_blk_of = [&](int unit) -> int { const int m = (unit / p.tiles_n) * CL + rank; return m < p.tiles_m ? m : p.tiles_m - 1; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -395,7 +410,7 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full_bar[a], 1);
@@ -408,6 +423,7 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 2) tmem_alloc(&tmem_base_slot, Cfg::TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
+  if constexpr (CL == 2) cluster_sync_all();  // the peer's barriers are initialised before anything is sent to them
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -416,15 +432,21 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.tiles_n;
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+        const int m_blk = m_blk_of(tile);
         const int n_blk = tile % p.tiles_n;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           tma_load_2d_a(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-          tma_load_2d_a(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          if constexpr (CL == 2) {
+            // my half of the W slice, into both CTAs (tmB's box is BN / 2 rows)
+            tma_load_2d_mc(sa + Cfg::A_BYTES + rank * (BN / 2) * 128, &tmB, &full_bar[stage], kb * GEMM_BK,
+                           n_blk * BN + rank * (BN / 2), static_cast<uint16_t>(3));
+          } else {
+            tma_load_2d_a(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -440,7 +462,7 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
         mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1u);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -455,7 +477,8 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
                          (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (CL == 2) umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>(3));
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -474,7 +497,7 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // arm staging buffer `b` for tile `tile`: residual tile lands there (complete_tx) or it is simply marked free
       auto arm = [&](int b, int tile) {
         if (has_res) {
-          const int m_blk = tile / p.tiles_n;
+          const int m_blk = m_blk_of(tile);
           const int n_blk = tile % p.tiles_n;
           int nsub_ok = 0;
           for (int s = 0; s < NSUB; ++s) nsub_ok += (n_blk * Cfg::OUT_COLS + s * SUB_COLS < n_out) ? 1 : 0;
@@ -487,14 +510,14 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_arrive(&buf_ready_bar[b]);
         }
       };
-      int tile = blockIdx.x;
+      int tile = unit0;
       if (tile < num_tiles) arm(0, tile);
-      if (tile + static_cast<int>(gridDim.x) < num_tiles) arm(1, tile + gridDim.x);
+      if (tile + unit_step < num_tiles) arm(1, tile + unit_step);
       int it = 0;
-      for (; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (; tile < num_tiles; tile += unit_step, ++it) {
         const int b = it & 1;
         const uint32_t ph = static_cast<uint32_t>(it >> 1) & 1u;
-        const int m_blk = tile / p.tiles_n;
+        const int m_blk = m_blk_of(tile);
         const int n_blk = tile % p.tiles_n;
         mbar_wait(&out_ready_bar[b], ph);
         for (int s = 0; s < NSUB; ++s) {
@@ -507,7 +530,7 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
         }
         tma_store_commit();
-        const int next2 = tile + 2 * static_cast<int>(gridDim.x);
+        const int next2 = tile + 2 * unit_step;
         if (next2 < num_tiles) {
           tma_store_wait_read<0>();  // the store has drained buffer b: reuse it for the tile after next
           arm(b, next2);
@@ -526,10 +549,10 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t row_off = static_cast<uint32_t>(r_in_tile) * 64u;
     const uint32_t sw = static_cast<uint32_t>((r_in_tile >> 1) & 3);
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++it) {
       const int b = it & 1;
       const uint32_t ph = static_cast<uint32_t>(it >> 1) & 1u;
-      const int m_blk = tile / p.tiles_n;
+      const int m_blk = m_blk_of(tile);
       const int n_blk = tile % p.tiles_n;
       const int row = m_blk * GEMM_BM + r_in_tile;
       const float* rb = nullptr;
@@ -619,27 +642,41 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   tc_fence_before_sync();
   __syncthreads();
+  if constexpr (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 2) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, int CL>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                         GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN, GEGLU>;
   static bool attr_set = false;
   if (!attr_set) {
-    FMC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tma_kernel<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FMC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tma_kernel<BN, GEGLU, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
     attr_set = true;
   }
   p.tiles_m = ceil_div(p.M, GEMM_BM);
   p.tiles_n = ceil_div(p.N, BN);
-  const int tiles = p.tiles_m * p.tiles_n;
-  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  gemm_bf16_tma_kernel<BN, GEGLU><<<grid, GEMM2_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
+  const int units = ceil_div(p.tiles_m, CL) * p.tiles_n;
+  const int max_units = device_sm_count() / CL;
+  const int grid = (units < max_units ? units : max_units) * CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(GEMM2_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  FMC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tma_kernel<BN, GEGLU, CL>, tmA, tmB, tmC, tmR, p));
   return check_launch("gemm_bf16_tma_kernel");
 }
 
@@ -699,6 +736,12 @@ extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long l
     FMC_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, FMC_ERR_SHAPE, "fmc_gemm_bf16: unsupported tile_n %d", bn);
   }
 
+  // two-CTA clusters sharing the W stream by TMA multicast (see gemm_bf16_tma_kernel).  Measured on all twelve
+  // level 0-2 shapes of the step: within +-3 % of the plain kernel (profiles/r01_gemm_cluster_multicast.txt) -- L2
+  // already merges the CTAs' identical requests -- so it is OFF unless FMC_GEMM_CLUSTER=1.
+  static const bool cluster_allowed = getenv("FMC_GEMM_CLUSTER") != nullptr;
+  const bool use_cluster = tma_epilogue && cluster_allowed && M > GEMM_BM;
+
   CUtensorMap tmA, tmB;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
@@ -710,7 +753,7 @@ extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long l
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-    const uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(bn)};
+    const uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(use_cluster ? bn / 2 : bn)};
     int rc = make_tmap_bf16(&tmB, W, 2, dims, strides, box, true);
     if (rc != FMC_OK) return rc;
   }
@@ -738,14 +781,25 @@ extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long l
     } else {
       tmR = tmC;
     }
+    if (use_cluster) {
+      if (geglu) {
+        if (bn == 256) return launch_gemm2<256, true, 2>(tmA, tmB, tmC, tmR, p, stream);
+        return launch_gemm2<128, true, 2>(tmA, tmB, tmC, tmR, p, stream);
+      }
+      switch (bn) {
+        case 64: return launch_gemm2<64, false, 2>(tmA, tmB, tmC, tmR, p, stream);
+        case 128: return launch_gemm2<128, false, 2>(tmA, tmB, tmC, tmR, p, stream);
+        default: return launch_gemm2<160, false, 2>(tmA, tmB, tmC, tmR, p, stream);
+      }
+    }
     if (geglu) {
-      if (bn == 256) return launch_gemm2<256, true>(tmA, tmB, tmC, tmR, p, stream);
-      return launch_gemm2<128, true>(tmA, tmB, tmC, tmR, p, stream);
+      if (bn == 256) return launch_gemm2<256, true, 1>(tmA, tmB, tmC, tmR, p, stream);
+      return launch_gemm2<128, true, 1>(tmA, tmB, tmC, tmR, p, stream);
     }
     switch (bn) {
-      case 64: return launch_gemm2<64, false>(tmA, tmB, tmC, tmR, p, stream);
-      case 128: return launch_gemm2<128, false>(tmA, tmB, tmC, tmR, p, stream);
-      default: return launch_gemm2<160, false>(tmA, tmB, tmC, tmR, p, stream);
+      case 64: return launch_gemm2<64, false, 1>(tmA, tmB, tmC, tmR, p, stream);
+      case 128: return launch_gemm2<128, false, 1>(tmA, tmB, tmC, tmR, p, stream);
+      default: return launch_gemm2<160, false, 1>(tmA, tmB, tmC, tmR, p, stream);
     }
   }
   switch (bn) {

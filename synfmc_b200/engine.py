@@ -182,7 +182,7 @@ class AttnPlan:
         self.w_head_major = None
         if FUSED_TEMPORAL and fused_temporal and not self.is_cross and C == 320 and heads == 8:
             blocks = [w.view(heads, d, C) for w in (folded("to_q"), folded("to_k"), wv)]
-            blocks.append(torch.zeros(heads, 128 - 3 * d, C))
+            blocks.append(blocks[0].new_zeros(heads, 128 - 3 * d, C))
             self.w_head_major = _dev_bf16(torch.cat(blocks, dim=1).reshape(heads * 128, C), device)
 
 
