@@ -353,6 +353,29 @@ __device__ __forceinline__ float gelu_fast(float g) {
   return 0.5f * g * one_plus_erf;
 }
 
+// Two GEGLU outputs at once, a * gelu_erf(g), on packed fp32 pairs (same polynomial as gelu_fast): the level-0 GEGLU
+// GEMM (K = 320) is bound by its epilogue's issue slots, and the pair form needs ~12 instructions per output instead
+// of ~20.  1 + erf(g / sqrt 2) = 1 + copysign(1 - r, g) with r = (1 / p(|g| / sqrt 2))^16.
+__device__ __forceinline__ void geglu_pair(float a0, float a1, float g0, float g1, float& o0, float& o1) {
+  const uint64_t g2 = f2_pack(g0, g1);
+  const uint64_t x2 = f2_mul(g2, f2_pack(0.70710678118654752440f, 0.70710678118654752440f)) & 0x7FFFFFFF7FFFFFFFull;
+  uint64_t p2 = f2_fma(x2, f2_pack(0.0000430638f, 0.0000430638f), f2_pack(0.0002765672f, 0.0002765672f));
+  p2 = f2_fma(x2, p2, f2_pack(0.0001520143f, 0.0001520143f));
+  p2 = f2_fma(x2, p2, f2_pack(0.0092705272f, 0.0092705272f));
+  p2 = f2_fma(x2, p2, f2_pack(0.0422820123f, 0.0422820123f));
+  p2 = f2_fma(x2, p2, f2_pack(0.0705230784f, 0.0705230784f));
+  p2 = f2_fma(x2, p2, f2_pack(1.0f, 1.0f));
+  float p0, p1;
+  f2_unpack(p2, p0, p1);
+  uint64_t r2 = f2_pack(rcp_fast(p0), rcp_fast(p1));
+  r2 = f2_mul(r2, r2); r2 = f2_mul(r2, r2); r2 = f2_mul(r2, r2); r2 = f2_mul(r2, r2);   // 1 - erf(|x|)
+  const uint64_t s2 = f2_fma(r2, f2_pack(-1.0f, -1.0f), f2_pack(1.0f, 1.0f));            // erf(|x|) >= 0
+  const uint64_t e2 = s2 | (g2 & 0x8000000080000000ull);                                 // erf(x)
+  const uint64_t h2 = f2_fma(e2, f2_pack(0.5f, 0.5f), f2_pack(0.5f, 0.5f));              // (1 + erf) / 2
+  const uint64_t o2 = f2_mul(f2_mul(f2_pack(a0, a1), g2), h2);
+  f2_unpack(o2, o0, o1);
+}
+
 __device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t (&v)[4]) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
 }
@@ -609,11 +632,10 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               for (int j = 0; j < 32; ++j) bv[j] = 0.f;
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float a = __uint_as_float(rr[j]) + bv[j];
-              const float g = __uint_as_float(rr[16 + j]) + bv[16 + j];
-              v[hblk * 16 + j] = a * gelu_fast(g);
-            }
+            for (int j = 0; j < 16; j += 2)
+              geglu_pair(__uint_as_float(rr[j]) + bv[j], __uint_as_float(rr[j + 1]) + bv[j + 1],
+                         __uint_as_float(rr[16 + j]) + bv[16 + j], __uint_as_float(rr[17 + j]) + bv[17 + j],
+                         v[hblk * 16 + j], v[hblk * 16 + j + 1]);
           }
         }
         const uint32_t sub = buf + static_cast<uint32_t>(s * SUB_BYTES);
