@@ -179,13 +179,16 @@ def summarise_trace(trace, steps, peaks):
         shapes = {}
         for name, args, e0, e1 in trace:
             key = (name,) + tuple(a for a in args if isinstance(a, int) and abs(a) < (1 << 31))
-            rec = shapes.setdefault(key, [0, 0.0, 0.0])
+            rec = shapes.setdefault(key, [0, 0.0, 0.0, []])
             rec[0] += 1
             rec[1] += e0.elapsed_time(e1)
             rec[2] += flops_of(name, args)[0]
+            rec[3].append(e0.elapsed_time(e1))
         with open(dump, "w") as fh:
-            for key, (n, ms, fl) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
-                fh.write(f"{ms / steps:9.3f} ms/step  {n / steps:6.1f} calls/step  {fl / (ms * 1e-3) / 1e12 if ms else 0:8.1f} TF/s  {key}\n")
+            for key, (n, ms, fl, each) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+                each.sort()
+                fh.write(f"{ms / steps:9.3f} ms/step  {n / steps:6.1f} calls/step  {fl / (ms * 1e-3) / 1e12 if ms else 0:8.1f} TF/s  "
+                         f"[us min {each[0] * 1e3:.1f} med {each[len(each) // 2] * 1e3:.1f} max {each[-1] * 1e3:.1f}]  {key}\n")
     table = {}
     for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
         row = {"launches_per_step": round(a["launches"] / steps, 1), "ms_per_step": round(a["ms"] / steps, 3),

@@ -21,7 +21,8 @@ def gemm_case(M, N, K, res=False, geglu=False):
     a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
     bias = rnd(N, dtype=torch.float32)
     r = rnd(M, N // 2 if geglu else N) if res else None
-    return lambda: ops.gemm(a, w, bias=bias, residual=r, geglu=geglu)
+    tile_n = int(os.environ.get("FMC_PROBE_TILE_N", "0"))
+    return lambda: ops.gemm(a, w, bias=bias, residual=r, geglu=geglu, tile_n=tile_n)
 
 
 def spatial_case(images, d, n):

@@ -318,10 +318,10 @@ constexpr int GEMM2_THREADS = 384;
 constexpr int SUB_COLS = 32;                      // output columns per staging sub-tile
 constexpr int SUB_BYTES = GEMM_BM * SUB_COLS * 2;  // 8 KB
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, int CL = 1>
 struct Gemm2Cfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / CL) * GEMM_BK * 2;  // CL = 2: each CTA of the pair stages half of the W slice
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
   static constexpr int NSUB = OUT_COLS / SUB_COLS;
@@ -384,17 +384,21 @@ __device__ __forceinline__ void epi_bar_arrive_warp(uint64_t* bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
-// CL = 2: the kernel runs as clusters of two CTAs that work on vertically adjacent output tiles (m_blk = 2 i + rank,
-// same n_blk).  They need the same W k-slices at the same time, so each CTA fetches HALF of every W slice and
-// multicasts it into both CTAs' stages: L2 -> SM traffic per tile drops from (128 + BN) to (128 + BN / 2) rows per
-// k-block.  These GEMMs sit on the L2 -> SM delivery cap (14.6 TB/s measured: 128 x 256 tiles top out at 1245 TFLOP/s,
-// 128 x 160 at 1040), not on the tensor pipe.  A stage is handed back only when BOTH CTAs' MMAs have read it (commit
-// multicast to both empty barriers, count 2).
+// CL = 2: CTA-pair MMA (tcgen05 cta_group::2).  The two CTAs of a cluster own vertically adjacent output tiles
+// (m_blk = 2 i + rank, same n_blk) and execute ONE 256 x BN MMA stream issued by the even CTA: every CTA stages its own
+// 128 A rows and only HALF of the W slice (BN / 2 rows), the tensor cores of both SMs read the two halves.  Per SM and
+// k-block that is 128 + BN / 2 staged rows instead of 128 + BN: with both operands in shared memory a 128 x 256 tile
+// needs ~190 B/clk of smem traffic at the full MMA rate against ~128 B/clk available, which is what caps the 1-CTA
+// kernel near 57 % of the tensor peak on the K >= 1280 shapes.
+//   full barrier   : the even CTA's; it expects the bytes of all four loads (both CTAs' TMA signal it)
+//   empty barrier  : one per CTA, released by the issuing thread's commit, multicast to both CTAs
+//   acc_full       : commit multicast to both CTAs (each epilogue drains its own 128 rows from its own TMEM)
+//   acc_empty      : the even CTA's, 16 arrivals (the odd CTA's epilogue warps arrive remotely)
 template <int BN, bool GEGLU, int CL>
 __global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmParams p) {
-  using Cfg = Gemm2Cfg<BN, GEGLU>;
+  using Cfg = Gemm2Cfg<BN, GEGLU, CL>;
   static_assert(CL == 1 || CL == 2, "cluster size");
   static_assert(((BN / 2) * 128) % 1024 == 0, "half W slices must stay 1024-byte aligned");
   constexpr int STAGES = Cfg::STAGES;
@@ -433,20 +437,23 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);
+      mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full_bar[a], 1);
-      mbar_init(&acc_empty_bar[a], 8);
+      mbar_init(&acc_empty_bar[a], 8 * CL);
       mbar_init(&buf_ready_bar[a], 1);
       mbar_init(&out_ready_bar[a], 8);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_slot, Cfg::TMEM_COLS);
+  if (warp == 2) {
+    if constexpr (CL == 2) tmem_alloc_2sm(&tmem_base_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(&tmem_base_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before_sync();
   __syncthreads();
-  if constexpr (CL == 2) cluster_sync_all();  // the peer's barriers are initialised before anything is sent to them
+  if constexpr (CL == 2) cluster_sync_all();  // the peer's barriers / TMEM exist before anything is sent to them
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -460,14 +467,17 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int n_blk = tile % p.tiles_n;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          tma_load_2d_a(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
           if constexpr (CL == 2) {
-            // my half of the W slice, into both CTAs (tmB's box is BN / 2 rows)
-            tma_load_2d_mc(sa + Cfg::A_BYTES + rank * (BN / 2) * 128, &tmB, &full_bar[stage], kb * GEMM_BK,
-                           n_blk * BN + rank * (BN / 2), static_cast<uint16_t>(3));
+            // own A rows + own half of the W slice (tmB's box is BN / 2 rows) into own smem; the bytes of both CTAs
+            // are counted by the even CTA's full barrier
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_2sm(sa, &tmA, fb, kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, fb, kb * GEMM_BK, n_blk * BN + rank * (BN / 2));
           } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d_a(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
             tma_load_2d_a(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
           }
           if (++stage == STAGES) {
@@ -479,8 +489,9 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+    // CL = 2: only the even CTA of the pair issues (M = 256); its commits reach both CTAs.
+    if ((CL == 1 || rank == 0) && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CL, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -497,17 +508,22 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const uint64_t db = umma_desc_k_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                         (kb > 0 || k > 0) ? 1u : 0u);
+            if constexpr (CL == 2)
+              umma_bf16_ss_2sm(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                               (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
           }
-          if constexpr (CL == 2) umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>(3));
+          if constexpr (CL == 2) umma_commit_2sm(&empty_bar[stage], static_cast<uint16_t>(3));
           else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&acc_full_bar[acc]);
+        if constexpr (CL == 2) umma_commit_2sm(&acc_full_bar[acc], static_cast<uint16_t>(3));
+        else umma_commit(&acc_full_bar[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -657,24 +673,31 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       tc_fence_before_sync();
       fence_proxy_async_smem();  // staging writes -> visible to the TMA store
-      epi_bar_arrive_warp(&acc_empty_bar[b], lane);
+      if constexpr (CL == 2) {
+        // the accumulator pair is released to the issuing (even) CTA
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty_bar[b]), 0));
+      } else {
+        epi_bar_arrive_warp(&acc_empty_bar[b], lane);
+      }
       if (lane == 0) mbar_arrive(&out_ready_bar[b]);
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if constexpr (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
+  if constexpr (CL == 2) cluster_sync_all();  // no CTA leaves (or frees TMEM) while the pair's MMAs / arrivals are in flight
   if (warp == 2) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CL == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
 template <int BN, bool GEGLU, int CL>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                         GemmParams& p, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN, GEGLU>;
+  using Cfg = Gemm2Cfg<BN, GEGLU, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     FMC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tma_kernel<BN, GEGLU, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -750,7 +773,7 @@ extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long l
   if (tma_epilogue) {
     if (geglu) {
       if (bn != 128 && bn != 256) bn = (N % 256 == 0 || N > 1024) ? 256 : 128;
-    } else if (bn != 64 && bn != 128 && bn != 160) {
+    } else if (bn != 64 && bn != 128 && bn != 160 && bn != 256) {
       bn = N <= 64 ? 64 : (N <= 128 ? 128 : 160);
     }
   } else {
@@ -758,11 +781,25 @@ extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long l
     FMC_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, FMC_ERR_SHAPE, "fmc_gemm_bf16: unsupported tile_n %d", bn);
   }
 
-  // two-CTA clusters sharing the W stream by TMA multicast (see gemm_bf16_tma_kernel).  Measured on all twelve
-  // level 0-2 shapes of the step: within +-3 % of the plain kernel (profiles/r01_gemm_cluster_multicast.txt) -- L2
-  // already merges the CTAs' identical requests -- so it is OFF unless FMC_GEMM_CLUSTER=1.
-  static const bool cluster_allowed = getenv("FMC_GEMM_CLUSTER") != nullptr;
-  const bool use_cluster = tma_epilogue && cluster_allowed && M > GEMM_BM;
+  // CTA-pair MMA (cta_group::2, see gemm_bf16_tma_kernel); FMC_GEMM_1CTA=1 forces the single-CTA kernel (A/B runs).
+  // (An earlier variant that only multicast the W slices to two independent CTAs measured within +-3 % of the plain
+  // kernel on all twelve level 0-2 shapes: profiles/r01_gemm_cluster_multicast.txt.)
+  // Measured per shape (profiles/r01_gemm_2cta.txt): the pair wins 5-15 % from K = 640 up, and loses 7-23 % at K = 320,
+  // where a tile is only 20 MMAs and the cross-CTA hand-offs per tile dominate.
+  static const bool cluster_allowed = getenv("FMC_GEMM_1CTA") == nullptr;
+  static const bool cluster_forced = getenv("FMC_GEMM_2CTA") != nullptr;
+  const bool use_cluster = tma_epilogue && cluster_allowed && M > GEMM_BM &&
+                           (cluster_forced || K >= 1280 || (K >= 640 && N > 640));
+  if (tma_epilogue && !geglu && tile_n == 0 && N > 128) {
+    // wave quantisation: with few row tiles (levels 2-3) 128-wide tiles can need fewer / cheaper rounds than 160-wide
+    const int cl = use_cluster ? 2 : 1;
+    const int slots = device_sm_count() / cl;
+    const int rows = ceil_div(ceil_div(M, GEMM_BM), cl);
+    const long long cost160 = static_cast<long long>(ceil_div(rows * ceil_div(N, 160), slots)) * 160;
+    const long long cost128 = static_cast<long long>(ceil_div(rows * ceil_div(N, 128), slots)) * 128;
+    bn = (cost128 * 10 < cost160 * 9) ? 128 : 160;
+  }
+  if (tma_epilogue && !geglu && bn == 256 && !use_cluster) bn = 160;  // 128 x 256 bf16 staging only fits the pair kernel
 
   CUtensorMap tmA, tmB;
   {
@@ -811,6 +848,7 @@ extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long l
       switch (bn) {
         case 64: return launch_gemm2<64, false, 2>(tmA, tmB, tmC, tmR, p, stream);
         case 128: return launch_gemm2<128, false, 2>(tmA, tmB, tmC, tmR, p, stream);
+        case 256: return launch_gemm2<256, false, 2>(tmA, tmB, tmC, tmR, p, stream);
         default: return launch_gemm2<160, false, 2>(tmA, tmB, tmC, tmR, p, stream);
       }
     }
