@@ -134,6 +134,9 @@ def flops_of(name, args):
     if name == "fmc_gemm_bf16":
         M, N, K = args[6], args[7], args[8]
         return 2.0 * M * N * K, 0.0
+    if name == "fmc_conv3x3_bf16":
+        images, Hh, Ww, cin, cout, stride = args[5], args[6], args[7], args[8], args[9], args[10]
+        return 2.0 * images * (Hh // stride) * (Ww // stride) * cout * 9 * cin, 0.0
     if name == "cudnn_conv2d":
         M, N, K = args
         return 2.0 * M * N * K, 0.0
@@ -162,33 +165,39 @@ def flops_of(name, args):
 
 
 def summarise_trace(trace, steps, peaks):
+    """Per-kernel time from the CUDA-event pairs of the traced pass.  Calls are grouped by (entry point, shape); a
+    group contributes `median duration x number of calls`, so a stray host stall between a start event and its kernel
+    (seen once in a while on the kernel-by-kernel launch path) does not leak into the kernel's figure."""
     import torch
     torch.cuda.synchronize()
-    agg = {}
+    groups = {}
     for name, args, e0, e1 in trace:
-        ms = e0.elapsed_time(e1)
+        key = (name,) + tuple(a for a in args if isinstance(a, int) and abs(a) < (1 << 31))
+        g = groups.setdefault(key, {"name": name, "each": [], "flops": 0.0, "bytes": 0.0})
+        g["each"].append(e0.elapsed_time(e1))
         fl, by = flops_of(name, args)
-        a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
-        a["launches"] += 1
-        a["ms"] += ms
-        a["flops"] += fl
-        a["bytes"] += by
+        g["flops"] += fl
+        g["bytes"] += by
+    agg = {}
+    for key, g in groups.items():
+        g["each"].sort()
+        n = len(g["each"])
+        g["median"] = g["each"][n // 2]
+        g["ms"] = g["median"] * n
+        a = agg.setdefault(g["name"], {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        a["launches"] += n
+        a["ms"] += g["ms"]
+        a["flops"] += g["flops"]
+        a["bytes"] += g["bytes"]
     total = sum(a["ms"] for a in agg.values()) or 1.0
     dump = os.environ.get("FMC_BENCH_TRACE")
     if dump:  # per-shape breakdown for kernel work (not part of the JSON line)
-        shapes = {}
-        for name, args, e0, e1 in trace:
-            key = (name,) + tuple(a for a in args if isinstance(a, int) and abs(a) < (1 << 31))
-            rec = shapes.setdefault(key, [0, 0.0, 0.0, []])
-            rec[0] += 1
-            rec[1] += e0.elapsed_time(e1)
-            rec[2] += flops_of(name, args)[0]
-            rec[3].append(e0.elapsed_time(e1))
         with open(dump, "w") as fh:
-            for key, (n, ms, fl, each) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
-                each.sort()
-                fh.write(f"{ms / steps:9.3f} ms/step  {n / steps:6.1f} calls/step  {fl / (ms * 1e-3) / 1e12 if ms else 0:8.1f} TF/s  "
-                         f"[us min {each[0] * 1e3:.1f} med {each[len(each) // 2] * 1e3:.1f} max {each[-1] * 1e3:.1f}]  {key}\n")
+            for key, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
+                n, ms, each = len(g["each"]), g["ms"], g["each"]
+                fh.write(f"{ms / steps:9.3f} ms/step  {n / steps:6.1f} calls/step  "
+                         f"{g['flops'] / (ms * 1e-3) / 1e12 if ms else 0:8.1f} TF/s  "
+                         f"[us min {each[0] * 1e3:.1f} med {g['median'] * 1e3:.1f} max {each[-1] * 1e3:.1f}]  {key}\n")
     table = {}
     for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
         row = {"launches_per_step": round(a["launches"] / steps, 1), "ms_per_step": round(a["ms"] / steps, 3),

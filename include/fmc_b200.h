@@ -41,6 +41,18 @@ int fmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, vo
                   int K, const float* bias, const void* residual, long long ldr, const float* rowbias,
                   int rows_per_group, long long ldrb, int flags, int tile_n, void* stream);
 
+/* 3x3 convolution, padding 1, stride 1 or 2, on channels-last bf16 images as an implicit GEMM on the same tcgen05
+ * kernel as fmc_gemm_bf16 (CTA-pair MMA): Out[n, oh, ow, :] = sum_{ky, kx, c} X[n, oh*s + ky - 1, ow*s + kx - 1, c] *
+ * W[:, ky, kx, c] (+ bias[Cout]) (+ residual[n, oh, ow, :]).  X [images, H, Wd, Cin], Out / residual
+ * [images, H/s, Wd/s, Cout] contiguous; W bf16 [Cout, 3, 3, Cin] (= torch conv weight in channels_last memory format).
+ * The shifted input windows are fetched by 4-D TMA boxes whose out-of-image part is zero-filled: no im2col buffer.
+ * Needs Cin % 64 == 0, Cout % 32 == 0 and an output width that divides 128; anything else is an error.
+ * Replaces the per-frame convolutions of diffusers ResnetBlock2D / Downsample2D / Upsample2D and InflatedConv3d as
+ * called at fmc/models/unet_blocks.py:402-404,420-422,686-688,701-704, fmc/models/resnet.py:16-24, and the 3x3
+ * convolutions of the CameraEncoder / ObjectEncoder (fmc/models/pose_adaptor.py:102-135, fmc/adapter.py:64-98). */
+int fmc_conv3x3_bf16(const void* X, const void* W, void* Out, const float* bias, const void* residual, int images,
+                     int H, int Wd, int Cin, int Cout, int stride, int tile_n, void* stream);
+
 /* O[i] = softmax(Q[i] K[kv(i)]^T * scale) V[kv(i)] per head, flash-style on tcgen05 (scores never leave the SM).
  * Replaces head_to_batch_dim + get_attention_scores (baddbmm, softmax) + bmm + batch_to_head_dim of the spatial
  * processors: fmc/models/attention_processor.py:148-154 (LoRAAttnProcessor, attn1 self / attn2 text cross).

@@ -47,6 +47,16 @@ def temporal_fused_case(B, F, HW):
     return lambda: ops.temporal_qkv_attn(x, w, out, B, F, HW, 8, 40 ** -0.5)
 
 
+def conv_case(N, H, W, cin, cout, stride=1, cudnn=False):
+    x = rnd(N, H, W, cin)
+    w = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5)
+    if cudnn:
+        wc = w.contiguous(memory_format=torch.channels_last)
+        return lambda: ops.conv2d_cl(x, wc, None, stride=stride, padding=1)
+    w2d = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    return lambda: ops.conv3x3(x, w2d, stride=stride)
+
+
 def groupnorm_case(images, HW, C):
     x, g, b = rnd(images * HW, C), rnd(C, dtype=torch.float32), rnd(C, dtype=torch.float32)
     return lambda: ops.groupnorm(x, g, b, 1e-6, images, HW, silu=True)
@@ -70,6 +80,18 @@ CASES = {
     "gemm_l2_geglu": lambda: gemm_case(5120, 10240, 1280, geglu=True),
     "gemm_l2_ff2": lambda: gemm_case(5120, 1280, 5120, res=True),
     "gemm_l1_ff2": lambda: gemm_case(20480, 640, 2560, res=True),
+    "conv_l0": lambda: conv_case(32, 40, 64, 320, 320),
+    "conv_l0_cudnn": lambda: conv_case(32, 40, 64, 320, 320, cudnn=True),
+    "conv_l0b": lambda: conv_case(32, 40, 64, 640, 320),
+    "conv_l0b_cudnn": lambda: conv_case(32, 40, 64, 640, 320, cudnn=True),
+    "conv_l1": lambda: conv_case(32, 20, 32, 640, 640),
+    "conv_l1_cudnn": lambda: conv_case(32, 20, 32, 640, 640, cudnn=True),
+    "conv_l2": lambda: conv_case(32, 10, 16, 1280, 1280),
+    "conv_l2_cudnn": lambda: conv_case(32, 10, 16, 1280, 1280, cudnn=True),
+    "conv_l3": lambda: conv_case(32, 5, 8, 1280, 1280),
+    "conv_l3_cudnn": lambda: conv_case(32, 5, 8, 1280, 1280, cudnn=True),
+    "conv_down0": lambda: conv_case(32, 40, 64, 320, 320, stride=2),
+    "conv_down0_cudnn": lambda: conv_case(32, 40, 64, 320, 320, stride=2, cudnn=True),
     "spatial_l0": lambda: spatial_case(32, 40, 2560),
     "spatial_l1": lambda: spatial_case(32, 80, 640),
     "temporal_fused_l0": lambda: temporal_fused_case(2, 16, 2560),

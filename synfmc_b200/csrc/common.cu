@@ -51,6 +51,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, int swizzle_bytes) {
+  const uint32_t ones[5] = {1, 1, 1, 1, 1};
+  return make_tmap_bf16_ex(out, base, rank, dims, strides_bytes, box, ones, swizzle_bytes);
+}
+
+int make_tmap_bf16_ex(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, const uint32_t* estr_in, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   FMC_REQUIRE(fn != nullptr, FMC_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   FMC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, FMC_ERR_SHAPE, "TMA base %p not 16-byte aligned", base);
@@ -61,7 +67,7 @@ int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = estr_in[i];
     if (i > 0) {
       gstr[i - 1] = strides_bytes[i - 1];
       FMC_REQUIRE((gstr[i - 1] & 15) == 0, FMC_ERR_SHAPE, "TMA stride %llu not a multiple of 16 bytes",

@@ -60,6 +60,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, int swizzle_bytes);
 
+// same with per-dimension element (traversal) strides: box[i] elements are traversed, every estr[i]-th one is copied
+int make_tmap_bf16_ex(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, const uint32_t* estr, int swizzle_bytes);
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace fmc

@@ -35,6 +35,10 @@ struct GemmParams {
   long long ldrb;
   int flags;
   int tiles_m, tiles_n;
+  // implicit-GEMM convolution (CONV kernels): A rows are output pixels (n, oh, ow) of a channels-last image, K runs over
+  // (ky, kx, cin); the A operand of k-block kb is the input shifted by tap kb / cchunks, fetched row by row with 4-D
+  // TMA boxes whose out-of-image part is zero-filled (= the convolution's zero padding)
+  int conv_oh, conv_ow, conv_stride, conv_cchunks, conv_rows;  // conv_rows = 128 / OW output rows per tile
 };
 
 template <int BN>
@@ -394,7 +398,7 @@ __device__ __forceinline__ void epi_bar_arrive_warp(uint64_t* bar, int lane) {
 //   empty barrier  : one per CTA, released by the issuing thread's commit, multicast to both CTAs
 //   acc_full       : commit multicast to both CTAs (each epilogue drains its own 128 rows from its own TMEM)
 //   acc_empty      : the even CTA's, 16 arrivals (the odd CTA's epilogue warps arrive remotely)
-template <int BN, bool GEGLU, int CL>
+template <int BN, bool GEGLU, int CL, bool CONV = false>
 __global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmParams p) {
@@ -468,16 +472,36 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          // CONV: tap (dy, dx) and 64-channel chunk of this k-block
+          const int tap = CONV ? kb / p.conv_cchunks : 0;
+          const int c0 = CONV ? (kb - tap * p.conv_cchunks) * GEMM_BK : 0;
+          const int dy = tap / 3, dx = tap - dy * 3;
           if constexpr (CL == 2) {
             // own A rows + own half of the W slice (tmB's box is BN / 2 rows) into own smem; the bytes of both CTAs
             // are counted by the even CTA's full barrier
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_2sm(sa, &tmA, fb, kb * GEMM_BK, m_blk * GEMM_BM);
+            if constexpr (CONV) {
+              for (int j = 0; j < p.conv_rows; ++j) {
+                const int pr = m_blk * p.conv_rows + j;  // output row (n, oh) of the flattened image stack
+                const int n = pr / p.conv_oh, oh = pr - n * p.conv_oh;
+                tma_load_4d_2sm(sa + j * p.conv_ow * 128, &tmA, fb, c0, dx - 1, oh * p.conv_stride + dy - 1, n);
+              }
+            } else {
+              tma_load_2d_2sm(sa, &tmA, fb, kb * GEMM_BK, m_blk * GEMM_BM);
+            }
             tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, fb, kb * GEMM_BK, n_blk * BN + rank * (BN / 2));
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_2d_a(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+            if constexpr (CONV) {
+              for (int j = 0; j < p.conv_rows; ++j) {
+                const int pr = m_blk * p.conv_rows + j;
+                const int n = pr / p.conv_oh, oh = pr - n * p.conv_oh;
+                tma_load_4d_a(sa + j * p.conv_ow * 128, &tmA, &full_bar[stage], c0, dx - 1, oh * p.conv_stride + dy - 1, n);
+              }
+            } else {
+              tma_load_2d_a(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+            }
             tma_load_2d_a(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
           }
           if (++stage == STAGES) {
@@ -694,13 +718,13 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
-template <int BN, bool GEGLU, int CL>
+template <int BN, bool GEGLU, int CL, bool CONV = false>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                         GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN, GEGLU, CL>;
   static bool attr_set = false;
   if (!attr_set) {
-    FMC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tma_kernel<BN, GEGLU, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FMC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tma_kernel<BN, GEGLU, CL, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -721,7 +745,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
-  FMC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tma_kernel<BN, GEGLU, CL>, tmA, tmB, tmC, tmR, p));
+  FMC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tma_kernel<BN, GEGLU, CL, CONV>, tmA, tmB, tmC, tmR, p));
   return check_launch("gemm_bf16_tma_kernel");
 }
 
@@ -868,4 +892,83 @@ extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long l
     case 160: return launch_gemm<160>(tmA, tmB, p, stream);
     default: return launch_gemm<256>(tmA, tmB, p, stream);
   }
+}
+
+
+// 3x3 convolution (padding 1, stride 1 or 2) on channels-last bf16 images as an implicit GEMM on the same tcgen05 kernel:
+// out[n, oh, ow, :] = sum_{ky,kx,c} x[n, oh*s + ky - 1, ow*s + kx - 1, c] * w[:, ky, kx, c] (+ bias) (+ residual).
+extern "C" int fmc_conv3x3_bf16(const void* X, const void* W, void* Out, const float* bias, const void* residual,
+                                int images, int H, int Wd, int Cin, int Cout, int stride, int tile_n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FMC_REQUIRE(X && W && Out, FMC_ERR_ARG, "fmc_conv3x3_bf16: null operand");
+  FMC_REQUIRE(stride == 1 || stride == 2, FMC_ERR_SHAPE, "fmc_conv3x3_bf16: stride %d not in {1, 2}", stride);
+  FMC_REQUIRE(images > 0 && H > 0 && Wd > 0 && H % stride == 0 && Wd % stride == 0, FMC_ERR_SHAPE,
+              "fmc_conv3x3_bf16: image %d x %d x %d not divisible by the stride", images, H, Wd);
+  const int OH = H / stride, OW = Wd / stride;
+  FMC_REQUIRE(Cin % 64 == 0 && Cout % 32 == 0, FMC_ERR_SHAPE,
+              "fmc_conv3x3_bf16: Cin=%d must be a multiple of 64 and Cout=%d of 32", Cin, Cout);
+  FMC_REQUIRE(OW <= 128 && 128 % OW == 0 && OW >= 4, FMC_ERR_SHAPE,
+              "fmc_conv3x3_bf16: output width %d must divide 128 (a 128-pixel tile is 128 / OW whole output rows)", OW);
+  FMC_REQUIRE((reinterpret_cast<uintptr_t>(Out) & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, FMC_ERR_SHAPE,
+              "fmc_conv3x3_bf16: tensors must be 16-byte aligned");
+  const int M = images * OH * OW, N = Cout, K = 9 * Cin;
+
+  static const bool cluster_allowed = getenv("FMC_GEMM_1CTA") == nullptr;
+  const bool use_cluster = cluster_allowed && M > GEMM_BM;
+  int bn = tile_n;
+  if (bn != 128 && bn != 160) {
+    const int cl = use_cluster ? 2 : 1;
+    const int slots = device_sm_count() / cl;
+    const int rows = ceil_div(ceil_div(M, GEMM_BM), cl);
+    const long long cost160 = static_cast<long long>(ceil_div(rows * ceil_div(N, 160), slots)) * 160;
+    const long long cost128 = static_cast<long long>(ceil_div(rows * ceil_div(N, 128), slots)) * 128;
+    bn = (N <= 128 || cost128 * 10 < cost160 * 9) ? 128 : 160;
+  }
+
+  CUtensorMap tmA, tmB, tmC, tmR;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Wd), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(images)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Wd) * Cin * 2,
+                                 static_cast<uint64_t>(H) * Wd * Cin * 2};
+    const uint32_t box[4] = {GEMM_BK, static_cast<uint32_t>(OW * stride), 1, 1};
+    const uint32_t estr[4] = {1, static_cast<uint32_t>(stride), 1, 1};
+    int rc = make_tmap_bf16_ex(&tmA, X, 4, dims, strides, box, estr, 128);
+    if (rc != FMC_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    const uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(use_cluster ? bn / 2 : bn)};
+    int rc = make_tmap_bf16(&tmB, W, 2, dims, strides, box, true);
+    if (rc != FMC_OK) return rc;
+  }
+  const uint32_t obox[2] = {SUB_COLS, GEMM_BM};
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(N) * 2};
+    int rc = make_tmap_bf16_sw(&tmC, Out, 2, dims, strides, obox, 64);
+    if (rc != FMC_OK) return rc;
+    if (residual != nullptr) {
+      FMC_REQUIRE((reinterpret_cast<uintptr_t>(residual) & 15) == 0, FMC_ERR_SHAPE, "fmc_conv3x3_bf16: residual alignment");
+      rc = make_tmap_bf16_sw(&tmR, residual, 2, dims, strides, obox, 64);
+      if (rc != FMC_OK) return rc;
+    } else {
+      tmR = tmC;
+    }
+  }
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.C = Out; p.ldc = N;
+  p.bias = bias;
+  p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = N;
+  p.rowbias = nullptr; p.rows_per_group = 1; p.ldrb = 0;
+  p.flags = 0;
+  p.conv_oh = OH; p.conv_ow = OW; p.conv_stride = stride; p.conv_cchunks = Cin / GEMM_BK; p.conv_rows = GEMM_BM / OW;
+  if (use_cluster) {
+    if (bn == 128) return launch_gemm2<128, false, 2, true>(tmA, tmB, tmC, tmR, p, stream);
+    return launch_gemm2<160, false, 2, true>(tmA, tmB, tmC, tmR, p, stream);
+  }
+  if (bn == 128) return launch_gemm2<128, false, 1, true>(tmA, tmB, tmC, tmR, p, stream);
+  return launch_gemm2<160, false, 1, true>(tmA, tmB, tmC, tmR, p, stream);
 }

@@ -151,6 +151,14 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const void* m
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t smem_dst, const void* map, uint32_t bar_cluster_addr, int c0,
+                                                int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t rank) {
   uint32_t r;

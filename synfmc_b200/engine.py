@@ -16,6 +16,11 @@ import torch
 from . import ops
 
 BF16 = torch.bfloat16
+# 3x3 convolutions: "own" = fmc_conv3x3_bf16 (tcgen05 implicit GEMM) wherever its geometry allows, "cudnn" = torch /
+# cuDNN everywhere, "auto" (default) = the faster of the two as measured on B200 (profiles/r01_conv3x3.txt): cuDNN wins
+# the wide convolutions by 1.7-3x in round 1 (its kernels reuse the input window across the nine taps in shared
+# memory; ours re-fetches it per tap), ours wins the 4-channel conv_in by 3x.
+CONV3X3 = os.environ.get("FMC_CONV3X3", "auto")
 # debugging switch: FMC_UNFUSED_TEMPORAL=1 runs the temporal attention as GEMM + attention kernels instead of the fused one
 FUSED_TEMPORAL = not os.environ.get("FMC_UNFUSED_TEMPORAL")
 
@@ -197,23 +202,38 @@ class NormPlan:
 class ConvPlan:
     def __init__(self, conv, device, use_bias=True):
         """use_bias=False: the caller folds conv.bias into the next kernel (saves the separate bias pass)."""
-        self.w = conv.weight.detach().to(device=device, dtype=BF16).contiguous(memory_format=torch.channels_last)
-        self.b = conv.bias.detach().to(device=device, dtype=BF16) if (conv.bias is not None and use_bias) else None
         self.stride = conv.stride
         self.padding = conv.padding
         self.cin, self.cout = conv.in_channels, conv.out_channels
         self.ksize = conv.kernel_size[0]
+        bias = conv.bias if use_bias else None
         # 1x1 convolutions are plain GEMMs over channels-last rows
         self.linear = LinearPlan(conv.weight.detach().float().view(self.cout, self.cin), conv.bias, device) \
             if self.ksize == 1 and self.cin % 8 == 0 and self.cout % 16 == 0 else None
+        # 3x3, padding 1: implicit GEMM on tcgen05 (fmc_conv3x3_bf16); weight as [Cout, ky, kx, Cin] rows
+        self.fast3x3 = (self.ksize == 3 and tuple(conv.padding) == (1, 1) and conv.stride[0] == conv.stride[1]
+                        and conv.stride[0] in (1, 2) and self.cin % 64 == 0 and self.cout % 32 == 0)
+        self.w2d = _dev_bf16(conv.weight.detach().float().permute(0, 2, 3, 1).reshape(self.cout, -1), device) \
+            if self.fast3x3 else None
+        self.b32 = _dev_f32(bias, device)
+        # other geometries (odd widths, channel counts that are not multiples of 64 / 32): cuDNN through torch
+        self.w = conv.weight.detach().to(device=device, dtype=BF16).contiguous(memory_format=torch.channels_last)
+        self.b = bias.detach().to(device=device, dtype=BF16) if bias is not None else None
 
-    def __call__(self, x_img, relu=False):
-        """x_img [N, h, w, Cin] -> [N, oh, ow, Cout]."""
+    def __call__(self, x_img, relu=False, residual=None):
+        """x_img [N, h, w, Cin] -> [N, oh, ow, Cout] (+ residual, same shape, fused where the kernel allows)."""
+        N, h, w, _ = x_img.shape
         if self.linear is not None:
-            N, h, w, _ = x_img.shape
-            y = self.linear(x_img.reshape(-1, self.cin)).view(N, h, w, self.cout)
+            res2d = residual.reshape(-1, self.cout) if residual is not None else None
+            y = self.linear(x_img.reshape(-1, self.cin), residual=res2d).view(N, h, w, self.cout)
+        elif (self.fast3x3 and (CONV3X3 == "own" or (CONV3X3 == "auto" and self.cin <= 64))
+              and ops.conv3x3_supported(h, w, self.cin, self.cout, self.stride[0])):
+            y = ops.conv3x3(x_img, self.w2d, bias=self.b32, residual=residual, stride=self.stride[0])
         else:
             y = ops.conv2d_cl(x_img, self.w, self.b, stride=self.stride, padding=self.padding)
+            if residual is not None:
+                y2 = y.view(-1, self.cout)
+                ops.add(y2, residual.reshape(-1, self.cout), out=y2)
         if relu:
             y2 = y.view(-1, self.cout)
             ops.add(y2, relu=True, out=y2)

@@ -259,9 +259,10 @@ class UNet3DConditionModelPoseCond(UNet3DConditionModel):
             te = self.time_embedding
             self._plan = {
                 "device": device,
-                # 4 latent channels are padded to 8 so the channels-last rows are 16-byte multiples
-                "conv_in": pad_conv(self.conv_in, 8, self.conv_in.out_channels),
-                "conv_out": pad_conv(self.conv_out, self.conv_out.in_channels, 8),
+                # the 4 latent channels are zero-padded to 64 in / 32 out: one k-block / one output sub-tile of the tcgen05
+                # implicit-GEMM convolution (fmc_conv3x3_bf16), which then carries conv_in / conv_out as well
+                "conv_in": pad_conv(self.conv_in, 64, self.conv_in.out_channels),
+                "conv_out": pad_conv(self.conv_out, self.conv_out.in_channels, 32),
                 "t1": engine.LinearPlan(te.linear_1.weight.detach().float(), te.linear_1.bias.detach().float(), device),
                 "t2": engine.LinearPlan(te.linear_2.weight.detach().float(), te.linear_2.bias.detach().float(), device),
                 "norm_out": engine.NormPlan(self.conv_norm_out, device),
@@ -297,7 +298,7 @@ class UNet3DConditionModelPoseCond(UNet3DConditionModel):
         temb = engine.Temb(emb)
 
         text = engine.TextCtx.of(encoder_hidden_states, B, 1, device)
-        x = CL(ops.to_channels_last(sample, c_pad=8))
+        x = CL(ops.to_channels_last(sample, c_pad=64))
         y = p["conv_in"](x.images())
         x = CL(y.view(B, F, H, W, y.shape[-1]))
 

@@ -276,6 +276,31 @@ def cfg_ddim_step(eps_uncond, eps_cond, guidance_scale, latents, alpha_t, alpha_
     return (out, eps_out) if return_eps else out
 
 
+def conv3x3_supported(H, W, cin, cout, stride):
+    """Geometry handled by fmc_conv3x3_bf16 (everything the FMC U-Net / encoders use at the BASELINE shapes)."""
+    if stride not in (1, 2) or H % stride or W % stride or cin % 64 or cout % 32:
+        return False
+    ow = W // stride
+    return 4 <= ow <= 128 and 128 % ow == 0
+
+
+def conv3x3(x, w2d, bias=None, residual=None, stride=1, tile_n=0):
+    """x [N, H, W, Cin] bf16 contiguous, w2d [Cout, 9 * Cin] bf16 (ky, kx, cin order) -> [N, H/s, W/s, Cout]."""
+    _check_cuda(x, w2d)
+    assert x.dtype == BF16 and x.is_contiguous() and w2d.dtype == BF16 and w2d.is_contiguous()
+    N, H, W, cin = x.shape
+    cout = w2d.shape[0]
+    assert w2d.shape[1] == 9 * cin
+    out = torch.empty((N, H // stride, W // stride, cout), device=x.device, dtype=BF16)
+    if residual is not None:
+        assert residual.dtype == BF16 and residual.is_contiguous() and residual.shape == out.shape
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == cout and bias.is_contiguous()
+    _cabi.call("fmc_conv3x3_bf16", x.data_ptr(), w2d.data_ptr(), out.data_ptr(), _ptr(bias), _ptr(residual), N, H, W, cin,
+               cout, stride, tile_n, _stream())
+    return out
+
+
 def conv2d_cl(x, weight, bias, stride=1, padding=1):
     """3x3 / strided convolutions on channels-last bf16 [N, h, w, Cin] -> [N, oh, ow, Cout].
 

@@ -158,6 +158,27 @@ def test_temporal_qkv_attention_fused(ops, cuda_device, B, F, HW):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("N,H,W,cin,cout,stride,extras", [
+    (2, 16, 32, 64, 64, 1, False), (3, 10, 16, 128, 160, 1, True), (4, 5, 8, 64, 32, 1, True), (3, 8, 16, 64, 96, 1, False),
+    (2, 16, 32, 64, 96, 2, True), (2, 20, 32, 192, 320, 2, False), (1, 40, 64, 320, 320, 1, True), (16, 4, 4, 64, 64, 1, False)])
+def test_conv3x3_implicit_gemm(ops, cuda_device, N, H, W, cin, cout, stride, extras):
+    """fmc_conv3x3_bf16 (implicit GEMM, 4-D TMA windows with zero-filled borders) against torch conv2d in fp32 on the
+    same bf16 inputs: tiles that span several images (H = 10, 5, 4), odd tile counts, stride 2, fused bias + residual."""
+    assert ops.conv3x3_supported(H, W, cin, cout, stride)
+    x = randn(N, H, W, cin, seed=1)
+    w = randn(cout, cin, 3, 3, seed=2, scale=(9 * cin) ** -0.5)
+    bias = randn(cout, seed=3) if extras else None
+    res = randn(N, H // stride, W // stride, cout, seed=4) if extras else None
+    want = Fn.conv2d(x.permute(0, 3, 1, 2), w, bias, stride=stride, padding=1).permute(0, 2, 3, 1)
+    if res is not None:
+        want = want + res
+    w2d = bf(w.permute(0, 2, 3, 1).reshape(cout, 9 * cin)).to(cuda_device).contiguous()
+    got = ops.conv3x3(bf(x).to(cuda_device), w2d, bias=None if bias is None else bias.to(cuda_device),
+                      residual=None if res is None else bf(res).to(cuda_device), stride=stride)
+    assert got.shape == want.shape
+    assert rel(got, want) < BF16_TOL
+
+
 # ---------------------------------------------------------------- norms / elementwise
 @pytest.mark.parametrize("rows,C", [(1000, 320), (77, 640), (4096, 1280)])
 def test_layernorm_plain(ops, cuda_device, rows, C):
