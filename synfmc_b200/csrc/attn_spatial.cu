@@ -71,6 +71,7 @@ template <int D>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, FaParams p) {
+  pdl_wait();
   using Cfg = FaCfg<D>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int DK = Cfg::DK;
@@ -363,6 +364,7 @@ template <int D>
 __global__ void __launch_bounds__(FA2_THREADS, 1)
 spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, FaParams p) {
+  pdl_wait();
   using Cfg = Fa2Cfg<D>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int DK = Cfg::DK;
@@ -512,13 +514,23 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       uint32_t pk[16];
       if (valid >= FA_BN) {
         float mr = -INFINITY;  // raw (unscaled) maximum: c > 0, so max commutes with the scale
+        // scale-and-shift and the row sum run on packed fp32 pairs (fma / add .f32x2): two fewer issue slots per pair
+        const uint64_t c2 = f2_pack(c, c), nm2 = f2_pack(-m, -m);
+        uint64_t ls2 = f2_pack(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const float v0 = __uint_as_float(v[i]), v1 = __uint_as_float(v[i + 1]);
           mr = fmaxf(mr, fmaxf(v0, v1));
-          const float p0 = fast_exp2(fmaf(v0, c, -m)), p1 = fast_exp2(fmaf(v1, c, -m));
-          lsum += p0 + p1;
+          float x0, x1;
+          f2_unpack(f2_fma(f2_pack(v0, v1), c2, nm2), x0, x1);
+          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+          ls2 = f2_add(ls2, f2_pack(p0, p1));
           pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        {
+          float la, lb;
+          f2_unpack(ls2, la, lb);
+          lsum += la + lb;
         }
         mx = fmaxf(mx, mr * c);
       } else {
@@ -674,7 +686,7 @@ static int launch_fa2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
   }
   const int items = p.images * p.heads * ((p.nq + 2 * FA_BM - 1) / (2 * FA_BM));
   const int grid = items < device_sm_count() ? items : device_sm_count();
-  spatial_attn2_kernel<D><<<grid, FA2_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  launch_k(spatial_attn2_kernel<D>, dim3(grid), dim3(FA2_THREADS), Cfg::SMEM_BYTES, stream, tmQ, tmK, tmV, p);
   return check_launch("spatial_attn2_kernel");
 }
 
@@ -689,7 +701,7 @@ static int launch_fa(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUten
   }
   const int items = p.images * p.heads * p.q_blocks;
   const int grid = items < device_sm_count() ? items : device_sm_count();
-  spatial_attn_kernel<D><<<grid, FA_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  launch_k(spatial_attn_kernel<D>, dim3(grid), dim3(FA_THREADS), Cfg::SMEM_BYTES, stream, tmQ, tmK, tmV, p);
   return check_launch("spatial_attn_kernel");
 }
 

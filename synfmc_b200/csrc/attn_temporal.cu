@@ -54,6 +54,7 @@ __device__ __forceinline__ float ta_exp2(float x) {
 template <int D>
 __global__ void __launch_bounds__(TA_THREADS, 1)
 temporal_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, TaParams p) {
+  pdl_wait();
   using Cfg = TaCfg<D>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int DK = Cfg::DK;
@@ -282,7 +283,7 @@ static int launch_ta(const CUtensorMap& tm, const TaParams& p, cudaStream_t stre
   }
   const int items = p.B * p.tiles_per_b * p.heads;
   const int grid = items < device_sm_count() ? items : device_sm_count();
-  temporal_attn_kernel<D><<<grid, TA_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, p);
+  launch_k(temporal_attn_kernel<D>, dim3(grid), dim3(TA_THREADS), Cfg::SMEM_BYTES, stream, tm, p);
   return check_launch("temporal_attn_kernel");
 }
 

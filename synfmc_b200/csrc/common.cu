@@ -1,6 +1,7 @@
 #include "common.cuh"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -13,6 +14,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FMC_PDL");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
 }
 
 int device_sm_count() {

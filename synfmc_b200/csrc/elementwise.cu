@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256)
 add_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const __nv_bfloat16* __restrict__ b, long long ldb,
            const float* __restrict__ rowbias, int rows_per_group, long long ldrb, __nv_bfloat16* __restrict__ out,
            long long ldo, long long rows, int C, int relu) {
+  pdl_wait();
   const int nvec = C >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= rows * nvec) return;
@@ -53,6 +54,7 @@ add_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const __nv_bfloat
 __global__ void __launch_bounds__(256)
 resize_nearest_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int h, int w, int oh,
                       int ow, int C, float sh, float sw) {
+  pdl_wait();
   const int nvec = C >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(N) * oh * ow * nvec;
@@ -72,6 +74,7 @@ resize_nearest_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __rest
 // 2x2 average pooling (AvgPool2d(2), floor) of [N, h, w, C].
 __global__ void __launch_bounds__(256)
 avgpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int h, int w, int C) {
+  pdl_wait();
   const int oh = h >> 1, ow = w >> 1, nvec = C >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(N) * oh * ow * nvec;
@@ -102,6 +105,7 @@ avgpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 __global__ void __launch_bounds__(256)
 copy2d_kernel(const __nv_bfloat16* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd,
               long long rows, int cols) {
+  pdl_wait();
   const int nvec = cols >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= rows * nvec) return;
@@ -114,6 +118,7 @@ copy2d_kernel(const __nv_bfloat16* __restrict__ src, long long lds, __nv_bfloat1
 __global__ void __launch_bounds__(256)
 ncfhw_to_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int F, long long HW,
                    int Cpad) {
+  pdl_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * F * HW * Cpad;
   if (idx >= total) return;
@@ -131,6 +136,7 @@ ncfhw_to_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
 __global__ void __launch_bounds__(256)
 cl_to_ncfhw_kernel(const __nv_bfloat16* __restrict__ x, long long ldc, float* __restrict__ out, int B, int C, int F,
                    long long HW) {
+  pdl_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * C * F * HW;
   if (idx >= total) return;
@@ -146,6 +152,7 @@ cl_to_ncfhw_kernel(const __nv_bfloat16* __restrict__ x, long long ldc, float* __
 // fp32 -> bf16 with optional SiLU (time-embedding activations feeding the projection GEMMs).
 __global__ void __launch_bounds__(256)
 cast_act_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n, int silu) {
+  pdl_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= n) return;
   float v = x[idx];
@@ -155,6 +162,7 @@ cast_act_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, lo
 
 // diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): out[b] = [cos(t e_i) | sin(t e_i)], e_i = 1e4^(-i/half).
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int B, int dim) {
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (idx >= B * half) return;
@@ -195,6 +203,7 @@ __device__ __forceinline__ void plucker_pixel(const float* __restrict__ K, const
 __global__ void __launch_bounds__(256)
 plucker_plain_kernel(const float* __restrict__ K, const float* __restrict__ c2w, float* __restrict__ out, int BF, int H,
                      int W) {
+  pdl_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(BF) * H * W;
   if (idx >= total) return;
@@ -212,6 +221,7 @@ plucker_plain_kernel(const float* __restrict__ K, const float* __restrict__ c2w,
 __global__ void __launch_bounds__(256)
 plucker_unshuffle_kernel(const float* __restrict__ K, const float* __restrict__ c2w, __nv_bfloat16* __restrict__ out,
                          int BF, int H, int W) {
+  pdl_wait();
   const int h8 = H >> 3, w8 = W >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(BF) * h8 * w8 * 8;  // x 8 dy; the 6 comps are produced together
@@ -270,6 +280,7 @@ __device__ __forceinline__ void traj_pixel(const float* __restrict__ info, const
 __global__ void __launch_bounds__(256)
 traj_plain_kernel(const float* __restrict__ info, const float* __restrict__ masks, float* __restrict__ feat,
                   float* __restrict__ mask_out, int BF, int n_obj, int H, int W) {
+  pdl_wait();
   const long long HW = static_cast<long long>(H) * W;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= BF * HW) return;
@@ -285,6 +296,7 @@ traj_plain_kernel(const float* __restrict__ info, const float* __restrict__ mask
 __global__ void __launch_bounds__(256)
 traj_unshuffle_kernel(const float* __restrict__ info, const float* __restrict__ masks, __nv_bfloat16* __restrict__ feat,
                       float* __restrict__ mask_out, int BF, int n_obj, int H, int W) {
+  pdl_wait();
   const int h8 = H >> 3, w8 = W >> 3;
   const long long HW = static_cast<long long>(H) * W;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -321,6 +333,7 @@ traj_unshuffle_kernel(const float* __restrict__ info, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 mask_modulate_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mask, const int* __restrict__ ry,
                      const int* __restrict__ rx, __nv_bfloat16* __restrict__ out, int N, int h, int w, int C, int H, int W) {
+  pdl_wait();
   const int nvec = C >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(N) * h * w * nvec;
@@ -347,6 +360,7 @@ __global__ void __launch_bounds__(256)
 cfg_ddim_kernel(const float* __restrict__ eps_u, const float* __restrict__ eps_c, float guidance,
                 const float* __restrict__ x, float* __restrict__ x_out, float* __restrict__ eps_out, float sqrt_a_t,
                 float sqrt_1m_a_t, float sqrt_a_prev, float sqrt_1m_a_prev, long long n) {
+  pdl_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= n) return;
   const float eu = eps_u[idx];
@@ -370,7 +384,7 @@ extern "C" int fmc_add_bf16(const void* a, long long lda, const void* b, long lo
               "fmc_add_bf16: C and strides must be multiples of 8");
   FMC_REQUIRE(rowbias == nullptr || rows_per_group > 0, FMC_ERR_ARG, "fmc_add_bf16: rows_per_group must be positive");
   if (rows == 0) return FMC_OK;
-  add_kernel<<<blocks_for(rows * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(add_kernel, dim3(blocks_for(rows * (C / 8))), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(a), lda, static_cast<const __nv_bfloat16*>(b), ldb, rowbias,
       rows_per_group > 0 ? rows_per_group : 1, ldrb, static_cast<__nv_bfloat16*>(out), ldo, rows, C, relu);
   return check_launch("add_kernel");
@@ -382,7 +396,7 @@ extern "C" int fmc_resize_nearest_bf16(const void* x, void* out, int N, int h, i
   FMC_REQUIRE(C % 8 == 0, FMC_ERR_SHAPE, "fmc_resize_nearest_bf16: C must be a multiple of 8");
   const long long total = static_cast<long long>(N) * oh * ow * (C / 8);
   if (total == 0) return FMC_OK;
-  resize_nearest_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(resize_nearest_kernel, dim3(blocks_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, h, w, oh, ow, C,
       static_cast<float>(h) / oh, static_cast<float>(w) / ow);
   return check_launch("resize_nearest_kernel");
@@ -393,7 +407,7 @@ extern "C" int fmc_avgpool2_bf16(const void* x, void* out, int N, int h, int w, 
   FMC_REQUIRE(C % 8 == 0, FMC_ERR_SHAPE, "fmc_avgpool2_bf16: C must be a multiple of 8");
   const long long total = static_cast<long long>(N) * (h / 2) * (w / 2) * (C / 8);
   if (total == 0) return FMC_OK;
-  avgpool2_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(avgpool2_kernel, dim3(blocks_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, h, w, C);
   return check_launch("avgpool2_kernel");
 }
@@ -403,7 +417,7 @@ extern "C" int fmc_copy2d_bf16(const void* src, long long lds, void* dst, long l
   FMC_REQUIRE(src && dst, FMC_ERR_ARG, "fmc_copy2d_bf16: null operand");
   FMC_REQUIRE(cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, FMC_ERR_SHAPE, "fmc_copy2d_bf16: cols/strides must be multiples of 8");
   if (rows == 0 || cols == 0) return FMC_OK;
-  copy2d_kernel<<<blocks_for(rows * (cols / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(copy2d_kernel, dim3(blocks_for(rows * (cols / 8))), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(src), lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
   return check_launch("copy2d_kernel");
 }
@@ -413,7 +427,7 @@ extern "C" int fmc_ncfhw_f32_to_cl_bf16(const float* x, void* out, int B, int C,
   FMC_REQUIRE(x && out && Cpad >= C, FMC_ERR_ARG, "fmc_ncfhw_f32_to_cl_bf16: bad arguments");
   const long long total = static_cast<long long>(B) * F * HW * Cpad;
   if (total == 0) return FMC_OK;
-  ncfhw_to_cl_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(ncfhw_to_cl_kernel, dim3(blocks_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, static_cast<__nv_bfloat16*>(out), B, C, F, HW, Cpad);
   return check_launch("ncfhw_to_cl_kernel");
 }
@@ -423,7 +437,7 @@ extern "C" int fmc_cl_bf16_to_ncfhw_f32(const void* x, long long ldc, float* out
   FMC_REQUIRE(x && out && ldc >= C, FMC_ERR_ARG, "fmc_cl_bf16_to_ncfhw_f32: bad arguments");
   const long long total = static_cast<long long>(B) * C * F * HW;
   if (total == 0) return FMC_OK;
-  cl_to_ncfhw_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(cl_to_ncfhw_kernel, dim3(blocks_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), ldc, out, B, C, F, HW);
   return check_launch("cl_to_ncfhw_kernel");
 }
@@ -431,14 +445,14 @@ extern "C" int fmc_cl_bf16_to_ncfhw_f32(const void* x, long long ldc, float* out
 extern "C" int fmc_cast_act_bf16(const float* x, void* out, long long n, int silu, void* stream) {
   FMC_REQUIRE(x && out, FMC_ERR_ARG, "fmc_cast_act_bf16: null operand");
   if (n == 0) return FMC_OK;
-  cast_act_kernel<<<blocks_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(out), n, silu);
+  launch_k(cast_act_kernel, dim3(blocks_for(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, static_cast<__nv_bfloat16*>(out), n, silu);
   return check_launch("cast_act_kernel");
 }
 
 extern "C" int fmc_timestep_embedding_bf16(const float* t, void* out, int B, int dim, void* stream) {
   FMC_REQUIRE(t && out && dim % 2 == 0, FMC_ERR_ARG, "fmc_timestep_embedding_bf16: bad arguments");
   if (B == 0) return FMC_OK;
-  timestep_embedding_kernel<<<(B * dim / 2 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(timestep_embedding_kernel, dim3((B * dim / 2 + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), 
       t, static_cast<__nv_bfloat16*>(out), B, dim);
   return check_launch("timestep_embedding_kernel");
 }
@@ -447,7 +461,7 @@ extern "C" int fmc_plucker_f32(const float* K, const float* c2w, float* out, int
   FMC_REQUIRE(K && c2w && out, FMC_ERR_ARG, "fmc_plucker_f32: null operand");
   const long long total = static_cast<long long>(BF) * H * W;
   if (total == 0) return FMC_OK;
-  plucker_plain_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(K, c2w, out, BF, H, W);
+  launch_k(plucker_plain_kernel, dim3(blocks_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), K, c2w, out, BF, H, W);
   return check_launch("plucker_plain_kernel");
 }
 
@@ -457,7 +471,7 @@ extern "C" int fmc_plucker_unshuffle_bf16(const float* K, const float* c2w, void
   FMC_REQUIRE(H % 8 == 0 && W % 8 == 0, FMC_ERR_SHAPE, "fmc_plucker_unshuffle_bf16: H=%d W=%d must be multiples of 8", H, W);
   const long long total = static_cast<long long>(BF) * (H / 8) * (W / 8) * 8;
   if (total == 0) return FMC_OK;
-  plucker_unshuffle_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(plucker_unshuffle_kernel, dim3(blocks_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       K, c2w, static_cast<__nv_bfloat16*>(out), BF, H, W);
   return check_launch("plucker_unshuffle_kernel");
 }
@@ -467,7 +481,7 @@ extern "C" int fmc_traj_scatter_f32(const float* info, const float* masks, float
   FMC_REQUIRE(info && masks && feat && mask_out, FMC_ERR_ARG, "fmc_traj_scatter_f32: null operand");
   const long long total = static_cast<long long>(BF) * H * W;
   if (total == 0) return FMC_OK;
-  traj_plain_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(info, masks, feat, mask_out, BF, n_obj, H, W);
+  launch_k(traj_plain_kernel, dim3(blocks_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), info, masks, feat, mask_out, BF, n_obj, H, W);
   return check_launch("traj_plain_kernel");
 }
 
@@ -477,7 +491,7 @@ extern "C" int fmc_traj_scatter_unshuffle_bf16(const float* info, const float* m
   FMC_REQUIRE(H % 8 == 0 && W % 8 == 0, FMC_ERR_SHAPE, "fmc_traj_scatter_unshuffle_bf16: H=%d W=%d must be multiples of 8", H, W);
   const long long total = static_cast<long long>(BF) * (H / 8) * (W / 8) * 8;
   if (total == 0) return FMC_OK;
-  traj_unshuffle_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(traj_unshuffle_kernel, dim3(blocks_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       info, masks, static_cast<__nv_bfloat16*>(feat), mask_out, BF, n_obj, H, W);
   return check_launch("traj_unshuffle_kernel");
 }
@@ -488,7 +502,7 @@ extern "C" int fmc_mask_modulate_bf16(const void* x, const float* mask, const in
   FMC_REQUIRE(C % 8 == 0, FMC_ERR_SHAPE, "fmc_mask_modulate_bf16: C must be a multiple of 8");
   const long long total = static_cast<long long>(N) * h * w * (C / 8);
   if (total == 0) return FMC_OK;
-  mask_modulate_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(mask_modulate_kernel, dim3(blocks_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), mask, row_index, col_index, static_cast<__nv_bfloat16*>(out), N, h, w, C, H, W);
   return check_launch("mask_modulate_kernel");
 }
@@ -500,7 +514,7 @@ extern "C" int fmc_cfg_ddim_step_f32(const float* eps_uncond, const float* eps_c
   FMC_REQUIRE(alpha_t > 0.f && alpha_t <= 1.f && alpha_prev > 0.f && alpha_prev <= 1.f, FMC_ERR_ARG,
               "fmc_cfg_ddim_step_f32: alphas must be in (0, 1]");
   if (n == 0) return FMC_OK;
-  cfg_ddim_kernel<<<blocks_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(cfg_ddim_kernel, dim3(blocks_for(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       eps_uncond, eps_cond, guidance_scale, latents, latents_out, eps_out, sqrtf(alpha_t), sqrtf(1.f - alpha_t),
       sqrtf(alpha_prev), sqrtf(1.f - alpha_prev), n);
   return check_launch("cfg_ddim_kernel");

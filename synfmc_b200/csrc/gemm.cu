@@ -58,6 +58,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  pdl_wait();
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -402,6 +403,7 @@ template <int BN, bool GEGLU, int CL, bool CONV = false>
 __global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmParams p) {
+  pdl_wait();
   using Cfg = Gemm2Cfg<BN, GEGLU, CL>;
   static_assert(CL == 1 || CL == 2, "cluster size");
   static_assert(((BN / 2) * 128) % 1024 == 0, "half W slices must stay 1024-byte aligned");
@@ -738,13 +740,22 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   cfg.blockDim = dim3(GEMM2_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   FMC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tma_kernel<BN, GEGLU, CL, CONV>, tmA, tmB, tmC, tmR, p));
   return check_launch("gemm_bf16_tma_kernel");
 }
@@ -761,7 +772,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   p.tiles_n = ceil_div(p.N, BN);
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  launch_k(gemm_bf16_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p);
   return check_launch("gemm_bf16_kernel");
 }
 

@@ -25,6 +25,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out, long long ldo,
                  const float* __restrict__ pe, int F, int HW, const __nv_bfloat16* __restrict__ add, long long ldadd,
                  __nv_bfloat16* __restrict__ out2, long long ldo2, long long rows, int C) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row0 = (blockIdx.x * static_cast<long long>(LN_WARPS) + (threadIdx.x >> 5)) * R;
   if (row0 >= rows) return;
@@ -143,6 +144,7 @@ layernorm40_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const flo
                    const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out, long long ldo,
                    const float* __restrict__ pe, int F, int HW, const __nv_bfloat16* __restrict__ add, long long ldadd,
                    __nv_bfloat16* __restrict__ out2, long long ldo2, long long rows) {
+  pdl_wait();
   constexpr int C = 40 * LPR;
   constexpr int RPW = 32 / LPR;  // rows per warp pass
   constexpr int NV = 5;
@@ -251,12 +253,12 @@ static int launch_layernorm40(const void* x, long long ldx, const float* gamma, 
   const long long per_block = static_cast<long long>(LN_WARPS) * (32 / LPR) * R;
   const unsigned grid = static_cast<unsigned>((rows + per_block - 1) / per_block);
   if (out2 != nullptr) {
-    layernorm40_kernel<LPR, R, true><<<grid, LN_WARPS * 32, 0, stream>>>(
+    launch_k(layernorm40_kernel<LPR, R, true>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, 
         static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo, pe,
         F > 0 ? F : 1, HW > 0 ? HW : 1, static_cast<const __nv_bfloat16*>(add), ldadd,
         static_cast<__nv_bfloat16*>(out2), ldo2, rows);
   } else {
-    layernorm40_kernel<LPR, R, false><<<grid, LN_WARPS * 32, 0, stream>>>(
+    launch_k(layernorm40_kernel<LPR, R, false>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, 
         static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo, pe,
         F > 0 ? F : 1, HW > 0 ? HW : 1, nullptr, 0, nullptr, 0, rows);
   }
@@ -279,6 +281,7 @@ constexpr int GN_MAX_GROUPS = 64;
 __global__ void __launch_bounds__(1024)
 groupnorm_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float* __restrict__ partial, int HW, int C,
                          int G, int chunks, const float* __restrict__ rowbias, long long ldrb, int rb_div) {
+  pdl_wait();
   extern __shared__ float gn_smem[];  // [rows_par][C] sums, then [rows_par][C] squares
   const int img = blockIdx.y;
   const int row0 = blockIdx.x * GN_ROWS;
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(256)
 groupnorm_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
                           const float* __restrict__ beta, float eps, float2* __restrict__ ab, int HW, int C, int G,
                           int chunks, const float* __restrict__ rowbias, long long ldrb, int rb_div) {
+  pdl_wait();
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
   const int img = blockIdx.x;
   const int cpg = C / G;
@@ -367,6 +371,7 @@ constexpr int GN_UNROLL = 4;
 __global__ void __launch_bounds__(1024)
 groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float2* __restrict__ ab,
                        __nv_bfloat16* __restrict__ out, long long ldo, int HW, int C, int silu) {
+  pdl_wait();
   const int img = blockIdx.y;
   const int nvec = C >> 3;
   const int rows_par = blockDim.x / nvec;
@@ -417,12 +422,12 @@ static int launch_layernorm(const void* x, long long ldx, const float* gamma, co
   const long long per_block = static_cast<long long>(LN_WARPS) * R;
   const unsigned grid = static_cast<unsigned>((rows + per_block - 1) / per_block);
   if (out2 != nullptr) {
-    layernorm_kernel<NV, R, true><<<grid, LN_WARPS * 32, 0, stream>>>(
+    launch_k(layernorm_kernel<NV, R, true>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, 
         static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo, pe,
         F > 0 ? F : 1, HW > 0 ? HW : 1, static_cast<const __nv_bfloat16*>(add), ldadd,
         static_cast<__nv_bfloat16*>(out2), ldo2, rows, C);
   } else {
-    layernorm_kernel<NV, R, false><<<grid, LN_WARPS * 32, 0, stream>>>(
+    launch_k(layernorm_kernel<NV, R, false>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, 
         static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo, pe,
         F > 0 ? F : 1, HW > 0 ? HW : 1, nullptr, 0, nullptr, 0, rows, C);
   }
@@ -482,15 +487,15 @@ extern "C" int fmc_groupnorm_bf16(const void* x, long long ldx, const float* gam
   }
   const int rb_div = rowbias_div > 0 ? rowbias_div : 1;
   float2* ab = reinterpret_cast<float2*>(stats_ws + static_cast<size_t>(2) * groups * images * chunks);
-  groupnorm_partial_kernel<<<dim3(chunks, images), threads, smem, stream>>>(
+  launch_k(groupnorm_partial_kernel, dim3(dim3(chunks, images)), dim3(threads), smem, stream, 
       static_cast<const __nv_bfloat16*>(x), ldx, stats_ws, HW, C, groups, chunks, rowbias, ldrb, rb_div);
   int rc = check_launch("groupnorm_partial_kernel");
   if (rc != FMC_OK) return rc;
-  groupnorm_finalize_kernel<<<images, 256, 0, stream>>>(stats_ws, gamma, beta, eps, ab, HW, C, groups, chunks, rowbias,
+  launch_k(groupnorm_finalize_kernel, dim3(images), dim3(256), 0, stream, stats_ws, gamma, beta, eps, ab, HW, C, groups, chunks, rowbias,
                                                         ldrb, rb_div);
   rc = check_launch("groupnorm_finalize_kernel");
   if (rc != FMC_OK) return rc;
-  groupnorm_apply_kernel<<<dim3(ceil_div(HW, rows_par * GN_UNROLL), images), threads, 0, stream>>>(
+  launch_k(groupnorm_apply_kernel, dim3(dim3(ceil_div(HW, rows_par * GN_UNROLL), images)), dim3(threads), 0, stream, 
       static_cast<const __nv_bfloat16*>(x), ldx, ab, static_cast<__nv_bfloat16*>(out), ldo, HW, C, silu);
   return check_launch("groupnorm_apply_kernel");
 }

@@ -124,6 +124,7 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
 
 __global__ void __launch_bounds__(TF_THREADS, 1)
 temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, TfParams p) {
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[TF_KB], a_free[TF_KB];
   __shared__ uint64_t w_full[TF_W_STAGES], w_empty[TF_W_STAGES];
@@ -508,6 +509,6 @@ extern "C" int fmc_temporal_qkv_attn_bf16(const void* X, long long ldx, const vo
   }
   const int items = B * p.tiles_per_b * TF_HEADS;
   const int grid = items < device_sm_count() ? items : device_sm_count();
-  temporal_qkv_attn_kernel<<<grid, TF_THREADS, TF_SMEM_BYTES, stream>>>(tmX, tmW, p);
+  launch_k(temporal_qkv_attn_kernel, dim3(grid), dim3(TF_THREADS), TF_SMEM_BYTES, stream, tmX, tmW, p);
   return check_launch("temporal_qkv_attn_kernel");
 }
