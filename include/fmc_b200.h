@@ -25,6 +25,8 @@ extern "C" {
 /* flags for fmc_gemm_bf16 */
 #define FMC_GEMM_GEGLU 1   /* W rows interleaved (16 value, 16 gate); C[M, N/2] = value * gelu_erf(gate) */
 #define FMC_GEMM_OUT_F32 2 /* C is fp32 instead of bf16 */
+#define FMC_GEMM_F16_TAIL 4 /* output columns >= 32 * (flags >> 8) are written as IEEE fp16 (V of a fused q|k|v
+                               projection feeding fmc_spatial_attn_vf16); bf16 output path only, no GEGLU / residual */
 
 int fmc_abi_version(void);
 const char* fmc_last_error_string(void);
@@ -60,6 +62,14 @@ int fmc_conv3x3_bf16(const void* X, const void* W, void* Out, const float* bias,
  * Head h of Q / K starts at column q_col0 / k_col0 + h*head_stride (head_stride = 48 with zero padding when
  * head_dim = 40); head h of V at column v_col0 + h*head_dim.  Q, K, V may alias one fused [token, q|k|v] buffer. */
 int fmc_spatial_attn_bf16(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K, long long ldk,
+                          int k_col0, const void* V, long long ldv, int v_col0, long long kv_rows, int head_stride,
+                          void* O, long long ldo, int images, int heads, int head_dim, int nq, int nk, int kv_div,
+                          int kv_stride, float scale, void* stream);
+
+/* Same with V (row layout as above) holding IEEE fp16 instead of bf16 -- written by fmc_gemm_bf16 with
+ * FMC_GEMM_F16_TAIL.  head_dim 40 only.  The probabilities are then fp16 too and come from ex2.approx.f16x2 (two
+ * exponentials per MUFU operation): this case is MUFU bound.  Q, K, O stay bf16. */
+int fmc_spatial_attn_vf16(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K, long long ldk,
                           int k_col0, const void* V, long long ldv, int v_col0, long long kv_rows, int head_stride,
                           void* O, long long ldo, int images, int heads, int head_dim, int nq, int nk, int kv_div,
                           int kv_stride, float scale, void* stream);

@@ -33,6 +33,15 @@ def spatial_case(images, d, n):
                                     d ** -0.5)
 
 
+def spatial_f16_case(images, n):
+    heads, d, hs = 8, 40, 48
+    qkv = rnd(images * n, 2 * heads * hs + heads * d)
+    qkv[:, 2 * heads * hs:] = torch.randn(images * n, heads * d, device=dev).half().view(BF)
+    out = torch.empty(images * n, heads * d, device=dev, dtype=BF)
+    return lambda: ops.spatial_attn(qkv, 0, qkv, heads * hs, qkv, 2 * heads * hs, hs, out, images, heads, d, n, n, 1, n,
+                                    d ** -0.5, v_f16=True)
+
+
 def temporal_case(B, F, HW, d):
     heads, hs = 8, (d + 15) // 16 * 16
     qkv = rnd(B * F * HW, 2 * heads * hs + heads * d)
@@ -92,6 +101,7 @@ CASES = {
     "conv_l3_cudnn": lambda: conv_case(32, 5, 8, 1280, 1280, cudnn=True),
     "conv_down0": lambda: conv_case(32, 40, 64, 320, 320, stride=2),
     "conv_down0_cudnn": lambda: conv_case(32, 40, 64, 320, 320, stride=2, cudnn=True),
+    "spatial_l0_f16": lambda: spatial_f16_case(32, 2560),
     "spatial_l0": lambda: spatial_case(32, 40, 2560),
     "spatial_l1": lambda: spatial_case(32, 80, 640),
     "temporal_fused_l0": lambda: temporal_fused_case(2, 16, 2560),

@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cmath>
 #include "ptx.cuh"
 
 using namespace fmc;
@@ -135,6 +137,62 @@ __global__ void __launch_bounds__(128, 1) ts_check_kernel(const __nv_bfloat16* A
   if (t < 32) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
 }
 
+// Mixed operand formats: A = fp16, B = bf16 (both K-major in smem), D = fp32.
+__global__ void __launch_bounds__(128, 1) mixed_check_kernel(const __half* A, const __nv_bfloat16* B, float* D) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + 16384;
+  const int t = threadIdx.x;
+  for (uint32_t off = t * 16; off < 32768; off += 128 * 16) st_shared_v4(base + off, 0, 0, 0, 0);
+  __syncthreads();
+  {  // A row t: 16 halves = 2 chunks
+    const uint4* src = reinterpret_cast<const uint4*>(A + t * 16);
+    for (int j = 0; j < 2; ++j) { const uint4 v = src[j]; st_shared_v4(sA + t * 128 + ((j ^ (t & 7)) << 4), v.x, v.y, v.z, v.w); }
+  }
+  if (t < 32) {
+    const uint4* src = reinterpret_cast<const uint4*>(B + t * 16);
+    for (int j = 0; j < 2; ++j) { const uint4 v = src[j]; st_shared_v4(sB + t * 128 + ((j ^ (t & 7)) << 4), v.x, v.y, v.z, v.w); }
+  }
+  fence_proxy_async_smem();
+  if (t == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (t < 32) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (t < 32 && elect_one()) {
+    // idesc: D = F32 (bit 4), A format = F16 (0 at bits 7-9), B format = BF16 (1 at bits 10-12)
+    const uint32_t idesc = (1u << 4) | (0u << 7) | (1u << 10) | (static_cast<uint32_t>(32 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+    umma_bf16_ss(tmem, umma_desc_k_sw128(sA), umma_desc_k_sw128(sB), idesc, 0);
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after_sync();
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>((t >> 5) * 32) << 16);
+  uint32_t d[32];
+  tmem_ld_x32(lane_addr, d);
+  tmem_ld_wait();
+  for (int i = 0; i < 32; ++i) D[t * 32 + i] = __uint_as_float(d[i]);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (t < 32) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+}
+
+// ex2.approx.f16x2 availability / accuracy
+__global__ void ex2h_kernel(const float* x, float* y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (2 * i + 1 < n) {
+    uint32_t h, r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x[2 * i + 1]), "f"(x[2 * i]));
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
+    const __half2 v = *reinterpret_cast<__half2*>(&r);
+    y[2 * i] = __low2float(v);
+    y[2 * i + 1] = __high2float(v);
+  }
+}
+
 int main() {
   long long* out;
   cudaMalloc(&out, 16);
@@ -177,5 +235,25 @@ int main() {
     }
   printf("TS layout check (lane = row, column c = k pair (2c, 2c+1)): max |err| = %g  %s\n", maxerr,
          maxerr < 1e-3 ? "OK" : "MISMATCH");
+  // (A = fp16 with B = bf16 in one tcgen05.mma kind::f16 was tried here: "illegal instruction" -- the operand
+  // formats must match)
+  {  // f16x2 exp2
+    const int n = 4096;
+    std::vector<float> hx(n), hy(n);
+    for (int i = 0; i < n; ++i) hx[i] = -20.0f * i / n;
+    float *dx, *dy;
+    cudaMalloc(&dx, n * 4); cudaMalloc(&dy, n * 4);
+    cudaMemcpy(dx, hx.data(), n * 4, cudaMemcpyHostToDevice);
+    ex2h_kernel<<<n / 2 / 128, 128>>>(dx, dy, n);
+    cudaMemcpy(hy.data(), dy, n * 4, cudaMemcpyDeviceToHost);
+    double worst = 0, worst_hi = 0;
+    for (int i = 0; i < n; ++i) {
+      const double ref = exp2(double(hx[i]));
+      const double rel = fabs(hy[i] - ref) / ref;
+      if (hx[i] > -13) worst = std::max(worst, rel);
+      if (hx[i] > -4) worst_hi = std::max(worst_hi, rel);
+    }
+    printf("ex2.approx.f16x2: max rel err %.4f (x > -13), %.5f (x > -4)\n", worst, worst_hi);
+  }
   return 0;
 }

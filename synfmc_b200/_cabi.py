@@ -16,6 +16,7 @@ SIGNATURES = {
     "fmc_gemm_bf16": [P, L, P, L, P, L, I, I, I, P, P, L, P, I, L, I, I, P],
     "fmc_conv3x3_bf16": [P, P, P, P, P, I, I, I, I, I, I, I, P],
     "fmc_spatial_attn_bf16": [P, L, I, L, P, L, I, P, L, I, L, I, P, L, I, I, I, I, I, I, I, F, P],
+    "fmc_spatial_attn_vf16": [P, L, I, L, P, L, I, P, L, I, L, I, P, L, I, I, I, I, I, I, I, F, P],
     "fmc_temporal_attn_bf16": [P, L, I, I, I, I, P, L, I, I, I, I, I, F, P],
     "fmc_temporal_qkv_attn_bf16": [P, L, P, L, P, L, I, I, I, I, I, F, P],
     "fmc_debug_set_timeline": [P],

@@ -360,7 +360,10 @@ struct Fa2Cfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int D>
+// VF16: V (and therefore P) are IEEE fp16 instead of bf16 -- the projection GEMM writes its V columns as fp16
+// (FMC_GEMM_F16_TAIL).  The probabilities then come from ex2.approx.f16x2, TWO exponentials per MUFU operation: at
+// head_dim 40 this kernel is MUFU bound, and fp16 P carries three more mantissa bits than bf16 P.
+template <int D, bool VF16>
 __global__ void __launch_bounds__(FA2_THREADS, 1)
 spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, FaParams p) {
@@ -440,7 +443,7 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ------------------------------------ MMA issuer ------------------------------------
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(FA_BM, FA_BN);
-      constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(FA_BM, DK);
+      constexpr uint32_t idesc_o = VF16 ? umma_idesc_f16_bmn(FA_BM, DK) : umma_idesc_bf16_bmn(FA_BM, DK);
       uint32_t t = 0, it = 0;
       // O_w += P_w(tile u) V(tile u)
       auto issue_pv = [&](int w, uint32_t u, bool first_of_item) {
@@ -516,18 +519,32 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         float mr = -INFINITY;  // raw (unscaled) maximum: c > 0, so max commutes with the scale
         // scale-and-shift and the row sum run on packed fp32 pairs (fma / add .f32x2): two fewer issue slots per pair
         const uint64_t c2 = f2_pack(c, c), nm2 = f2_pack(-m, -m);
-        uint64_t ls2 = f2_pack(0.f, 0.f);
+        if constexpr (VF16) {
+          uint32_t ha = 0u, hb = 0u;  // two fp16x2 partial sums (<= 16 terms of <= 1 each)
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float v0 = __uint_as_float(v[i]), v1 = __uint_as_float(v[i + 1]);
-          mr = fmaxf(mr, fmaxf(v0, v1));
-          float x0, x1;
-          f2_unpack(f2_fma(f2_pack(v0, v1), c2, nm2), x0, x1);
-          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-          ls2 = f2_add(ls2, f2_pack(p0, p1));
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        {
+          for (int i = 0; i < 32; i += 2) {
+            const float v0 = __uint_as_float(v[i]), v1 = __uint_as_float(v[i + 1]);
+            mr = fmaxf(mr, fmaxf(v0, v1));
+            float x0, x1;
+            f2_unpack(f2_fma(f2_pack(v0, v1), c2, nm2), x0, x1);
+            const uint32_t ph = ex2_f16x2(pack_f16x2(x0, x1));
+            if (i & 2) hb = add_f16x2(hb, ph);
+            else ha = add_f16x2(ha, ph);
+            pk[i >> 1] = ph;
+          }
+          lsum += sum_f16x2(ha) + sum_f16x2(hb);
+        } else {
+          uint64_t ls2 = f2_pack(0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float v0 = __uint_as_float(v[i]), v1 = __uint_as_float(v[i + 1]);
+            mr = fmaxf(mr, fmaxf(v0, v1));
+            float x0, x1;
+            f2_unpack(f2_fma(f2_pack(v0, v1), c2, nm2), x0, x1);
+            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+            ls2 = f2_add(ls2, f2_pack(p0, p1));
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
           float la, lb;
           f2_unpack(ls2, la, lb);
           lsum += la + lb;
@@ -542,7 +559,7 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mx = fmaxf(mx, fmaxf(s0, s1));
           const float p0 = ok0 ? fast_exp2(s0 - m) : 0.f, p1 = ok1 ? fast_exp2(s1 - m) : 0.f;
           lsum += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+          pk[i >> 1] = VF16 ? pack_f16x2(p0, p1) : pack_bf16x2(p0, p1);
         }
       }
 #pragma unroll
@@ -675,18 +692,18 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
-template <int D>
+template <int D, bool VF16>
 static int launch_fa2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FaParams& p,
                       cudaStream_t stream) {
   using Cfg = Fa2Cfg<D>;
   static bool attr_set = false;
   if (!attr_set) {
-    FMC_CUDA_OK(cudaFuncSetAttribute(spatial_attn2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    FMC_CUDA_OK(cudaFuncSetAttribute(spatial_attn2_kernel<D, VF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int items = p.images * p.heads * ((p.nq + 2 * FA_BM - 1) / (2 * FA_BM));
   const int grid = items < device_sm_count() ? items : device_sm_count();
-  launch_k(spatial_attn2_kernel<D>, dim3(grid), dim3(FA2_THREADS), Cfg::SMEM_BYTES, stream, tmQ, tmK, tmV, p);
+  launch_k(spatial_attn2_kernel<D, VF16>, dim3(grid), dim3(FA2_THREADS), Cfg::SMEM_BYTES, stream, tmQ, tmK, tmV, p);
   return check_launch("spatial_attn2_kernel");
 }
 
@@ -709,11 +726,10 @@ static int launch_fa(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUten
 
 using namespace fmc;
 
-extern "C" int fmc_spatial_attn_bf16(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K,
-                                     long long ldk, int k_col0, const void* V, long long ldv, int v_col0,
-                                     long long kv_rows, int head_stride, void* O, long long ldo, int images, int heads,
-                                     int head_dim, int nq, int nk, int kv_div, int kv_stride, float scale,
-                                     void* stream_) {
+static int spatial_attn_impl(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K, long long ldk,
+                             int k_col0, const void* V, long long ldv, int v_col0, long long kv_rows, int head_stride,
+                             void* O, long long ldo, int images, int heads, int head_dim, int nq, int nk, int kv_div,
+                             int kv_stride, float scale, bool v_f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FMC_REQUIRE(Q && K && V && O, FMC_ERR_ARG, "fmc_spatial_attn_bf16: null operand");
   FMC_REQUIRE(head_dim == 40 || head_dim == 80 || head_dim == 160, FMC_ERR_SHAPE,
@@ -764,9 +780,28 @@ extern "C" int fmc_spatial_attn_bf16(const void* Q, long long ldq, int q_col0, l
   p.scale_log2e = scale * 1.4426950408889634f;
   p.O = static_cast<__nv_bfloat16*>(O);
   p.ldo = ldo;
+  FMC_REQUIRE(!v_f16 || head_dim == 40, FMC_ERR_SHAPE, "fp16 V is implemented for head_dim 40 only (got %d)", head_dim);
   switch (head_dim) {
-    case 40: return launch_fa2<40>(tmQ, tmK, tmV, p, stream);
+    case 40: return v_f16 ? launch_fa2<40, true>(tmQ, tmK, tmV, p, stream) : launch_fa2<40, false>(tmQ, tmK, tmV, p, stream);
     case 80: return launch_fa<80>(tmQ, tmK, tmV, p, stream);
     default: return launch_fa<160>(tmQ, tmK, tmV, p, stream);
   }
+}
+
+extern "C" int fmc_spatial_attn_bf16(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K,
+                                     long long ldk, int k_col0, const void* V, long long ldv, int v_col0,
+                                     long long kv_rows, int head_stride, void* O, long long ldo, int images, int heads,
+                                     int head_dim, int nq, int nk, int kv_div, int kv_stride, float scale,
+                                     void* stream_) {
+  return spatial_attn_impl(Q, ldq, q_col0, q_rows, K, ldk, k_col0, V, ldv, v_col0, kv_rows, head_stride, O, ldo, images,
+                           heads, head_dim, nq, nk, kv_div, kv_stride, scale, false, stream_);
+}
+
+extern "C" int fmc_spatial_attn_vf16(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K,
+                                     long long ldk, int k_col0, const void* V, long long ldv, int v_col0,
+                                     long long kv_rows, int head_stride, void* O, long long ldo, int images, int heads,
+                                     int head_dim, int nq, int nk, int kv_div, int kv_stride, float scale,
+                                     void* stream_) {
+  return spatial_attn_impl(Q, ldq, q_col0, q_rows, K, ldk, k_col0, V, ldv, v_col0, kv_rows, head_stride, O, ldo, images,
+                           heads, head_dim, nq, nk, kv_div, kv_stride, scale, true, stream_);
 }

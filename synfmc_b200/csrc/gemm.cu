@@ -34,6 +34,7 @@ struct GemmParams {
   int rows_per_group;
   long long ldrb;
   int flags;
+  int f16_col0;  // output columns >= f16_col0 are written as IEEE fp16 (FMC_GEMM_F16_TAIL), else INT_MAX
   int tiles_m, tiles_n;
   // implicit-GEMM convolution (CONV kernels): A rows are output pixels (n, oh, ow) of a channels-last image, K runs over
   // (ky, kx, cin); the A operand of k-block kb is the input shifted by tap kb / cchunks, fetched row by row with 4-D
@@ -693,8 +694,12 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               v[c * 8 + 2 * j + 1] += bf16_hi(w[j]);
             }
           }
-          st_shared_v4(addr, pack_bf16x2(v[c * 8], v[c * 8 + 1]), pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
-                       pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
+          if (ocol0 >= p.f16_col0)  // warp-uniform: this 32-column sub-tile belongs to the fp16 tail
+            st_shared_v4(addr, pack_f16x2(v[c * 8], v[c * 8 + 1]), pack_f16x2(v[c * 8 + 2], v[c * 8 + 3]),
+                         pack_f16x2(v[c * 8 + 4], v[c * 8 + 5]), pack_f16x2(v[c * 8 + 6], v[c * 8 + 7]));
+          else
+            st_shared_v4(addr, pack_bf16x2(v[c * 8], v[c * 8 + 1]), pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]),
+                         pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]));
         }
       }
       tc_fence_before_sync();
@@ -858,6 +863,13 @@ extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long l
   p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
   p.rowbias = rowbias; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; p.ldrb = ldrb;
   p.flags = flags;
+  p.f16_col0 = 0x7FFFFFFF;
+  if ((flags & FMC_GEMM_F16_TAIL) != 0) {
+    const int col0 = (flags >> 8) * 32;
+    FMC_REQUIRE(tma_epilogue && !geglu && residual == nullptr && col0 < N, FMC_ERR_ARG,
+                "fmc_gemm_bf16: FMC_GEMM_F16_TAIL needs the bf16 TMA-epilogue path without GEGLU / residual");
+    p.f16_col0 = col0;
+  }
   if (tma_epilogue) {
     CUtensorMap tmC, tmR;
     const uint32_t box[2] = {SUB_COLS, GEMM_BM};
@@ -975,6 +987,7 @@ extern "C" int fmc_conv3x3_bf16(const void* X, const void* W, void* Out, const f
   p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = N;
   p.rowbias = nullptr; p.rows_per_group = 1; p.ldrb = 0;
   p.flags = 0;
+  p.f16_col0 = 0x7FFFFFFF;
   p.conv_oh = OH; p.conv_ow = OW; p.conv_stride = stride; p.conv_cchunks = Cin / GEMM_BK; p.conv_rows = GEMM_BM / OW;
   if (use_cluster) {
     if (bn == 128) return launch_gemm2<128, false, 2, true>(tmA, tmB, tmC, tmR, p, stream);

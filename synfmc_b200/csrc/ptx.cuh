@@ -352,6 +352,32 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// two exponentials per MUFU operation; |rel err| <= 0.4 % for x in (-13, 0] (profiles/microbench/mma_bench.cu)
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t r;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t add_f16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ float sum_f16x2(uint32_t v) {
+  float lo, hi;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(lo), "=f"(hi) : "r"(v));
+  return lo + hi;
+}
+// kind::f16 instruction descriptor with fp16 operands (A K-major, B MN-major), fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_f16_bmn(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
 // MUFU.RCP (1 ulp); __frcp_rn compiles to a call with Newton refinement and range checks -- far too slow for epilogues
 __device__ __forceinline__ float rcp_fast(float x) {
   float y;

@@ -21,6 +21,10 @@ BF16 = torch.bfloat16
 # the wide convolutions by 1.7-3x in round 1 (its kernels reuse the input window across the nine taps in shared
 # memory; ours re-fetches it per tap), ours wins the 4-channel conv_in by 3x.
 CONV3X3 = os.environ.get("FMC_CONV3X3", "auto")
+# FMC_SPATIAL_VF16=1: level-0 spatial self-attention with fp16 V / P and two-per-MUFU-op fp16x2 exponentials
+# (fmc_spatial_attn_vf16).  Correct (tests/test_gpu_ops.py::test_spatial_attention_fp16_v) but 8 % SLOWER than the bf16
+# kernel in round 1 -- the kernel turned out not to be MUFU bound (profiles/r01_spatial_attention_experiments.md).
+SPATIAL_VF16 = bool(os.environ.get("FMC_SPATIAL_VF16"))
 # debugging switch: FMC_UNFUSED_TEMPORAL=1 runs the temporal attention as GEMM + attention kernels instead of the fused one
 FUSED_TEMPORAL = not os.environ.get("FMC_UNFUSED_TEMPORAL")
 
@@ -245,10 +249,12 @@ class ConvPlan:
 # --------------------------------------------------------------------------------------------------------------
 def run_spatial_self_attention(plan, x_norm, residual, images, n_tokens):
     """attn1 of a BasicTransformerBlock on rows [(images n_tokens), C]; returns to_out(attn) + residual."""
-    qkv = plan.qkv(x_norm)
+    # optional fp16 V / P path for head width 40 (see SPATIAL_VF16)
+    v_f16 = SPATIAL_VF16 and plan.d == 40 and plan.v_col0 % 32 == 0
+    qkv = ops.gemm(x_norm, plan.qkv.w, f16_from_col=plan.v_col0) if v_f16 else plan.qkv(x_norm)
     ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=BF16)
     ops.spatial_attn(qkv, plan.q_col0, qkv, plan.k_col0, qkv, plan.v_col0, plan.hs, ctx, images, plan.heads, plan.d,
-                     n_tokens, n_tokens, 1, n_tokens, plan.scale)
+                     n_tokens, n_tokens, 1, n_tokens, plan.scale, v_f16=v_f16)
     return plan.out(ctx, residual=residual)
 
 

@@ -28,8 +28,9 @@ def _rows2d(t, dtype=BF16):
 
 
 def gemm(a, w, bias=None, residual=None, out=None, geglu=False, out_f32=False, rowbias=None, rows_per_group=0,
-         tile_n=0):
-    """out[M, N(/2)] = epilogue(a[M, K] @ w[N, K]^T); see fmc_gemm_bf16."""
+         tile_n=0, f16_from_col=None):
+    """out[M, N(/2)] = epilogue(a[M, K] @ w[N, K]^T); see fmc_gemm_bf16.  `f16_from_col`: columns from there on are
+    written as IEEE fp16 bit patterns into the bf16 output tensor (FMC_GEMM_F16_TAIL)."""
     _check_cuda(a, w)
     _rows2d(a)
     _rows2d(w)
@@ -41,6 +42,9 @@ def gemm(a, w, bias=None, residual=None, out=None, geglu=False, out_f32=False, r
         out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_f32 else BF16)
     assert out.shape == (M, n_out) and out.stride(1) == 1
     flags = (1 if geglu else 0) | (2 if out_f32 else 0)
+    if f16_from_col is not None:
+        assert f16_from_col % 32 == 0 and not geglu and not out_f32 and residual is None
+        flags |= 4 | ((f16_from_col // 32) << 8)
     if residual is not None:
         _rows2d(residual)
         assert residual.shape == (M, n_out)
@@ -55,12 +59,13 @@ def gemm(a, w, bias=None, residual=None, out=None, geglu=False, out_f32=False, r
 
 
 def spatial_attn(q, q_col0, k, k_col0, v, v_col0, head_stride, out, images, heads, head_dim, nq, nk, kv_div, kv_stride,
-                 scale):
+                 scale, v_f16=False):
+    """`v_f16`: the V columns hold IEEE fp16 bit patterns (gemm(..., f16_from_col=v_col0)); head_dim 40 only."""
     _check_cuda(q, k, v, out)
     for t in (q, k, v, out):
         _rows2d(t)
     assert k.shape[0] == v.shape[0]
-    _cabi.call("fmc_spatial_attn_bf16", q.data_ptr(), q.stride(0), q_col0, q.shape[0], k.data_ptr(), k.stride(0), k_col0,
+    _cabi.call("fmc_spatial_attn_vf16" if v_f16 else "fmc_spatial_attn_bf16", q.data_ptr(), q.stride(0), q_col0, q.shape[0], k.data_ptr(), k.stride(0), k_col0,
                v.data_ptr(), v.stride(0), v_col0, k.shape[0], head_stride, out.data_ptr(), out.stride(0), images, heads,
                head_dim, nq, nk, kv_div, kv_stride, float(scale), _stream())
     return out

@@ -114,6 +114,30 @@ def test_spatial_attention(ops, cuda_device, images, d, nq, nk, kv_div):
     assert rel(out, want) < BF16_TOL
 
 
+@pytest.mark.parametrize("images,nq", [(2, 256), (2, 300), (1, 2560)])
+def test_spatial_attention_fp16_v(ops, cuda_device, images, nq):
+    """head_dim 40 self-attention with V projected to fp16 (FMC_GEMM_F16_TAIL) and fp16x2 exponentials
+    (fmc_spatial_attn_vf16): the fused q|k|v GEMM writes the fp16 tail, the attention consumes it."""
+    heads, d, hs = 8, 40, 48
+    C = heads * d
+    x = randn(images * nq, C, seed=1)
+    wq, wk, wv = (randn(C, C, seed=s, scale=C ** -0.5) for s in (2, 3, 4))
+    w = torch.cat([_pad_heads(wq.t(), heads, d, hs).t(), _pad_heads(wk.t(), heads, d, hs).t(), wv], dim=0).contiguous()
+    v_col0 = 2 * heads * hs
+    qkv = ops.gemm(bf(x).to(cuda_device), bf(w).to(cuda_device), f16_from_col=v_col0)
+    # the tail really is fp16
+    v_got = qkv[:, v_col0:].contiguous().view(torch.float16).float().cpu()
+    assert rel(v_got, x @ wv.t()) < 2e-3
+    out = torch.empty(images * nq, C, dtype=torch.bfloat16, device=cuda_device)
+    ops.spatial_attn(qkv, 0, qkv, heads * hs, qkv, v_col0, hs, out, images, heads, d, nq, nq, 1, nq, d ** -0.5, v_f16=True)
+    q, k, v = (bf(x @ m.t()).float() for m in (wq, wk, wv))
+
+    def hd(t):
+        return t.view(images, nq, heads, d).transpose(1, 2)
+    want = Fn.scaled_dot_product_attention(hd(q), hd(k), hd(v)).transpose(1, 2).reshape(images * nq, C)
+    assert rel(out, want) < BF16_TOL
+
+
 @pytest.mark.parametrize("B,F,HW,d", [(1, 16, 64, 40), (2, 16, 100, 40), (2, 16, 50, 80), (2, 16, 21, 160),
                                       (1, 4, 70, 40), (1, 8, 33, 80), (1, 32, 10, 40), (2, 16, 2560, 40)])
 def test_temporal_attention(ops, cuda_device, B, F, HW, d):
