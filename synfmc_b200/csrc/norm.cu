@@ -266,6 +266,9 @@ static int launch_layernorm40(const void* x, long long ldx, const float* gamma, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// (Folding the finalize step into the apply kernel -- every apply block reducing its image's partial sums itself, one
+// launch fewer per GroupNorm -- was measured 1-2 % SLOWER on the whole step in round 1: ~1700 apply blocks per level-0
+// call each pay the extra dependent L2 round trip before they start streaming.)
 // GroupNorm, deterministic two-kernel form (no atomics: a fixed reduction order, so two runs are bit-identical).
 //   partial: grid (chunks, images); a block reduces GN_ROWS rows of one image to (sum, sum of squares) per group and
 //            writes partial[img][chunk][g][2].
