@@ -225,6 +225,25 @@ def test_config1_full_unet(cuda_device):
     assert rel_l2(got, want) < UNET_TOL
 
 
+@pytest.mark.timeout(1800)
+def test_config2_full_size_unet_forward(cuda_device):
+    """BASELINE config 2 at its full size: 320x512x16f (latent 40x64), full 4-level U-Net with camera features and one
+    object's features injected (t = 961), conditional CFG half (U-Net batch 1 -- the fp32 oracle materialises a
+    3.4 GB score tensor per level-0 attention at this size) -- CUDA path vs the fp32 CPU oracle.  This is the shape
+    every level-0 kernel of the bench runs at (2560 tokens per frame, 5120 temporal sequences per clip)."""
+    channels = (320, 640, 1280, 1280)
+    o_unet = helpers.build_oracle_unet(tiny=False, obj=True)
+    p_unet = helpers.build_product_unet(o_unet, tiny=False, obj=True, device=cuda_device)
+    sample, text, feats, trajs = _unet_inputs(1, 16, 40, 64, channels, seed=11, traj=True)
+    with torch.no_grad():
+        want = o_unet(sample, 961, text, pose_embedding_features=feats, traj_features=trajs).sample
+    dev = cuda_device
+    got = p_unet(sample.to(dev), 961, text.to(dev), pose_embedding_features=[x.to(dev) for x in feats],
+                 traj_features=[x.to(dev) for x in trajs]).sample
+    assert got.shape == want.shape == (1, 4, 16, 40, 64)
+    assert rel_l2(got, want) < UNET_TOL
+
+
 def test_product_against_reference_golden_vectors(cuda_device):
     """CUDA path vs the committed vectors that the reference's own fmc/* code produced (tests/golden/make_golden.py):
     tiny U-Net cam / cam+obj forwards and the CameraAdapter motion module."""
