@@ -33,6 +33,14 @@ def spatial_case(images, d, n):
                                     d ** -0.5)
 
 
+def cross_case(images, d, n, frames=16, nk=77):
+    heads, hs = 8, (d + 15) // 16 * 16
+    q = rnd(images * n, heads * hs)
+    kv = rnd((images // frames) * 80, heads * hs + heads * d)
+    out = torch.empty(images * n, heads * d, device=dev, dtype=BF)
+    return lambda: ops.spatial_attn(q, 0, kv, 0, kv, heads * hs, hs, out, images, heads, d, n, nk, frames, 80, d ** -0.5)
+
+
 def spatial_f16_case(images, n):
     heads, d, hs = 8, 40, 48
     qkv = rnd(images * n, 2 * heads * hs + heads * d)
@@ -101,6 +109,8 @@ CASES = {
     "conv_l3_cudnn": lambda: conv_case(32, 5, 8, 1280, 1280, cudnn=True),
     "conv_down0": lambda: conv_case(32, 40, 64, 320, 320, stride=2),
     "conv_down0_cudnn": lambda: conv_case(32, 40, 64, 320, 320, stride=2, cudnn=True),
+    "cross_l0": lambda: cross_case(32, 40, 2560),
+    "cross_l1": lambda: cross_case(32, 80, 640),
     "spatial_l0_f16": lambda: spatial_f16_case(32, 2560),
     "spatial_l0": lambda: spatial_case(32, 40, 2560),
     "spatial_l1": lambda: spatial_case(32, 80, 640),

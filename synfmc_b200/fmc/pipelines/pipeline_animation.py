@@ -37,6 +37,7 @@ class _StepGraph:
         self.t = torch.zeros(1, device=dev, dtype=torch.float32)
         self.feats = [CL(torch.empty_like(f.t)) for f in feats]
         self.traj = None if traj is None else [CL(torch.empty_like(f.t)) for f in traj]
+        self._loaded = {}
         self._load(latents, text, feats, traj)
         self.t.fill_(1.0)
         # eager warm-up on a side stream: builds the weight plans, sets kernel attributes, lets cuDNN pick algorithms
@@ -62,13 +63,17 @@ class _StepGraph:
     def _load(self, latents, text, feats, traj):
         self.lat.copy_(latents)
         self.text.copy_(text)
-        for dst, src in zip(self.feats, feats):
-            if dst.t.data_ptr() != src.t.data_ptr():
+        # features are constant over a denoising loop: copy only when the caller hands in a different tensor object or
+        # has modified it in place since the last step (torch bumps `_version` on every in-place write).  The source
+        # tensor is kept referenced, so its address cannot be recycled for other data behind our back.
+        pairs = list(zip(self.feats, feats)) + (list(zip(self.traj, traj)) if self.traj is not None else [])
+        for slot, (dst, src) in enumerate(pairs):
+            if dst.t.data_ptr() == src.t.data_ptr():
+                continue
+            seen = self._loaded.get(slot)
+            if seen is None or seen[0] is not src.t or seen[1] != src.t._version:
                 dst.t.copy_(src.t)
-        if self.traj is not None:
-            for dst, src in zip(self.traj, traj):
-                if dst.t.data_ptr() != src.t.data_ptr():
-                    dst.t.copy_(src.t)
+                self._loaded[slot] = (src.t, src.t._version)
 
     def run(self, latents, t, text, feats, traj):
         self._load(latents, text, feats, traj)
