@@ -269,12 +269,12 @@ def prepare_text(text, device):
     return buf.view(B * TEXT_PAD, c), n
 
 
-def run_spatial_cross_attention(plan, x_norm, residual, images, n_tokens, text_rows, text_len, frames):
+def run_spatial_cross_attention(plan, x_norm, residual, images, n_tokens, text_rows, text_len, frames, text_kv=None):
     """attn2: queries from the latent tokens, keys / values from the text of the clip the frame belongs to.  The
     reference repeats the text f times ('b n c -> (b f) n c', unet.py:1110); here K/V are projected once per clip
     and image i reads kv group i // frames."""
     q = plan.q(x_norm)
-    kv = plan.kv(text_rows)
+    kv = text_kv if text_kv is not None else plan.kv(text_rows)
     ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=BF16)
     ops.spatial_attn(q, 0, kv, 0, kv, plan.heads * plan.hs, plan.hs, ctx, images, plan.heads, plan.d, n_tokens, text_len,
                      frames, TEXT_PAD, plan.scale)
@@ -311,12 +311,31 @@ def nearest_index_chain(sizes):
 # --------------------------------------------------------------------------------------------------------------
 # text context shared by every cross-attention of one U-Net call
 # --------------------------------------------------------------------------------------------------------------
+_TEXT_KV_CAT = {}  # concatenated text K | V projection weights of the last U-Net seen
+
+
 class TextCtx:
     """encoder_hidden_states [B, 77, 768] -> zero-padded bf16 rows [B * 80, 768]."""
 
     def __init__(self, text, device):
         self.rows, self.length = prepare_text(text, device)
         self.batch = text.shape[0]
+        self.kv = {}  # id(AttnPlan) -> [B * 80, heads * hs + C] bf16 view of the batched K | V projection
+
+    def project_all(self, transformers, device):
+        """K | V of the text for every cross-attention of the U-Net in ONE GEMM (16 tiny M = B * 80 GEMMs otherwise):
+        the row-concatenated to_k | to_v weights of all Transformer2D blocks against the same 160 text rows."""
+        plans = [bp["attn2"] for m in transformers for bp in plan_transformer2d(m, device)["blocks"]]
+        hit = _TEXT_KV_CAT.get("entry")  # (plans, weights): the plans are kept referenced, so identity is meaningful
+        if hit is None or len(hit[0]) != len(plans) or any(a is not b for a, b in zip(hit[0], plans)) \
+                or hit[1].device != device:
+            hit = (plans, torch.cat([p.kv.w for p in plans], dim=0).contiguous())
+            _TEXT_KV_CAT["entry"] = hit
+        allkv = ops.gemm(self.rows, hit[1])
+        off = 0
+        for p in plans:
+            self.kv[id(p)] = allkv[:, off:off + p.kv.N]
+            off += p.kv.N
 
     @staticmethod
     def of(x, batch, frames, device):
@@ -367,7 +386,8 @@ def run_transformer2d(mod, x, text):
         n1 = ops.layernorm(h, bp["norm1"].g, bp["norm1"].b, bp["norm1"].eps)
         h = run_spatial_self_attention(bp["attn1"], n1, h, images, N)
         n2 = ops.layernorm(h, bp["norm2"].g, bp["norm2"].b, bp["norm2"].eps)
-        h = run_spatial_cross_attention(bp["attn2"], n2, h, images, N, text.rows, text.length, F)
+        h = run_spatial_cross_attention(bp["attn2"], n2, h, images, N, text.rows, text.length, F,
+                                        text_kv=text.kv.get(id(bp["attn2"])))
         n3 = ops.layernorm(h, bp["norm3"].g, bp["norm3"].b, bp["norm3"].eps)
         h = bp["ff2"](bp["ff1"](n3), residual=h)
     out = p["proj_out"](h, residual=rows)
@@ -399,15 +419,38 @@ def plan_resnet(mod, device):
 
 
 class Temb:
-    """Time embedding `emb` [B, 1280] fp32 plus its cached silu(emb) in bf16 (the operand of every time_emb_proj)."""
+    """Time embedding `emb` [B, 1280] fp32 plus its cached silu(emb) in bf16 (the operand of every time_emb_proj).
+
+    `project_all(resnets)`: the time_emb_proj of every ResnetBlock2D of the U-Net depends only on `emb`, so the 22
+    of them (M = batch rows each, pure launch latency) run as ONE GEMM against the row-concatenated weights; each
+    block then reads its column slice."""
 
     def __init__(self, emb):
         self.emb = emb
         self.act = ops.cast_act(emb, silu=True)
+        self.proj = {}  # id(resnet module) -> [B, Cout] fp32 view
+
+    def project_all(self, resnets, device):
+        plans = [plan_resnet(m, device) for m in resnets]
+        hit = _TEMB_CAT.get("entry")  # (plans, weights, biases); plans kept referenced, compared by identity
+        if hit is None or len(hit[0]) != len(plans) or any(a is not b for a, b in zip(hit[0], plans)) \
+                or hit[1].device != device:
+            hit = (plans, torch.cat([p["temb"].w for p in plans], dim=0).contiguous(),
+                   torch.cat([p["temb"].b for p in plans], dim=0).contiguous())
+            _TEMB_CAT["entry"] = hit
+        allp = ops.gemm(self.act, hit[1], bias=hit[2], out_f32=True)
+        off = 0
+        for m, p in zip(resnets, plans):
+            n = p["temb"].N
+            self.proj[id(m)] = allp[:, off:off + n]
+            off += n
 
     @staticmethod
     def of(x):
         return x if isinstance(x, Temb) else Temb(x.float())
+
+
+_TEMB_CAT = {}  # concatenated time_emb_proj weights of the last U-Net seen (rebuilt when the module set changes)
 
 
 def run_resnet(mod, x, temb):
@@ -420,7 +463,10 @@ def run_resnet(mod, x, temb):
     n1 = ops.groupnorm(rows, p["norm1"].g, p["norm1"].b, p["norm1"].eps, images, HW, groups=p["norm1"].groups, silu=True)
     h = p["conv1"](n1.view(images, H, W, C))
     cout = h.shape[-1]
-    tproj = ops.gemm(temb_act, p["temb"].w, bias=p["temb"].b, out_f32=True)  # [B, Cout] fp32, broadcast over frames
+    temb = Temb.of(temb)
+    tproj = temb.proj.get(id(mod))  # [B, Cout] fp32, broadcast over frames
+    if tproj is None:
+        tproj = ops.gemm(temb_act, p["temb"].w, bias=p["temb"].b, out_f32=True)
     # the time-embedding add happens inside the second GroupNorm (before its statistics), saving a pass over h
     n2 = ops.groupnorm(h.view(-1, cout), p["norm2"].g, p["norm2"].b, p["norm2"].eps, images, HW, groups=p["norm2"].groups,
                        silu=True, rowbias=tproj, rowbias_div=F)

@@ -103,6 +103,8 @@ class UNet3DConditionModel(nn.Module):
         self.conv_act = nn.SiLU()
         self.conv_out = InflatedConv3d(ch0, out_channels, kernel_size=3, padding=1)
         self._plan = None
+        self._resnets = None  # ResnetBlock2D modules, for the batched time-embedding projection
+        self._transformers = None  # Transformer2DModel modules, for the batched text K | V projection
 
     # ---- processor maps, split on "motion_modules." (unet.py:323-468) ----
     def _collect_processors(self, want_motion):
@@ -296,8 +298,15 @@ class UNet3DConditionModelPoseCond(UNet3DConditionModel):
         h1 = ops.gemm(t_emb, p["t1"].w, bias=p["t1"].b, out_f32=True)
         emb = ops.gemm(ops.cast_act(h1, silu=True), p["t2"].w, bias=p["t2"].b, out_f32=True)
         temb = engine.Temb(emb)
+        if self._resnets is None:
+            self._resnets = [m for m in self.modules() if m.__class__.__name__ == "ResnetBlock2D"]
+        temb.project_all(self._resnets, device)
 
         text = engine.TextCtx.of(encoder_hidden_states, B, 1, device)
+        if self._transformers is None:
+            self._transformers = [m for m in self.modules() if m.__class__.__name__ == "Transformer2DModel"]
+        if not text.kv:
+            text.project_all(self._transformers, device)
         x = CL(ops.to_channels_last(sample, c_pad=64))
         y = p["conv_in"](x.images())
         x = CL(y.view(B, F, H, W, y.shape[-1]))
