@@ -60,6 +60,20 @@ def test_gemm_residual_rowbias_bf16(ops, cuda_device, M, N, K):
     assert rel(got, want) < BF16_TOL
 
 
+@pytest.mark.parametrize("M,N,K,res", [(300, 1280, 1280, True), (1000, 1920, 640, False), (129, 1088, 1280, False),
+                                       (5120, 1280, 5120, True), (257, 3840, 1280, False)])
+def test_gemm_cta_pair(ops, cuda_device, M, N, K, res):
+    """Shapes that take the CTA-pair MMA path (tcgen05 cta_group::2: K >= 1280, or K >= 640 with N > 640): odd numbers
+    of 128-row tiles (the last pair's odd CTA recomputes the last tile), ragged M, N that is not a tile multiple."""
+    a, w = randn(M, K, seed=1), randn(N, K, seed=2, scale=K ** -0.5)
+    bias = randn(N, seed=3)
+    r = randn(M, N, seed=4) if res else None
+    got = ops.gemm(bf(a).to(cuda_device), bf(w).to(cuda_device), bias=bias.to(cuda_device),
+                   residual=None if r is None else bf(r).to(cuda_device))
+    want = a @ w.t() + bias + (r if res else 0)
+    assert rel(got, want) < BF16_TOL
+
+
 @pytest.mark.parametrize("M,C", [(1000, 320), (333, 1280)])
 def test_gemm_geglu(ops, cuda_device, M, C):
     """diffusers FeedForward GEGLU (motion_module.py:297): proj -> chunk(2) -> value * gelu_erf(gate)."""
