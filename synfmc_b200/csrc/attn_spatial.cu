@@ -71,7 +71,7 @@ template <int D>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, FaParams p) {
-  pdl_wait();
+  pdl_launch_dependents();
   using Cfg = FaCfg<D>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int DK = Cfg::DK;
@@ -118,6 +118,7 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
@@ -367,7 +368,7 @@ template <int D, bool VF16>
 __global__ void __launch_bounds__(FA2_THREADS, 1)
 spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, FaParams p) {
-  pdl_wait();
+  pdl_launch_dependents();
   using Cfg = Fa2Cfg<D>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int DK = Cfg::DK;
@@ -413,6 +414,7 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------

@@ -54,7 +54,7 @@ __device__ __forceinline__ float ta_exp2(float x) {
 template <int D>
 __global__ void __launch_bounds__(TA_THREADS, 1)
 temporal_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, TaParams p) {
-  pdl_wait();
+  pdl_launch_dependents();
   using Cfg = TaCfg<D>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int DK = Cfg::DK;
@@ -96,6 +96,7 @@ temporal_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, TaParams p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlaps the previous kernel's tail
 
   // item -> (b, tile, head): heads innermost so that neighbouring CTAs touch the same rows
   auto decode = [&](int item, int& b, int& hw0, int& head) {

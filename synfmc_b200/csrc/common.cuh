@@ -55,9 +55,10 @@ int device_sm_count();
 // Programmatic dependent launch: every kernel of this library starts with pdl_wait() (griddepcontrol.wait: all memory
 // of the preceding kernel is visible once it returns) and is launched with programmatic stream serialisation allowed,
 // so its CTAs may be scheduled -- barrier init, TMEM allocation, descriptor prefetch -- while the tail of the
-// preceding kernel drains.  Measured on the graph-replayed step (round 1): 31.65 ms with, 31.13 ms without -- with
-// the implicit trigger (primary fully exited) there is nothing to overlap, so it is OFF unless FMC_PDL=1
-// (griddepcontrol.wait is a no-op for a kernel launched without the attribute); early triggers are round-2 work.
+// preceding kernel drains (every kernel triggers its dependents at its first instruction and waits after its own
+// prologue).  Measured on the graph-replayed step (round 1, two alternating runs each): 31.58 / 31.27 ms with,
+// 31.39 / 31.42 ms without -- no difference, so it is OFF unless FMC_PDL=1 (both instructions are no-ops for a kernel
+// launched without the attribute).
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>

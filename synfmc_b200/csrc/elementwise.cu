@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256)
 add_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const __nv_bfloat16* __restrict__ b, long long ldb,
            const float* __restrict__ rowbias, int rows_per_group, long long ldrb, __nv_bfloat16* __restrict__ out,
            long long ldo, long long rows, int C, int relu) {
+  pdl_launch_dependents();
   pdl_wait();
   const int nvec = C >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -54,6 +55,7 @@ add_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const __nv_bfloat
 __global__ void __launch_bounds__(256)
 resize_nearest_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int h, int w, int oh,
                       int ow, int C, float sh, float sw) {
+  pdl_launch_dependents();
   pdl_wait();
   const int nvec = C >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -74,6 +76,7 @@ resize_nearest_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __rest
 // 2x2 average pooling (AvgPool2d(2), floor) of [N, h, w, C].
 __global__ void __launch_bounds__(256)
 avgpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int h, int w, int C) {
+  pdl_launch_dependents();
   pdl_wait();
   const int oh = h >> 1, ow = w >> 1, nvec = C >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -105,6 +108,7 @@ avgpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 __global__ void __launch_bounds__(256)
 copy2d_kernel(const __nv_bfloat16* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd,
               long long rows, int cols) {
+  pdl_launch_dependents();
   pdl_wait();
   const int nvec = cols >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -118,6 +122,7 @@ copy2d_kernel(const __nv_bfloat16* __restrict__ src, long long lds, __nv_bfloat1
 __global__ void __launch_bounds__(256)
 ncfhw_to_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int F, long long HW,
                    int Cpad) {
+  pdl_launch_dependents();
   pdl_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * F * HW * Cpad;
@@ -136,6 +141,7 @@ ncfhw_to_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
 __global__ void __launch_bounds__(256)
 cl_to_ncfhw_kernel(const __nv_bfloat16* __restrict__ x, long long ldc, float* __restrict__ out, int B, int C, int F,
                    long long HW) {
+  pdl_launch_dependents();
   pdl_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * C * F * HW;
@@ -152,6 +158,7 @@ cl_to_ncfhw_kernel(const __nv_bfloat16* __restrict__ x, long long ldc, float* __
 // fp32 -> bf16 with optional SiLU (time-embedding activations feeding the projection GEMMs).
 __global__ void __launch_bounds__(256)
 cast_act_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n, int silu) {
+  pdl_launch_dependents();
   pdl_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= n) return;
@@ -162,6 +169,7 @@ cast_act_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, lo
 
 // diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): out[b] = [cos(t e_i) | sin(t e_i)], e_i = 1e4^(-i/half).
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int B, int dim) {
+  pdl_launch_dependents();
   pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
@@ -203,6 +211,7 @@ __device__ __forceinline__ void plucker_pixel(const float* __restrict__ K, const
 __global__ void __launch_bounds__(256)
 plucker_plain_kernel(const float* __restrict__ K, const float* __restrict__ c2w, float* __restrict__ out, int BF, int H,
                      int W) {
+  pdl_launch_dependents();
   pdl_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(BF) * H * W;
@@ -221,6 +230,7 @@ plucker_plain_kernel(const float* __restrict__ K, const float* __restrict__ c2w,
 __global__ void __launch_bounds__(256)
 plucker_unshuffle_kernel(const float* __restrict__ K, const float* __restrict__ c2w, __nv_bfloat16* __restrict__ out,
                          int BF, int H, int W) {
+  pdl_launch_dependents();
   pdl_wait();
   const int h8 = H >> 3, w8 = W >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -280,6 +290,7 @@ __device__ __forceinline__ void traj_pixel(const float* __restrict__ info, const
 __global__ void __launch_bounds__(256)
 traj_plain_kernel(const float* __restrict__ info, const float* __restrict__ masks, float* __restrict__ feat,
                   float* __restrict__ mask_out, int BF, int n_obj, int H, int W) {
+  pdl_launch_dependents();
   pdl_wait();
   const long long HW = static_cast<long long>(H) * W;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -296,6 +307,7 @@ traj_plain_kernel(const float* __restrict__ info, const float* __restrict__ mask
 __global__ void __launch_bounds__(256)
 traj_unshuffle_kernel(const float* __restrict__ info, const float* __restrict__ masks, __nv_bfloat16* __restrict__ feat,
                       float* __restrict__ mask_out, int BF, int n_obj, int H, int W) {
+  pdl_launch_dependents();
   pdl_wait();
   const int h8 = H >> 3, w8 = W >> 3;
   const long long HW = static_cast<long long>(H) * W;
@@ -333,6 +345,7 @@ traj_unshuffle_kernel(const float* __restrict__ info, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 mask_modulate_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mask, const int* __restrict__ ry,
                      const int* __restrict__ rx, __nv_bfloat16* __restrict__ out, int N, int h, int w, int C, int H, int W) {
+  pdl_launch_dependents();
   pdl_wait();
   const int nvec = C >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -360,6 +373,7 @@ __global__ void __launch_bounds__(256)
 cfg_ddim_kernel(const float* __restrict__ eps_u, const float* __restrict__ eps_c, float guidance,
                 const float* __restrict__ x, float* __restrict__ x_out, float* __restrict__ eps_out, float sqrt_a_t,
                 float sqrt_1m_a_t, float sqrt_a_prev, float sqrt_1m_a_prev, long long n) {
+  pdl_launch_dependents();
   pdl_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= n) return;

@@ -59,7 +59,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
-  pdl_wait();
+  pdl_launch_dependents();
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -98,6 +98,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -404,7 +405,7 @@ template <int BN, bool GEGLU, int CL, bool CONV = false>
 __global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, GemmParams p) {
-  pdl_wait();
+  pdl_launch_dependents();
   using Cfg = Gemm2Cfg<BN, GEGLU, CL>;
   static_assert(CL == 1 || CL == 2, "cluster size");
   static_assert(((BN / 2) * 128) % 1024 == 0, "half W slices must stay 1024-byte aligned");
@@ -463,6 +464,7 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if constexpr (CL == 2) cluster_sync_all();  // the peer's barriers / TMEM exist before anything is sent to them
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------ TMA producer (A, W) ------------------------------

@@ -25,6 +25,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out, long long ldo,
                  const float* __restrict__ pe, int F, int HW, const __nv_bfloat16* __restrict__ add, long long ldadd,
                  __nv_bfloat16* __restrict__ out2, long long ldo2, long long rows, int C) {
+  pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row0 = (blockIdx.x * static_cast<long long>(LN_WARPS) + (threadIdx.x >> 5)) * R;
@@ -144,6 +145,7 @@ layernorm40_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const flo
                    const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out, long long ldo,
                    const float* __restrict__ pe, int F, int HW, const __nv_bfloat16* __restrict__ add, long long ldadd,
                    __nv_bfloat16* __restrict__ out2, long long ldo2, long long rows) {
+  pdl_launch_dependents();
   pdl_wait();
   constexpr int C = 40 * LPR;
   constexpr int RPW = 32 / LPR;  // rows per warp pass
@@ -284,6 +286,7 @@ constexpr int GN_MAX_GROUPS = 64;
 __global__ void __launch_bounds__(1024)
 groupnorm_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float* __restrict__ partial, int HW, int C,
                          int G, int chunks, const float* __restrict__ rowbias, long long ldrb, int rb_div) {
+  pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float gn_smem[];  // [rows_par][C] sums, then [rows_par][C] squares
   const int img = blockIdx.y;
@@ -343,6 +346,7 @@ __global__ void __launch_bounds__(256)
 groupnorm_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
                           const float* __restrict__ beta, float eps, float2* __restrict__ ab, int HW, int C, int G,
                           int chunks, const float* __restrict__ rowbias, long long ldrb, int rb_div) {
+  pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
   const int img = blockIdx.x;
@@ -374,6 +378,7 @@ constexpr int GN_UNROLL = 4;
 __global__ void __launch_bounds__(1024)
 groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float2* __restrict__ ab,
                        __nv_bfloat16* __restrict__ out, long long ldo, int HW, int C, int silu) {
+  pdl_launch_dependents();
   pdl_wait();
   const int img = blockIdx.y;
   const int nvec = C >> 3;

@@ -34,6 +34,10 @@ __device__ __forceinline__ bool elect_one() {
 // Programmatic dependent launch: block until the preceding kernel of the stream has completed and its writes are
 // visible (no-op when the kernel was launched without the attribute).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Allow the next kernel of the stream (launched with programmatic stream serialisation) to be scheduled: once every CTA
+// of this grid has executed it (or exited), the dependent grid's CTAs take whatever SM resources are free and run
+// their prologue up to their own pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------
 // mbarrier

@@ -124,7 +124,7 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
 
 __global__ void __launch_bounds__(TF_THREADS, 1)
 temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, TfParams p) {
-  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[TF_KB], a_free[TF_KB];
   __shared__ uint64_t w_full[TF_W_STAGES], w_empty[TF_W_STAGES];
@@ -180,6 +180,7 @@ temporal_qkv_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlaps the previous kernel's tail
 
   // local item m -> global item g0 + m = (tile, head); `it` = index of the tile among this CTA's tiles
   auto head_of = [&](uint32_t m) -> int { return (g0 + static_cast<int>(m)) & (TF_HEADS - 1); };
