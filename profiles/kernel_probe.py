@@ -114,6 +114,8 @@ CASES = {
     "spatial_l0_f16": lambda: spatial_f16_case(32, 2560),
     "spatial_l0": lambda: spatial_case(32, 40, 2560),
     "spatial_l1": lambda: spatial_case(32, 80, 640),
+    "spatial_l2": lambda: spatial_case(32, 160, 160),
+    "cross_l2": lambda: cross_case(32, 160, 160),
     "temporal_fused_l0": lambda: temporal_fused_case(2, 16, 2560),
     "temporal_l0": lambda: temporal_case(2, 16, 2560, 40),
     "groupnorm_l0": lambda: groupnorm_case(32, 2560, 320),

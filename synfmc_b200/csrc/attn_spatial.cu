@@ -227,18 +227,35 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(&s_full[sb], sph);
         tc_fence_after_sync();
         const uint32_t s_addr = lane_addr + sb * 128u;
-        // pass A: row maximum (scaled to log2 units)
+        // pass A: row maximum (scaled to log2 units); the 32-column TMEM loads are software-pipelined and full tiles
+        // skip the per-key predicates (c > 0, so the maximum commutes with the scale)
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int c4 = 0; c4 < 4; ++c4) {
-          uint32_t v[32];
-          tmem_ld_x32(s_addr + c4 * 32, v);
-          tmem_ld_wait();
+        {
+          auto max_chunk = [&](const uint32_t (&v)[32], int c4) {
+            if (valid >= (c4 + 1) * 32) {
+              float mr = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float s = (c4 * 32 + i < valid) ? __uint_as_float(v[i]) * c : -INFINITY;
-            mx = fmaxf(mx, s);
-          }
+              for (int i = 0; i < 32; i += 2) mr = fmaxf(mr, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+              mx = fmaxf(mx, mr * c);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                mx = fmaxf(mx, (c4 * 32 + i < valid) ? __uint_as_float(v[i]) * c : -INFINITY);
+            }
+          };
+          uint32_t va[32], vb[32];
+          tmem_ld_x32(s_addr, va);
+          tmem_ld_wait();
+          tmem_ld_x32(s_addr + 32, vb);
+          max_chunk(va, 0);
+          tmem_ld_wait();
+          tmem_ld_x32(s_addr + 64, va);
+          max_chunk(vb, 1);
+          tmem_ld_wait();
+          tmem_ld_x32(s_addr + 96, vb);
+          max_chunk(va, 2);
+          tmem_ld_wait();
+          max_chunk(vb, 3);
         }
         const bool need = mx > m_used + FA_RESCALE_THRESHOLD;
         const float m_new = need ? mx : m_used;
@@ -262,25 +279,52 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         m_used = m_new;
         // pass B: P = exp2(S * c - m) -> bf16 -> smem (SWIZZLE_128B K-major: row r, 16-byte piece j at (j ^ (r & 7)))
         const uint32_t p_row = sP + r * 128;
-#pragma unroll 1
-        for (int c4 = 0; c4 < 4; ++c4) {
-          uint32_t v[32];
-          tmem_ld_x32(s_addr + c4 * 32, v);
+        {
+          auto exp_chunk = [&](const uint32_t (&v)[32], int c4) {
+            uint32_t pk[16];
+            if (valid >= (c4 + 1) * 32) {
+              const uint64_t c2 = f2_pack(c, c), nm2 = f2_pack(-m_used, -m_used);
+              uint64_t ls2 = f2_pack(0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                float x0, x1;
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nm2), x0, x1);
+                const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+                ls2 = f2_add(ls2, f2_pack(p0, p1));
+                pk[i >> 1] = pack_bf16x2(p0, p1);
+              }
+              float la, lb;
+              f2_unpack(ls2, la, lb);
+              l += la + lb;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float p0 = (c4 * 32 + i < valid) ? fast_exp2(fmaf(__uint_as_float(v[i]), c, -m_used)) : 0.f;
+                const float p1 = (c4 * 32 + i + 1 < valid) ? fast_exp2(fmaf(__uint_as_float(v[i + 1]), c, -m_used)) : 0.f;
+                l += p0 + p1;
+                pk[i >> 1] = pack_bf16x2(p0, p1);
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int piece = c4 * 4 + g;  // 16-byte piece index inside the 256-byte P row
+              const uint32_t addr = p_row + (piece >> 3) * (FA_BM * 128) + (((piece & 7) ^ (r & 7)) << 4);
+              st_shared_v4(addr, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            }
+          };
+          uint32_t va[32], vb[32];
+          tmem_ld_x32(s_addr, va);
           tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c4 * 32 + i < valid) ? fast_exp2(fmaf(__uint_as_float(v[i]), c, -m_used)) : 0.f;
-            const float p1 = (c4 * 32 + i + 1 < valid) ? fast_exp2(fmaf(__uint_as_float(v[i + 1]), c, -m_used)) : 0.f;
-            l += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int piece = c4 * 4 + g;  // 16-byte piece index inside the 256-byte P row
-            const uint32_t addr = p_row + (piece >> 3) * (FA_BM * 128) + (((piece & 7) ^ (r & 7)) << 4);
-            st_shared_v4(addr, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          }
+          tmem_ld_x32(s_addr + 32, vb);
+          exp_chunk(va, 0);
+          tmem_ld_wait();
+          tmem_ld_x32(s_addr + 64, va);
+          exp_chunk(vb, 1);
+          tmem_ld_wait();
+          tmem_ld_x32(s_addr + 96, vb);
+          exp_chunk(va, 2);
+          tmem_ld_wait();
+          exp_chunk(vb, 3);
         }
         tc_fence_before_sync();
         fence_proxy_async_smem();
