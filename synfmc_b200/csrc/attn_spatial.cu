@@ -14,6 +14,7 @@
 // Q, K and V are read exactly as the fused projection GEMM wrote them ([token, q | k | v] rows): Q and K are K-major
 // SWIZZLE_128B operands of S = Q K^T, V is the MN-major B operand of O += P V -- no transposes anywhere.
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -770,6 +771,13 @@ static int launch_fa(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUten
 
 }  // namespace fmc
 
+namespace fmc {
+int cross_attention_short_keys(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K, long long ldk,
+                               int k_col0, const void* V, long long ldv, int v_col0, long long kv_rows, int head_stride,
+                               void* O, long long ldo, int images, int heads, int head_dim, int nq, int nk, int kv_div,
+                               int kv_stride, float scale, cudaStream_t stream);
+}
+
 using namespace fmc;
 
 static int spatial_attn_impl(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K, long long ldk,
@@ -789,6 +797,14 @@ static int spatial_attn_impl(const void* Q, long long ldq, int q_col0, long long
                   v_col0 % 8 == 0,
               FMC_ERR_SHAPE, "fmc_spatial_attn_bf16: strides / column offsets must be multiples of 8 elements");
   FMC_REQUIRE((reinterpret_cast<uintptr_t>(O) & 15) == 0, FMC_ERR_SHAPE, "fmc_spatial_attn_bf16: O not 16-byte aligned");
+
+  // short-key cross-attention (text: 77 keys): K / V stay resident per (kv group, head), the query tiles stream
+  // (attn_cross.cu); FMC_CROSS_GENERIC=1 keeps the generic flash kernel
+  static const bool cross_generic = getenv("FMC_CROSS_GENERIC") != nullptr;
+  if (!cross_generic && !v_f16 && nk <= 80 && kv_stride >= 80 && images % kv_div == 0 &&
+      (images / kv_div) * static_cast<long long>(kv_stride) <= kv_rows)
+    return cross_attention_short_keys(Q, ldq, q_col0, q_rows, K, ldk, k_col0, V, ldv, v_col0, kv_rows, head_stride, O, ldo,
+                                      images, heads, head_dim, nq, nk, kv_div, kv_stride, scale, stream);
 
   CUtensorMap tmQ, tmK, tmV;
   const uint32_t box[2] = {64, 128};

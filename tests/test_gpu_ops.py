@@ -106,7 +106,9 @@ def _pad_heads(x, heads, d, hs):
 
 @pytest.mark.parametrize("images,d,nq,nk,kv_div", [(2, 40, 256, 256, 1), (2, 40, 300, 300, 1), (2, 80, 640, 640, 1),
                                                    (3, 160, 160, 160, 1), (2, 160, 40, 40, 1), (4, 40, 200, 77, 2),
-                                                   (4, 160, 160, 77, 4), (2, 40, 2560, 2560, 1)])
+                                                   (4, 160, 160, 77, 4), (2, 40, 2560, 2560, 1),
+                                                   (32, 80, 640, 77, 16), (16, 160, 40, 77, 16), (32, 40, 2560, 77, 16),
+                                                   (6, 40, 100, 77, 3), (2, 160, 160, 64, 1)])
 def test_spatial_attention(ops, cuda_device, images, d, nq, nk, kv_div):
     """softmax(q k^T d^-1/2) v per head == attention_processor.py:148-154 (head_to_batch_dim, baddbmm, softmax, bmm)."""
     heads, hs = 8, (d + 15) // 16 * 16
