@@ -117,6 +117,8 @@ CASES = {
     "spatial_l2": lambda: spatial_case(32, 160, 160),
     "cross_l2": lambda: cross_case(32, 160, 160),
     "temporal_fused_l0": lambda: temporal_fused_case(2, 16, 2560),
+    "temporal_l1": lambda: temporal_case(2, 16, 640, 80),
+    "temporal_l2": lambda: temporal_case(2, 16, 160, 160),
     "temporal_l0": lambda: temporal_case(2, 16, 2560, 40),
     "groupnorm_l0": lambda: groupnorm_case(32, 2560, 320),
     "layernorm_l0": lambda: layernorm_case(81920, 320),

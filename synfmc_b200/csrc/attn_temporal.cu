@@ -9,7 +9,10 @@
 // tile, the 128x128 score tile is computed on the tensor cores and only its block diagonal is kept: each softmax
 // thread (= query row = TMEM lane) reads the 32-column block of its warp and masks the other sequences.
 //   warp 0 TMA (3-D maps, one box of f rows per sequence), warp 1 MMA issuer, warp 2 TMEM alloc,
-//   warps 4-7 softmax + epilogue, software-pipelined over (tile, head) items with S / P / O double buffered.
+//   warps 4-7 softmax + epilogue, software-pipelined over (tile, head) items with S / O double buffered.
+// P never touches shared memory: it is written back to tensor memory as packed bf16 in place over the scores and read
+// as the A operand of the PV MMA (tcgen05.mma with A in TMEM); the 64 KB this frees let head width 80 run with two
+// Q|K|V stages (loads of item n+1 behind the MMAs of item n) instead of one.
 // V is used as stored ([token, channel], MN-major B operand of the PV MMA).
 #include <cuda_bf16.h>
 
@@ -37,9 +40,8 @@ struct TaCfg {
   static constexpr int QCH = (DK + 63) / 64;
   static constexpr int T_BYTES = QCH * 128 * 128;   // one of Q / K / V for one (tile, head)
   static constexpr int ITEM_BYTES = 3 * T_BYTES;
-  static constexpr int P_BYTES = 2 * 128 * 128;
-  static constexpr int STAGES = (QCH == 1) ? 3 : 1;  // 227 KB smem: 2 x 96 KB + 64 KB of P does not fit for d = 80
-  static constexpr int SMEM_BYTES = 2 * P_BYTES + STAGES * ITEM_BYTES + 1024;
+  static constexpr int STAGES = (QCH == 1) ? 4 : (QCH == 2 ? 2 : 1);  // 227 KB smem: 144 KB per item at d = 160
+  static constexpr int SMEM_BYTES = STAGES * ITEM_BYTES + 1024;
   static constexpr bool O_DOUBLE = (256 + 2 * DK) <= 512;
   static constexpr int O_COL0 = 256;
   static constexpr int O_COL1 = O_DOUBLE ? 256 + DK : 256;
@@ -66,16 +68,10 @@ temporal_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, TaParams p) {
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sP = smem_base;                    // two P buffers
-  const uint32_t sIn = sP + 2 * Cfg::P_BYTES;       // STAGES x (Q | K | V)
+  const uint32_t sIn = smem_base;                   // STAGES x (Q | K | V)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_items = p.B * p.tiles_per_b * p.heads;
-
-  // zero both P buffers once: only the block-diagonal 32-column blocks are ever rewritten
-  for (uint32_t off = threadIdx.x * 16; off < 2 * Cfg::P_BYTES; off += TA_THREADS * 16)
-    st_shared_v4(sP + off, 0u, 0u, 0u, 0u);
-  fence_proxy_async_smem();
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
   if (warp == 1 && lane == 0) {
@@ -164,13 +160,20 @@ temporal_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, TaParams p) {
         mbar_wait(&o_free[o_index(n)], o_phase(n) ^ 1u);
         tc_fence_after_sync();
         const uint32_t sV = sIn + st * Cfg::ITEM_BYTES + 2 * Cfg::T_BYTES;
-        const uint32_t sPn = sP + (n & 1u) * Cfg::P_BYTES;
         const uint32_t o_col = o_index(n) ? Cfg::O_COL1 : Cfg::O_COL0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint64_t da = umma_desc_k_sw128(sPn + (k >> 2) * (128 * 128) + (k & 3) * 32);
+          // A = P(n): packed bf16 in the first 64 columns of score buffer n & 1 (S(n+2), the next writer of that
+          // buffer, is issued behind this MMA by the same thread)
           const uint64_t db = umma_desc_mn_sw128(sV + k * (16 * 128), 128 * 128, 1024);
-          umma_bf16_ss(tmem_base + o_col, da, db, idesc_o, k > 0 ? 1u : 0u);
+          asm volatile(
+              "{\n\t"
+              ".reg .pred p;\n\t"
+              "setp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+              "}\n" ::"r"(tmem_base + o_col),
+              "r"(tmem_base + (n & 1u) * 128u + 8u * k), "l"(db), "r"(idesc_o), "r"(k > 0 ? 1u : 0u)
+              : "memory");
         }
         umma_commit(&o_full[o_index(n)]);
         umma_commit(&in_empty[st]);
@@ -248,15 +251,18 @@ temporal_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, TaParams p) {
         l += p0 + p1;
         pk[i >> 1] = pack_bf16x2(p0, p1);
       }
-      const uint32_t p_row = sP + (n & 1u) * Cfg::P_BYTES + r * 128;
+      // P (64 packed columns) over the scores: this warp's rows are non-zero only in its own 32-key block
+      {
+        const uint32_t zeros[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const uint32_t p_addr = lane_addr + (n & 1u) * 128u;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int piece = q * 4 + g;
-        const uint32_t addr = p_row + (piece >> 3) * (128 * 128) + (((piece & 7) ^ (r & 7)) << 4);
-        st_shared_v4(addr, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        for (int g = 0; g < 4; ++g) {
+          if (g == q) tmem_st_x16(p_addr + 16 * g, pk);
+          else tmem_st_x16(p_addr + 16 * g, zeros);
+        }
+        tmem_st_wait();
       }
       tc_fence_before_sync();
-      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[n & 1u]);
       if (prev_item >= 0) epilogue(n - 1, prev_item, inv_prev);
