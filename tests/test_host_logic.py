@@ -1,0 +1,67 @@
+"""CPU checks of the host-side weight preparation that feeds the CUDA kernels (no kernel is launched here): the layouts
+below are contracts between synfmc_b200/engine.py and the kernels of include/fmc_b200.h."""
+import torch
+import torch.nn.functional as Fn
+from torch import nn
+
+from synfmc_b200 import engine, ops
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def test_fused_temporal_weight_layout():
+    """fmc_temporal_qkv_attn_bf16 wants, per head h, the rows [to_q(h) 40 | to_k(h) 40 | to_v(h) 40 | 8 zero rows]."""
+    from synfmc_b200.fmc.models.attention_processor import AttnProcessor
+    from synfmc_b200.fmc.models.motion_module import TemporalSelfAttention
+    torch.manual_seed(0)
+    attn = TemporalSelfAttention(attention_mode="Temporal_Self", cross_attention_dim=None, query_dim=320, heads=8,
+                                 dim_head=40, temporal_position_encoding=True)
+    attn.set_processor(AttnProcessor())
+    plan = engine.AttnPlan(attn, torch.device("cpu"), fused_temporal=True)
+    w = plan.w_head_major.float()
+    assert w.shape == (8 * 128, 320)
+    for h in (0, 3, 7):
+        blk = w[h * 128:(h + 1) * 128]
+        assert torch.equal(blk[0:40], _bf(attn.to_q.weight.detach()[h * 40:(h + 1) * 40]))
+        assert torch.equal(blk[40:80], _bf(attn.to_k.weight.detach()[h * 40:(h + 1) * 40]))
+        assert torch.equal(blk[80:120], _bf(attn.to_v.weight.detach()[h * 40:(h + 1) * 40]))
+        assert torch.count_nonzero(blk[120:]) == 0
+    # the un-fused layout (q | k heads padded 40 -> 48, then v) stays available for the other widths
+    assert plan.qkv.w.shape == (8 * 48 * 2 + 320, 320)
+
+
+def test_conv3x3_weight_layout_is_tap_major():
+    """fmc_conv3x3_bf16 walks K as (ky, kx, cin): an explicit im2col product with ConvPlan.w2d must equal conv2d."""
+    torch.manual_seed(1)
+    conv = nn.Conv2d(64, 32, 3, padding=1)
+    plan = engine.ConvPlan(conv, torch.device("cpu"))
+    assert plan.fast3x3 and plan.w2d.shape == (32, 9 * 64)
+    x = _bf(torch.randn(2, 64, 6, 8))
+    want = Fn.conv2d(x, _bf(conv.weight.detach()), None, padding=1)
+    xp = Fn.pad(x, (1, 1, 1, 1)).permute(0, 2, 3, 1)  # NHWC, zero border
+    cols = torch.cat([xp[:, ky:ky + 6, kx:kx + 8, :] for ky in range(3) for kx in range(3)], dim=-1)  # [N, H, W, 9 * Cin]
+    got = (cols.reshape(-1, 9 * 64) @ plan.w2d.float().t()).view(2, 6, 8, 32).permute(0, 3, 1, 2)
+    assert torch.allclose(got, want, atol=1e-4, rtol=1e-4)
+    assert torch.equal(plan.b32, conv.bias.detach())
+
+
+def test_conv3x3_geometry_predicate():
+    assert ops.conv3x3_supported(40, 64, 320, 320, 1)       # level 0 of BASELINE config 2
+    assert ops.conv3x3_supported(40, 64, 320, 320, 2)       # Downsample2D
+    assert ops.conv3x3_supported(5, 8, 1280, 1280, 1)       # level 3: tiles span images
+    assert ops.conv3x3_supported(32, 32, 64, 320, 1)        # conv_in of config 1 (latent channels padded to 64)
+    assert not ops.conv3x3_supported(40, 40, 320, 320, 1)   # 128 % 40 != 0 -> cuDNN path
+    assert not ops.conv3x3_supported(40, 64, 8, 320, 1)     # Cin not a multiple of 64
+    assert not ops.conv3x3_supported(41, 64, 320, 320, 2)   # stride does not divide the image
+
+
+def test_geglu_and_lora_plans_are_device_agnostic():
+    """LinearPlan interleaves GEGLU rows in blocks of 16 (value | gate) and keeps N, K; _fold_lora is exact in fp32."""
+    w, b = torch.randn(64, 16), torch.randn(64)
+    plan = engine.LinearPlan(w, b, torch.device("cpu"), geglu=True)
+    assert (plan.N, plan.K) == (64, 16)
+    val, gate = w[:32], w[32:]
+    assert torch.equal(plan.w[:16].float(), _bf(val[:16])) and torch.equal(plan.w[16:32].float(), _bf(gate[:16]))
+    assert torch.equal(plan.b[:16], b[:16]) and torch.equal(plan.b[16:32], b[32:48])
