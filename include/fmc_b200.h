@@ -43,6 +43,19 @@ int fmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, vo
                   int K, const float* bias, const void* residual, long long ldr, const float* rowbias,
                   int rows_per_group, long long ldrb, int flags, int tile_n, void* stream);
 
+/* C = LayerNorm(A) Wo^T + b with the normalisation folded into the GEMM: A holds the UN-normalised rows; W = Wo scaled
+ * by gamma per input channel (bf16); colsum[n] = sum_k W[n, k] of the bf16 weights; bias[n] = b[n] + sum_k Wo[n, k]
+ * beta[k]; rowstats = float2 (mean, rstd) per row from fmc_rowstats_bf16.  Epilogue: acc * rstd - mean * rstd *
+ * colsum[n] + bias[n] (then GEGLU if flagged).  Saves the LayerNorm write pass and the GEMM's read of it.
+ * Replaces nn.LayerNorm + the following Linear at diffusers BasicTransformerBlock norm1 -> attn1.to_q|k|v,
+ * norm2 -> attn2.to_q, norm3 -> ff.net.0 and fmc/models/motion_module.py:297 (ff_norm -> ff). */
+int fmc_gemm_ln_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
+                     int K, const float* bias, const float* colsum, const void* rowstats, int flags, int tile_n,
+                     void* stream);
+
+/* stats[row] = (mean, rstd = 1 / sqrt(var + eps)) over the C channels of each bf16 row (float2 per row). */
+int fmc_rowstats_bf16(const void* x, long long ldx, void* stats, long long rows, int C, float eps, void* stream);
+
 /* 3x3 convolution, padding 1, stride 1 or 2, on channels-last bf16 images as an implicit GEMM on the same tcgen05
  * kernel as fmc_gemm_bf16 (CTA-pair MMA): Out[n, oh, ow, :] = sum_{ky, kx, c} X[n, oh*s + ky - 1, ow*s + kx - 1, c] *
  * W[:, ky, kx, c] (+ bias[Cout]) (+ residual[n, oh, ow, :]).  X [images, H, Wd, Cin], Out / residual

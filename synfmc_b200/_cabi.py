@@ -14,6 +14,8 @@ ABI_VERSION = 1  # FMC_B200_ABI_VERSION of include/fmc_b200.h
 # name -> argtypes, in the order of include/fmc_b200.h
 SIGNATURES = {
     "fmc_gemm_bf16": [P, L, P, L, P, L, I, I, I, P, P, L, P, I, L, I, I, P],
+    "fmc_gemm_ln_bf16": [P, L, P, L, P, L, I, I, I, P, P, P, I, I, P],
+    "fmc_rowstats_bf16": [P, L, P, L, I, F, P],
     "fmc_conv3x3_bf16": [P, P, P, P, P, I, I, I, I, I, I, I, P],
     "fmc_spatial_attn_bf16": [P, L, I, L, P, L, I, P, L, I, L, I, P, L, I, I, I, I, I, I, I, F, P],
     "fmc_spatial_attn_vf16": [P, L, I, L, P, L, I, P, L, I, L, I, P, L, I, I, I, I, I, I, I, F, P],

@@ -35,6 +35,10 @@ struct GemmParams {
   long long ldrb;
   int flags;
   int f16_col0;  // output columns >= f16_col0 are written as IEEE fp16 (FMC_GEMM_F16_TAIL), else INT_MAX
+  // LayerNorm folded into the GEMM (fmc_gemm_ln_bf16): A holds the UN-normalised rows, W the weights scaled by gamma;
+  // epilogue: acc * rstd[row] - mean[row] * rstd[row] * colsum[n] (+ bias, which carries W beta)
+  const float2* rowstats;
+  const float* colsum;
   int tiles_m, tiles_n;
   // implicit-GEMM convolution (CONV kernels): A rows are output pixels (n, oh, ow) of a channels-last image, K runs over
   // (ky, kx, cin); the A operand of k-block kb is the input shifted by tap kb / cchunks, fetched row by row with 4-D
@@ -625,6 +629,12 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int row = m_blk * GEMM_BM + r_in_tile;
       const float* rb = nullptr;
       if (p.rowbias != nullptr && row < p.M) rb = p.rowbias + static_cast<long long>(row / p.rows_per_group) * p.ldrb;
+      float ln_rstd = 1.f, ln_shift = 0.f;  // folded LayerNorm of this row: acc * rstd - mean * rstd * colsum[n]
+      if (p.rowstats != nullptr && row < p.M) {
+        const float2 st = __ldg(p.rowstats + row);
+        ln_rstd = st.y;
+        ln_shift = -st.x * st.y;
+      }
       mbar_wait(&acc_full_bar[b], ph);
       mbar_wait(&buf_ready_bar[b], ph);
       tc_fence_after_sync();
@@ -641,6 +651,14 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.rowstats != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.colsum + ocol0 + j));
+              v[j] = fmaf(v[j], ln_rstd, ln_shift * s4.x); v[j + 1] = fmaf(v[j + 1], ln_rstd, ln_shift * s4.y);
+              v[j + 2] = fmaf(v[j + 2], ln_rstd, ln_shift * s4.z); v[j + 3] = fmaf(v[j + 3], ln_rstd, ln_shift * s4.w);
+            }
+          }
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -676,10 +694,20 @@ gemm_bf16_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
               for (int j = 0; j < 32; ++j) bv[j] = 0.f;
             }
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(rr[j]);
+            if (p.rowstats != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.colsum + ncol0 + hblk * 32 + j));
+                acc[j] = fmaf(acc[j], ln_rstd, ln_shift * s4.x); acc[j + 1] = fmaf(acc[j + 1], ln_rstd, ln_shift * s4.y);
+                acc[j + 2] = fmaf(acc[j + 2], ln_rstd, ln_shift * s4.z); acc[j + 3] = fmaf(acc[j + 3], ln_rstd, ln_shift * s4.w);
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 16; j += 2)
-              geglu_pair(__uint_as_float(rr[j]) + bv[j], __uint_as_float(rr[j + 1]) + bv[j + 1],
-                         __uint_as_float(rr[16 + j]) + bv[16 + j], __uint_as_float(rr[17 + j]) + bv[17 + j],
+              geglu_pair(acc[j] + bv[j], acc[j + 1] + bv[j + 1], acc[16 + j] + bv[16 + j], acc[17 + j] + bv[17 + j],
                          v[hblk * 16 + j], v[hblk * 16 + j + 1]);
           }
         }
@@ -787,10 +815,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
 
 using namespace fmc;
 
-extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
-                             int N, int K, const float* bias, const void* residual, long long ldr,
-                             const float* rowbias, int rows_per_group, long long ldrb, int flags, int tile_n,
-                             void* stream_) {
+static int gemm_impl(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                     const float* bias, const void* residual, long long ldr, const float* rowbias, int rows_per_group,
+                     long long ldrb, int flags, int tile_n, const float2* rowstats, const float* colsum, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FMC_REQUIRE(A && W && C, FMC_ERR_ARG, "fmc_gemm_bf16: null operand");
   FMC_REQUIRE(M > 0 && N > 0 && K > 0, FMC_ERR_SHAPE, "fmc_gemm_bf16: empty problem %dx%dx%d", M, N, K);
@@ -865,6 +892,10 @@ extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long l
   p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
   p.rowbias = rowbias; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; p.ldrb = ldrb;
   p.flags = flags;
+  p.rowstats = rowstats;
+  p.colsum = colsum;
+  FMC_REQUIRE(rowstats == nullptr || (tma_epilogue && colsum != nullptr), FMC_ERR_ARG,
+              "fmc_gemm_ln_bf16: the folded LayerNorm needs the bf16 TMA-epilogue path and a column-sum vector");
   p.f16_col0 = 0x7FFFFFFF;
   if ((flags & FMC_GEMM_F16_TAIL) != 0) {
     const int col0 = (flags >> 8) * 32;
@@ -919,6 +950,24 @@ extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long l
   }
 }
 
+
+extern "C" int fmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
+                             int N, int K, const float* bias, const void* residual, long long ldr,
+                             const float* rowbias, int rows_per_group, long long ldrb, int flags, int tile_n,
+                             void* stream_) {
+  return gemm_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, rowbias, rows_per_group, ldrb, flags, tile_n,
+                   nullptr, nullptr, stream_);
+}
+
+// C = LayerNorm(A) Wo^T + b with the normalisation folded into the GEMM: W = Wo * gamma (per input channel), colsum[n] =
+// sum_k W[n, k], bias = b + Wo beta, rowstats[row] = (mean, rstd) of A's rows (fmc_rowstats_bf16).
+extern "C" int fmc_gemm_ln_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
+                                int N, int K, const float* bias, const float* colsum, const void* rowstats, int flags,
+                                int tile_n, void* stream_) {
+  FMC_REQUIRE(colsum != nullptr && rowstats != nullptr, FMC_ERR_ARG, "fmc_gemm_ln_bf16: null colsum / rowstats");
+  return gemm_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, nullptr, 0, nullptr, 0, 0, flags, tile_n,
+                   static_cast<const float2*>(rowstats), colsum, stream_);
+}
 
 // 3x3 convolution (padding 1, stride 1 or 2) on channels-last bf16 images as an implicit GEMM on the same tcgen05 kernel:
 // out[n, oh, ow, :] = sum_{ky,kx,c} x[n, oh*s + ky - 1, ow*s + kx - 1, c] * w[:, ky, kx, c] (+ bias) (+ residual).

@@ -423,6 +423,61 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const
   }
 }
 
+// Row statistics only: stats[row] = (mean, rstd) over C channels.  The LayerNorm itself is then applied inside the
+// consuming GEMM (fmc_gemm_ln_bf16): one read pass instead of a read + write pass and a second read by the GEMM.
+template <int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+rowstats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float2* __restrict__ stats, long long rows, int C,
+                float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int R = 2;
+  const int lane = threadIdx.x & 31;
+  const long long row0 = (blockIdx.x * static_cast<long long>(LN_WARPS) + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
+  const int nvec = C >> 3;
+  const float inv_c = 1.0f / static_cast<float>(C);
+  uint4 raw[R][NV];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r < rows ? row0 + r : rows - 1;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      raw[r][i] = vi < nvec ? __ldg(xr + vi) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s += bf16_lo(w[j]) + bf16_hi(w[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nvec) {
+        const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = bf16_lo(w[j]) - mean, b = bf16_hi(w[j]) - mean;
+          ss = fmaf(a, a, fmaf(b, b, ss));
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0 && row0 + r < rows) stats[row0 + r] = make_float2(mean, rsqrtf(ss * inv_c + eps));
+  }
+}
+
 template <int NV, int R>
 static int launch_layernorm(const void* x, long long ldx, const float* gamma, const float* beta, float eps, void* out,
                             long long ldo, const float* pe, int F, int HW, const void* add, long long ldadd, void* out2,
@@ -506,4 +561,25 @@ extern "C" int fmc_groupnorm_bf16(const void* x, long long ldx, const float* gam
   launch_k(groupnorm_apply_kernel, dim3(dim3(ceil_div(HW, rows_par * GN_UNROLL), images)), dim3(threads), 0, stream, 
       static_cast<const __nv_bfloat16*>(x), ldx, ab, static_cast<__nv_bfloat16*>(out), ldo, HW, C, silu);
   return check_launch("groupnorm_apply_kernel");
+}
+
+extern "C" int fmc_rowstats_bf16(const void* x, long long ldx, void* stats, long long rows, int C, float eps,
+                                 void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FMC_REQUIRE(x && stats, FMC_ERR_ARG, "fmc_rowstats_bf16: null operand");
+  FMC_REQUIRE(C % 8 == 0 && C <= 32 * 8 * LN_MAX_VEC && ldx % 8 == 0, FMC_ERR_SHAPE,
+              "fmc_rowstats_bf16: C=%d must be a multiple of 8 and <= %d, ldx a multiple of 8", C, 32 * 8 * LN_MAX_VEC);
+  if (rows == 0) return FMC_OK;
+  const unsigned grid = static_cast<unsigned>((rows + LN_WARPS * 2 - 1) / (LN_WARPS * 2));
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  float2* sp = static_cast<float2*>(stats);
+  const int nv = (C / 8 + 31) / 32;
+  switch (nv) {
+    case 1: FMC_CUDA_OK(launch_k(rowstats_kernel<1>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, xp, ldx, sp, rows, C, eps)); break;
+    case 2: FMC_CUDA_OK(launch_k(rowstats_kernel<2>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, xp, ldx, sp, rows, C, eps)); break;
+    case 3: FMC_CUDA_OK(launch_k(rowstats_kernel<3>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, xp, ldx, sp, rows, C, eps)); break;
+    case 4: FMC_CUDA_OK(launch_k(rowstats_kernel<4>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, xp, ldx, sp, rows, C, eps)); break;
+    default: FMC_CUDA_OK(launch_k(rowstats_kernel<5>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, xp, ldx, sp, rows, C, eps)); break;
+  }
+  return check_launch("rowstats_kernel");
 }

@@ -25,6 +25,9 @@ CONV3X3 = os.environ.get("FMC_CONV3X3", "auto")
 # (fmc_spatial_attn_vf16).  Correct (tests/test_gpu_ops.py::test_spatial_attention_fp16_v) but 8 % SLOWER than the bf16
 # kernel in round 1 -- the kernel turned out not to be MUFU bound (profiles/r01_spatial_attention_experiments.md).
 SPATIAL_VF16 = bool(os.environ.get("FMC_SPATIAL_VF16"))
+# LayerNorm folded into the GEMM that consumes it (row statistics kernel + epilogue correction) for the spatial
+# transformer blocks and the feed-forward of the temporal blocks; FMC_LN_UNFUSED=1 keeps the separate LayerNorm kernel
+LN_FUSED = not os.environ.get("FMC_LN_UNFUSED")
 # debugging switch: FMC_UNFUSED_TEMPORAL=1 runs the temporal attention as GEMM + attention kernels instead of the fused one
 FUSED_TEMPORAL = not os.environ.get("FMC_UNFUSED_TEMPORAL")
 
@@ -90,18 +93,37 @@ def _dev_f32(w, device):
 
 
 class LinearPlan:
-    def __init__(self, weight, bias, device, geglu=False):
-        """weight [N, K] fp32 (already folded / fused), bias [N] or None."""
+    def __init__(self, weight, bias, device, geglu=False, pre_norm=None):
+        """weight [N, K] fp32 (already folded / fused), bias [N] or None.
+
+        `pre_norm` (nn.LayerNorm): the LayerNorm in front of this Linear is folded into the GEMM
+        (fmc_gemm_ln_bf16): W' = W * gamma, bias' = bias + W beta, colsum = row sums of the bf16 W'; the call then takes
+        the UN-normalised rows plus their (mean, rstd) from ops.rowstats."""
+        self.colsum = None
+        self.eps = None
+        if pre_norm is not None:
+            weight = weight.detach().float()
+            gamma, beta = pre_norm.weight.detach().float().to(weight.device), pre_norm.bias.detach().float().to(weight.device)
+            extra = weight @ beta
+            bias = extra if bias is None else bias.detach().float().to(weight.device) + extra
+            weight = weight * gamma[None, :]
+            self.eps = float(pre_norm.eps)
         if geglu:
             weight, bias = _interleave_geglu(weight, bias)
         self.w = _dev_bf16(weight, device)
         self.b = _dev_f32(bias, device)
         self.geglu = geglu
         self.N, self.K = self.w.shape
+        if pre_norm is not None:
+            self.colsum = self.w.float().sum(dim=1).contiguous()  # of the ROUNDED weights: the mean term cancels exactly
 
-    def __call__(self, a, residual=None, out=None, rowbias=None, rows_per_group=0):
+    def __call__(self, a, residual=None, out=None, rowbias=None, rows_per_group=0, ln_stats=None, f16_from_col=None):
+        if self.colsum is not None:
+            assert ln_stats is not None and residual is None and rowbias is None
+            return ops.gemm(a, self.w, bias=self.b, out=out, geglu=self.geglu, ln_stats=ln_stats, ln_colsum=self.colsum,
+                            f16_from_col=f16_from_col)
         return ops.gemm(a, self.w, bias=self.b, residual=residual, out=out, geglu=self.geglu, rowbias=rowbias,
-                        rows_per_group=rows_per_group)
+                        rows_per_group=rows_per_group, f16_from_col=f16_from_col)
 
 
 def _interleave_geglu(weight, bias):
@@ -141,7 +163,7 @@ def _pad_heads(w, heads, d, hs):
 class AttnPlan:
     """One attention (spatial self, spatial text-cross, or temporal self) with everything foldable folded."""
 
-    def __init__(self, attn, device, lora_scale_override=None, fused_temporal=False):
+    def __init__(self, attn, device, lora_scale_override=None, fused_temporal=False, pre_norm=None):
         from .fmc.models.attention_processor import (LoRAAttnProcessor, LORAPoseAdaptorAttnProcessor,
                                                      PoseAdaptorAttnProcessor)
         proc = attn.processor
@@ -166,11 +188,14 @@ class AttnPlan:
         wk = _pad_heads(folded("to_k"), heads, d, hs)
         wv = folded("to_v")
         self.is_cross = bool(getattr(attn, "is_cross_attention", False))
+        # pre_norm: the LayerNorm in front of the query-side projection is folded into that GEMM (LN_FUSED)
+        self.ln_fused = pre_norm is not None and LN_FUSED
+        fold = pre_norm if self.ln_fused else None
         if self.is_cross:
-            self.q = LinearPlan(wq, None, device)
+            self.q = LinearPlan(wq, None, device, pre_norm=fold)
             self.kv = LinearPlan(torch.cat([wk, wv], dim=0), None, device)
         else:
-            self.qkv = LinearPlan(torch.cat([wq, wk, wv], dim=0), None, device)
+            self.qkv = LinearPlan(torch.cat([wq, wk, wv], dim=0), None, device, pre_norm=fold)
         wo = folded("to_out") / self.rescale
         bo = attn.to_out[0].bias.detach().float() / self.rescale if attn.to_out[0].bias is not None else None
         self.out = LinearPlan(wo, bo, device)
@@ -247,11 +272,12 @@ class ConvPlan:
 # --------------------------------------------------------------------------------------------------------------
 # executors
 # --------------------------------------------------------------------------------------------------------------
-def run_spatial_self_attention(plan, x_norm, residual, images, n_tokens):
-    """attn1 of a BasicTransformerBlock on rows [(images n_tokens), C]; returns to_out(attn) + residual."""
+def run_spatial_self_attention(plan, x_norm, residual, images, n_tokens, ln_stats=None):
+    """attn1 of a BasicTransformerBlock on rows [(images n_tokens), C]; returns to_out(attn) + residual.  With
+    `ln_stats` (plan.ln_fused) `x_norm` is the UN-normalised input and the LayerNorm happens inside the q|k|v GEMM."""
     # optional fp16 V / P path for head width 40 (see SPATIAL_VF16)
     v_f16 = SPATIAL_VF16 and plan.d == 40 and plan.v_col0 % 32 == 0
-    qkv = ops.gemm(x_norm, plan.qkv.w, f16_from_col=plan.v_col0) if v_f16 else plan.qkv(x_norm)
+    qkv = plan.qkv(x_norm, ln_stats=ln_stats, f16_from_col=plan.v_col0 if v_f16 else None)
     ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=BF16)
     ops.spatial_attn(qkv, plan.q_col0, qkv, plan.k_col0, qkv, plan.v_col0, plan.hs, ctx, images, plan.heads, plan.d,
                      n_tokens, n_tokens, 1, n_tokens, plan.scale, v_f16=v_f16)
@@ -269,11 +295,12 @@ def prepare_text(text, device):
     return buf.view(B * TEXT_PAD, c), n
 
 
-def run_spatial_cross_attention(plan, x_norm, residual, images, n_tokens, text_rows, text_len, frames, text_kv=None):
+def run_spatial_cross_attention(plan, x_norm, residual, images, n_tokens, text_rows, text_len, frames, text_kv=None,
+                                ln_stats=None):
     """attn2: queries from the latent tokens, keys / values from the text of the clip the frame belongs to.  The
     reference repeats the text f times ('b n c -> (b f) n c', unet.py:1110); here K/V are projected once per clip
     and image i reads kv group i // frames."""
-    q = plan.q(x_norm)
+    q = plan.q(x_norm, ln_stats=ln_stats)
     kv = text_kv if text_kv is not None else plan.kv(text_rows)
     ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=BF16)
     ops.spatial_attn(q, 0, kv, 0, kv, plan.heads * plan.hs, plan.hs, ctx, images, plan.heads, plan.d, n_tokens, text_len,
@@ -355,11 +382,11 @@ def plan_transformer2d(mod, device):
         blocks = []
         for blk in mod.transformer_blocks:
             blocks.append({
-                "norm1": NormPlan(blk.norm1, device), "attn1": AttnPlan(blk.attn1, device),
-                "norm2": NormPlan(blk.norm2, device), "attn2": AttnPlan(blk.attn2, device),
+                "norm1": NormPlan(blk.norm1, device), "attn1": AttnPlan(blk.attn1, device, pre_norm=blk.norm1),
+                "norm2": NormPlan(blk.norm2, device), "attn2": AttnPlan(blk.attn2, device, pre_norm=blk.norm2),
                 "norm3": NormPlan(blk.norm3, device),
                 "ff1": LinearPlan(blk.ff.net[0].proj.weight.detach().float(), blk.ff.net[0].proj.bias.detach().float(),
-                                  device, geglu=True),
+                                  device, geglu=True, pre_norm=blk.norm3 if LN_FUSED else None),
                 "ff2": LinearPlan(blk.ff.net[2].weight.detach().float(), blk.ff.net[2].bias.detach().float(), device),
             })
         c_in = mod.proj_in.weight.shape[1]
@@ -383,13 +410,24 @@ def run_transformer2d(mod, x, text):
     n = ops.groupnorm(rows, p["norm"].g, p["norm"].b, p["norm"].eps, images, N, groups=p["norm"].groups)
     h = p["proj_in"](n)
     for bp in p["blocks"]:
-        n1 = ops.layernorm(h, bp["norm1"].g, bp["norm1"].b, bp["norm1"].eps)
-        h = run_spatial_self_attention(bp["attn1"], n1, h, images, N)
-        n2 = ops.layernorm(h, bp["norm2"].g, bp["norm2"].b, bp["norm2"].eps)
-        h = run_spatial_cross_attention(bp["attn2"], n2, h, images, N, text.rows, text.length, F,
-                                        text_kv=text.kv.get(id(bp["attn2"])))
-        n3 = ops.layernorm(h, bp["norm3"].g, bp["norm3"].b, bp["norm3"].eps)
-        h = bp["ff2"](bp["ff1"](n3), residual=h)
+        # each LayerNorm is either its own kernel or a row-statistics pass + a correction in the consuming GEMM
+        if bp["attn1"].ln_fused:
+            h = run_spatial_self_attention(bp["attn1"], h, h, images, N, ln_stats=ops.rowstats(h, bp["norm1"].eps))
+        else:
+            n1 = ops.layernorm(h, bp["norm1"].g, bp["norm1"].b, bp["norm1"].eps)
+            h = run_spatial_self_attention(bp["attn1"], n1, h, images, N)
+        kv = text.kv.get(id(bp["attn2"]))
+        if bp["attn2"].ln_fused:
+            h = run_spatial_cross_attention(bp["attn2"], h, h, images, N, text.rows, text.length, F, text_kv=kv,
+                                            ln_stats=ops.rowstats(h, bp["norm2"].eps))
+        else:
+            n2 = ops.layernorm(h, bp["norm2"].g, bp["norm2"].b, bp["norm2"].eps)
+            h = run_spatial_cross_attention(bp["attn2"], n2, h, images, N, text.rows, text.length, F, text_kv=kv)
+        if bp["ff1"].colsum is not None:
+            h = bp["ff2"](bp["ff1"](h, ln_stats=ops.rowstats(h, bp["norm3"].eps)), residual=h)
+        else:
+            n3 = ops.layernorm(h, bp["norm3"].g, bp["norm3"].b, bp["norm3"].eps)
+            h = bp["ff2"](bp["ff1"](n3), residual=h)
     out = p["proj_out"](h, residual=rows)
     return CL(out.view(B, F, H, W, C))
 

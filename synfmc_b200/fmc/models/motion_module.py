@@ -72,7 +72,8 @@ class TemporalTransformerBlock(nn.Module):
                                if attn.pos_encoder is not None else None)
             p["ff_norm"] = engine.NormPlan(self.ff_norm, device)
             p["ff1"] = engine.LinearPlan(self.ff.net[0].proj.weight.detach().float(),
-                                         self.ff.net[0].proj.bias.detach().float(), device, geglu=True)
+                                         self.ff.net[0].proj.bias.detach().float(), device, geglu=True,
+                                         pre_norm=self.ff_norm if engine.LN_FUSED else None)
             p["ff2"] = engine.LinearPlan(self.ff.net[2].weight.detach().float(), self.ff.net[2].bias.detach().float(), device)
             self._plan = p
         return self._plan
@@ -91,6 +92,8 @@ class TemporalTransformerBlock(nn.Module):
             else:
                 x, xp = ops.layernorm(h, npl.g, npl.b, npl.eps, pe=pe, F=F, HW=HW), None
             h = engine.run_temporal_attention(ap, x, xp, h, B, F, HW)
+        if p["ff1"].colsum is not None:  # ff_norm folded into the GEGLU GEMM
+            return p["ff2"](p["ff1"](h, ln_stats=ops.rowstats(h, p["ff_norm"].eps)), residual=h)
         n = ops.layernorm(h, p["ff_norm"].g, p["ff_norm"].b, p["ff_norm"].eps)
         return p["ff2"](p["ff1"](n), residual=h)
 

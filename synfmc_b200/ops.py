@@ -27,8 +27,18 @@ def _rows2d(t, dtype=BF16):
     return t
 
 
+def rowstats(x, eps=1e-5):
+    """(mean, rstd) per row of a bf16 [rows, C] tensor -> fp32 [rows, 2] (fmc_rowstats_bf16)."""
+    _check_cuda(x)
+    _rows2d(x)
+    stats = torch.empty((x.shape[0], 2), device=x.device, dtype=torch.float32)
+    _cabi.call("fmc_rowstats_bf16", x.data_ptr(), x.stride(0), stats.data_ptr(), x.shape[0], x.shape[1], float(eps),
+               _stream())
+    return stats
+
+
 def gemm(a, w, bias=None, residual=None, out=None, geglu=False, out_f32=False, rowbias=None, rows_per_group=0,
-         tile_n=0, f16_from_col=None):
+         tile_n=0, f16_from_col=None, ln_stats=None, ln_colsum=None):
     """out[M, N(/2)] = epilogue(a[M, K] @ w[N, K]^T); see fmc_gemm_bf16.  `f16_from_col`: columns from there on are
     written as IEEE fp16 bit patterns into the bf16 output tensor (FMC_GEMM_F16_TAIL)."""
     _check_cuda(a, w)
@@ -52,6 +62,14 @@ def gemm(a, w, bias=None, residual=None, out=None, geglu=False, out_f32=False, r
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
     if rowbias is not None:
         assert rowbias.dtype == torch.float32 and rowbias.stride(1) == 1 and rowbias.shape[1] == N
+    if ln_stats is not None:
+        # LayerNorm folded into the GEMM: `a` un-normalised, `w` scaled by gamma, bias carrying W beta
+        assert residual is None and rowbias is None and not out_f32
+        assert ln_stats.dtype == torch.float32 and ln_stats.shape == (M, 2) and ln_stats.is_contiguous()
+        assert ln_colsum.dtype == torch.float32 and ln_colsum.numel() == N and ln_colsum.is_contiguous()
+        _cabi.call("fmc_gemm_ln_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
+                   M, N, K, _ptr(bias), ln_colsum.data_ptr(), ln_stats.data_ptr(), flags, tile_n, _stream())
+        return out
     _cabi.call("fmc_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), M, N,
                K, _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, _ptr(rowbias),
                rows_per_group, rowbias.stride(0) if rowbias is not None else 0, flags, tile_n, _stream())

@@ -88,6 +88,32 @@ def test_gemm_geglu(ops, cuda_device, M, C):
     assert rel(got, want) < BF16_TOL
 
 
+@pytest.mark.parametrize("M,C,N,geglu", [(1000, 320, 1088, False), (333, 640, 384, False), (1000, 320, 2560, True),
+                                         (5120, 1280, 10240, True)])
+def test_gemm_with_folded_layernorm(ops, cuda_device, M, C, N, geglu):
+    """LayerNorm folded into the consuming GEMM (fmc_rowstats_bf16 + fmc_gemm_ln_bf16) against LayerNorm -> Linear
+    (-> GEGLU) in fp32 torch, on rows with a non-zero mean (the term the epilogue has to cancel)."""
+    import torch.nn as nn
+    from synfmc_b200.engine import LinearPlan
+    x = randn(M, C, seed=1) * 1.5 + 0.7
+    norm = nn.LayerNorm(C)
+    norm.weight.data = 1 + 0.2 * randn(C, seed=2)
+    norm.bias.data = 0.3 * randn(C, seed=3)
+    w, b = randn(N, C, seed=4, scale=C ** -0.5), randn(N, seed=5)
+    plan = LinearPlan(w, b, cuda_device, geglu=geglu, pre_norm=norm)
+    xd = bf(x).to(cuda_device)
+    stats = ops.rowstats(xd, norm.eps)
+    xf = bf(x).float()
+    assert rel(stats[:, 0], xf.mean(1)) < 1e-5
+    assert rel(stats[:, 1], (xf.var(1, unbiased=False) + norm.eps).rsqrt()) < 1e-5
+    got = plan(xd, ln_stats=stats)
+    y = Fn.layer_norm(xf, (C,), norm.weight.data, norm.bias.data, norm.eps) @ w.t() + b
+    if geglu:
+        val, gate = y.chunk(2, dim=-1)
+        y = val * Fn.gelu(gate)
+    assert rel(got, y) < BF16_TOL
+
+
 def test_gemm_rejects_bad_shapes(ops, cuda_device):
     from synfmc_b200._cabi import FmcError
     a = torch.zeros(16, 30, dtype=torch.bfloat16, device=cuda_device)  # K not a multiple of 8 -> unaligned row stride

@@ -65,3 +65,22 @@ def test_geglu_and_lora_plans_are_device_agnostic():
     val, gate = w[:32], w[32:]
     assert torch.equal(plan.w[:16].float(), _bf(val[:16])) and torch.equal(plan.w[16:32].float(), _bf(gate[:16]))
     assert torch.equal(plan.b[:16], b[:16]) and torch.equal(plan.b[16:32], b[32:48])
+
+
+def test_layernorm_fold_algebra():
+    """LinearPlan(pre_norm=...): rstd * (x W'^T - mean * colsum) + bias' == Linear(LayerNorm(x)) with W' = W * gamma,
+    colsum = row sums of the bf16 W', bias' = bias + W beta."""
+    torch.manual_seed(2)
+    C, N = 64, 48
+    norm = nn.LayerNorm(C)
+    norm.weight.data = 1 + 0.2 * torch.randn(C)
+    norm.bias.data = 0.3 * torch.randn(C)
+    w, b = torch.randn(N, C) / 8, torch.randn(N)
+    plan = engine.LinearPlan(w, b, torch.device("cpu"), pre_norm=norm)
+    x = _bf(torch.randn(10, C) + 0.5)
+    mean, rstd = x.mean(1, keepdim=True), (x.var(1, unbiased=False, keepdim=True) + norm.eps).rsqrt()
+    got = rstd * (x @ plan.w.float().t() - mean * plan.colsum[None, :]) + plan.b[None, :]
+    want = Fn.layer_norm(x, (C,), norm.weight.data, norm.bias.data, norm.eps) @ w.t() + b
+    assert torch.allclose(got, want, atol=2e-2, rtol=2e-2)  # bf16 weights
+    exact = rstd * (x @ (w * norm.weight.data).t() - mean * (w * norm.weight.data).sum(1)[None, :]) + (b + w @ norm.bias.data)
+    assert torch.allclose(exact, want, atol=1e-4, rtol=1e-4)
