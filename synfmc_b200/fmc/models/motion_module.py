@@ -73,7 +73,7 @@ class TemporalTransformerBlock(nn.Module):
             p["ff_norm"] = engine.NormPlan(self.ff_norm, device)
             p["ff1"] = engine.LinearPlan(self.ff.net[0].proj.weight.detach().float(),
                                          self.ff.net[0].proj.bias.detach().float(), device, geglu=True,
-                                         pre_norm=self.ff_norm if engine.LN_FUSED else None)
+                                         pre_norm=self.ff_norm if engine.ln_fold_wanted(*self.ff.net[0].proj.weight.shape) else None)
             p["ff2"] = engine.LinearPlan(self.ff.net[2].weight.detach().float(), self.ff.net[2].bias.detach().float(), device)
             self._plan = p
         return self._plan
