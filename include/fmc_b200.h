@@ -128,6 +128,12 @@ int fmc_groupnorm_bf16(const void* x, long long ldx, const float* gamma, const f
                        long long ldo, float* stats_ws, int images, int HW, int C, int groups, int silu,
                        const float* rowbias, long long ldrb, int rowbias_div, void* stream);
 
+/* Launch accounting only (never fails): how many kernels one fmc_groupnorm_bf16 call of this shape launches -- 1 when
+ * the single-pass cluster kernel takes it (x read once: a cluster of CTAs holds one image's channel chunk in
+ * registers and exchanges per-group partial sums through distributed shared memory), 3 for the partial / finalize /
+ * apply form. */
+int fmc_groupnorm_launches(int HW, int C, int groups);
+
 /* out = a (+ b) (+ rowbias[row / rows_per_group]) (ReLU optional).  Residual adds, the ObjectEncoder feature
  * injection fmc/modified_modules.py:115-117, time-embedding broadcast, nn.ReLU of fmc/adapter.py:93. */
 int fmc_add_bf16(const void* a, long long lda, const void* b, long long ldb, const float* rowbias, int rows_per_group,

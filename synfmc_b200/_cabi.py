@@ -59,6 +59,8 @@ def lib():
         handle.fmc_last_error_string.argtypes = []
         handle.fmc_abi_version.restype = c_int
         handle.fmc_abi_version.argtypes = []
+        handle.fmc_groupnorm_launches.restype = c_int
+        handle.fmc_groupnorm_launches.argtypes = [c_int, c_int, c_int]
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the .so does not export what the header declares
             fn.restype = c_int
@@ -67,8 +69,12 @@ def lib():
     return _lib
 
 
-# kernels launched by one call of each entry point (groupnorm = partial sums + finalize + apply); everything else launches one
-KERNELS_PER_CALL = {"fmc_groupnorm_bf16": 3}
+# kernels launched by one call of each entry point: everything launches one except GroupNorm, which is either the
+# single-pass cluster kernel (1) or partial sums + finalize + apply (3) depending on the shape -- the library says which
+def _kernels_per_call(handle, name, args):
+    if name == "fmc_groupnorm_bf16":
+        return handle.fmc_groupnorm_launches(args[9], args[10], args[11])  # HW, C, groups
+    return 1
 launch_count = 0  # kernels of this library launched by this process (bench.py reports it as gpu_launches)
 trace = None      # when set to a list by bench.py: (name, args, start_event, end_event) per call, CUDA events on the
                   # launching stream -- the per-kernel timing behind the roofline figures
@@ -89,4 +95,4 @@ def call(name, *args):
         rc = getattr(handle, name)(*args)
     if rc != 0:
         raise FmcError(f"{name} failed (rc={rc}): {handle.fmc_last_error_string().decode()}")
-    launch_count += KERNELS_PER_CALL.get(name, 1)
+    launch_count += _kernels_per_call(handle, name, args)

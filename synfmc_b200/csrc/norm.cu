@@ -6,6 +6,8 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include <cstdlib>
+
 #include "ptx.cuh"
 
 namespace fmc {
@@ -18,6 +20,7 @@ namespace fmc {
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_MAX_VEC = 5;  // per lane: 5 vectors of 8 channels -> C <= 1280
 constexpr int LN_WARPS = 8;
+constexpr int LN_ADD_R_DEFAULT = 1;  // measured: 72 -> 53 us at level 0 (profiles/r01_norm_bench.txt)
 
 template <int NV, int R, bool HAS_ADD>
 __global__ void __launch_bounds__(LN_WARPS * 32)
@@ -279,6 +282,26 @@ static int launch_layernorm40(const void* x, long long ldx, const float* gamma, 
 //            streams its rows: y = x * a + b (optional SiLU).
 // Thread layout in both: `nvec = C / 8` lanes per row (one 16-byte vector each), blockDim / nvec rows in flight.
 // ------------------------------------------------------------------------------------------------
+// y * sigmoid(y) on a packed pair: the same arithmetic as the scalar `y * rcp_fast(1 + __expf(-y))` of the apply kernel
+// (ex2 of y * -log2(e), + 1, MUFU.RCP, * y) with the three fp32 operations issued as .f32x2 and the exponential without
+// the denormal-range fix-up of the non-ftz form (an exponent below -126 flushes to 0, and 1 + 0 == 1 + denormal)
+__device__ __forceinline__ uint64_t silu_f2(uint64_t y2) {
+  float t0, t1;
+  f2_unpack(f2_mul(y2, f2_pack(-1.4426950408889634f, -1.4426950408889634f)), t0, t1);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  float d0, d1;
+  f2_unpack(f2_add(f2_pack(e0, e1), f2_pack(1.0f, 1.0f)), d0, d1);
+  return f2_mul(y2, f2_pack(rcp_fast(d0), rcp_fast(d1)));
+}
+__device__ __forceinline__ uint64_t bf16x2_to_f2(uint32_t w) { return f2_pack(bf16_lo(w), bf16_hi(w)); }
+__device__ __forceinline__ uint32_t f2_to_bf16x2(uint64_t v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+
 constexpr int GN_ROWS = 64;       // rows per block, partial kernel
 constexpr int GN_APPLY_ROWS = 32;  // rows per block, apply kernel
 constexpr int GN_MAX_GROUPS = 64;
@@ -299,19 +322,28 @@ groupnorm_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, flo
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
   if (rsub < rows_par) {
-    float rb[8];
+    uint64_t rb2[4], a2[4], b2[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) rb[j] = rowbias != nullptr ? __ldg(rowbias + (img / rb_div) * ldrb + vi * 8 + j) : 0.f;
+    for (int j = 0; j < 4; ++j) {
+      rb2[j] = rowbias != nullptr ? f2_pack(__ldg(rowbias + (img / rb_div) * ldrb + vi * 8 + 2 * j),
+                                            __ldg(rowbias + (img / rb_div) * ldrb + vi * 8 + 2 * j + 1)) : 0ull;
+      a2[j] = b2[j] = 0ull;
+    }
     const int rend = min(row0 + GN_ROWS, HW);
     for (int r = row0 + rsub; r < rend; r += rows_par) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<long long>(img) * HW + r) * ldx) + vi);
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float lo = bf16_lo(w[j]) + rb[2 * j], hi = bf16_hi(w[j]) + rb[2 * j + 1];
-        a[2 * j] += lo; b[2 * j] = fmaf(lo, lo, b[2 * j]);
-        a[2 * j + 1] += hi; b[2 * j + 1] = fmaf(hi, hi, b[2 * j + 1]);
+        const uint64_t xr = f2_add(bf16x2_to_f2(w[j]), rb2[j]);
+        a2[j] = f2_add(a2[j], xr);
+        b2[j] = f2_fma(xr, xr, b2[j]);
       }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      f2_unpack(a2[j], a[2 * j], a[2 * j + 1]);
+      f2_unpack(b2[j], b[2 * j], b[2 * j + 1]);
     }
     float* ssum = gn_smem + static_cast<size_t>(rsub) * C + vi * 8;
     float* ssq = gn_smem + static_cast<size_t>(rows_par + rsub) * C + vi * 8;
@@ -386,13 +418,14 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const
   const int vi = threadIdx.x % nvec;
   const int rsub = threadIdx.x / nvec;
   if (rsub >= rows_par) return;
-  float sa[8], sb[8];
+  uint64_t sa2[4], sb2[4];
   {
     const float4* p4 = reinterpret_cast<const float4*>(ab + static_cast<long long>(img) * C + vi * 8);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float4 v = __ldg(p4 + j);
-      sa[2 * j] = v.x; sb[2 * j] = v.y; sa[2 * j + 1] = v.z; sb[2 * j + 1] = v.w;
+      sa2[j] = f2_pack(v.x, v.z);
+      sb2[j] = f2_pack(v.y, v.w);
     }
   }
   const int row0 = blockIdx.x * (rows_par * GN_UNROLL) + rsub;
@@ -407,20 +440,293 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const
     const int r = row0 + k * rows_par;
     if (r < HW) {
       const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-      float y[8];
+      uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        y[2 * j] = fmaf(bf16_lo(w[j]), sa[2 * j], sb[2 * j]);
-        y[2 * j + 1] = fmaf(bf16_hi(w[j]), sa[2 * j + 1], sb[2 * j + 1]);
+        uint64_t y2 = f2_fma(bf16x2_to_f2(w[j]), sa2[j], sb2[j]);
+        if (silu) y2 = silu_f2(y2);
+        o[j] = f2_to_bf16x2(y2);
       }
-      if (silu) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = y[j] * rcp_fast(1.0f + __expf(-y[j]));
-      }
-      *reinterpret_cast<uint4*>(out + (static_cast<long long>(img) * HW + r) * ldo + vi * 8) = make_uint4(
-          pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+      *reinterpret_cast<uint4*>(out + (static_cast<long long>(img) * HW + r) * ldo + vi * 8) =
+          make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm in ONE pass over HBM (read x once, write y once; the three-kernel form above reads x twice and pays three
+// dependent launches, which is all that is left of a GroupNorm at the two coarse U-Net levels).
+//   work item = (image, channel chunk): CH = lcm(C / G, 8) channels, i.e. whole groups AND whole 16-byte vectors
+//               (40 channels = 4 groups at C = 320, 2 groups at C = 640, 1 at C = 1280; 80 at C = 2560; 120 at
+//               C = 960 / 1920).  A cluster of R CTAs (R = 1, 2, 4, 8) splits the HW rows of the item; each CTA keeps
+//               its rows x CH slab in REGISTERS (<= VMAX 16-byte vectors per thread), reduces it to per-group
+//               (sum, sum of squares), publishes the pair in its shared memory, and after one cluster barrier every
+//               CTA folds the R partials in rank order through distributed shared memory -- a fixed order, so all CTAs
+//               get the same bits and two runs are identical.  Then y = x * a + b (+ SiLU) straight from the registers.
+// Thread layout: VPR = CH / 8 lanes per row, 256 / VPR rows per pass, like the kernels above.
+// ------------------------------------------------------------------------------------------------
+constexpr int GN_FUSED_DEFAULT = 1;  // measured: GroupNorm 3.33 -> 2.43 ms per step, step 31.47 -> 31.0 ms (profiles/r01_norm_bench.txt)
+constexpr int GNF_THREADS = 256;
+constexpr int GNF_MAX_CH = 128;     // VPR <= 16
+constexpr int GNF_MAX_CLUSTER = 8;  // portable cluster size
+
+__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t cluster_addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int VMAX>
+__global__ void __launch_bounds__(GNF_THREADS)
+groupnorm_fused_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out, long long ldo,
+                       int HW, int cpg, int CH, int rows_cta, int silu, const float* __restrict__ rowbias,
+                       long long ldrb, int rb_div) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red_s[2 * GNF_THREADS], red_q[2 * GNF_THREADS];  // [slot = vc * 2 + which][rsub]
+  __shared__ float tot_s[2 * GNF_MAX_CH / 8], tot_q[2 * GNF_MAX_CH / 8];
+  __shared__ float2 part[8];                                         // this CTA's (sum, sum of squares) per group
+  __shared__ float s_mean[8], s_rstd[8];
+  const int tid = threadIdx.x;
+  const int R = gridDim.x, rank = blockIdx.x, chunk = blockIdx.y, img = blockIdx.z;
+  const int VPR = CH >> 3;
+  const int rows_par = GNF_THREADS / VPR;
+  const int vc = tid % VPR, rsub = tid / VPR;
+  const bool active = rsub < rows_par;
+  const int ngc = CH / cpg;                       // groups per chunk (<= 8)
+  const int c0 = chunk * CH + vc * 8;             // first channel of this thread's vector
+  const int g_first = c0 / cpg;                   // group of channel c0 (global index)
+  const int split = min(8, (g_first + 1) * cpg - c0);  // channels [0, split) -> g_first, [split, 8) -> g_first + 1
+  const int row_begin = rank * rows_cta;
+  const int row_end = min(HW, row_begin + rows_cta);
+  // this thread's rows: row_begin + rsub + i * rows_par for i < nvalid
+  const int mine = row_end - row_begin - rsub;
+  const int nvalid = (active && mine > 0) ? min(VMAX, (mine + rows_par - 1) / rows_par) : 0;
+  const long long first_row = static_cast<long long>(img) * HW + row_begin + rsub;
+  const uint4* xp = reinterpret_cast<const uint4*>(x + first_row * ldx + c0);
+  const long long xstep = static_cast<long long>(rows_par) * ldx / 8;  // in 16-byte vectors (ldx % 8 == 0)
+
+  uint4 v[VMAX];
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i) v[i] = i < nvalid ? __ldg(xp + i * xstep) : make_uint4(0u, 0u, 0u, 0u);
+  uint64_t rb2[4];
+  if (rowbias != nullptr) {
+    const float4* rp = reinterpret_cast<const float4*>(rowbias + (img / rb_div) * ldrb + c0);
+    const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+    rb2[0] = f2_pack(r0.x, r0.y); rb2[1] = f2_pack(r0.z, r0.w); rb2[2] = f2_pack(r1.x, r1.y); rb2[3] = f2_pack(r1.z, r1.w);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rb2[j] = 0ull;
+  }
+
+  // ---- per-thread channel sums (packed fp32 pairs), split into the (at most two) groups the vector touches
+  {
+    uint64_t a2[4], b2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a2[j] = b2[j] = 0ull;
+#pragma unroll
+    for (int i = 0; i < VMAX; ++i) {
+      if (i < nvalid) {
+        const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t xr = f2_add(bf16x2_to_f2(w[j]), rb2[j]);
+          a2[j] = f2_add(a2[j], xr);
+          b2[j] = f2_fma(xr, xr, b2[j]);
+        }
+      }
+    }
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      f2_unpack(a2[j], a[2 * j], a[2 * j + 1]);
+      f2_unpack(b2[j], b[2 * j], b[2 * j + 1]);
+    }
+    float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < split) { s_lo += a[j]; q_lo += b[j]; } else { s_hi += a[j]; q_hi += b[j]; }
+    }
+    if (active) {
+      red_s[(vc * 2) * rows_par + rsub] = s_lo;
+      red_q[(vc * 2) * rows_par + rsub] = q_lo;
+      red_s[(vc * 2 + 1) * rows_par + rsub] = s_hi;
+      red_q[(vc * 2 + 1) * rows_par + rsub] = q_hi;
+    }
+  }
+  __syncthreads();
+  // ---- rows -> one pair per slot (a warp per slot, fixed butterfly), slots -> groups (slot order)
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int s = warp; s < 2 * VPR; s += GNF_THREADS / 32) {
+      float ss = 0.f, qq = 0.f;
+      for (int r = lane; r < rows_par; r += 32) {
+        ss += red_s[s * rows_par + r];
+        qq += red_q[s * rows_par + r];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        qq += __shfl_xor_sync(0xffffffffu, qq, o);
+      }
+      if (lane == 0) { tot_s[s] = ss; tot_q[s] = qq; }
+    }
+  }
+  __syncthreads();
+  if (tid < ngc) {
+    const int g = chunk * ngc + tid;
+    float ss = 0.f, qq = 0.f;
+    for (int s = 0; s < 2 * VPR; ++s) {
+      const int sc0 = chunk * CH + (s >> 1) * 8;
+      if (sc0 / cpg + (s & 1) == g) { ss += tot_s[s]; qq += tot_q[s]; }
+    }
+    part[tid] = make_float2(ss, qq);
+  }
+  // ---- cluster exchange: every CTA folds the R partials in rank order
+  if (R > 1) { cluster_arrive_release(); cluster_wait_acquire(); } else { __syncthreads(); }
+  if (tid < ngc) {
+    float ss = 0.f, qq = 0.f;
+    if (R > 1) {
+      // all remote loads first (independent, ~0.5 us each when serialised behind their adds), then the fixed-order fold
+      const uint32_t mine_addr = smem_u32(&part[tid]);
+      float2 p[GNF_MAX_CLUSTER];
+#pragma unroll
+      for (int r = 0; r < GNF_MAX_CLUSTER; ++r)
+        p[r] = r < R ? ld_dsmem_f2(mapa_shared(mine_addr, static_cast<uint32_t>(r))) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < GNF_MAX_CLUSTER; ++r) {
+        if (r < R) { ss += p[r].x; qq += p[r].y; }
+      }
+    } else {
+      ss = part[tid].x; qq = part[tid].y;
+    }
+    const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
+    const float mean = ss * inv_n;
+    const float var = fmaxf(qq * inv_n - mean * mean, 0.f);
+    s_mean[tid] = mean;
+    s_rstd[tid] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  if (R > 1) cluster_arrive_release();  // my remote reads are done; peers may exit once everybody got here
+
+  // ---- apply from registers: y = x * a + b with a = rstd * gamma, b = beta + (rowbias - mean) * a
+  if (nvalid > 0) {
+    float sa[8], sb[8], rbf[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + j));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c0 + j));
+      sa[j] = g4.x; sa[j + 1] = g4.y; sa[j + 2] = g4.z; sa[j + 3] = g4.w;
+      sb[j] = b4.x; sb[j + 1] = b4.y; sb[j + 2] = b4.z; sb[j + 3] = b4.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f2_unpack(rb2[j], rbf[2 * j], rbf[2 * j + 1]);
+    const int gl = g_first - chunk * ngc;
+    const float m0 = s_mean[gl], r0 = s_rstd[gl];
+    const float m1 = split < 8 ? s_mean[gl + 1] : 0.f, r1 = split < 8 ? s_rstd[gl + 1] : 0.f;
+    uint64_t sa2[4], sb2[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = (j < split ? r0 : r1) * sa[j];
+      sb[j] = fmaf(rbf[j] - (j < split ? m0 : m1), a, sb[j]);
+      sa[j] = a;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sa2[j] = f2_pack(sa[2 * j], sa[2 * j + 1]);
+      sb2[j] = f2_pack(sb[2 * j], sb[2 * j + 1]);
+    }
+    uint4* op = reinterpret_cast<uint4*>(out + first_row * ldo + c0);
+    const long long ostep = static_cast<long long>(rows_par) * ldo / 8;
+#pragma unroll
+    for (int i = 0; i < VMAX; ++i) {
+      if (i < nvalid) {
+        const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint64_t y2 = f2_fma(bf16x2_to_f2(w[j]), sa2[j], sb2[j]);
+          if (silu) y2 = silu_f2(y2);
+          o[j] = f2_to_bf16x2(y2);
+        }
+        op[i * ostep] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  if (R > 1) cluster_wait_acquire();
+}
+
+// Shape plan of the single-pass kernel: returns 0 when the shape does not fit (the three-kernel form takes it).
+struct GnFusedPlan {
+  int ch, cluster, rows_cta, vmax;
+};
+static bool gn_fused_plan(int HW, int C, int G, GnFusedPlan* p) {
+  const int cpg = C / G;
+  if (cpg < 8) return false;  // a 16-byte vector must not span more than two groups
+  int g8 = 8, a = cpg;
+  while (a) { const int t = g8 % a; g8 = a; a = t; }  // gcd(cpg, 8)
+  const int ch = cpg * (8 / g8);
+  if (ch > GNF_MAX_CH || C % ch != 0 || ch / cpg > 8) return false;
+  const int rows_par = GNF_THREADS / (ch / 8);
+  for (int r = 1; r <= GNF_MAX_CLUSTER; r *= 2) {
+    const int rows_cta = ceil_div(HW, r);
+    const int need = ceil_div(rows_cta, rows_par);
+    if (need <= 8) {
+      p->ch = ch; p->cluster = r; p->rows_cta = rows_cta; p->vmax = need <= 2 ? 2 : need <= 4 ? 4 : 8;
+      return true;
+    }
+  }
+  return false;
+}
+
+static int gn_fused_mode() {
+  const char* e = getenv("FMC_GN_FUSED");  // read per call (A/B inside one process); a captured graph keeps its choice
+  return e != nullptr ? (e[0] - '0') : GN_FUSED_DEFAULT;
+}
+// mode 0: never; 1: 40- and 80-channel chunks only (the 120-channel chunks of C = 960 / 1920 measured slower than the
+// three-kernel form in the first version: 255 of 256 threads on 240-byte row pieces); 2: every shape that fits
+static bool gn_fused_wanted(int HW, int C, int groups, GnFusedPlan* pl) {
+  const int mode = gn_fused_mode();
+  if (mode <= 0 || !gn_fused_plan(HW, C, groups, pl)) return false;
+  return mode >= 2 || pl->ch <= 80;
+}
+
+template <int VMAX>
+static cudaError_t launch_gn_fused(const GnFusedPlan& pl, const void* x, long long ldx, const float* gamma,
+                                   const float* beta, float eps, void* out, long long ldo, int images, int HW, int C,
+                                   int groups, int silu, const float* rowbias, long long ldrb, int rb_div,
+                                   cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl.cluster, C / pl.ch, images);
+  cfg.blockDim = dim3(GNF_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pl.cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = pl.cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, groupnorm_fused_kernel<VMAX>, static_cast<const __nv_bfloat16*>(x), ldx, gamma, beta,
+                            eps, static_cast<__nv_bfloat16*>(out), ldo, HW, C / groups, pl.ch, pl.rows_cta, silu,
+                            rowbias, ldrb, rb_div);
 }
 
 // Row statistics only: stats[row] = (mean, rstd) over C channels.  The LayerNorm itself is then applied inside the
@@ -512,6 +818,16 @@ extern "C" int fmc_layernorm_bf16(const void* x, long long ldx, const float* gam
   FMC_REQUIRE((out2 == nullptr) == (add == nullptr), FMC_ERR_ARG, "fmc_layernorm_bf16: add and out2 go together");
   FMC_REQUIRE(pe == nullptr || (F > 0 && HW > 0), FMC_ERR_ARG, "fmc_layernorm_bf16: pe needs F and HW");
   if (rows == 0) return FMC_OK;
+  // row passes in flight per warp: 2, except the two-output form (x + pose): it holds twice the vectors and lands at
+  // 169 - 232 registers with 2 (one 8-warp block per SM, 2.9 TB/s); with 1 it needs 98 (two blocks, 3.95 TB/s).
+  // FMC_LN_ADD_R=2 restores the old choice (A/B switch)
+  int add_r = LN_ADD_R_DEFAULT;
+  if (const char* e = getenv("FMC_LN_ADD_R")) add_r = atoi(e);
+  if (add != nullptr && add_r == 1) {
+    if (C == 320) return launch_layernorm40<8, 1>(x, ldx, gamma, beta, eps, out, ldo, pe, F, HW, add, ldadd, out2, ldo2, rows, stream);
+    if (C == 640) return launch_layernorm40<16, 1>(x, ldx, gamma, beta, eps, out, ldo, pe, F, HW, add, ldadd, out2, ldo2, rows, stream);
+    if (C == 1280) return launch_layernorm40<32, 1>(x, ldx, gamma, beta, eps, out, ldo, pe, F, HW, add, ldadd, out2, ldo2, rows, stream);
+  }
   if (C == 320) return launch_layernorm40<8, 2>(x, ldx, gamma, beta, eps, out, ldo, pe, F, HW, add, ldadd, out2, ldo2, rows, stream);
   if (C == 640) return launch_layernorm40<16, 2>(x, ldx, gamma, beta, eps, out, ldo, pe, F, HW, add, ldadd, out2, ldo2, rows, stream);
   if (C == 1280) return launch_layernorm40<32, 2>(x, ldx, gamma, beta, eps, out, ldo, pe, F, HW, add, ldadd, out2, ldo2, rows, stream);
@@ -536,6 +852,16 @@ extern "C" int fmc_groupnorm_bf16(const void* x, long long ldx, const float* gam
               "fmc_groupnorm_bf16: unsupported C=%d groups=%d", C, groups);
   FMC_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0, FMC_ERR_SHAPE, "fmc_groupnorm_bf16: row strides must be multiples of 8");
   if (images == 0 || HW == 0) return FMC_OK;
+  const int rb_div0 = rowbias_div > 0 ? rowbias_div : 1;
+  GnFusedPlan pl;
+  if (images <= 65535 && gn_fused_wanted(HW, C, groups, &pl)) {
+    cudaError_t e;
+    if (pl.vmax == 2) e = launch_gn_fused<2>(pl, x, ldx, gamma, beta, eps, out, ldo, images, HW, C, groups, silu, rowbias, ldrb, rb_div0, stream);
+    else if (pl.vmax == 4) e = launch_gn_fused<4>(pl, x, ldx, gamma, beta, eps, out, ldo, images, HW, C, groups, silu, rowbias, ldrb, rb_div0, stream);
+    else e = launch_gn_fused<8>(pl, x, ldx, gamma, beta, eps, out, ldo, images, HW, C, groups, silu, rowbias, ldrb, rb_div0, stream);
+    FMC_CUDA_OK(e);
+    return check_launch("groupnorm_fused_kernel");
+  }
   // stats_ws: [images][chunks][groups][2] partial sums, then [images][C] (scale, shift) pairs
   const int chunks = ceil_div(HW, GN_ROWS);
   const int nvec = C / 8;
@@ -582,4 +908,12 @@ extern "C" int fmc_rowstats_bf16(const void* x, long long ldx, void* stats, long
     default: FMC_CUDA_OK(launch_k(rowstats_kernel<5>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, xp, ldx, sp, rows, C, eps)); break;
   }
   return check_launch("rowstats_kernel");
+}
+
+/* number of kernels one fmc_groupnorm_bf16 call of this shape launches (1: single-pass cluster kernel, 3: partial sums +
+ * finalize + apply) -- for launch accounting only */
+extern "C" int fmc_groupnorm_launches(int HW, int C, int groups) {
+  GnFusedPlan pl;
+  if (groups <= 0 || C % groups != 0) return 3;
+  return gn_fused_wanted(HW, C, groups, &pl) ? 1 : 3;
 }

@@ -280,6 +280,54 @@ def test_groupnorm(ops, cuda_device, images, HW, C, silu):
     assert rel(got, want.permute(0, 2, 1).reshape(images * HW, C)) < BF16_TOL
 
 
+@pytest.mark.parametrize("images,HW,C,silu", [
+    (3, 2560, 320, True),    # cluster of 8, 4 groups per 40-channel chunk
+    (2, 1000, 320, False),   # cluster of 4, ragged rows (last CTA short)
+    (3, 640, 640, True),     # cluster of 2, 2 groups per chunk
+    (2, 160, 1280, True),    # one CTA per (image, group)
+    (2, 40, 2560, True),     # 80-channel chunks
+    (2, 640, 1920, True),    # 120-channel chunks (60 channels per group), cluster of 8
+    (2, 37, 960, False),     # 30 channels per group: vectors straddle groups
+    (1, 2560, 960, True),    # does not fit the single-pass kernel: three-kernel form behind the same call
+])
+def test_groupnorm_single_pass(ops, cuda_device, monkeypatch, images, HW, C, silu):
+    """The single-pass cluster GroupNorm (FMC_GN_FUSED=1) against torch and against the three-kernel form; two runs are
+    bit-identical (fixed reduction order through distributed shared memory)."""
+    x, g, b = randn(images * HW, C, seed=1) + 0.3, 1 + 0.1 * randn(C, seed=2), 0.1 * randn(C, seed=3)
+    xd, gd, bd = bf(x).to(cuda_device), g.to(cuda_device), b.to(cuda_device)
+    monkeypatch.setenv("FMC_GN_FUSED", "1")
+    got = ops.groupnorm(xd, gd, bd, 1e-6, images, HW, silu=silu)
+    again = ops.groupnorm(xd, gd, bd, 1e-6, images, HW, silu=silu)
+    monkeypatch.setenv("FMC_GN_FUSED", "0")
+    three = ops.groupnorm(xd, gd, bd, 1e-6, images, HW, silu=silu)
+    assert torch.equal(got, again)
+    want = Fn.group_norm(bf(x).float().view(images, HW, C).permute(0, 2, 1), 32, g, b, 1e-6)
+    want = (Fn.silu(want) if silu else want).permute(0, 2, 1).reshape(images * HW, C)
+    assert rel(got, want) < BF16_TOL
+    assert rel(got, three.float().cpu()) < BF16_TOL
+    # strided input / output rows (a channel slice of a wider tensor)
+    wide = torch.zeros(images * HW, C + 64, device=cuda_device, dtype=torch.bfloat16)
+    wide[:, 32:32 + C] = xd
+    out_wide = torch.zeros_like(wide)
+    monkeypatch.setenv("FMC_GN_FUSED", "1")
+    ops.groupnorm(wide[:, 32:32 + C], gd, bd, 1e-6, images, HW, silu=silu, out=out_wide[:, 32:32 + C])
+    assert torch.equal(out_wide[:, 32:32 + C], got)
+    assert float(out_wide[:, :32].abs().max()) == 0.0 and float(out_wide[:, 32 + C:].abs().max()) == 0.0
+
+
+def test_groupnorm_single_pass_time_embedding_bias(ops, cuda_device, monkeypatch):
+    B, F, HW, C = 2, 3, 640, 640
+    images = B * F
+    x, g, b = randn(images * HW, C, seed=1), 1 + 0.1 * randn(C, seed=2), 0.1 * randn(C, seed=3)
+    tb = randn(B, C, seed=4)
+    monkeypatch.setenv("FMC_GN_FUSED", "1")
+    got = ops.groupnorm(bf(x).to(cuda_device), g.to(cuda_device), b.to(cuda_device), 1e-5, images, HW, silu=True,
+                        rowbias=tb.to(cuda_device), rowbias_div=F)
+    xi = (bf(x).float().view(B, F, HW, C) + tb[:, None, None, :]).view(images, HW, C).permute(0, 2, 1)
+    want = Fn.silu(Fn.group_norm(xi, 32, g, b, 1e-5)).permute(0, 2, 1).reshape(images * HW, C)
+    assert rel(got, want) < BF16_TOL
+
+
 def test_groupnorm_time_embedding_bias(ops, cuda_device):
     """h + time_emb_proj(silu(temb))[:, :, None, None] folded in front of norm2 of diffusers ResnetBlock2D."""
     B, F, HW, C = 2, 3, 64, 320
