@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""GroupNorm / LayerNorm / row-statistics kernels at the config-2 shapes: three-kernel vs single-pass GroupNorm
-(FMC_GN_FUSED read per call), CUDA events around batches of launches on the current stream.
+"""GroupNorm / LayerNorm / row-statistics kernels at the config-2 shapes.  GroupNorm modes (FMC_GN_FUSED, read per
+call): 0 = partial + finalize + apply, 1 = single-pass cluster kernel with the slab in registers (40 / 80-channel
+chunks), 3 = 1 with the TMA-staged shared-memory slab where it is 8 - 32 KB, 4 = 3 including 120-channel chunks.
 `cold` rotates over enough buffers to exceed the 126 MB L2 (the producer did not just write x), `hot` reuses one buffer
 (x fully L2-resident when it fits) -- inside a denoising step the truth lies in between.
-usage: python profiles/norm_bench.py [reps]"""
+usage: python profiles/norm_bench.py [reps] [gn]"""
 import os
 import sys
 
@@ -56,15 +57,16 @@ def gn_row(images, HW, C, silu=True):
     xs = buffers(rows, C, ncold)
     outs = [torch.empty_like(x) for x in xs]
     g, b = torch.randn(C, device=dev), torch.randn(C, device=dev)
-    res = []
-    for mode in ("0", "1", "2"):
+    cols = []
+    best = 1e30
+    for mode in ("0", "1", "3", "4"):
         os.environ["FMC_GN_FUSED"] = mode
         cold = time_us([lambda x=x, o=o: ops.groupnorm(x, g, b, 1e-6, images, HW, silu=silu, out=o) for x, o in zip(xs, outs)])
         hot = time_us([lambda: ops.groupnorm(xs[0], g, b, 1e-6, images, HW, silu=silu, out=outs[0])])
-        res += [cold, hot, ops._cabi.lib().fmc_groupnorm_launches(HW, C, 32)]
-    print(f"groupnorm  images {images:3d} HW {HW:5d} C {C:5d}  {2 * mb:7.1f} MB r+w | three-kernel cold {res[0]:7.1f} hot {res[1]:7.1f} us"
-          f" | mode 1 ({res[5]} launch) cold {res[3]:7.1f} hot {res[4]:7.1f} us | mode 2 ({res[8]}) cold {res[6]:7.1f} hot {res[7]:7.1f} us"
-          f" | best cold {2 * mb / min(res[0], res[3], res[6]):5.2f} TB/s", flush=True)
+        best = min(best, cold)
+        cols.append(f"mode {mode} cold {cold:6.1f} hot {hot:6.1f}")
+    print(f"groupnorm  images {images:3d} HW {HW:5d} C {C:5d}  {2 * mb:6.1f} MB r+w | " + " | ".join(cols) +
+          f" us | best cold {2 * mb / best:5.2f} TB/s", flush=True)
 
 
 def ln_row(rows, C, F=16, HW=0, add=False):
@@ -100,6 +102,8 @@ if __name__ == "__main__":
         except Exception as e:  # keep the table going
             print("groupnorm", images, HW, C, "failed:", repr(e)[:200], flush=True)
     os.environ.pop("FMC_GN_FUSED", None)
+    if len(sys.argv) > 2 and sys.argv[2] == "gn":
+        sys.exit(0)
     for rows, C, HW in [(81920, 320, 2560), (20480, 640, 640), (5120, 1280, 160), (1280, 1280, 40)]:
         ln_row(rows, C)
         ln_row(rows, C, HW=HW, add=True)

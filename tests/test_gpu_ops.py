@@ -280,6 +280,13 @@ def test_groupnorm(ops, cuda_device, images, HW, C, silu):
     assert rel(got, want.permute(0, 2, 1).reshape(images * HW, C)) < BF16_TOL
 
 
+def _tma_gate(mode):
+    """the TMA-staged GroupNorm variants (modes 3 / 4) run only when asked for until they have a measured verdict"""
+    import os
+    if mode in ("3", "4") and not os.environ.get("FMC_TEST_GN_TMA"):
+        pytest.skip("TMA-staged GroupNorm is an experiment: set FMC_TEST_GN_TMA=1")
+
+
 @pytest.mark.parametrize("images,HW,C,silu", [
     (3, 2560, 320, True),    # cluster of 8, 4 groups per 40-channel chunk
     (2, 1000, 320, False),   # cluster of 4, ragged rows (last CTA short)
@@ -290,12 +297,15 @@ def test_groupnorm(ops, cuda_device, images, HW, C, silu):
     (2, 37, 960, False),     # 30 channels per group: vectors straddle groups
     (1, 2560, 960, True),    # does not fit the single-pass kernel: three-kernel form behind the same call
 ])
-def test_groupnorm_single_pass(ops, cuda_device, monkeypatch, images, HW, C, silu):
-    """The single-pass cluster GroupNorm (FMC_GN_FUSED=1) against torch and against the three-kernel form; two runs are
-    bit-identical (fixed reduction order through distributed shared memory)."""
+@pytest.mark.parametrize("mode", ["1", "2", "3", "4"])
+def test_groupnorm_single_pass(ops, cuda_device, monkeypatch, images, HW, C, silu, mode):
+    """The single-pass cluster GroupNorm (FMC_GN_FUSED: 1 / 2 slab in registers, 3 / 4 slab staged by TMA) against torch
+    and against the three-kernel form; two runs are bit-identical (fixed reduction order through distributed shared
+    memory)."""
+    _tma_gate(mode)
     x, g, b = randn(images * HW, C, seed=1) + 0.3, 1 + 0.1 * randn(C, seed=2), 0.1 * randn(C, seed=3)
     xd, gd, bd = bf(x).to(cuda_device), g.to(cuda_device), b.to(cuda_device)
-    monkeypatch.setenv("FMC_GN_FUSED", "1")
+    monkeypatch.setenv("FMC_GN_FUSED", mode)
     got = ops.groupnorm(xd, gd, bd, 1e-6, images, HW, silu=silu)
     again = ops.groupnorm(xd, gd, bd, 1e-6, images, HW, silu=silu)
     monkeypatch.setenv("FMC_GN_FUSED", "0")
@@ -309,18 +319,20 @@ def test_groupnorm_single_pass(ops, cuda_device, monkeypatch, images, HW, C, sil
     wide = torch.zeros(images * HW, C + 64, device=cuda_device, dtype=torch.bfloat16)
     wide[:, 32:32 + C] = xd
     out_wide = torch.zeros_like(wide)
-    monkeypatch.setenv("FMC_GN_FUSED", "1")
+    monkeypatch.setenv("FMC_GN_FUSED", mode)
     ops.groupnorm(wide[:, 32:32 + C], gd, bd, 1e-6, images, HW, silu=silu, out=out_wide[:, 32:32 + C])
     assert torch.equal(out_wide[:, 32:32 + C], got)
     assert float(out_wide[:, :32].abs().max()) == 0.0 and float(out_wide[:, 32 + C:].abs().max()) == 0.0
 
 
-def test_groupnorm_single_pass_time_embedding_bias(ops, cuda_device, monkeypatch):
+@pytest.mark.parametrize("mode", ["1", "3"])
+def test_groupnorm_single_pass_time_embedding_bias(ops, cuda_device, monkeypatch, mode):
     B, F, HW, C = 2, 3, 640, 640
     images = B * F
     x, g, b = randn(images * HW, C, seed=1), 1 + 0.1 * randn(C, seed=2), 0.1 * randn(C, seed=3)
     tb = randn(B, C, seed=4)
-    monkeypatch.setenv("FMC_GN_FUSED", "1")
+    _tma_gate(mode)
+    monkeypatch.setenv("FMC_GN_FUSED", mode)
     got = ops.groupnorm(bf(x).to(cuda_device), g.to(cuda_device), b.to(cuda_device), 1e-5, images, HW, silu=True,
                         rowbias=tb.to(cuda_device), rowbias_div=F)
     xi = (bf(x).float().view(B, F, HW, C) + tb[:, None, None, :]).view(images, HW, C).permute(0, 2, 1)
