@@ -131,9 +131,12 @@ def synth_clip(rank):
 
 def flops_of(name, args):
     """Algorithmic FLOPs / bytes of one traced call (kernels table)."""
-    if name == "fmc_gemm_bf16":
+    if name in ("fmc_gemm_bf16", "fmc_gemm_ln_bf16"):
         M, N, K = args[6], args[7], args[8]
         return 2.0 * M * N * K, 0.0
+    if name == "fmc_rowstats_bf16":
+        rows, C = args[3], args[4]
+        return 0.0, rows * C * 2.0
     if name == "fmc_conv3x3_bf16":
         images, Hh, Ww, cin, cout, stride = args[5], args[6], args[7], args[8], args[9], args[10]
         return 2.0 * images * (Hh // stride) * (Ww // stride) * cout * 9 * cin, 0.0
@@ -157,7 +160,7 @@ def flops_of(name, args):
         return 0.0, rows * C * 2.0 * n_tensors
     if name == "fmc_groupnorm_bf16":
         images, HW, C = args[8], args[9], args[10]
-        return 0.0, images * HW * C * 2.0 * 3  # stats read + apply read + write
+        return 0.0, images * HW * C * 2.0 * 2  # algorithmic minimum: x read once, y written once (the single-pass kernel)
     if name == "fmc_add_bf16":
         rows, C = args[9], args[10]
         return 0.0, rows * C * 2.0 * (3 if args[2] else 2)
@@ -207,9 +210,19 @@ def summarise_trace(trace, steps, peaks):
         elif a["bytes"]:
             row["gbs"] = round(a["bytes"] / (a["ms"] * 1e-3) / 1e9, 1)
         table[name] = row
-    mine = {k: v for k, v in agg.items() if k.startswith("fmc_")}
+    # the dominant KERNEL: fmc_gemm_bf16 and fmc_gemm_ln_bf16 are two entry points of one kernel (gemm_bf16_tma_kernel,
+    # the second with the LayerNorm correction in its epilogue), so they are judged together
+    same_kernel = {"fmc_gemm_ln_bf16": "fmc_gemm_bf16"}
+    mine = {}
+    for k, v in agg.items():
+        if k.startswith("fmc_"):
+            m = mine.setdefault(same_kernel.get(k, k), {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            for f in m:
+                m[f] += v[f]
     top = max(mine, key=lambda k: mine[k]["ms"])
     a = mine[top]
+    if top == "fmc_gemm_bf16" and "fmc_gemm_ln_bf16" in agg:
+        top = "fmc_gemm_bf16 + fmc_gemm_ln_bf16 (one kernel: gemm_bf16_tma_kernel)"
     if a["flops"] and a["flops"] / (a["ms"] * 1e-3) / 1e12 > 1.0:
         achieved, peak, bound, unit = a["flops"] / (a["ms"] * 1e-3) / 1e12, peaks["tflops_sustained"], "tensor", "TFLOP/s"
     else:
@@ -217,7 +230,7 @@ def summarise_trace(trace, steps, peaks):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(top)
+        traffic = json.load(open(tpath)).get(top.split(" ")[0])
     roofline = {"kernel": top, "bound": bound, "achieved": round(achieved, 1), "peak": peak, "unit": unit,
                 "frac": round(achieved / peak, 4), "traffic": traffic,
                 "peak_source": f"{peaks['source']} MEASURED_PEAKS.json, sustained figure (kernel timed inside a long step)",

@@ -465,7 +465,7 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const
 //               get the same bits and two runs are identical.  Then y = x * a + b (+ SiLU) straight from the registers.
 // Thread layout: VPR = CH / 8 lanes per row, 256 / VPR rows per pass, like the kernels above.
 // ------------------------------------------------------------------------------------------------
-constexpr int GN_FUSED_DEFAULT = 1;  // measured: GroupNorm 3.33 -> 2.43 ms per step, step 31.47 -> 31.0 ms (profiles/r01_norm_bench.txt)
+constexpr int GN_FUSED_DEFAULT = 4;  // measured (profiles/r01_norm_bench.txt): GroupNorm 3.33 (mode 0) -> 2.43 (1) -> 2.21 ms (3) per step
 constexpr int GNF_THREADS = 256;
 constexpr int GNF_MAX_CH = 128;     // VPR <= 16
 constexpr int GNF_MAX_CLUSTER = 8;  // portable cluster size
@@ -673,7 +673,7 @@ groupnorm_fused_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const
 // an SM (<= 32 KB slab + 4.5 KB reduction scratch each, 48 registers; 6 CTAs = 40 registers spill).
 // ------------------------------------------------------------------------------------------------
 constexpr int GNT_MAX_SLAB = 32768;
-constexpr int GNT_MIN_SLAB = 8192;  // below this the TMA round trip costs more than direct loads
+constexpr int GNT_MIN_SLAB = 16384;  // below this the TMA round trip costs more than direct loads (measured: 12.8 KB slabs lose 10 %)
 
 __global__ void __launch_bounds__(GNF_THREADS, 5)
 groupnorm_tma_kernel(const __grid_constant__ CUtensorMap tmx, const float* __restrict__ gamma,

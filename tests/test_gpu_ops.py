@@ -280,13 +280,6 @@ def test_groupnorm(ops, cuda_device, images, HW, C, silu):
     assert rel(got, want.permute(0, 2, 1).reshape(images * HW, C)) < BF16_TOL
 
 
-def _tma_gate(mode):
-    """the TMA-staged GroupNorm variants (modes 3 / 4) run only when asked for until they have a measured verdict"""
-    import os
-    if mode in ("3", "4") and not os.environ.get("FMC_TEST_GN_TMA"):
-        pytest.skip("TMA-staged GroupNorm is an experiment: set FMC_TEST_GN_TMA=1")
-
-
 @pytest.mark.parametrize("images,HW,C,silu", [
     (3, 2560, 320, True),    # cluster of 8, 4 groups per 40-channel chunk
     (2, 1000, 320, False),   # cluster of 4, ragged rows (last CTA short)
@@ -302,7 +295,6 @@ def test_groupnorm_single_pass(ops, cuda_device, monkeypatch, images, HW, C, sil
     """The single-pass cluster GroupNorm (FMC_GN_FUSED: 1 / 2 slab in registers, 3 / 4 slab staged by TMA) against torch
     and against the three-kernel form; two runs are bit-identical (fixed reduction order through distributed shared
     memory)."""
-    _tma_gate(mode)
     x, g, b = randn(images * HW, C, seed=1) + 0.3, 1 + 0.1 * randn(C, seed=2), 0.1 * randn(C, seed=3)
     xd, gd, bd = bf(x).to(cuda_device), g.to(cuda_device), b.to(cuda_device)
     monkeypatch.setenv("FMC_GN_FUSED", mode)
@@ -331,7 +323,6 @@ def test_groupnorm_single_pass_time_embedding_bias(ops, cuda_device, monkeypatch
     images = B * F
     x, g, b = randn(images * HW, C, seed=1), 1 + 0.1 * randn(C, seed=2), 0.1 * randn(C, seed=3)
     tb = randn(B, C, seed=4)
-    _tma_gate(mode)
     monkeypatch.setenv("FMC_GN_FUSED", mode)
     got = ops.groupnorm(bf(x).to(cuda_device), g.to(cuda_device), b.to(cuda_device), 1e-5, images, HW, silu=True,
                         rowbias=tb.to(cuda_device), rowbias_div=F)
