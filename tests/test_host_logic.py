@@ -84,3 +84,22 @@ def test_layernorm_fold_algebra():
     assert torch.allclose(got, want, atol=2e-2, rtol=2e-2)  # bf16 weights
     exact = rstd * (x @ (w * norm.weight.data).t() - mean * (w * norm.weight.data).sum(1)[None, :]) + (b + w @ norm.bias.data)
     assert torch.allclose(exact, want, atol=1e-4, rtol=1e-4)
+
+
+def test_groupnorm_kernel_plan(monkeypatch):
+    """fmc_groupnorm_launches is pure host logic (the shape plan of norm.cu): the single-pass cluster kernel takes every
+    GroupNorm shape of the config-2 U-Net except C = 960 at 2560 tokens (120-channel chunks x 2560 rows do not fit a
+    cluster of 8), FMC_GN_FUSED=0 forces the three-kernel form, mode 1 leaves the 120-channel chunks to it."""
+    from synfmc_b200 import _cabi
+    fn = _cabi.lib().fmc_groupnorm_launches
+    unet_shapes = [(2560, 320), (2560, 640), (2560, 960), (640, 320), (640, 640), (640, 960), (640, 1280), (640, 1920),
+                   (160, 640), (160, 1280), (160, 1920), (160, 2560), (40, 1280), (40, 2560)]
+    monkeypatch.delenv("FMC_GN_FUSED", raising=False)
+    assert {s: fn(s[0], s[1], 32) for s in unet_shapes} == {s: (3 if s == (2560, 960) else 1) for s in unet_shapes}
+    monkeypatch.setenv("FMC_GN_FUSED", "0")
+    assert all(fn(hw, c, 32) == 3 for hw, c in unet_shapes)
+    monkeypatch.setenv("FMC_GN_FUSED", "1")
+    assert fn(640, 960, 32) == 3 and fn(640, 1920, 32) == 3 and fn(640, 640, 32) == 1
+    monkeypatch.delenv("FMC_GN_FUSED", raising=False)
+    assert fn(64, 128, 32) == 3      # 4 channels per group: a 16-byte vector would span more than two groups
+    assert fn(64, 320, 0) == 3 and fn(64, 321, 32) == 3   # nonsense arguments never fail, they just say "three-kernel"
