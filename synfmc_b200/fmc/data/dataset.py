@@ -1,8 +1,18 @@
 """Mirror of the one hot-path function of fmc/data/dataset.py: `ray_condition` (:930-972), the Pluecker-ray embedding,
-computed on the GPU by fmc_plucker_f32 instead of on the CPU (train_cam_ctrl.py:87 passes device='cpu')."""
+computed on the GPU by fmc_plucker_f32 instead of on the CPU (train_cam_ctrl.py:87 passes device='cpu').
+
+Everything else the trainers import from this module (`UnrealTrajVideoDataset`, `UnrealTrajLoraDataset`,
+train_cam_ctrl.py:37) is CPU data loading outside the hot path: those names resolve lazily to the reference's own
+module when a checkout is known (synfmc_b200/dropin.py), and raise an explanatory AttributeError otherwise."""
 import torch
 
-from ... import ops
+from ... import dropin, ops
+
+
+def __getattr__(name):
+    if name.startswith("__"):
+        raise AttributeError(name)
+    return dropin.reference_attr("data.dataset", name)
 
 
 def ray_condition(K, c2w, H, W, device, flip_flag=None):
