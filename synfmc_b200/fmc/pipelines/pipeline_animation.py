@@ -157,12 +157,23 @@ class CameraCtrlPipeline:
     @torch.no_grad()
     def denoise(self, latents, text_embeddings, pose_features, video_length, traj_features=None,
                 num_inference_steps=25, guidance_scale=8.0, multidiff_total_steps=1, multidiff_overlaps=12,
-                omcm_min_step=None, max_steps=None, callback=None, callback_steps=1):
+                omcm_min_step=None, max_steps=None, callback=None, callback_steps=1, cfg_pair=None):
         """latents [b, 4, F, h, w] fp32 (device); text_embeddings [(2)b, 77, 768]; pose_features: 4 CL features over all
-        F frames (already duplicated for CFG); traj_features: 4 CL features (CFG: zeros ++ features) or None."""
+        F frames (already duplicated for CFG); traj_features: 4 CL features (CFG: zeros ++ features) or None.
+        cfg_pair = (which, group) from synfmc_b200.shard.cfg_pair(): single-clip latency mode, this rank evaluates only
+        half `which` of the CFG pair (0 = unconditional) and exchanges noise predictions once per step."""
         self.scheduler.set_timesteps(num_inference_steps)
         L = video_length
         latents = latents.float().contiguous()
+        if cfg_pair is not None:
+            if not guidance_scale > 1.0 or multidiff_total_steps != 1:
+                raise ValueError("cfg_pair needs classifier-free guidance (guidance_scale > 1) and a single window")
+            which, b = cfg_pair[0], latents.shape[0]
+            half = slice(which * b, (which + 1) * b)
+            text_embeddings = text_embeddings[half].contiguous()
+            pose_features = [CL(CL.from_reference(f).t[half].contiguous()) for f in pose_features]
+            if traj_features is not None:  # the unconditional half carries zeros, i.e. no object features at all
+                traj_features = None if which == 0 else [CL(CL.from_reference(f).t[half].contiguous()) for f in traj_features]
         for i, t in enumerate(self.scheduler.timesteps.tolist()):
             if max_steps is not None and i >= max_steps:
                 break
@@ -171,21 +182,38 @@ class CameraCtrlPipeline:
                 step_traj = None
             latents = self.denoise_step(latents, t, text_embeddings, pose_features, L, traj_features=step_traj,
                                         guidance_scale=guidance_scale, multidiff_total_steps=multidiff_total_steps,
-                                        multidiff_overlaps=multidiff_overlaps)
+                                        multidiff_overlaps=multidiff_overlaps, cfg_pair=cfg_pair)
             if callback is not None and i % callback_steps == 0:
                 callback(i, t, latents)
         return latents
 
     @torch.no_grad()
     def denoise_step(self, latents, t, text_embeddings, pose_features, video_length, traj_features=None,
-                     guidance_scale=8.0, multidiff_total_steps=1, multidiff_overlaps=12):
+                     guidance_scale=8.0, multidiff_total_steps=1, multidiff_overlaps=12, cfg_pair=None):
         """One iteration of the loop at pipeline_animation.py:669-707 / pipeline_animation_cm_om.py:678-726: per-window
         U-Net on the CFG-doubled latents, CFG combine, window averaging, DDIM update.  `t` is a Python int taken from
-        `scheduler.timesteps` after `set_timesteps`; returns the new fp32 latents."""
+        `scheduler.timesteps` after `set_timesteps`; returns the new fp32 latents.
+        With cfg_pair = (which, group) the text / feature arguments are THIS RANK'S HALF of the CFG pair (as `denoise`
+        prepares them): the U-Net runs at batch b, the two ranks all-gather their predictions, both apply the update."""
         do_cfg = guidance_scale > 1.0
         L = video_length
         b = latents.shape[0]
         a_t, a_prev = self.scheduler.alphas_for(t)
+        if cfg_pair is not None:
+            from ... import shard
+            feats = [CL.from_reference(f) for f in pose_features]
+            traj = traj_features if self._accepts_traj else None
+            if traj is not None:
+                traj = [CL.from_reference(f) for f in traj]
+            if self.use_cuda_graph and _cabi.trace is None and not torch.is_tensor(t):
+                eps_half = self._step_graph(latents, text_embeddings, feats, traj, False).run(latents, t, text_embeddings,
+                                                                                               feats, traj)
+            else:
+                kw = {"traj_features": traj} if self._accepts_traj else {}
+                eps_half = self.unet(latents, t, encoder_hidden_states=text_embeddings, pose_embedding_features=feats,
+                                     **kw).sample
+            e_u, e_c = shard.cfg_exchange(eps_half, cfg_pair[1])
+            return ops.cfg_ddim_step(e_u, e_c, guidance_scale, latents, a_t, a_prev)
         if (self.use_cuda_graph and multidiff_total_steps == 1 and _cabi.trace is None and not torch.is_tensor(t)
                 and torch.is_tensor(text_embeddings) and latents.dtype == torch.float32):
             feats = [CL.from_reference(f) for f in pose_features]

@@ -75,3 +75,42 @@ def barrier():
         dist.barrier()
     if torch.cuda.is_available():
         torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------
+# Single-clip latency mode ("optional"): the two classifier-free-guidance halves of ONE clip on two GPUs.
+# Rank `which` = 0 evaluates the unconditional half of the U-Net batch, 1 the conditional half (pose features are the
+# same for both, object features are zero -- i.e. absent -- for the unconditional half,
+# pipeline_animation_cm_om.py:671-676); per step the halves exchange their noise prediction ([b, 4, f, h, w] fp32 =
+# 0.66 MB at 320x512x16f) with ONE all-gather and both ranks apply the CFG combine + DDIM update redundantly, so the
+# latents stay identical on both without a second message.
+# ------------------------------------------------------------------------------------------------
+def cfg_pair(rank=None, size=None):
+    """(which, group, pair_index): consecutive ranks (2p, 2p + 1) form pair p.  Creates one process group per pair (every
+    rank must call this, as torch.distributed.new_group is collective); size 2 uses the default group."""
+    if rank is None or size is None:
+        rank, size, _ = world()
+    if size < 2 or size % 2:
+        raise ValueError(f"the CFG-pair mode needs an even number of ranks, got {size}")
+    if size == 2:
+        return rank, None, 0
+    mine = None
+    for p in range(size // 2):
+        g = dist.new_group(ranks=[2 * p, 2 * p + 1])
+        if rank // 2 == p:
+            mine = g
+    return rank % 2, mine, rank // 2
+
+
+def cfg_half(which, b, text_embeddings, features):
+    """This rank's half of CFG-doubled inputs: text [2b, 77, 768] -> [b, 77, 768]; every feature [2b, ...] -> [b, ...]."""
+    sl = slice(which * b, (which + 1) * b)
+    return text_embeddings[sl], [f[sl] for f in features]
+
+
+def cfg_exchange(eps_half, group=None):
+    """all-gather of the two halves' noise predictions -> (eps_uncond, eps_cond), identical on both ranks"""
+    eps_half = eps_half.contiguous()
+    both = [torch.empty_like(eps_half), torch.empty_like(eps_half)]
+    dist.all_gather(both, eps_half, group=group)
+    return both[0], both[1]
