@@ -144,6 +144,18 @@ def install_shims():
         def device(self):
             return next(self.parameters()).device
 
+        def __getattr__(self, name):
+            """diffusers 0.24.0 ModelMixin.__getattr__: a missing attribute that is a config entry is served from the
+            config (with a deprecation warning there) -- the reference pipelines read `unet.in_channels` this way
+            (pipeline_animation_cm_om.py:630)."""
+            try:
+                return super().__getattr__(name)
+            except AttributeError:
+                cfg = self.__dict__.get("config")
+                if cfg is not None and not name.startswith("_") and hasattr(cfg, name):
+                    return getattr(cfg, name)
+                raise
+
     class UNet2DConditionLoadersMixin:
         pass
 

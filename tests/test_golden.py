@@ -92,3 +92,87 @@ def test_traj_features_match_reference(gold, inp):
     for g, w in zip(got, gold["traj_features"]):
         assert g.shape == w.shape and rel(g, w) < TOL
         assert torch.equal(g == 0, w == 0)  # mask support (scatter order + nearest resize) is identical
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the denoising loop against vectors produced by running the reference's own pipelines
+# (tests/golden/make_golden_pipeline.py)
+# ---------------------------------------------------------------------------------------------------------------
+PIPE_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fmc_reference_pipeline.pt")
+LOOP_TOL = TOL    # measured 0.0 here (bit-identical through all 25 steps); the margin is for other BLAS thread counts
+
+
+@pytest.fixture(scope="module")
+def pgold():
+    return torch.load(PIPE_GOLDEN, weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def pinp():
+    from tests.golden.make_golden_pipeline import pipeline_inputs
+    return pipeline_inputs()
+
+
+def _text_embeddings(pinp, negative=True):
+    """prompt -> [uncond ++ cond] embeddings through the same stand-in tokenizer / text encoder the generator used"""
+    from tests.golden.make_golden_pipeline import HashTokenizer, TableTextEncoder
+    tok, enc = HashTokenizer(), TableTextEncoder()
+    cond = enc(tok(pinp["prompt"], max_length=77).input_ids)[0]
+    neg = pinp["negative_prompt"] if negative else [""] * len(pinp["prompt"])
+    return torch.cat([enc(tok(neg, max_length=77).input_ids)[0], cond])
+
+
+def _decode(latents):
+    """decode_latents of the reference (pipeline_animation_cm_om.py:465-478) on the stand-in VAE, at stride 8"""
+    from tests.golden.make_golden_pipeline import UpsampleVAE
+    vae = UpsampleVAE()
+    f = latents.shape[2]
+    z = (1 / 0.18215 * latents).permute(0, 2, 1, 3, 4).flatten(0, 1)
+    video = torch.cat([vae.decode(z[i:i + 1]).sample for i in range(z.shape[0])])
+    video = video.reshape(-1, f, *video.shape[1:]).permute(0, 2, 1, 3, 4)
+    return (video / 2 + 0.5).clamp(0, 1)[..., ::8, ::8]
+
+
+def test_cam_obj_pipeline_loop_matches_reference(pgold, pinp, gold):
+    """CameraObjCtrlPipeline.__call__ (pipeline_animation_cm_om.py:570-740): timesteps 961 ... 1, CFG batch doubling with
+    [negative ++ prompt] text and [zeros ++ features] object features, object features dropped below t = 700,
+    guidance combine, DDIM update; latents after every step via the reference's callback protocol."""
+    from oracle.diffusers_restated import DDIMScheduler
+    from oracle.pipeline import denoise
+    assert [t for _, t in pgold["obj_steps"]] == [961 - 40 * i for i in range(25)]
+    assert [i for i, _ in pgold["obj_steps"]] == list(range(25))
+    text = _text_embeddings(pinp)
+    assert torch.allclose(text[:, :12, :8], pgold["text_embeddings_head"], rtol=0, atol=0)
+    unet = harness.build_oracle_unet(tiny=True, obj=True)
+    enc = harness.build_oracle_pose_encoder(pinp["channels"])
+    plucker = gold["rays"].permute(0, 4, 1, 2, 3).contiguous()
+    for steps in (1, 7, 8, 25):   # 7 -> 8 crosses the omcm_min_step = 700 gate (t = 681 is the first step without)
+        got = denoise(unet, DDIMScheduler(), enc, pinp["latents"].clone(), text, plucker, pinp["f"],
+                      traj_features=pinp["traj_feats"], num_inference_steps=25, guidance_scale=8.0, omcm_min_step=700,
+                      max_steps=steps)
+        assert rel(got, pgold["obj_latents"][steps - 1]) < LOOP_TOL, steps
+    # the gate matters: without it step 8 differs
+    ungated = denoise(unet, DDIMScheduler(), enc, pinp["latents"].clone(), text, plucker, pinp["f"],
+                      traj_features=pinp["traj_feats"], num_inference_steps=25, guidance_scale=8.0, max_steps=8)
+    assert rel(ungated, pgold["obj_latents"][7]) > 1e-3
+    assert pgold["obj_videos_shape"] == (1, 3, pinp["f"], pinp["H"], pinp["W"])
+    assert torch.allclose(_decode(got), pgold["obj_videos_stride8"], rtol=0, atol=1e-3)
+
+
+def test_cam_pipeline_multidiff_windows_match_reference(pgold, pinp):
+    """CameraCtrlPipeline.__call__ (pipeline_animation.py:570-719) with two overlapping windows: 4-frame U-Net calls
+    at frame offsets 0 and 2 over 6 frames, per-frame averaging of the guided predictions, one DDIM update."""
+    from oracle.diffusers_restated import DDIMScheduler
+    from oracle.pipeline import denoise
+    from oracle.rays import to_plucker_embedding
+    assert [t for _, t in pgold["cam_steps"]] == [831, 665, 499, 333, 167, 1]
+    text = _text_embeddings(pinp, negative=False)
+    unet = harness.build_oracle_unet(tiny=True, obj=False)
+    enc = harness.build_oracle_pose_encoder(pinp["channels"])
+    plucker6 = to_plucker_embedding(pinp["c2w6"], pinp["K6"], (pinp["H"], pinp["W"])).permute(0, 2, 1, 3, 4).contiguous()
+    for steps in (1, 6):
+        got = denoise(unet, DDIMScheduler(), enc, pinp["latents6"].clone(), text, plucker6, 4, num_inference_steps=6,
+                      guidance_scale=7.5, multidiff_total_steps=2, multidiff_overlaps=2, max_steps=steps)
+        assert got.shape == (1, 4, 6, 8, 8)
+        assert rel(got, pgold["cam_latents"][steps - 1]) < LOOP_TOL, steps
+    assert torch.allclose(_decode(got), pgold["cam_videos_stride8"], rtol=0, atol=1e-3)
