@@ -265,10 +265,23 @@ class CameraCtrlPipeline:
         return feats
 
     @torch.no_grad()
-    def __call__(self, prompt, pose_embedding, video_length, traj_features=None, height=None, width=None,
-                 num_inference_steps=50, guidance_scale=7.5, negative_prompt=None, num_videos_per_prompt=1, eta=0.0,
-                 generator=None, latents=None, output_type="tensor", return_dict=True, callback=None,
-                 callback_steps=1, multidiff_total_steps=1, multidiff_overlaps=12, prompt_embeds=None, **kwargs):
+    def __call__(self, prompt, pose_embedding, video_length, height=None, width=None, num_inference_steps=50,
+                 guidance_scale=7.5, negative_prompt=None, num_videos_per_prompt=1, eta=0.0, generator=None,
+                 latents=None, output_type="tensor", return_dict=True, callback=None, callback_steps=1,
+                 multidiff_total_steps=1, multidiff_overlaps=12, **kwargs):
+        """Parameter order and defaults of the reference's CameraCtrlPipeline.__call__ (pipeline_animation.py:570-593);
+        extras ride in **kwargs: `prompt_embeds` ([(2)b, 77, 768], skips the text encoder), `max_steps`."""
+        if "traj_features" in kwargs:
+            raise TypeError("traj_features needs CameraObjCtrlPipeline")
+        return self._sample(prompt, pose_embedding, video_length, None, height, width, num_inference_steps,
+                            guidance_scale, negative_prompt, num_videos_per_prompt, eta, generator, latents, output_type,
+                            return_dict, callback, callback_steps, multidiff_total_steps, multidiff_overlaps, **kwargs)
+
+    @torch.no_grad()
+    def _sample(self, prompt, pose_embedding, video_length, traj_features=None, height=None, width=None,
+                num_inference_steps=50, guidance_scale=7.5, negative_prompt=None, num_videos_per_prompt=1, eta=0.0,
+                generator=None, latents=None, output_type="tensor", return_dict=True, callback=None,
+                callback_steps=1, multidiff_total_steps=1, multidiff_overlaps=12, prompt_embeds=None, **kwargs):
         assert eta == 0.0 and num_videos_per_prompt == 1
         if traj_features is not None and not self._accepts_traj:
             raise TypeError("traj_features needs CameraObjCtrlPipeline")

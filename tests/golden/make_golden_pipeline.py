@@ -186,6 +186,14 @@ def main():
     out["cam_latents"] = torch.stack([lat for _, _, lat in trace_c])
     out["cam_videos_stride8"] = res_c.videos[..., ::8, ::8].clone()
     out["cam_videos_shape"] = tuple(res_c.videos.shape)
+    import inspect
+
+    def signature(fn):
+        return [(n, None if q.default is inspect.Parameter.empty else q.default, q.kind.name)
+                for n, q in inspect.signature(fn).parameters.items() if n != "self"]
+    out["call_signature_obj"] = signature(p_obj.CameraObjCtrlPipeline.__call__)
+    out["call_signature_cam"] = signature(p_cam.CameraCtrlPipeline.__call__)
+    out["init_signature_obj"] = [n for n, _, _ in signature(p_obj.CameraObjCtrlPipeline.__init__)]
     path = os.path.join(HERE, "fmc_reference_pipeline.pt")
     torch.save(out, path)
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KB)", out["obj_steps"][:3], out["obj_latents"].shape,
