@@ -13,7 +13,10 @@ def _not_callable(self, *a, **k):
 
 class AttnProcessor:
     """Plain attention (:15-82).  The trainers only use it in an isinstance() filter (train_cam_ctrl.py:263-266)."""
-    __call__ = _not_callable
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
+                 pose_feature=None):
+        return _not_callable(self, attn, hidden_states)
 
 
 class LoRAAttnProcessor(nn.Module):

@@ -154,7 +154,7 @@ class UNet3DConditionModel(nn.Module):
         return next(self.parameters()).device
 
     @classmethod
-    def from_pretrained_2d(cls, pretrained_model_path, subfolder=None, unet_additional_kwargs=None):
+    def from_pretrained_2d(cls, pretrained_model_path, subfolder=None, unet_additional_kwargs=None, logger=None):
         """unet.py:762-826: build from an SD1.5 `unet/config.json`, rename the 2-D block types to their 3-D
         counterparts and load the 2-D weights non-strictly (motion-module keys stay at their initial values)."""
         path = os.path.join(pretrained_model_path, subfolder) if subfolder is not None else pretrained_model_path
@@ -181,7 +181,19 @@ class UNet3DConditionModel(nn.Module):
         if weights is None:
             raise RuntimeError(f"no diffusion_pytorch_model.[safetensors|bin] under {path}")
         missing, unexpected = model.load_state_dict(weights, strict=False)
+        if logger is not None:
+            logger.info(f"loaded 2-D weights from {path}: {len(missing)} missing (motion modules), {len(unexpected)} unexpected keys")
         return model
+
+
+def _reject_unsupported(down_block_additional_residuals, mid_block_additional_residual, motion_module_alphas, debug):
+    """trailing parameters of the reference's forward (unet.py:1033-1047) that no trainer or pipeline of FMC sets"""
+    if down_block_additional_residuals is not None or mid_block_additional_residual is not None:
+        raise NotImplementedError("ControlNet-style additional residuals are not part of the FMC hot path")
+    if not (isinstance(motion_module_alphas, (int, float)) and float(motion_module_alphas) == 1.0):
+        raise NotImplementedError("motion_module_alphas other than 1.0 is not part of the FMC hot path")
+    if debug:
+        raise NotImplementedError("debug=True (intermediate feature dump) is not supported")
 
 
 class UNet3DConditionModelPoseCond(UNet3DConditionModel):
@@ -190,6 +202,15 @@ class UNet3DConditionModelPoseCond(UNet3DConditionModel):
     def __init__(self, decoder_add_posecond=True, **kwargs):
         super().__init__(**kwargs)
         self.decoder_add_posecond = decoder_add_posecond
+
+    def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, attention_mask=None,
+                cross_attention_kwargs=None, pose_embedding_features=None, return_dict=True,
+                down_block_additional_residuals=None, mid_block_additional_residual=None, motion_module_alphas=1.0,
+                debug=False):
+        """Parameter order and defaults of the reference's forward (unet.py:1033-1047)."""
+        _reject_unsupported(down_block_additional_residuals, mid_block_additional_residual, motion_module_alphas, debug)
+        return self._forward_impl(sample, timestep, encoder_hidden_states, class_labels, attention_mask,
+                                  cross_attention_kwargs, pose_embedding_features, None, return_dict)
 
     def _hidden_size_of(self, name):
         ch = self.config.block_out_channels
@@ -271,9 +292,8 @@ class UNet3DConditionModelPoseCond(UNet3DConditionModel):
             }
         return self._plan
 
-    def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, attention_mask=None,
-                cross_attention_kwargs=None, pose_embedding_features=None, traj_features=None, return_dict=True,
-                **unused):
+    def _forward_impl(self, sample, timestep, encoder_hidden_states, class_labels=None, attention_mask=None,
+                      cross_attention_kwargs=None, pose_embedding_features=None, traj_features=None, return_dict=True):
         if attention_mask is not None or class_labels is not None or cross_attention_kwargs is not None:
             raise NotImplementedError("attention_mask / class_labels / cross_attention_kwargs are unused on the FMC hot path")
         if traj_features is not None and not self._accepts_traj_features:
