@@ -21,9 +21,17 @@ def ray_condition(K, c2w, H, W, device, flip_flag=None):
     if flip_flag is not None and int(torch.as_tensor(flip_flag).sum().item()) > 0:
         raise NotImplementedError("horizontal flip is never enabled by the trainers (flip_flag = zeros)")
     dev = torch.device(device)
-    if dev.type != "cuda":
-        raise RuntimeError("synfmc_b200.fmc.data.dataset.ray_condition runs on CUDA only (no CPU fallback)")
+    # `device` says where the RESULT lives.  The trainers ask for 'cpu' (train_cam_ctrl.py:87) and move the embedding
+    # to the GPU afterwards: the rays are still built by the kernel on the current CUDA device and copied back -- there
+    # is no CPU implementation behind this function.
+    if dev.type == "cuda":
+        compute = dev
+    elif torch.cuda.is_available():
+        compute = torch.device("cuda", torch.cuda.current_device())
+    else:
+        raise RuntimeError("synfmc_b200.fmc.data.dataset.ray_condition needs a CUDA device (no CPU fallback)")
     B, V = K.shape[:2]
-    Kd = K.to(dev, torch.float32).reshape(B * V, 4)
-    M = c2w.to(dev, torch.float32)[..., :3, :].reshape(B * V, 3, 4)
-    return ops.plucker(Kd, M, H, W).view(B, V, H, W, 6)
+    Kd = K.to(compute, torch.float32).reshape(B * V, 4)
+    M = c2w.to(compute, torch.float32)[..., :3, :].reshape(B * V, 3, 4)
+    rays = ops.plucker(Kd, M, H, W).view(B, V, H, W, 6)
+    return rays if dev == compute else rays.to(dev)

@@ -407,6 +407,25 @@ def test_plucker_rays(ops, cuda_device, b, f, H, W):
     assert rel(un, want_un) < BF16_TOL
 
 
+def test_ray_condition_as_the_trainers_call_it(cuda_device):
+    """train_cam_ctrl.py:77-90: host tensors in, a 4x4 c2w with the bottom row, `device='cpu'`, a zero flip flag -- the
+    result comes back on the CPU (built by the kernel on the current CUDA device), equal to the device='cuda' result."""
+    from oracle.rays import to_plucker_embedding
+    from synfmc_b200 import synth
+    from synfmc_b200.fmc.data.dataset import ray_condition
+    b, f, H, W = 1, 16, 64, 96
+    K, c2w = synth.synth_camera(b, f, H, W, seed=8)
+    bottom = torch.tensor([0, 0, 0, 1.0]).view(1, 1, 1, 4).expand(b, f, 1, 4)
+    c2w44 = torch.cat([c2w, bottom], dim=2)
+    flip = torch.zeros(16, dtype=torch.bool)
+    on_cpu = ray_condition(K, c2w44, H, W, device="cpu", flip_flag=flip)
+    on_gpu = ray_condition(K, c2w44, H, W, device=cuda_device, flip_flag=flip)
+    assert on_cpu.device.type == "cpu" and on_gpu.is_cuda and on_cpu.shape == (b, f, H, W, 6)
+    assert torch.equal(on_cpu, on_gpu.cpu())
+    want = to_plucker_embedding(c2w, K, (H, W)).permute(0, 1, 3, 4, 2)
+    assert rel(on_cpu, want) < F32_TOL
+
+
 @pytest.mark.parametrize("n_obj,gaussian", [(1, True), (3, True), (3, False)])
 def test_traj_scatter_bit_exact(ops, cuda_device, n_obj, gaussian):
     """get_traj_features_v2 fmc/util.py:161-200: last object with mask > 0 wins, channels (info*m)*m and m*m --
