@@ -89,6 +89,12 @@ def pipeline_inputs():
     K6, c2w6 = synth.synth_camera(b, 6, inp["H"], inp["W"], seed=13)
     inp["K6"], inp["c2w6"] = K6, c2w6
     inp["latents6"] = torch.randn(b, 4, 6, h, w, generator=g)
+    # a training-style batch of two clips with per-sample timesteps (train_cam_obj_ctrl.py:840-866)
+    inp["train_latents"] = torch.randn(2, 4, f, h, w, generator=g)
+    inp["train_text"] = 0.5 * torch.randn(2, 77, 768, generator=g)
+    inp["train_timesteps"] = torch.tensor([961, 41])
+    inp["train_K"], inp["train_c2w"] = synth.synth_camera(2, f, inp["H"], inp["W"], seed=14)
+    inp["train_obj_infos"], inp["train_obj_masks"] = synth.synth_objects(2, f, inp["H"], inp["W"], 2, seed=15, gaussian=True)
     inp["prompt"] = ["a red car drives along the coast road"]
     inp["negative_prompt"] = ["blurry low quality"]
     return inp
@@ -186,6 +192,24 @@ def main():
     out["cam_latents"] = torch.stack([lat for _, _, lat in trace_c])
     out["cam_videos_stride8"] = res_c.videos[..., ::8, ::8].clone()
     out["cam_videos_shape"] = tuple(res_c.videos.shape)
+    # ---- the training forward: get_traj_features_v2 with random nulling (python `random`, seeded) -> CamObjPoseAdaptor
+    import random
+    omcm = ref.adapter.Adapter(channels=list(inp["channels"]), **harness.OMCM_KWARGS)
+    synth_init_(omcm, seed=2)
+    omcm.eval()
+    wrapper = importlib.import_module("fmc.models.pose_obj_adaptor").CamObjPoseAdaptor(unet_o, enc)
+    plucker2 = _plucker(ray_condition, inp["train_K"], inp["train_c2w"], inp["H"], inp["W"])
+    with torch.no_grad():
+        random.seed(1)   # first draw 0.134 -> clip 0 loses its object features, second 0.847 -> clip 1 keeps them
+        trajs = ref.util.get_traj_features_v2(inp["train_obj_infos"], inp["train_obj_masks"], omcm, True, 0.5, [False, False],
+                                              "cpu", torch.float32)
+        out["train_traj_features_c8"] = [t[:, ::8].clone() for t in trajs]   # every 8th channel
+        out["train_noise_pred"] = wrapper(inp["train_latents"], inp["train_timesteps"], inp["train_text"], plucker2,
+                                          trajs).clone()
+        wrapper_c = ref.pose.PoseAdaptor(unet_c, enc)
+        out["train_noise_pred_cam"] = wrapper_c(inp["train_latents"], inp["train_timesteps"], inp["train_text"],
+                                                plucker2).clone()
+
     import inspect
 
     def signature(fn):

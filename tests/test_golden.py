@@ -176,3 +176,34 @@ def test_cam_pipeline_multidiff_windows_match_reference(pgold, pinp):
         assert got.shape == (1, 4, 6, 8, 8)
         assert rel(got, pgold["cam_latents"][steps - 1]) < LOOP_TOL, steps
     assert torch.allclose(_decode(got), pgold["cam_videos_stride8"], rtol=0, atol=1e-3)
+
+
+def test_training_forward_matches_reference(pgold, pinp):
+    """The training-side forward of both stages on a batch of two clips with per-sample timesteps [961, 41]:
+    get_traj_features_v2 with random nulling (python `random` seeded: clip 0 loses its object features, clip 1 keeps
+    them; util.py:203-207) -> CamObjPoseAdaptor.forward (pose_obj_adaptor.py:13-23), and PoseAdaptor.forward
+    (pose_adaptor.py:250-262), produced by the reference's own classes."""
+    import random
+
+    from oracle.pose_adaptor import CamObjPoseAdaptor, PoseAdaptor
+    from oracle.rays import to_plucker_embedding
+    from oracle.util import get_traj_features_v2
+    unet_o = harness.build_oracle_unet(tiny=True, obj=True)
+    unet_c = harness.build_oracle_unet(tiny=True, obj=False)
+    enc = harness.build_oracle_pose_encoder(pinp["channels"])
+    omcm = harness.build_oracle_omcm(pinp["channels"])
+    plucker = to_plucker_embedding(pinp["train_c2w"], pinp["train_K"], (pinp["H"], pinp["W"])).permute(0, 2, 1, 3, 4).contiguous()
+    with torch.no_grad():
+        random.seed(1)
+        trajs = get_traj_features_v2(pinp["train_obj_infos"], pinp["train_obj_masks"], omcm, True, 0.5, [False, False],
+                                     "cpu", torch.float32)
+        kept = get_traj_features_v2(pinp["train_obj_infos"], pinp["train_obj_masks"], omcm, False, 0.5, [False, False],
+                                    "cpu", torch.float32)
+        for got, want in zip(trajs, pgold["train_traj_features_c8"]):
+            assert rel(got[:, ::8], want) < TOL
+        assert rel(trajs[0][1], kept[0][1]) == 0.0 and rel(trajs[0][0], kept[0][0]) > 1e-2   # only clip 0 was nulled
+        got = CamObjPoseAdaptor(unet_o, enc)(pinp["train_latents"], pinp["train_timesteps"], pinp["train_text"], plucker, trajs)
+        assert rel(got, pgold["train_noise_pred"]) < TOL
+        got_c = PoseAdaptor(unet_c, enc)(pinp["train_latents"], pinp["train_timesteps"], pinp["train_text"], plucker)
+        assert rel(got_c, pgold["train_noise_pred_cam"]) < TOL
+    assert rel(pgold["train_noise_pred"], pgold["train_noise_pred_cam"]) > 1e-3   # the object features matter
