@@ -156,20 +156,37 @@ class UNet3DConditionModel(nn.Module):
     @classmethod
     def from_pretrained_2d(cls, pretrained_model_path, subfolder=None, unet_additional_kwargs=None, logger=None):
         """unet.py:762-826: build from an SD1.5 `unet/config.json`, rename the 2-D block types to their 3-D
-        counterparts and load the 2-D weights non-strictly (motion-module keys stay at their initial values)."""
+        counterparts and load the 2-D weights non-strictly (motion-module keys stay at their initial values).
+        Like diffusers' `from_config` behind the reference (with the `extract_init_dict` override at unet.py:832-880),
+        entries of the config and of `unet_additional_kwargs` that no constructor takes are dropped and reported, not an
+        error: the shipped yamls carry `unet_use_cross_frame_attention` / `unet_use_temporal_attention`
+        (configs/cam.yaml:88-89), which nothing reads; `unet_additional_kwargs` wins over the config file."""
+        if logger is not None:
+            logger.info(f"Loading unet's pretrained weights from {pretrained_model_path} ...")
         path = os.path.join(pretrained_model_path, subfolder) if subfolder is not None else pretrained_model_path
-        with open(os.path.join(path, "config.json")) as f:
+        config_file = os.path.join(path, "config.json")
+        if not os.path.isfile(config_file):
+            raise RuntimeError(f"{config_file} does not exist")
+        with open(config_file) as f:
             config = json.load(f)
         config = {k: v for k, v in config.items() if not k.startswith("_")}
         config["down_block_types"] = ["CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "DownBlock3D"]
         config["up_block_types"] = ["UpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D"]
+        if "mid_block_type" in config:
+            config["mid_block_type"] = "UNetMidBlock3DCrossAttn"
         import inspect
-        accepted = set(inspect.signature(UNet3DConditionModel.__init__).parameters) | \
-            set(inspect.signature(cls.__init__).parameters)
-        config = {k: v for k, v in config.items() if k in accepted}
-        model = cls(**config, **(unet_additional_kwargs or {}))
+        accepted = (set(inspect.signature(UNet3DConditionModel.__init__).parameters) |
+                    set(inspect.signature(cls.__init__).parameters)) - {"self", "kwargs"}
+        merged = dict(config)
+        merged.update(unet_additional_kwargs or {})
+        unused = {k: v for k, v in merged.items() if k not in accepted}
+        if logger is not None:
+            logger.info("please check unused kwargs in 'unet_additional_kwargs' config:")
+            for k, v in unused.items():
+                logger.info(f"{k:50s}: {repr(v)}")
+        model = cls(**{k: v for k, v in merged.items() if k in accepted})
         weights = None
-        for name in ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.bin"):
+        for name in ("diffusion_pytorch_model.bin", "diffusion_pytorch_model.safetensors"):
             file = os.path.join(path, name)
             if os.path.isfile(file):
                 if name.endswith(".safetensors"):
@@ -179,10 +196,11 @@ class UNet3DConditionModel(nn.Module):
                     weights = torch.load(file, map_location="cpu")
                 break
         if weights is None:
-            raise RuntimeError(f"no diffusion_pytorch_model.[safetensors|bin] under {path}")
+            raise RuntimeError(f"{os.path.join(path, 'diffusion_pytorch_model.bin')} does not exist")
         missing, unexpected = model.load_state_dict(weights, strict=False)
-        if logger is not None:
-            logger.info(f"loaded 2-D weights from {path}: {len(missing)} missing (motion modules), {len(unexpected)} unexpected keys")
+        print(f"### missing keys: {len(missing)}; \n### unexpected keys: {len(unexpected)};")
+        params = [p.numel() if "motion_modules." in n else 0 for n, p in model.named_parameters()]
+        print(f"### Motion Module Parameters: {sum(params) / 1e6} M")
         return model
 
 

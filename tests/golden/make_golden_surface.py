@@ -89,6 +89,17 @@ def main():
     with open(os.path.join(HERE, "fmc_reference_surface.json"), "w") as fh:
         json.dump(surface, fh, indent=1, sort_keys=True)
     print(f"recorded {len(surface)} signatures")
+    # the constructor / processor / scheduler sections of the shipped configs, verbatim
+    import yaml
+    keep = ("unet_additional_kwargs", "lora_rank", "lora_scale", "pose_encoder_kwargs", "attention_processor_kwargs",
+            "noise_scheduler_kwargs", "omcm_config", "validation_data")
+    configs = {}
+    for name in ("cam", "obj"):
+        y = yaml.safe_load(open(os.path.join(mg.REFERENCE, "configs", f"{name}.yaml")))
+        configs[name] = {k: y[k] for k in keep if k in y}
+    with open(os.path.join(HERE, "fmc_reference_configs.json"), "w") as fh:
+        json.dump(configs, fh, indent=1, sort_keys=True)
+    print({k: sorted(v) for k, v in configs.items()})
 
 
 if __name__ == "__main__":

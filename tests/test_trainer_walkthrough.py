@@ -4,6 +4,7 @@ A 4-level U-Net with narrow channels keeps it light; the trainers' logic does no
 import json
 import os
 
+import pytest
 import torch
 
 from oracle import harness as helpers
@@ -178,3 +179,51 @@ def test_train_cam_ctrl_model_setup_and_checkpoint_round_trip(tmp_path):
     assert len(unexpected) == 0
     for k in attention_names:
         assert torch.equal(fresh.state_dict()[k], unet.state_dict()[k])
+
+
+def _shipped(name):
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fmc_reference_configs.json")
+    return json.load(open(path))[name]
+
+
+def test_shipped_yaml_sections_construct_the_mirror_verbatim(tmp_path):
+    """configs/cam.yaml / obj.yaml sections (tests/golden/fmc_reference_configs.json, copied from the reference by
+    make_golden_surface.py) go into the constructors exactly as the trainers pass them: `unet_additional_kwargs` with
+    its two entries nothing reads (dropped and reported like diffusers' from_config does), `pose_encoder_kwargs`,
+    `attention_processor_kwargs`, `omcm_config.params`, `noise_scheduler_kwargs`.  Only the channel widths are
+    narrowed to keep the test light."""
+    from synfmc_b200.fmc._blocks import DDIMScheduler
+    from synfmc_b200.fmc.adapter import Adapter
+    from synfmc_b200.fmc.models.pose_adaptor import CameraPoseEncoder
+    from synfmc_b200.fmc.models.unet_cam_obj import UNet3DConditionModelCamObjCond
+    y = _shipped("obj")
+    assert y["unet_additional_kwargs"] == _shipped("cam")["unet_additional_kwargs"]
+    pretrained_model_path, _ = _sd15_like_dir(tmp_path)
+    seen = []
+    logger = type("L", (), {"info": lambda self, m: seen.append(m)})()
+    unet = UNet3DConditionModelCamObjCond.from_pretrained_2d(pretrained_model_path, subfolder="unet",
+                                                             unet_additional_kwargs=y["unet_additional_kwargs"], logger=logger)
+    assert any(m.startswith("unet_use_cross_frame_attention") for m in seen)
+    assert any(m.startswith("unet_use_temporal_attention") for m in seen)
+    apk = dict(y["attention_processor_kwargs"], pose_feature_dimensions=CHANNELS)
+    unet.set_all_attn_processor(add_spatial_lora=True, add_motion_lora=False,
+                                lora_kwargs={"lora_rank": y["lora_rank"], "lora_scale": y["lora_scale"]},
+                                motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0}, **apk)
+    assert len(unet.mm_attn_processors) == 40
+    CameraPoseEncoder(**dict(y["pose_encoder_kwargs"], channels=CHANNELS))
+    Adapter(**dict(y["omcm_config"]["params"], channels=CHANNELS))
+    sched = DDIMScheduler(**y["noise_scheduler_kwargs"])
+    sched.set_timesteps(y["validation_data"]["num_inference_steps"])
+    assert sched.timesteps.tolist()[:3] == [961, 921, 881] and y["validation_data"]["guidance_scale"] == 8.0
+    with pytest.raises(RuntimeError):
+        UNet3DConditionModelCamObjCond.from_pretrained_2d(str(tmp_path / "nowhere"), subfolder="unet")
+
+    # the constants the bench / tests build the workload from are these yaml values
+    uak = {k: v for k, v in y["unet_additional_kwargs"].items() if not k.startswith("unet_use_")}
+    norm = lambda d: json.loads(json.dumps(d))   # tuples -> lists  # noqa: E731
+    assert norm(wc.UNET_ADDITIONAL_KWARGS) == uak
+    assert norm(wc.POSE_ENCODER_KWARGS) == {k: v for k, v in y["pose_encoder_kwargs"].items() if k != "channels"}
+    assert norm(wc.ATTENTION_PROCESSOR_KWARGS) == {k: v for k, v in y["attention_processor_kwargs"].items()
+                                                  if k != "pose_feature_dimensions"}
+    assert norm(wc.OMCM_KWARGS) == {k: v for k, v in y["omcm_config"]["params"].items() if k != "channels"}
+    assert wc.LORA_KWARGS == {"lora_rank": y["lora_rank"], "lora_scale": y["lora_scale"]}
