@@ -20,6 +20,34 @@ def _slice_frames(feat, start, length):
     return feat if t.shape[1] == feat.t.shape[1] else CL(t.contiguous())
 
 
+def ddim_alphas(scheduler, t):
+    """(alpha_bar_t, alpha_bar_prev) of the DDIM update (eta = 0) that fmc_cfg_ddim_step_f32 applies, from the mirror's
+    own DDIMScheduler or from ANY object with diffusers' DDIMScheduler attributes -- the trainers construct diffusers'
+    scheduler themselves and hand it to the pipeline (train_cam_ctrl.py:220, :480).  Same arithmetic as
+    DDIMScheduler.step: prev = t - num_train_timesteps // num_inference_steps; alpha_prev = final_alpha_cumprod
+    below 0.  Anything that is not an epsilon-prediction DDIM without sample clipping is refused."""
+    if hasattr(scheduler, "alphas_for"):
+        return scheduler.alphas_for(t)
+    cfg = getattr(scheduler, "config", None)
+
+    def conf(name, default=None):
+        if cfg is not None:
+            if isinstance(cfg, dict) and name in cfg:
+                return cfg[name]
+            if hasattr(cfg, name):
+                return getattr(cfg, name)
+        return getattr(scheduler, name, default)
+    if not all(hasattr(scheduler, a) for a in ("alphas_cumprod", "final_alpha_cumprod", "num_inference_steps")):
+        raise NotImplementedError(f"{type(scheduler).__name__}: the denoising step fuses the DDIM update; pass a DDIMScheduler")
+    if conf("prediction_type", "epsilon") != "epsilon" or conf("clip_sample", False) or conf("thresholding", False):
+        raise NotImplementedError("only epsilon-prediction DDIM without clipping / thresholding is on the hot path")
+    t = int(t)
+    prev_t = t - int(conf("num_train_timesteps")) // int(scheduler.num_inference_steps)
+    a_t = float(scheduler.alphas_cumprod[t])
+    a_prev = float(scheduler.alphas_cumprod[prev_t]) if prev_t >= 0 else float(scheduler.final_alpha_cumprod)
+    return a_t, a_prev
+
+
 class _StepGraph:
     """The CFG-doubled U-Net forward of one denoising step, captured once into a CUDA graph for fixed shapes.
 
@@ -198,7 +226,7 @@ class CameraCtrlPipeline:
         do_cfg = guidance_scale > 1.0
         L = video_length
         b = latents.shape[0]
-        a_t, a_prev = self.scheduler.alphas_for(t)
+        a_t, a_prev = ddim_alphas(self.scheduler, t)
         if cfg_pair is not None:
             from ... import shard
             feats = [CL.from_reference(f) for f in pose_features]

@@ -92,3 +92,31 @@ def test_positional_call_of_the_object_pipeline_and_its_kwargs():
     assert pipe.seen["latents"].shape == (1, 4, 4, 8, 8) and pipe.seen["pose_cfg"] is False
     want = torch.randn((1, 4, 4, 8, 8), generator=torch.Generator().manual_seed(3))
     assert torch.equal(pipe.seen["latents"], want)
+
+
+def test_a_diffusers_style_scheduler_object_drives_the_update():
+    """The trainers build diffusers' own DDIMScheduler and pass it in: the pipeline reads alpha-bar from its public
+    attributes (alphas_cumprod, final_alpha_cumprod, num_inference_steps, config.num_train_timesteps)."""
+    from types import SimpleNamespace
+
+    from synfmc_b200.fmc.pipelines.pipeline_animation import ddim_alphas
+    ours = DDIMScheduler()
+    ours.set_timesteps(25)
+
+    class DiffusersLike:   # what diffusers.DDIMScheduler exposes, nothing of the mirror's
+        def __init__(self):
+            self.config = SimpleNamespace(num_train_timesteps=1000, prediction_type="epsilon", clip_sample=False,
+                                          thresholding=False, steps_offset=1)
+            betas = torch.linspace(0.00085, 0.012, 1000, dtype=torch.float32)
+            self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+            self.final_alpha_cumprod = torch.tensor(1.0)
+            self.num_inference_steps = 25
+    theirs = DiffusersLike()
+    for t in ours.timesteps.tolist():
+        assert ddim_alphas(theirs, t) == ours.alphas_for(t)
+    assert ddim_alphas(theirs, 1)[1] == 1.0    # last step: alpha_prev = final_alpha_cumprod
+    theirs.config.prediction_type = "v_prediction"
+    with pytest.raises(NotImplementedError):
+        ddim_alphas(theirs, 961)
+    with pytest.raises(NotImplementedError):
+        ddim_alphas(SimpleNamespace(timesteps=[1]), 1)
