@@ -207,3 +207,21 @@ def test_training_forward_matches_reference(pgold, pinp):
         got_c = PoseAdaptor(unet_c, enc)(pinp["train_latents"], pinp["train_timesteps"], pinp["train_text"], plucker)
         assert rel(got_c, pgold["train_noise_pred_cam"]) < TOL
     assert rel(pgold["train_noise_pred"], pgold["train_noise_pred_cam"]) > 1e-3   # the object features matter
+
+
+def test_full_depth_unet_matches_reference():
+    """The 4-level U-Net with 2 layers per block, the mid block and the trainer-bound object-feature injection, at the
+    level sizes of BASELINE config 1 (32 / 16 / 8 / 4, 4 frames): oracle vs the output of the reference's own classes
+    (tests/golden/make_golden_full.py).  The GPU tests compare the CUDA path with this oracle at the same depth."""
+    from tests.golden.make_golden_full import full_inputs
+    gold_full = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fmc_reference_full_unet.pt"),
+                           weights_only=False)
+    inp = full_inputs()
+    unet = harness.build_oracle_unet(tiny=False, obj=True)
+    with torch.no_grad():
+        got = unet(inp["sample"], 961, inp["text"], pose_embedding_features=inp["pose_feats"],
+                   traj_features=inp["traj_feats"]).sample
+        assert rel(got, gold_full["unet_obj_full"]) < TOL
+        got = unet(inp["sample"], 41, inp["text"], pose_embedding_features=inp["pose_feats"], traj_features=None).sample
+        assert rel(got, gold_full["unet_obj_full_no_traj"]) < TOL
+    assert rel(gold_full["unet_obj_full"], gold_full["unet_obj_full_no_traj"]) > 1e-2
