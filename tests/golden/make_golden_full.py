@@ -59,8 +59,26 @@ def main():
                                     traj_features=inp["traj_feats"]).sample.clone()
         out["unet_obj_full_no_traj"] = unet(inp["sample"], 41, inp["text"], pose_embedding_features=inp["pose_feats"],
                                             traj_features=None).sample.clone()
+    # ---- the two encoders at their full four-level configuration (make_golden.py runs them with two levels)
+    from make_golden import golden_inputs
+    gi = golden_inputs()
+    ray_condition = ref.dataset.ray_condition if ref.dataset is not None else mg._ray_condition_from_source()
+    b, f, H, W = gi["b"], gi["f"], gi["H"], gi["W"]
+    bottom = torch.tensor([0, 0, 0, 1.0]).view(1, 1, 1, 4).expand(b, f, 1, 4)
+    rays = ray_condition(gi["K"], torch.cat([gi["c2w"], bottom], dim=2), H, W, device="cpu",
+                         flip_flag=torch.zeros(f, dtype=torch.bool))
+    enc = ref.pose.CameraPoseEncoder(channels=list(CHANNELS), **harness.POSE_ENCODER_KWARGS)
+    synth_init_(enc, seed=1)
+    enc.eval()
+    omcm = ref.adapter.Adapter(channels=list(CHANNELS), **harness.OMCM_KWARGS)
+    synth_init_(omcm, seed=2)
+    omcm.eval()
+    with torch.no_grad():
+        out["pose_encoder_full_c16"] = [t[:, ::16].clone() for t in enc(rays.permute(0, 4, 1, 2, 3).contiguous())]
+        feats = ref.util.get_traj_features_v2(gi["obj_infos"], gi["obj_masks"], omcm, False, 0.0, None, "cpu", torch.float32)
+        out["traj_features_full_c16"] = [t[:, ::16].clone() for t in feats]
     torch.save(out, os.path.join(HERE, "fmc_reference_full_unet.pt"))
-    print(f"build + init {t1 - t0:.0f} s, two forwards {time.time() - t1:.0f} s;", {k: tuple(v.shape) for k, v in out.items()},
+    print(f"build + init {t1 - t0:.0f} s, two forwards {time.time() - t1:.0f} s;", {k: (tuple(v.shape) if torch.is_tensor(v) else [tuple(t.shape) for t in v]) for k, v in out.items()},
           float(out["unet_obj_full"].std()))
 
 

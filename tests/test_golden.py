@@ -225,3 +225,23 @@ def test_full_depth_unet_matches_reference():
         got = unet(inp["sample"], 41, inp["text"], pose_embedding_features=inp["pose_feats"], traj_features=None).sample
         assert rel(got, gold_full["unet_obj_full_no_traj"]) < TOL
     assert rel(gold_full["unet_obj_full"], gold_full["unet_obj_full_no_traj"]) > 1e-2
+
+
+def test_four_level_encoders_match_reference(gold, inp):
+    """CameraPoseEncoder and get_traj_features_v2 -> Adapter at their full four-level configuration (every 16th channel of
+    each of the four feature maps), against the reference's own classes."""
+    from oracle.util import get_traj_features_v2
+    gold_full = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fmc_reference_full_unet.pt"),
+                           weights_only=False)
+    ch = (320, 640, 1280, 1280)
+    enc = harness.build_oracle_pose_encoder(ch)
+    omcm = harness.build_oracle_omcm(ch)
+    with torch.no_grad():
+        got = enc(gold["rays"].permute(0, 4, 1, 2, 3).contiguous())
+        assert len(got) == 4
+        for g, w in zip(got, gold_full["pose_encoder_full_c16"]):
+            assert rel(g[:, ::16], w) < TOL
+        feats = get_traj_features_v2(inp["obj_infos"], inp["obj_masks"], omcm, False, 0.0, None, "cpu", torch.float32)
+        assert [tuple(t.shape[1:2]) for t in feats] == [(c,) for c in ch]
+        for g, w in zip(feats, gold_full["traj_features_full_c16"]):
+            assert rel(g[:, ::16], w) < TOL
