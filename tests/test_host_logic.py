@@ -103,3 +103,37 @@ def test_groupnorm_kernel_plan(monkeypatch):
     monkeypatch.delenv("FMC_GN_FUSED", raising=False)
     assert fn(64, 128, 32) == 3      # 4 channels per group: a 16-byte vector would span more than two groups
     assert fn(64, 320, 0) == 3 and fn(64, 321, 32) == 3   # nonsense arguments never fail, they just say "three-kernel"
+
+
+def test_domain_lora_fold_and_the_no_lora_configuration():
+    """engine.AttnPlan for the spatial attentions: with a LoRAAttnProcessor the projection the kernels see is
+    W + s * up @ down (attention_processor.py:138-157: q, k, v, out; text cross-attention has k / v of width 768) with q / k
+    heads padded 40 -> 48; with the plain processor (`add_spatial_lora=False`, what the trainers configure when no image
+    LoRA checkpoint is given, train_cam_ctrl.py:230) it is W itself."""
+    from synfmc_b200.fmc._blocks import Attention
+    from synfmc_b200.fmc.models.attention_processor import AttnProcessor, LoRAAttnProcessor
+    torch.manual_seed(3)
+    for cross_dim in (None, 768):
+        attn = Attention(query_dim=320, cross_attention_dim=cross_dim, heads=8, dim_head=40)
+        proc = LoRAAttnProcessor(hidden_size=320, cross_attention_dim=cross_dim, rank=160, lora_scale=0.7)
+        for lin in (proc.to_q_lora, proc.to_k_lora, proc.to_v_lora, proc.to_out_lora):
+            nn.init.normal_(lin.up.weight, std=0.02)
+        attn.set_processor(proc)
+        plan = engine.AttnPlan(attn, torch.device("cpu"))
+
+        def want(name):
+            lin = attn.to_out[0] if name == "to_out" else getattr(attn, name)
+            lora = getattr(proc, name + "_lora")
+            return lin.weight.detach() + 0.7 * (lora.up.weight.detach() @ lora.down.weight.detach())
+        q = want("to_q").view(8, 40, 320)
+        got_q = (plan.q.w if cross_dim else plan.qkv.w)[:8 * 48].float().view(8, 48, 320)
+        assert torch.equal(got_q[:, :40], _bf(q)) and torch.count_nonzero(got_q[:, 40:]) == 0
+        kv = plan.kv.w.float() if cross_dim else plan.qkv.w.float()[8 * 48:]
+        assert torch.equal(kv[:8 * 48].view(8, 48, -1)[:, :40], _bf(want("to_k")).view(8, 40, -1))
+        assert torch.equal(kv[8 * 48:], _bf(want("to_v")))
+        assert torch.equal(plan.out.w.float(), _bf(want("to_out")))
+        attn.set_processor(AttnProcessor())
+        plain = engine.AttnPlan(attn, torch.device("cpu"))
+        assert torch.equal(plain.out.w.float(), _bf(attn.to_out[0].weight.detach()))
+        got_q = (plain.q.w if cross_dim else plain.qkv.w)[:8 * 48].float().view(8, 48, 320)
+        assert torch.equal(got_q[:, :40], _bf(attn.to_q.weight.detach()).view(8, 40, 320))
