@@ -120,3 +120,22 @@ def test_a_diffusers_style_scheduler_object_drives_the_update():
         ddim_alphas(theirs, 961)
     with pytest.raises(NotImplementedError):
         ddim_alphas(SimpleNamespace(timesteps=[1]), 1)
+
+
+def test_prompt_encoding_and_video_decoding_equal_the_reference_pipeline():
+    """The two frozen-network edges of `__call__` on the stand-in CLIP / VAE: [negative ++ prompt] embedding order
+    (pipeline_animation_cm_om.py:480-567) and decode_latents (per-frame decode, /0.18215, (x/2+0.5).clamp, fp32 on the
+    CPU, :465-478), against what the reference pipeline produced from the same stand-ins."""
+    from tests.golden.make_golden_pipeline import pipeline_inputs
+    inp = pipeline_inputs()
+    pipe = CameraObjCtrlPipeline(UpsampleVAE(), TableTextEncoder(), HashTokenizer(), _Unet(), DDIMScheduler(), object())
+    emb = pipe._encode_prompt(inp["prompt"], torch.device("cpu"), True, inp["negative_prompt"])
+    assert emb.shape == (2, 77, 768) and torch.equal(emb[:, :12, :8], GOLD["text_embeddings_head"])
+    assert pipe._encode_prompt(inp["prompt"], torch.device("cpu"), False, None).shape == (1, 77, 768)
+    empty = pipe._encode_prompt(inp["prompt"], torch.device("cpu"), True, None)       # negative prompt defaults to ""
+    assert torch.equal(empty[1], emb[1]) and not torch.equal(empty[0], emb[0])
+    video = pipe.decode_latents(GOLD["obj_latents"][-1])
+    assert tuple(video.shape) == GOLD["obj_videos_shape"] and video.dtype == torch.float32
+    assert torch.equal(video[..., ::8, ::8], GOLD["obj_videos_stride8"])
+    video6 = pipe.decode_latents(GOLD["cam_latents"][-1])
+    assert torch.equal(video6[..., ::8, ::8], GOLD["cam_videos_stride8"])
