@@ -10,7 +10,17 @@ from oracle import harness as helpers
 sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
 from make_golden_full import full_inputs
 
-def bf(x): return x.to(torch.bfloat16).float() if torch.is_tensor(x) and x.is_floating_point() else x
+MODE = {"round": "bf16"}
+
+
+def bf(x):
+    """round a tensor to the operand precision under test: bf16 (8 mantissa bits) or tf32 (11)"""
+    if not (torch.is_tensor(x) and x.is_floating_point()):
+        return x
+    if MODE["round"] == "tf32":
+        i = x.float().contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    return x.to(torch.bfloat16).float()
 
 @contextlib.contextmanager
 def matmul_inputs_bf16(round_outputs=False):
@@ -55,5 +65,10 @@ for tiny in (True, False):
             b = u(sample, 961, text, pose_embedding_features=feats, traj_features=trajs).sample
         with torch.autocast("cpu", dtype=torch.bfloat16):
             c = u(sample, 961, text, pose_embedding_features=feats, traj_features=trajs).sample.float()
+        MODE["round"] = "tf32"
+        with matmul_inputs_bf16(False):
+            d = u(sample, 961, text, pose_embedding_features=feats, traj_features=trajs).sample
+        MODE["round"] = "bf16"
     print(f"{'tiny' if tiny else 'full'} U-Net: A (bf16 at matmul inputs only, fp32 residual stream) {rel(a, want):.2e} | "
-          f"B (+ bf16 outputs of every op) {rel(b, want):.2e} | torch autocast bf16 {rel(c, want):.2e}", flush=True)
+          f"B (+ bf16 outputs of every op) {rel(b, want):.2e} | torch autocast bf16 {rel(c, want):.2e} | "
+          f"tf32 at matmul inputs only {rel(d, want):.2e}", flush=True)
