@@ -115,7 +115,7 @@ def build_product(device):
     bind_omcm_forwards(unet)
     enc = synth_init_(CameraPoseEncoder(channels=list(CHANNELS), **wc.POSE_ENCODER_KWARGS), seed=1)
     omcm = synth_init_(Adapter(channels=list(CHANNELS), **wc.OMCM_KWARGS), seed=2)
-    unet, enc, omcm = unet.to(device).eval(), enc.to(device).eval(), omcm.to(device).eval()
+    unet, enc, omcm = (m.to(device).eval().requires_grad_(False) for m in (unet, enc, omcm))  # inference: forward only
     sched = DDIMScheduler()
     sched.set_timesteps(SCHEDULE_STEPS)
     return CameraObjCtrlPipeline(None, None, None, unet, sched, enc), omcm

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FMC_B200_ABI_VERSION 1
+#define FMC_B200_ABI_VERSION 2
 
 /* flags for fmc_gemm_bf16 */
 #define FMC_GEMM_GEGLU 1   /* W rows interleaved (16 value, 16 gate); C[M, N/2] = value * gelu_erf(gate) */
@@ -187,6 +187,57 @@ int fmc_mask_modulate_bf16(const void* x, const float* mask, const int* row_inde
 int fmc_cfg_ddim_step_f32(const float* eps_uncond, const float* eps_cond, float guidance_scale, const float* latents,
                           float* latents_out, float* eps_out, float alpha_t, float alpha_prev, long long n,
                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Reference-precision mode (BASELINE config 1, "output parity vs reference" at 1e-3 rel): fp32 activations between
+ * kernels, linears on tcgen05.mma.kind::tf32, attention / norms / glue in fp32 (csrc/precise.cu).  Each entry point
+ * shadows the bf16 one of the same name and replaces the same reference lines.
+ * --------------------------------------------------------------------------------------------------------------- */
+
+/* C[M,N] = A[M,K] W[N,K]^T (+ bias) (+ rowbias[row / rows_per_group]) (+ residual), all fp32, tf32 tensor-core products,
+ * fp32 accumulation.  split = 1: operands are read as tf32 (10-bit mantissa).  split = 3: A is [M, 2K] = [tf32(a) | a -
+ * tf32(a)] (fmc_split_tf32), W is [N, 2K] likewise; the kernel accumulates a_lo w_hi + a_hi w_lo + a_hi w_hi (fp32-class
+ * products).  flags: FMC_GEMM_GEGLU only.  Same reference lines as fmc_gemm_bf16. */
+int fmc_gemm_tf32(const float* A, long long lda, const float* W, long long ldw, float* C, long long ldc, int M, int N,
+                  int K, const float* bias, const float* residual, long long ldr, const float* rowbias,
+                  int rows_per_group, long long ldrb, int flags, int split, void* stream);
+
+/* out[r, 0:K] = x[r] rounded to tf32 (nearest), out[r, K:2K] = x[r] - that (exact): operand form of split = 3. */
+int fmc_split_tf32(const float* x, long long ldx, float* out, long long ldo, long long rows, int K, void* stream);
+
+/* O = softmax(Q K^T * scale) V per (sequence, head) in fp32 (SIMT flash attention, head_dim 40 / 80 / 160).
+ * Row of element t of sequence i: (i / inner) * len * inner + (i % inner) + t * inner.  inner = 1: spatial tokens of an
+ * image (fmc_spatial_attn_bf16 semantics incl. kv_div / kv_stride for the text keys); inner = HW: the frame axis of
+ * channels-last [B, F, HW, C] rows (fmc_temporal_attn_bf16 semantics).  Head h at column col0 + h * head_dim.
+ * Replaces fmc/models/attention_processor.py:61-67,148-154,271-281. */
+int fmc_attention_f32(const float* Q, long long ldq, int q_col0, const float* K, long long ldk, int k_col0,
+                      const float* V, long long ldv, int v_col0, float* O, long long ldo, int images, int heads,
+                      int head_dim, int nq, int nk, int kv_div, int kv_stride, int inner, float scale, void* stream);
+
+/* fp32 forms of fmc_layernorm_bf16 / fmc_groupnorm_bf16 (stats_ws: 2 * images * groups floats). */
+int fmc_layernorm_f32(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* out,
+                      long long ldo, const float* pe, int F, int HW, const float* add, long long ldadd, float* out2,
+                      long long ldo2, long long rows, int C, void* stream);
+int fmc_groupnorm_f32(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* out,
+                      long long ldo, float* stats_ws, int images, int HW, int C, int groups, int silu,
+                      const float* rowbias, long long ldrb, int rowbias_div, void* stream);
+
+/* out[(n, oy, ox), (ky, kx, c)] = x[n, oy*s + ky - 1, ox*s + kx - 1, c] (zero outside): the A operand of a 3x3,
+ * padding-1 convolution as a GEMM against W[Cout, (ky, kx, cin)] -- same reference lines as fmc_conv3x3_bf16. */
+int fmc_im2col3x3_f32(const float* x, float* out, int N, int H, int W, int C, int stride, void* stream);
+
+/* fp32 forms of the glue kernels (C % 4 == 0 instead of % 8). */
+int fmc_add_f32(const float* a, long long lda, const float* b, long long ldb, const float* rowbias, int rows_per_group,
+                long long ldrb, float* out, long long ldo, long long rows, int C, int relu, void* stream);
+int fmc_resize_nearest_f32(const float* x, float* out, int N, int h, int w, int oh, int ow, int C, void* stream);
+int fmc_avgpool2_f32(const float* x, float* out, int N, int h, int w, int C, void* stream);
+int fmc_copy2d_f32(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols, void* stream);
+int fmc_ncfhw_f32_to_cl_f32(const float* x, float* out, int B, int C, int F, long long HW, int Cpad, void* stream);
+int fmc_cl_f32_to_ncfhw_f32(const float* x, long long ldc, float* out, int B, int C, int F, long long HW, void* stream);
+int fmc_silu_f32(const float* x, float* out, long long n, void* stream);
+int fmc_timestep_embedding_f32(const float* t, float* out, int B, int dim, void* stream);
+int fmc_mask_modulate_f32(const float* x, const float* mask, const int* row_index, const int* col_index, float* out,
+                          int N, int h, int w, int C, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

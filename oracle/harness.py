@@ -58,7 +58,7 @@ def build_product_unet(oracle_unet, tiny=True, obj=False, device="cuda"):
     assert not missing and not unexpected
     if obj:
         bind_omcm_forwards(unet)
-    return unet.to(device).eval()
+    return unet.to(device).eval().requires_grad_(False)  # inference: the mirror raises under autograd (forward only)
 
 
 def build_oracle_pose_encoder(channels, seed=1):
@@ -71,7 +71,7 @@ def build_product_pose_encoder(oracle_enc, channels, device="cuda"):
     from synfmc_b200.fmc.models.pose_adaptor import CameraPoseEncoder
     enc = CameraPoseEncoder(channels=list(channels), **POSE_ENCODER_KWARGS)
     enc.load_state_dict(oracle_enc.state_dict(), strict=True)
-    return enc.to(device).eval()
+    return enc.to(device).eval().requires_grad_(False)
 
 
 def build_oracle_omcm(channels, seed=2):
@@ -84,7 +84,7 @@ def build_product_omcm(oracle_m, channels, device="cuda"):
     from synfmc_b200.fmc.adapter import Adapter
     m = Adapter(channels=list(channels), **OMCM_KWARGS)
     m.load_state_dict(oracle_m.state_dict(), strict=True)
-    return m.to(device).eval()
+    return m.to(device).eval().requires_grad_(False)
 
 
 def rel_l2(got, want):

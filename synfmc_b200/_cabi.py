@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FMC_B200_LIB") or os.path.join(_HERE, "libfmc_b200.so")
 
 P, I, L, F = c_void_p, c_int, c_longlong, c_float
-ABI_VERSION = 1  # FMC_B200_ABI_VERSION of include/fmc_b200.h
+ABI_VERSION = 2  # FMC_B200_ABI_VERSION of include/fmc_b200.h
 
 # name -> argtypes, in the order of include/fmc_b200.h
 SIGNATURES = {
@@ -38,6 +38,22 @@ SIGNATURES = {
     "fmc_traj_scatter_unshuffle_bf16": [P, P, P, P, I, I, I, I, P],
     "fmc_mask_modulate_bf16": [P, P, P, P, P, I, I, I, I, I, I, P],
     "fmc_cfg_ddim_step_f32": [P, P, F, P, P, P, F, F, L, P],
+    # reference-precision mode (csrc/precise.cu)
+    "fmc_gemm_tf32": [P, L, P, L, P, L, I, I, I, P, P, L, P, I, L, I, I, P],
+    "fmc_split_tf32": [P, L, P, L, L, I, P],
+    "fmc_attention_f32": [P, L, I, P, L, I, P, L, I, P, L, I, I, I, I, I, I, I, I, F, P],
+    "fmc_layernorm_f32": [P, L, P, P, F, P, L, P, I, I, P, L, P, L, L, I, P],
+    "fmc_groupnorm_f32": [P, L, P, P, F, P, L, P, I, I, I, I, I, P, L, I, P],
+    "fmc_im2col3x3_f32": [P, P, I, I, I, I, I, P],
+    "fmc_add_f32": [P, L, P, L, P, I, L, P, L, L, I, I, P],
+    "fmc_resize_nearest_f32": [P, P, I, I, I, I, I, I, P],
+    "fmc_avgpool2_f32": [P, P, I, I, I, I, P],
+    "fmc_copy2d_f32": [P, L, P, L, L, I, P],
+    "fmc_ncfhw_f32_to_cl_f32": [P, P, I, I, I, L, I, P],
+    "fmc_cl_f32_to_ncfhw_f32": [P, L, P, I, I, I, L, P],
+    "fmc_silu_f32": [P, P, L, P],
+    "fmc_timestep_embedding_f32": [P, P, I, I, P],
+    "fmc_mask_modulate_f32": [P, P, P, P, P, I, I, I, I, I, I, P],
 }
 
 _lib = None
@@ -65,6 +81,9 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the .so does not export what the header declares
             fn.restype = c_int
             fn.argtypes = argtypes
+        if handle.fmc_abi_version() != ABI_VERSION:  # a stale in-tree build (or FMC_B200_LIB) against newer bindings
+            raise FmcError(f"{LIB_PATH} reports ABI version {handle.fmc_abi_version()}, the bindings expect {ABI_VERSION}: "
+                           "rebuild with `make -C synfmc_b200/csrc`")
         _lib = handle
     return _lib
 
@@ -74,6 +93,8 @@ def lib():
 def _kernels_per_call(handle, name, args):
     if name == "fmc_groupnorm_bf16":
         return handle.fmc_groupnorm_launches(args[9], args[10], args[11])  # HW, C, groups
+    if name == "fmc_groupnorm_f32":
+        return 2  # statistics + apply
     return 1
 launch_count = 0  # kernels of this library launched by this process (bench.py reports it as gpu_launches)
 trace = None      # when set to a list by bench.py: (name, args, start_event, end_event) per call, CUDA events on the

@@ -64,8 +64,27 @@ int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64
   return make_tmap_bf16_ex(out, base, rank, dims, strides_bytes, box, ones, swizzle_bytes);
 }
 
+static int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr_in, int swizzle_bytes);
+
 int make_tmap_bf16_ex(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, const uint32_t* estr_in, int swizzle_bytes) {
+  return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, estr_in, swizzle_bytes);
+}
+
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, int swizzle_bytes) {
+  static const bool tf = [] {
+    const char* e = getenv("FMC_TF32_TMA");
+    return e != nullptr && strcmp(e, "tfloat32") == 0;
+  }();
+  const uint32_t ones[5] = {1, 1, 1, 1, 1};
+  return make_tmap_typed(out, tf ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims,
+                         strides_bytes, box, ones, swizzle_bytes);
+}
+
+static int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr_in, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   FMC_REQUIRE(fn != nullptr, FMC_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   FMC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, FMC_ERR_SHAPE, "TMA base %p not 16-byte aligned", base);
@@ -83,7 +102,7 @@ int make_tmap_bf16_ex(CUtensorMap* out, const void* base, int rank, const uint64
                   (unsigned long long)gstr[i - 1]);
     }
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+  CUresult r = fn(out, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
                   gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B

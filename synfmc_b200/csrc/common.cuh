@@ -90,6 +90,11 @@ int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64
 int make_tmap_bf16_ex(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, const uint32_t* estr, int swizzle_bytes);
 
+// fp32 tensor map (reference-precision mode, csrc/precise.cu); swizzle128: inner box must be <= 32 floats.
+// FMC_TF32_TMA=tfloat32 encodes CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 instead of FLOAT32 (diagnostic switch).
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, int swizzle_bytes);
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace fmc

@@ -16,6 +16,118 @@ import torch
 from . import ops
 
 BF16 = torch.bfloat16
+F32 = torch.float32
+
+# --------------------------------------------------------------------------------------------------------------
+# precision mode
+# --------------------------------------------------------------------------------------------------------------
+# "bf16"   production: bf16 activations between kernels, bf16 tensor-core operands, fp32 inside every kernel.
+# "tf32x3" reference precision (BASELINE config 1, 1e-3 vs the fp32 reference): fp32 activations, linears / convolutions
+#          as three-pass split tf32 tensor-core GEMMs (fp32-class products), fp32 attention / norms (csrc/precise.cu).
+# "tf32"   the same with single-pass tf32 operands (10-bit mantissa).
+# The mode is process-wide; weight plans are keyed by (device, mode), so switching rebuilds them lazily.
+PRECISIONS = ("bf16", "tf32", "tf32x3")
+_precision = os.environ.get("FMC_PRECISION", "bf16")
+assert _precision in PRECISIONS, _precision
+
+
+def set_precision(mode):
+    """Select the arithmetic of every following forward: "bf16" (default), "tf32", "tf32x3" / "reference"."""
+    global _precision
+    mode = "tf32x3" if mode == "reference" else mode
+    if mode not in PRECISIONS:
+        raise ValueError(f"precision {mode!r} not in {PRECISIONS}")
+    _precision = mode
+
+
+def get_precision():
+    return _precision
+
+
+class precision:
+    """Context manager: `with engine.precision("reference"): unet(...)`."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = _precision
+        set_precision(self.mode)
+
+    def __exit__(self, *exc):
+        set_precision(self.prev)
+
+
+def precise():
+    return _precision != "bf16"
+
+
+def act_dtype():
+    return F32 if precise() else BF16
+
+
+def gemm_split():
+    return 3 if _precision == "tf32x3" else 1
+
+
+def plan_key(device):
+    return (torch.device(device), _precision)
+
+
+def fingerprint(module):
+    """Cheap identity of everything a module's plans were derived from: (storage address, in-place version) of every
+    parameter / buffer plus the processor scalars.  optimizer.step(), param.data.copy_(), load_state_dict on a
+    submodule and set_processor all change it (stale folded weights / stale CUDA graphs)."""
+    h = 0
+    for t in list(module.parameters()) + list(module.buffers()):
+        h = hash((h, t.data_ptr(), t._version))
+    for m in module.modules():
+        proc = getattr(m, "processor", None)
+        if proc is not None:
+            h = hash((h, id(proc), getattr(proc, "scale", None), getattr(proc, "lora_scale", None)))
+    return h
+
+
+def invalidate_plans(root):
+    """Drop every cached plan below `root` and start a new plan generation of that module (CUDA graphs captured against
+    the old plans are keyed on it and are re-captured)."""
+    for m in root.modules():
+        if hasattr(m, "_plan"):
+            m._plan = None
+    root._fmc_fingerprint = None
+    root._fmc_generation = getattr(root, "_fmc_generation", 0) + 1
+
+
+def generation(root):
+    return getattr(root, "_fmc_generation", 0)
+
+
+def refresh_plans(root):
+    """Called at the top of every forward of a top-level mirror module (U-Net, CameraPoseEncoder, Adapter): if any
+    parameter, buffer or processor setting changed since the plans were built, drop them."""
+    fp = fingerprint(root)
+    if getattr(root, "_fmc_fingerprint", None) != fp:
+        if getattr(root, "_fmc_fingerprint", None) is not None:
+            invalidate_plans(root)
+        root._fmc_fingerprint = fp
+
+
+def require_no_grad(module, *tensors):
+    """The product implements the FORWARD of the hot path (backward is a later row).  Under autograd the
+    result would silently carry no grad_fn and `loss.backward()` would fail far away with torch's generic message -- fail
+    here, loudly, instead (train_cam_ctrl.py:586-648 runs the wrapper with grad enabled)."""
+    if not torch.is_grad_enabled():
+        return
+    needs = [n for n, p in module.named_parameters() if p.requires_grad]
+    tens = [t for t in tensors if torch.is_tensor(t) and t.requires_grad]
+    if needs or tens:
+        what = f"{len(needs)} parameters (first: {needs[0]})" if needs else f"{len(tens)} input tensor(s)"
+        raise RuntimeError(
+            f"{type(module).__name__}: called with autograd enabled and {what} requiring grad, but synfmc_b200 implements "
+            "the forward pass only (no backward kernels yet: SURVEY.md section 8f row 2). Wrap inference in "
+            "torch.no_grad(), or call .requires_grad_(False) on the module; training needs the reference path.")
+
+
 # 3x3 convolutions: "own" = fmc_conv3x3_bf16 (tcgen05 implicit GEMM) wherever its geometry allows, "cudnn" = torch /
 # cuDNN everywhere, "auto" (default) = the faster of the two as measured on B200 (profiles/r01_conv3x3.txt): cuDNN wins
 # the wide convolutions by 1.7-3x in round 1 (its kernels reuse the input window across the nine taps in shared
@@ -35,7 +147,7 @@ LN_FUSED_POLICY = os.environ.get("FMC_LN_FUSED_POLICY", "all")
 
 
 def ln_fold_wanted(n_out, k_in):
-    if not LN_FUSED:
+    if not LN_FUSED or precise():
         return False
     return LN_FUSED_POLICY == "all" or k_in >= 1280 or n_out <= 640
 # debugging switch: FMC_UNFUSED_TEMPORAL=1 runs the temporal attention as GEMM + attention kernels instead of the fused one
@@ -54,12 +166,12 @@ class CL:
     __slots__ = ("t",)
 
     def __init__(self, t):
-        assert t.dtype == BF16 and t.ndim == 5 and t.is_contiguous()
+        assert t.dtype == act_dtype() and t.ndim == 5 and t.is_contiguous(), (t.dtype, _precision, t.shape)
         self.t = t
 
     @staticmethod
     def from_reference(x):
-        return x if isinstance(x, CL) else CL(ops.to_channels_last(x))
+        return x if isinstance(x, CL) else CL(ops.to_channels_last(x, dtype=act_dtype()))
 
     def to_reference(self):
         return ops.from_channels_last(self.t)
@@ -98,6 +210,19 @@ def _dev_bf16(w, device):
     return w.detach().to(device=device, dtype=torch.float32).to(BF16).contiguous()
 
 
+def _dev_weight(w, device):
+    """GEMM weight [N, K] in the operand form of the current precision: bf16; fp32; or fp32 [N, 2K] = [hi | lo]."""
+    if not precise():
+        return _dev_bf16(w, device)
+    w = w.detach().to(device=device, dtype=torch.float32).contiguous()
+    if gemm_split() == 3:
+        if not w.is_cuda:  # ops.DRY_RUN (host-logic tests)
+            return ops.split_tf32(w)
+        with torch.cuda.device(w.device):
+            return ops.split_tf32(w)
+    return w
+
+
 def _dev_f32(w, device):
     return None if w is None else w.detach().to(device=device, dtype=torch.float32).contiguous()
 
@@ -120,14 +245,26 @@ class LinearPlan:
             self.eps = float(pre_norm.eps)
         if geglu:
             weight, bias = _interleave_geglu(weight, bias)
-        self.w = _dev_bf16(weight, device)
+        assert pre_norm is None or not precise(), "the LayerNorm fold is a bf16-mode optimisation"
+        self.split = gemm_split() if precise() else 0  # 0: bf16 operands
+        self.N, self.K = weight.shape
+        self.w = _dev_weight(weight, device)
         self.b = _dev_f32(bias, device)
         self.geglu = geglu
-        self.N, self.K = self.w.shape
         if pre_norm is not None:
             self.colsum = self.w.float().sum(dim=1).contiguous()  # of the ROUNDED weights: the mean term cancels exactly
 
+    def f32out(self, a):
+        """fp32 result (time-embedding MLP / projections): the FMC_GEMM_OUT_F32 form in bf16 mode."""
+        if self.split:
+            return ops.gemm_f32(a, self.w, bias=self.b, split=self.split)
+        return ops.gemm(a, self.w, bias=self.b, out_f32=True)
+
     def __call__(self, a, residual=None, out=None, rowbias=None, rows_per_group=0, ln_stats=None, f16_from_col=None):
+        if self.split:
+            assert ln_stats is None and f16_from_col is None
+            return ops.gemm_f32(a, self.w, bias=self.b, residual=residual, out=out, geglu=self.geglu, rowbias=rowbias,
+                                rows_per_group=rows_per_group, split=self.split)
         if self.colsum is not None:
             assert ln_stats is not None and residual is None and rowbias is None
             return ops.gemm(a, self.w, bias=self.b, out=out, geglu=self.geglu, ln_stats=ln_stats, ln_colsum=self.colsum,
@@ -180,7 +317,7 @@ class AttnPlan:
         heads = attn.heads
         C = attn.to_q.weight.shape[0]
         d = C // heads
-        hs = (d + 15) // 16 * 16
+        hs = d if precise() else (d + 15) // 16 * 16  # the fp32 attention kernel takes un-padded heads
         self.heads, self.d, self.hs, self.C = heads, d, hs, C
         self.scale = attn.scale
         self.rescale = float(getattr(attn, "rescale_output_factor", 1.0))
@@ -225,7 +362,7 @@ class AttnPlan:
         # fused projection + temporal attention kernel (fmc_temporal_qkv_attn_bf16): per head the rows
         # [q (40) | k (40) | v (40) | 8 zero rows]
         self.w_head_major = None
-        if FUSED_TEMPORAL and fused_temporal and not self.is_cross and C == 320 and heads == 8:
+        if FUSED_TEMPORAL and fused_temporal and not self.is_cross and C == 320 and heads == 8 and not precise():
             blocks = [w.view(heads, d, C) for w in (folded("to_q"), folded("to_k"), wv)]
             blocks.append(blocks[0].new_zeros(heads, 128 - 3 * d, C))
             self.w_head_major = _dev_bf16(torch.cat(blocks, dim=1).reshape(heads * 128, C), device)
@@ -242,11 +379,24 @@ class NormPlan:
 class ConvPlan:
     def __init__(self, conv, device, use_bias=True):
         """use_bias=False: the caller folds conv.bias into the next kernel (saves the separate bias pass)."""
+        self.key = plan_key(device)
         self.stride = conv.stride
         self.padding = conv.padding
         self.cin, self.cout = conv.in_channels, conv.out_channels
         self.ksize = conv.kernel_size[0]
         bias = conv.bias if use_bias else None
+        self.precise = precise()
+        if self.precise:
+            # reference precision: 1x1 = GEMM; 3x3 (padding 1) = fp32 im2col + the same tf32 GEMM; nothing else exists
+            self.linear = self.lin3 = None
+            if self.ksize == 1:
+                self.linear = LinearPlan(conv.weight.detach().float().view(self.cout, self.cin), bias, device)
+            elif self.ksize == 3 and tuple(conv.padding) == (1, 1) and conv.stride[0] == conv.stride[1] \
+                    and conv.stride[0] in (1, 2):
+                self.lin3 = LinearPlan(conv.weight.detach().float().permute(0, 2, 3, 1).reshape(self.cout, -1), bias, device)
+            else:
+                raise NotImplementedError(f"reference-precision mode: unsupported convolution geometry {conv}")
+            return
         # 1x1 convolutions are plain GEMMs over channels-last rows
         self.linear = LinearPlan(conv.weight.detach().float().view(self.cout, self.cin), conv.bias, device) \
             if self.ksize == 1 and self.cin % 8 == 0 and self.cout % 16 == 0 else None
@@ -263,7 +413,11 @@ class ConvPlan:
     def __call__(self, x_img, relu=False, residual=None):
         """x_img [N, h, w, Cin] -> [N, oh, ow, Cout] (+ residual, same shape, fused where the kernel allows)."""
         N, h, w, _ = x_img.shape
-        if self.linear is not None:
+        if self.precise and self.linear is None:
+            cols, oh, ow = ops.im2col3x3(x_img, self.stride[0])
+            res2d = residual.reshape(-1, self.cout) if residual is not None else None
+            y = self.lin3(cols, residual=res2d).view(N, oh, ow, self.cout)
+        elif self.linear is not None:
             res2d = residual.reshape(-1, self.cout) if residual is not None else None
             y = self.linear(x_img.reshape(-1, self.cin), residual=res2d).view(N, h, w, self.cout)
         elif (self.fast3x3 and (CONV3X3 == "own" or (CONV3X3 == "auto" and self.cin <= 64))
@@ -289,7 +443,7 @@ def run_spatial_self_attention(plan, x_norm, residual, images, n_tokens, ln_stat
     # optional fp16 V / P path for head width 40 (see SPATIAL_VF16)
     v_f16 = SPATIAL_VF16 and plan.d == 40 and plan.v_col0 % 32 == 0
     qkv = plan.qkv(x_norm, ln_stats=ln_stats, f16_from_col=plan.v_col0 if v_f16 else None)
-    ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=BF16)
+    ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=x_norm.dtype)
     ops.spatial_attn(qkv, plan.q_col0, qkv, plan.k_col0, qkv, plan.v_col0, plan.hs, ctx, images, plan.heads, plan.d,
                      n_tokens, n_tokens, 1, n_tokens, plan.scale, v_f16=v_f16)
     return plan.out(ctx, residual=residual)
@@ -299,10 +453,11 @@ TEXT_PAD = 80  # text keys per batch item, 77 padded to a multiple of 8 rows (TM
 
 
 def prepare_text(text, device):
-    """[B, 77, 768] fp32 -> zero-padded bf16 rows [B * 80, 768] shared by every cross-attention of the step."""
+    """[B, 77, 768] fp32 -> zero-padded bf16 (fp32 in the reference-precision mode) rows [B * 80, 768] shared by every
+    cross-attention of the step."""
     B, n, c = text.shape
-    buf = torch.zeros((B, TEXT_PAD, c), device=device, dtype=BF16)
-    buf[:, :n] = text.to(device=device, dtype=BF16)
+    buf = torch.zeros((B, TEXT_PAD, c), device=device, dtype=act_dtype())
+    buf[:, :n] = text.to(device=device, dtype=act_dtype())
     return buf.view(B * TEXT_PAD, c), n
 
 
@@ -313,7 +468,7 @@ def run_spatial_cross_attention(plan, x_norm, residual, images, n_tokens, text_r
     and image i reads kv group i // frames."""
     q = plan.q(x_norm, ln_stats=ln_stats)
     kv = text_kv if text_kv is not None else plan.kv(text_rows)
-    ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=BF16)
+    ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=x_norm.dtype)
     ops.spatial_attn(q, 0, kv, 0, kv, plan.heads * plan.hs, plan.hs, ctx, images, plan.heads, plan.d, n_tokens, text_len,
                      frames, TEXT_PAD, plan.scale)
     return plan.out(ctx, residual=residual)
@@ -324,7 +479,7 @@ def run_temporal_attention(plan, x_norm, x_plus_pose, residual, B, F, HW):
     src = x_norm
     if plan.merge is not None:
         src = plan.merge(x_plus_pose, residual=x_norm)  # m = qkv_merge(x + pose) * s + x
-    ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=BF16)
+    ctx = torch.empty((x_norm.shape[0], plan.C), device=x_norm.device, dtype=x_norm.dtype)
     if plan.w_head_major is not None and F in (4, 8, 16, 32):
         ops.temporal_qkv_attn(src, plan.w_head_major, ctx, B, F, HW, plan.heads, plan.scale)
         return plan.out(ctx, residual=residual)
@@ -349,8 +504,6 @@ def nearest_index_chain(sizes):
 # --------------------------------------------------------------------------------------------------------------
 # text context shared by every cross-attention of one U-Net call
 # --------------------------------------------------------------------------------------------------------------
-_TEXT_KV_CAT = {}  # concatenated text K | V projection weights of the last U-Net seen
-
 
 class TextCtx:
     """encoder_hidden_states [B, 77, 768] -> zero-padded bf16 rows [B * 80, 768]."""
@@ -360,16 +513,19 @@ class TextCtx:
         self.batch = text.shape[0]
         self.kv = {}  # id(AttnPlan) -> [B * 80, heads * hs + C] bf16 view of the batched K | V projection
 
-    def project_all(self, transformers, device):
+    def project_all(self, transformers, device, cache):
         """K | V of the text for every cross-attention of the U-Net in ONE GEMM (16 tiny M = B * 80 GEMMs otherwise):
-        the row-concatenated to_k | to_v weights of all Transformer2D blocks against the same 160 text rows."""
+        the row-concatenated to_k | to_v weights of all Transformer2D blocks against the same 160 text rows.  `cache`:
+        a dict owned by the U-Net (dropped with its plans) holding the concatenated weights."""
         plans = [bp["attn2"] for m in transformers for bp in plan_transformer2d(m, device)["blocks"]]
-        hit = _TEXT_KV_CAT.get("entry")  # (plans, weights): the plans are kept referenced, so identity is meaningful
-        if hit is None or len(hit[0]) != len(plans) or any(a is not b for a, b in zip(hit[0], plans)) \
-                or hit[1].device != device:
+        hit = cache.get("text_kv")  # (plans, weights): the plans are kept referenced, so identity is meaningful
+        if hit is None or len(hit[0]) != len(plans) or any(a is not b for a, b in zip(hit[0], plans)):
             hit = (plans, torch.cat([p.kv.w for p in plans], dim=0).contiguous())
-            _TEXT_KV_CAT["entry"] = hit
-        allkv = ops.gemm(self.rows, hit[1])
+            cache["text_kv"] = hit
+        if plans[0].kv.split:
+            allkv = ops.gemm_f32(self.rows, hit[1], split=plans[0].kv.split)
+        else:
+            allkv = ops.gemm(self.rows, hit[1])
         off = 0
         for p in plans:
             self.kv[id(p)] = allkv[:, off:off + p.kv.N]
@@ -388,8 +544,22 @@ class TextCtx:
 # --------------------------------------------------------------------------------------------------------------
 # Transformer2DModel / ResnetBlock2D / resamplers on channels-last activations
 # --------------------------------------------------------------------------------------------------------------
+def _reject_spatial_pose(mod):
+    """set_all_attn_processor(add_spatial=True) puts pose-adaptor processors on the SPATIAL attentions; the reference then
+    computes qkv_merge(h + pose) * scale + h there too (attention_processor.py:255-257).  No shipped config does that
+    (configs/cam.yaml:121: add_spatial false) and the spatial kernels do not implement it: refuse instead of silently
+    dropping the camera conditioning."""
+    from .fmc.models.attention_processor import LORAPoseAdaptorAttnProcessor, PoseAdaptorAttnProcessor
+    for blk in mod.transformer_blocks:
+        for attn in (blk.attn1, blk.attn2):
+            if isinstance(attn.processor, (PoseAdaptorAttnProcessor, LORAPoseAdaptorAttnProcessor)):
+                raise NotImplementedError("pose-adaptor processors on the spatial attentions (add_spatial=True) are not "
+                                          "implemented: the shipped FMC configs condition the temporal attentions only")
+
+
 def plan_transformer2d(mod, device):
-    if getattr(mod, "_plan", None) is None or mod._plan["device"] != device:
+    if getattr(mod, "_plan", None) is None or mod._plan["device"] != plan_key(device):
+        _reject_spatial_pose(mod)
         blocks = []
         for blk in mod.transformer_blocks:
             blocks.append({
@@ -404,7 +574,7 @@ def plan_transformer2d(mod, device):
         c_in = mod.proj_in.weight.shape[1]
         inner = mod.proj_in.weight.shape[0]
         mod._plan = {
-            "device": device, "norm": NormPlan(mod.norm, device), "blocks": blocks,
+            "device": plan_key(device), "norm": NormPlan(mod.norm, device), "blocks": blocks,
             "proj_in": LinearPlan(mod.proj_in.weight.detach().float().view(inner, c_in), mod.proj_in.bias.detach().float(), device),
             "proj_out": LinearPlan(mod.proj_out.weight.detach().float().view(c_in, inner), mod.proj_out.bias.detach().float(), device),
         }
@@ -445,7 +615,7 @@ def run_transformer2d(mod, x, text):
 
 
 def plan_resnet(mod, device):
-    if getattr(mod, "_plan", None) is None or mod._plan["device"] != device:
+    if getattr(mod, "_plan", None) is None or mod._plan["device"] != plan_key(device):
         # conv1.bias rides on the time-embedding projection (both are per-channel adds in front of norm2), conv2.bias
         # on the shortcut GEMM bias or the residual add: the 3x3 convolutions themselves run bias-free
         b1 = mod.conv1.bias.detach().float()
@@ -456,7 +626,7 @@ def plan_resnet(mod, device):
             shortcut = LinearPlan(sc.weight.detach().float().view(sc.out_channels, sc.in_channels),
                                   sc.bias.detach().float() + b2, device)
         mod._plan = {
-            "device": device,
+            "device": plan_key(device),
             "norm1": NormPlan(mod.norm1, device), "conv1": ConvPlan(mod.conv1, device, use_bias=False),
             "temb": LinearPlan(mod.time_emb_proj.weight.detach().float(), mod.time_emb_proj.bias.detach().float() + b1,
                                device),
@@ -477,18 +647,21 @@ class Temb:
 
     def __init__(self, emb):
         self.emb = emb
-        self.act = ops.cast_act(emb, silu=True)
+        self.act = ops.cast_act(emb, silu=True, dtype=act_dtype())
         self.proj = {}  # id(resnet module) -> [B, Cout] fp32 view
 
-    def project_all(self, resnets, device):
+    def project_all(self, resnets, device, cache):
+        """`cache`: a dict owned by the U-Net (dropped with its plans) holding the concatenated weights."""
         plans = [plan_resnet(m, device) for m in resnets]
-        hit = _TEMB_CAT.get("entry")  # (plans, weights, biases); plans kept referenced, compared by identity
-        if hit is None or len(hit[0]) != len(plans) or any(a is not b for a, b in zip(hit[0], plans)) \
-                or hit[1].device != device:
+        hit = cache.get("temb")  # (plans, weights, biases); plans kept referenced, compared by identity
+        if hit is None or len(hit[0]) != len(plans) or any(a is not b for a, b in zip(hit[0], plans)):
             hit = (plans, torch.cat([p["temb"].w for p in plans], dim=0).contiguous(),
                    torch.cat([p["temb"].b for p in plans], dim=0).contiguous())
-            _TEMB_CAT["entry"] = hit
-        allp = ops.gemm(self.act, hit[1], bias=hit[2], out_f32=True)
+            cache["temb"] = hit
+        if plans[0]["temb"].split:
+            allp = ops.gemm_f32(self.act, hit[1], bias=hit[2], split=plans[0]["temb"].split)
+        else:
+            allp = ops.gemm(self.act, hit[1], bias=hit[2], out_f32=True)
         off = 0
         for m, p in zip(resnets, plans):
             n = p["temb"].N
@@ -499,8 +672,6 @@ class Temb:
     def of(x):
         return x if isinstance(x, Temb) else Temb(x.float())
 
-
-_TEMB_CAT = {}  # concatenated time_emb_proj weights of the last U-Net seen (rebuilt when the module set changes)
 
 
 def run_resnet(mod, x, temb):
@@ -516,7 +687,7 @@ def run_resnet(mod, x, temb):
     temb = Temb.of(temb)
     tproj = temb.proj.get(id(mod))  # [B, Cout] fp32, broadcast over frames
     if tproj is None:
-        tproj = ops.gemm(temb_act, p["temb"].w, bias=p["temb"].b, out_f32=True)
+        tproj = p["temb"].f32out(temb_act)
     # the time-embedding add happens inside the second GroupNorm (before its statistics), saving a pass over h
     n2 = ops.groupnorm(h.view(-1, cout), p["norm2"].g, p["norm2"].b, p["norm2"].eps, images, HW, groups=p["norm2"].groups,
                        silu=True, rowbias=tproj, rowbias_div=F)
@@ -530,7 +701,7 @@ def run_resnet(mod, x, temb):
 
 def run_downsample(mod, x):
     B, F, H, W, C = x.dims
-    if getattr(mod, "_plan", None) is None or mod._plan.w.device != x.t.device:
+    if getattr(mod, "_plan", None) is None or mod._plan.key != plan_key(x.t.device):
         mod._plan = ConvPlan(mod.conv, x.t.device)
     y = mod._plan(x.images())
     return CL(y.view(B, F, *y.shape[1:]))
@@ -538,7 +709,7 @@ def run_downsample(mod, x):
 
 def run_upsample(mod, x, output_size=None):
     B, F, H, W, C = x.dims
-    if getattr(mod, "_plan", None) is None or mod._plan.w.device != x.t.device:
+    if getattr(mod, "_plan", None) is None or mod._plan.key != plan_key(x.t.device):
         mod._plan = ConvPlan(mod.conv, x.t.device)
     oh, ow = (2 * H, 2 * W) if output_size is None else (int(output_size[-2]), int(output_size[-1]))
     up = ops.resize_nearest(x.images(), oh, ow)
@@ -550,7 +721,7 @@ def concat_channels(a, b):
     """torch.cat([a, b], dim=1) of the reference layout = channel concat of channels-last rows."""
     B, F, H, W, Ca = a.dims
     Cb = b.dims[-1]
-    out = torch.empty((B, F, H, W, Ca + Cb), device=a.t.device, dtype=BF16)
+    out = torch.empty((B, F, H, W, Ca + Cb), device=a.t.device, dtype=a.t.dtype)
     rows = out.view(-1, Ca + Cb)
     ops.copy2d(a.rows(), rows[:, :Ca])
     ops.copy2d(b.rows(), rows[:, Ca:])

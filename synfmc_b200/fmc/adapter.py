@@ -44,9 +44,7 @@ class Adapter(nn.Module):
         self._plan = None
 
     def invalidate_plans(self):
-        for m in self.modules():
-            if hasattr(m, "_plan"):
-                m._plan = None
+        engine.invalidate_plans(self)
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
@@ -54,10 +52,11 @@ class Adapter(nn.Module):
         return out
 
     def plan(self, device):
-        if self._plan is None or self._plan["device"] != device:
+        engine.refresh_plans(self)
+        if self._plan is None or self._plan["device"] != engine.plan_key(device):
             def maybe(m):
                 return engine.ConvPlan(m, device) if isinstance(m, nn.Conv2d) else None
-            self._plan = {"device": device, "conv_in": engine.ConvPlan(self.conv_in, device),
+            self._plan = {"device": engine.plan_key(device), "conv_in": engine.ConvPlan(self.conv_in, device),
                           "zero_in": maybe(self.zero_conv_in), "zero_out": [maybe(m) for m in self.zero_conv_out_list]}
         return self._plan
 
@@ -87,8 +86,8 @@ class Adapter(nn.Module):
 
     def forward(self, x, mask_feat):
         """Reference signature (:154): x [(b f), 13, H, W], mask_feat [(b f), 1, H, W] -> 4 x [(b f), C_l, h_l, w_l]."""
-        if not x.is_cuda:
-            raise RuntimeError("synfmc_b200 runs on CUDA tensors only (no CPU fallback)")
+        ops.require_cuda(x)
+        engine.require_no_grad(self, x, mask_feat)
         n, c, H, W = x.shape
         x_cl = unshuffle8_to_cl(x.float().view(n, c, 1, H, W)).view(n, H // 8, W // 8, c * 64)
         mask = mask_feat.float().reshape(n, H, W).contiguous() if mask_feat is not None else None

@@ -63,8 +63,8 @@ class TemporalTransformerBlock(nn.Module):
         self._plan = None
 
     def plan(self, device):
-        if self._plan is None or self._plan["device"] != device:
-            p = {"device": device, "attn": [], "norms": [], "pe": []}
+        if self._plan is None or self._plan["device"] != engine.plan_key(device):
+            p = {"device": engine.plan_key(device), "attn": [], "norms": [], "pe": []}
             for attn, norm in zip(self.attention_blocks, self.norms):
                 p["attn"].append(engine.AttnPlan(attn, device, fused_temporal=True))
                 p["norms"].append(engine.NormPlan(norm, device))
@@ -129,9 +129,9 @@ class TemporalTransformer3DModel(nn.Module):
         self._plan = None
 
     def plan(self, device):
-        if self._plan is None or self._plan["device"] != device:
+        if self._plan is None or self._plan["device"] != engine.plan_key(device):
             self._plan = {
-                "device": device,
+                "device": engine.plan_key(device),
                 "norm": engine.NormPlan(self.norm, device),
                 "proj_in": engine.LinearPlan(self.proj_in.weight.detach().float(), self.proj_in.bias.detach().float(), device),
                 "proj_out": engine.LinearPlan(self.proj_out.weight.detach().float(), self.proj_out.bias.detach().float(), device),

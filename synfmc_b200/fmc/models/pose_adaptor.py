@@ -43,9 +43,9 @@ class ResnetBlock(nn.Module):
         self._plan = None
 
     def plan(self, device):
-        if self._plan is None or self._plan["device"] != device:
+        if self._plan is None or self._plan["device"] != engine.plan_key(device):
             self._plan = {
-                "device": device,
+                "device": engine.plan_key(device),
                 "in_conv": engine.ConvPlan(self.in_conv, device) if self.in_conv is not None else None,
                 "block1": engine.ConvPlan(self.block1, device),
                 "block2": engine.ConvPlan(self.block2, device),
@@ -77,7 +77,7 @@ def unshuffle8_to_cl(x):
     drop-in entry point; the fused kernels fmc_plucker_unshuffle_bf16 / fmc_traj_scatter_unshuffle_bf16 avoid it)."""
     b, c, f, H, W = x.shape
     y = torch.nn.functional.pixel_unshuffle(x.permute(0, 2, 1, 3, 4).reshape(b * f, c, H, W), 8)
-    return y.permute(0, 2, 3, 1).reshape(b, f, H // 8, W // 8, c * 64).to(torch.bfloat16).contiguous()
+    return y.permute(0, 2, 3, 1).reshape(b, f, H // 8, W // 8, c * 64).to(engine.act_dtype()).contiguous()
 
 
 def cl_to_frames_nchw(x):
@@ -128,9 +128,7 @@ class CameraPoseEncoder(nn.Module):
         return next(self.parameters()).dtype
 
     def invalidate_plans(self):
-        for m in self.modules():
-            if hasattr(m, "_plan"):
-                m._plan = None
+        engine.invalidate_plans(self)
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
@@ -140,7 +138,8 @@ class CameraPoseEncoder(nn.Module):
     def encode_cl(self, x_cl):
         """x_cl: unshuffled rays [b, f, H/8, W/8, 384] bf16 -> list of 4 CL features [b, f, h_l, w_l, C_l]."""
         b, f, h, w, cin = x_cl.shape
-        if self._plan is None or self._plan.w.device != x_cl.device:
+        engine.refresh_plans(self)
+        if self._plan is None or self._plan.key != engine.plan_key(x_cl.device):
             self._plan = engine.ConvPlan(self.encoder_conv_in, x_cl.device)
         x = self._plan(x_cl.view(b * f, h, w, cin))
         features = []
@@ -157,12 +156,15 @@ class CameraPoseEncoder(nn.Module):
         """K [b, f, 4] = (fx, fy, cx, cy), c2w [b, f, 3, 4] (device tensors) -> 4 CL features, rays built on the GPU."""
         b, f = K.shape[:2]
         rays = ops.plucker_unshuffle(K.reshape(b * f, 4), c2w.reshape(b * f, 3, 4), H, W)
+        if engine.precise():  # the fused ray kernel writes bf16; the reference-precision mode takes the fp32 rays
+            rays6 = ops.plucker(K.reshape(b * f, 4), c2w.reshape(b * f, 3, 4), H, W)  # [bf, H, W, 6]
+            return self.encode_cl(unshuffle8_to_cl(rays6.view(b, f, H, W, 6).permute(0, 4, 1, 2, 3)))
         return self.encode_cl(rays.view(b, f, H // 8, W // 8, 384))
 
     def forward(self, x):
         """Reference signature (:224-240): x [b, 6, f, H, W] -> 4 tensors [(b f), C_l, h_l, w_l] (fp32)."""
-        if not x.is_cuda:
-            raise RuntimeError("synfmc_b200 runs on CUDA tensors only (no CPU fallback)")
+        ops.require_cuda(x)
+        engine.require_no_grad(self, x)
         return [cl_to_frames_nchw(f) for f in self.encode_cl(unshuffle8_to_cl(x.float()))]
 
 
@@ -174,5 +176,6 @@ class PoseAdaptor(nn.Module):
 
     def forward(self, noisy_latents, timesteps, encoder_hidden_states, pose_embedding):
         assert pose_embedding.ndim == 5
+        engine.require_no_grad(self, noisy_latents, encoder_hidden_states, pose_embedding)
         feats = self.pose_encoder.encode_cl(unshuffle8_to_cl(pose_embedding.float()))
         return self.unet(noisy_latents, timesteps, encoder_hidden_states, pose_embedding_features=feats).sample

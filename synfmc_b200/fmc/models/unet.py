@@ -103,6 +103,7 @@ class UNet3DConditionModel(nn.Module):
         self.conv_act = nn.SiLU()
         self.conv_out = InflatedConv3d(ch0, out_channels, kernel_size=3, padding=1)
         self._plan = None
+        self._cat_cache = {}   # concatenated time-embedding / text K|V projection weights (dropped with the plans)
         self._resnets = None  # ResnetBlock2D modules, for the batched time-embedding projection
         self._transformers = None  # Transformer2DModel modules, for the batched text K | V projection
 
@@ -135,10 +136,12 @@ class UNet3DConditionModel(nn.Module):
         self._assign_processors(processor, True)
 
     def invalidate_plans(self):
-        """Drop every cached device plan (folded / fused bf16 weights); call after changing parameters."""
-        for m in self.modules():
-            if hasattr(m, "_plan"):
-                m._plan = None
+        """Drop every cached device plan (folded / fused weights) and everything derived from them (the concatenated
+        projection weights, captured CUDA graphs -- their keys carry engine's plan generation).  Called automatically when
+        the parameter fingerprint changes (optimizer steps, in-place copies, load_state_dict on a submodule, processor
+        edits); calling it by hand is never needed but harmless."""
+        engine.invalidate_plans(self)
+        self._cat_cache = {}
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
@@ -286,7 +289,7 @@ class UNet3DConditionModelPoseCond(UNet3DConditionModel):
 
     # ---- device plan of the UNet-level layers ----
     def plan(self, device):
-        if self._plan is None or self._plan["device"] != device:
+        if self._plan is None or self._plan["device"] != engine.plan_key(device):
             def pad_conv(conv, cin_pad, cout_pad):
                 w = torch.zeros(cout_pad, cin_pad, *conv.weight.shape[2:])
                 w[:conv.out_channels, :conv.in_channels] = conv.weight.detach().float()
@@ -299,7 +302,7 @@ class UNet3DConditionModelPoseCond(UNet3DConditionModel):
 
             te = self.time_embedding
             self._plan = {
-                "device": device,
+                "device": engine.plan_key(device),
                 # the 4 latent channels are zero-padded to 64 in / 32 out: one k-block / one output sub-tile of the tcgen05
                 # implicit-GEMM convolution (fmc_conv3x3_bf16), which then carries conv_in / conv_out as well
                 "conv_in": pad_conv(self.conv_in, 64, self.conv_in.out_channels),
@@ -312,13 +315,15 @@ class UNet3DConditionModelPoseCond(UNet3DConditionModel):
 
     def _forward_impl(self, sample, timestep, encoder_hidden_states, class_labels=None, attention_mask=None,
                       cross_attention_kwargs=None, pose_embedding_features=None, traj_features=None, return_dict=True):
+        engine.require_no_grad(self, sample, encoder_hidden_states, *(pose_embedding_features or ()),
+                               *(traj_features or ()))
         if attention_mask is not None or class_labels is not None or cross_attention_kwargs is not None:
             raise NotImplementedError("attention_mask / class_labels / cross_attention_kwargs are unused on the FMC hot path")
         if traj_features is not None and not self._accepts_traj_features:
             raise TypeError("traj_features is only accepted by UNet3DConditionModelCamObjCond")
-        if not sample.is_cuda:
-            raise RuntimeError("synfmc_b200 runs on CUDA tensors only (no CPU fallback)")
+        ops.require_cuda(sample)
         device = sample.device
+        engine.refresh_plans(self)
         p = self.plan(device)
         B, _, F, H, W = sample.shape
         up_factor = 2 ** self.num_upsamplers
@@ -332,20 +337,21 @@ class UNet3DConditionModelPoseCond(UNet3DConditionModel):
         elif timesteps.ndim == 0:
             timesteps = timesteps[None]
         timesteps = timesteps.to(device=device, dtype=torch.float32).expand(B).contiguous()
-        t_emb = ops.timestep_embedding(timesteps, self.config.block_out_channels[0])
-        h1 = ops.gemm(t_emb, p["t1"].w, bias=p["t1"].b, out_f32=True)
-        emb = ops.gemm(ops.cast_act(h1, silu=True), p["t2"].w, bias=p["t2"].b, out_f32=True)
+        adt = engine.act_dtype()
+        t_emb = ops.timestep_embedding(timesteps, self.config.block_out_channels[0], dtype=adt)
+        h1 = p["t1"].f32out(t_emb)
+        emb = p["t2"].f32out(ops.cast_act(h1, silu=True, dtype=adt))
         temb = engine.Temb(emb)
         if self._resnets is None:
             self._resnets = [m for m in self.modules() if m.__class__.__name__ == "ResnetBlock2D"]
-        temb.project_all(self._resnets, device)
+        temb.project_all(self._resnets, device, self._cat_cache)
 
         text = engine.TextCtx.of(encoder_hidden_states, B, 1, device)
         if self._transformers is None:
             self._transformers = [m for m in self.modules() if m.__class__.__name__ == "Transformer2DModel"]
         if not text.kv:
-            text.project_all(self._transformers, device)
-        x = CL(ops.to_channels_last(sample, c_pad=64))
+            text.project_all(self._transformers, device, self._cat_cache)
+        x = CL(ops.to_channels_last(sample, c_pad=64, dtype=adt))
         y = p["conv_in"](x.images())
         x = CL(y.view(B, F, H, W, y.shape[-1]))
 

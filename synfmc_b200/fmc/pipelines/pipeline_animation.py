@@ -6,7 +6,7 @@ from types import SimpleNamespace
 
 import torch
 
-from ... import _cabi, ops
+from ... import _cabi, engine, ops
 from ...engine import CL, TextCtx
 from ..models.pose_adaptor import unshuffle8_to_cl
 
@@ -123,8 +123,14 @@ class CameraCtrlPipeline:
         self._graphs = {}
 
     def _step_graph(self, latents, text, feats, traj, do_cfg):
+        # a graph freezes device pointers into the U-Net's weight plans: the key carries the U-Net's identity, its plan
+        # generation (bumped when refresh_plans sees changed parameters / processors) and the precision mode
+        engine.refresh_plans(self.unet)
         key = (tuple(latents.shape), tuple(text.shape), do_cfg, tuple(f.dims for f in feats),
-               None if traj is None else tuple(f.dims for f in traj), latents.device)
+               None if traj is None else tuple(f.dims for f in traj), latents.device, id(self.unet),
+               engine.generation(self.unet), engine.get_precision())
+        for stale in [k for k in self._graphs if k[-3] == id(self.unet) and k[-2] != engine.generation(self.unet)]:
+            del self._graphs[stale]  # graphs of dropped plans must not be replayed, nor keep their buffers alive
         g = self._graphs.get(key)
         if g is None:
             while len(self._graphs) >= self.max_graphs:
@@ -133,7 +139,8 @@ class CameraCtrlPipeline:
         return g
 
     def reset_graphs(self):
-        """Drop captured graphs (call after changing weights / processors: plans and graphs freeze them)."""
+        """Drop captured graphs (never required: graphs are keyed on the U-Net's plan generation and re-captured when its
+        weights or processors change; kept for callers that want the memory back)."""
         self._graphs.clear()
 
     def enable_vae_slicing(self):

@@ -7,8 +7,9 @@ import random
 import numpy as np
 import torch
 
-from .. import ops
+from .. import engine, ops
 from ..engine import CL
+from .models.pose_adaptor import unshuffle8_to_cl
 
 
 def pack_objects(obj_info_list_list, obj_mask_list_list, device):
@@ -32,7 +33,12 @@ def pack_objects(obj_info_list_list, obj_mask_list_list, device):
 def traj_features_cl(info, masks, omcm, null_clips=None):
     """info [B, F, n, 12], masks [B, F, n, H, W] (device fp32) -> 4 CL features [B, F, h_l, w_l, C_l]."""
     B, Fn, n, H, W = masks.shape
-    feat, mask = ops.traj_scatter_unshuffle(info.view(B * Fn, n, 12), masks.view(B * Fn, n, H, W))
+    if engine.precise():
+        # reference-precision mode: the bit-exact fp32 scatter (reference layout), then PixelUnshuffle(8) as plumbing
+        feat13, mask = ops.traj_scatter(info.view(B * Fn, n, 12), masks.view(B * Fn, n, H, W))
+        feat = unshuffle8_to_cl(feat13.view(B * Fn, 13, 1, H, W)).view(B * Fn, H // 8, W // 8, 13 * 64)
+    else:
+        feat, mask = ops.traj_scatter_unshuffle(info.view(B * Fn, n, 12), masks.view(B * Fn, n, H, W))
     if null_clips:
         fv = feat.view(B, Fn, *feat.shape[1:])
         for i in null_clips:

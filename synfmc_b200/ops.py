@@ -6,25 +6,111 @@ import torch
 from . import _cabi
 
 BF16 = torch.bfloat16
+F32 = torch.float32
+# Activation dtypes: bf16 = the production layout; fp32 = the reference-precision mode (csrc/precise.cu: tf32 tensor-core
+# linears, fp32 everything else).  Every wrapper picks the entry point from the dtype of its activation operand and
+# refuses mixed operands -- one backend, two precisions.
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    return 0 if DRY_RUN else torch.cuda.current_stream().cuda_stream
 
 
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+# Host-logic tests only (tests/test_dry_run.py): with DRY_RUN set and _cabi.call replaced by a recorder the wrappers run on
+# CPU tensors WITHOUT executing any kernel -- outputs are uninitialised memory.  Never set outside tests.
+DRY_RUN = False
+
+
+def require_cuda(t):
+    if not (t.is_cuda or DRY_RUN):
+        raise RuntimeError("synfmc_b200 runs on CUDA tensors only (no CPU fallback)")
+
+
 def _check_cuda(*tensors):
+    """Operands must live on the CURRENT CUDA device: kernels are launched on its current stream."""
+    if DRY_RUN:
+        return
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _cabi.FmcError("synfmc_b200 ops run on CUDA tensors only (no CPU fallback)")
+        if t.device.index != torch.cuda.current_device():
+            raise _cabi.FmcError(f"operand on {t.device} but the current device is cuda:{torch.cuda.current_device()}: "
+                                 "wrap the call in torch.cuda.device(tensor.device)")
 
 
 def _rows2d(t, dtype=BF16):
     assert t.dtype == dtype and t.ndim == 2 and t.stride(1) == 1, (t.dtype, t.shape, t.stride())
     return t
+
+
+def _act(t):
+    """dtype of an activation operand: bf16 or fp32 (anything else is a caller error)."""
+    assert t.dtype in (BF16, F32), t.dtype
+    return t.dtype
+
+
+def split_tf32(x):
+    """fp32 [rows, K] -> [rows, 2K] = [tf32(x) | x - tf32(x)]: the operand form of the three-pass tf32 GEMM."""
+    _check_cuda(x)
+    _rows2d(x, F32)
+    rows, K = x.shape
+    out = torch.empty((rows, 2 * K), device=x.device, dtype=F32)
+    _cabi.call("fmc_split_tf32", x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, K, _stream())
+    return out
+
+
+def gemm_f32(a, w, bias=None, residual=None, out=None, geglu=False, rowbias=None, rows_per_group=0, split=1):
+    """Reference-precision linear: fp32 a [M, K]; w fp32 [N, K] (split = 1) or [N, 2K] = [hi | lo] (split = 3, the
+    activation is split here)."""
+    _check_cuda(a, w)
+    _rows2d(a, F32)
+    _rows2d(w, F32)
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K * (2 if split == 3 else 1), (w.shape, K, split)
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=F32)
+    assert out.dtype == F32 and out.shape == (M, n_out) and out.stride(1) == 1
+    if residual is not None:
+        _rows2d(residual, F32)
+        assert residual.shape == (M, n_out)
+    if bias is not None:
+        assert bias.dtype == F32 and bias.numel() == N and bias.is_contiguous()
+    if rowbias is not None:
+        assert rowbias.dtype == F32 and rowbias.stride(1) == 1 and rowbias.shape[1] == N
+    a_op = split_tf32(a) if split == 3 else a
+    _cabi.call("fmc_gemm_tf32", a_op.data_ptr(), a_op.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
+               M, N, K, _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, _ptr(rowbias),
+               rows_per_group, rowbias.stride(0) if rowbias is not None else 0, 1 if geglu else 0, split, _stream())
+    return out
+
+
+def attention_f32(q, q_col0, k, k_col0, v, v_col0, out, images, heads, head_dim, nq, nk, kv_div, kv_stride, inner, scale):
+    _check_cuda(q, k, v, out)
+    for t in (q, k, v, out):
+        _rows2d(t, F32)
+    _cabi.call("fmc_attention_f32", q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
+               v.stride(0), v_col0, out.data_ptr(), out.stride(0), images, heads, head_dim, nq, nk, kv_div, kv_stride,
+               inner, float(scale), _stream())
+    return out
+
+
+def im2col3x3(x, stride=1):
+    """fp32 [N, H, W, C] -> [N * OH * OW, 9 * C] rows in (ky, kx, c) order (3x3, padding 1)."""
+    _check_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous()
+    N, H, W, C = x.shape
+    OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty((N * OH * OW, 9 * C), device=x.device, dtype=F32)
+    _cabi.call("fmc_im2col3x3_f32", x.data_ptr(), out.data_ptr(), N, H, W, C, stride, _stream())
+    return out, OH, OW
 
 
 def rowstats(x, eps=1e-5):
@@ -79,6 +165,10 @@ def gemm(a, w, bias=None, residual=None, out=None, geglu=False, out_f32=False, r
 def spatial_attn(q, q_col0, k, k_col0, v, v_col0, head_stride, out, images, heads, head_dim, nq, nk, kv_div, kv_stride,
                  scale, v_f16=False):
     """`v_f16`: the V columns hold IEEE fp16 bit patterns (gemm(..., f16_from_col=v_col0)); head_dim 40 only."""
+    if _act(q) == F32:
+        assert not v_f16 and head_stride == head_dim
+        return attention_f32(q, q_col0, k, k_col0, v, v_col0, out, images, heads, head_dim, nq, nk, kv_div, kv_stride, 1,
+                             scale)
     _check_cuda(q, k, v, out)
     for t in (q, k, v, out):
         _rows2d(t)
@@ -90,6 +180,9 @@ def spatial_attn(q, q_col0, k, k_col0, v, v_col0, head_stride, out, images, head
 
 
 def temporal_attn(qkv, q_col0, k_col0, v_col0, head_stride, out, B, F, HW, heads, head_dim, scale):
+    if _act(qkv) == F32:
+        assert head_stride == head_dim and qkv.shape[0] == B * F * HW == out.shape[0]
+        return attention_f32(qkv, q_col0, qkv, k_col0, qkv, v_col0, out, B * HW, heads, head_dim, F, F, 1, F, HW, scale)
     _check_cuda(qkv, out)
     _rows2d(qkv)
     _rows2d(out)
@@ -113,13 +206,16 @@ def temporal_qkv_attn(x, w_qkv, out, B, F, HW, heads, scale):
 
 def layernorm(x, gamma, beta, eps=1e-5, out=None, pe=None, F=0, HW=0, add=None, out2=None):
     _check_cuda(x)
-    _rows2d(x)
+    dt = _act(x)
+    _rows2d(x, dt)
     rows, C = x.shape
     if out is None:
-        out = torch.empty((rows, C), device=x.device, dtype=BF16)
+        out = torch.empty((rows, C), device=x.device, dtype=dt)
     if add is not None and out2 is None:
-        out2 = torch.empty((rows, C), device=x.device, dtype=BF16)
-    _cabi.call("fmc_layernorm_bf16", x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps),
+        out2 = torch.empty((rows, C), device=x.device, dtype=dt)
+    if add is not None:
+        _rows2d(add, dt)
+    _cabi.call("fmc_layernorm_f32" if dt == F32 else "fmc_layernorm_bf16", x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps),
                out.data_ptr(), out.stride(0), _ptr(pe), F, HW, _ptr(add), add.stride(0) if add is not None else 0,
                _ptr(out2), out2.stride(0) if out2 is not None else 0, rows, C, _stream())
     return (out, out2) if add is not None else out
@@ -128,15 +224,16 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None, pe=None, F=0, HW=0, add=None, 
 def groupnorm(x, gamma, beta, eps, images, HW, groups=32, silu=False, rowbias=None, rowbias_div=1, out=None):
     """x: [images*HW, C] rows (channels-last); statistics per (image, group)."""
     _check_cuda(x)
-    _rows2d(x)
+    dt = _act(x)
+    _rows2d(x, dt)
     rows, C = x.shape
     assert rows == images * HW
     if out is None:
-        out = torch.empty((rows, C), device=x.device, dtype=BF16)
+        out = torch.empty((rows, C), device=x.device, dtype=dt)
     stats = torch.empty((2 * images * (groups * ((HW + 63) // 64) + C),), device=x.device, dtype=torch.float32)
     if rowbias is not None:
         assert rowbias.dtype == torch.float32 and rowbias.shape == (images // rowbias_div, C) and rowbias.stride(1) == 1
-    _cabi.call("fmc_groupnorm_bf16", x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps),
+    _cabi.call("fmc_groupnorm_f32" if dt == F32 else "fmc_groupnorm_bf16", x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps),
                out.data_ptr(), out.stride(0), stats.data_ptr(), images, HW, C, groups, 1 if silu else 0, _ptr(rowbias),
                rowbias.stride(0) if rowbias is not None else 0, rowbias_div, _stream())
     return out
@@ -144,85 +241,96 @@ def groupnorm(x, gamma, beta, eps, images, HW, groups=32, silu=False, rowbias=No
 
 def add(a, b=None, rowbias=None, rows_per_group=0, relu=False, out=None):
     _check_cuda(a)
-    _rows2d(a)
+    dt = _act(a)
+    _rows2d(a, dt)
     rows, C = a.shape
     if out is None:
-        out = torch.empty((rows, C), device=a.device, dtype=BF16)
+        out = torch.empty((rows, C), device=a.device, dtype=dt)
     if b is not None:
-        _rows2d(b)
+        _rows2d(b, dt)
         assert b.shape == a.shape
-    _cabi.call("fmc_add_bf16", a.data_ptr(), a.stride(0), _ptr(b), b.stride(0) if b is not None else 0, _ptr(rowbias),
+    _cabi.call("fmc_add_f32" if dt == F32 else "fmc_add_bf16", a.data_ptr(), a.stride(0), _ptr(b), b.stride(0) if b is not None else 0, _ptr(rowbias),
                rows_per_group, rowbias.stride(0) if rowbias is not None else 0, out.data_ptr(), out.stride(0), rows, C,
                1 if relu else 0, _stream())
     return out
 
 
 def resize_nearest(x, oh, ow):
-    """x: [N, h, w, C] contiguous bf16."""
+    """x: [N, h, w, C] contiguous bf16 / fp32."""
     _check_cuda(x)
-    assert x.dtype == BF16 and x.is_contiguous()
+    dt = _act(x)
+    assert x.is_contiguous()
     N, h, w, C = x.shape
-    out = torch.empty((N, oh, ow, C), device=x.device, dtype=BF16)
-    _cabi.call("fmc_resize_nearest_bf16", x.data_ptr(), out.data_ptr(), N, h, w, oh, ow, C, _stream())
+    out = torch.empty((N, oh, ow, C), device=x.device, dtype=dt)
+    _cabi.call("fmc_resize_nearest_f32" if dt == F32 else "fmc_resize_nearest_bf16", x.data_ptr(), out.data_ptr(), N, h, w, oh, ow, C, _stream())
     return out
 
 
 def avgpool2(x):
     _check_cuda(x)
-    assert x.dtype == BF16 and x.is_contiguous()
+    dt = _act(x)
+    assert x.is_contiguous()
     N, h, w, C = x.shape
-    out = torch.empty((N, h // 2, w // 2, C), device=x.device, dtype=BF16)
-    _cabi.call("fmc_avgpool2_bf16", x.data_ptr(), out.data_ptr(), N, h, w, C, _stream())
+    out = torch.empty((N, h // 2, w // 2, C), device=x.device, dtype=dt)
+    _cabi.call("fmc_avgpool2_f32" if dt == F32 else "fmc_avgpool2_bf16", x.data_ptr(), out.data_ptr(), N, h, w, C, _stream())
     return out
 
 
 def copy2d(src, dst):
     """dst[:, :cols] = src (both row-strided 2-D bf16 views)."""
     _check_cuda(src, dst)
-    _rows2d(src)
-    _rows2d(dst)
+    dt = _act(src)
+    _rows2d(src, dt)
+    _rows2d(dst, dt)
     assert src.shape == dst.shape
-    _cabi.call("fmc_copy2d_bf16", src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), src.shape[0],
+    _cabi.call("fmc_copy2d_f32" if dt == F32 else "fmc_copy2d_bf16", src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), src.shape[0],
                src.shape[1], _stream())
     return dst
 
 
-def to_channels_last(x, c_pad=None):
-    """[B, C, F, H, W] fp32 -> [B, F, H, W, Cpad] bf16."""
+def to_channels_last(x, c_pad=None, dtype=BF16):
+    """[B, C, F, H, W] fp32 -> [B, F, H, W, Cpad] bf16 (or fp32 in the reference-precision mode)."""
     _check_cuda(x)
     x = x.contiguous().float()
     B, C, F, H, W = x.shape
     c_pad = c_pad or C
-    out = torch.empty((B, F, H, W, c_pad), device=x.device, dtype=BF16)
-    _cabi.call("fmc_ncfhw_f32_to_cl_bf16", x.data_ptr(), out.data_ptr(), B, C, F, H * W, c_pad, _stream())
+    out = torch.empty((B, F, H, W, c_pad), device=x.device, dtype=dtype)
+    _cabi.call("fmc_ncfhw_f32_to_cl_f32" if dtype == F32 else "fmc_ncfhw_f32_to_cl_bf16", x.data_ptr(), out.data_ptr(), B, C, F, H * W, c_pad, _stream())
     return out
 
 
 def from_channels_last(x, C=None):
-    """[B, F, H, W, ld] bf16 -> [B, C, F, H, W] fp32."""
+    """[B, F, H, W, ld] bf16 / fp32 -> [B, C, F, H, W] fp32."""
     _check_cuda(x)
-    assert x.dtype == BF16 and x.is_contiguous()
+    dt = _act(x)
+    assert x.is_contiguous()
     B, F, H, W, ld = x.shape
     C = C or ld
     out = torch.empty((B, C, F, H, W), device=x.device, dtype=torch.float32)
-    _cabi.call("fmc_cl_bf16_to_ncfhw_f32", x.data_ptr(), ld, out.data_ptr(), B, C, F, H * W, _stream())
+    _cabi.call("fmc_cl_f32_to_ncfhw_f32" if dt == F32 else "fmc_cl_bf16_to_ncfhw_f32", x.data_ptr(), ld, out.data_ptr(), B, C, F, H * W, _stream())
     return out
 
 
-def cast_act(x, silu=False):
+def cast_act(x, silu=False, dtype=BF16):
     _check_cuda(x)
     x = x.contiguous()
     assert x.dtype == torch.float32
+    if dtype == F32:
+        if not silu:
+            return x
+        out = torch.empty_like(x)
+        _cabi.call("fmc_silu_f32", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+        return out
     out = torch.empty(x.shape, device=x.device, dtype=BF16)
     _cabi.call("fmc_cast_act_bf16", x.data_ptr(), out.data_ptr(), x.numel(), 1 if silu else 0, _stream())
     return out
 
 
-def timestep_embedding(t, dim):
+def timestep_embedding(t, dim, dtype=BF16):
     _check_cuda(t)
     t = t.contiguous().float()
-    out = torch.empty((t.numel(), dim), device=t.device, dtype=BF16)
-    _cabi.call("fmc_timestep_embedding_bf16", t.data_ptr(), out.data_ptr(), t.numel(), dim, _stream())
+    out = torch.empty((t.numel(), dim), device=t.device, dtype=dtype)
+    _cabi.call("fmc_timestep_embedding_f32" if dtype == F32 else "fmc_timestep_embedding_bf16", t.data_ptr(), out.data_ptr(), t.numel(), dim, _stream())
     return out
 
 
@@ -275,12 +383,13 @@ def traj_scatter_unshuffle(info, masks):
 
 
 def mask_modulate(x, mask, row_index, col_index):
-    """x [N, h, w, C] bf16, mask [N, H, W] fp32, index maps int32 [h], [w]."""
+    """x [N, h, w, C] bf16 / fp32, mask [N, H, W] fp32, index maps int32 [h], [w]."""
     _check_cuda(x, mask)
-    assert x.dtype == BF16 and x.is_contiguous() and mask.is_contiguous()
+    dt = _act(x)
+    assert x.is_contiguous() and mask.is_contiguous()
     N, h, w, C = x.shape
     out = torch.empty_like(x)
-    _cabi.call("fmc_mask_modulate_bf16", x.data_ptr(), mask.data_ptr(), row_index.data_ptr(), col_index.data_ptr(),
+    _cabi.call("fmc_mask_modulate_f32" if dt == F32 else "fmc_mask_modulate_bf16", x.data_ptr(), mask.data_ptr(), row_index.data_ptr(), col_index.data_ptr(),
                out.data_ptr(), N, h, w, C, mask.shape[1], mask.shape[2], _stream())
     return out
 

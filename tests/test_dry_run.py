@@ -1,0 +1,152 @@
+"""Host-logic dry run on CPU: the mirror modules issue their C-ABI calls against a recorder instead of the library
+(ops.DRY_RUN; no kernel executes, outputs are uninitialised), so the Python plumbing of BOTH precision modes -- plan
+building, dtype routing, buffer shapes, pointer / stride arguments -- is exercised without a GPU.  What the kernels
+compute is the business of the `-m gpu` parity tests."""
+import ctypes
+
+import pytest
+import torch
+
+from oracle import harness as helpers
+from synfmc_b200 import _cabi, engine, ops
+
+
+class Recorder:
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, name, *args):
+        sig = _cabi.SIGNATURES[name]
+        assert len(args) == len(sig), (name, len(args), len(sig))
+        for a, ty in zip(args, sig):  # every argument must convert to its declared ctypes type
+            ty(a)
+        self.calls.append((name, args))
+
+    def names(self):
+        return [n for n, _ in self.calls]
+
+
+@pytest.fixture
+def recorder(monkeypatch):
+    rec = Recorder()
+    monkeypatch.setattr(ops, "DRY_RUN", True)
+    monkeypatch.setattr(_cabi, "call", rec)
+    yield rec
+    engine.set_precision("bf16")
+
+
+def _inputs(b=2, f=4, h=8, w=8, channels=(320, 640), traj=False):
+    g = torch.Generator().manual_seed(0)
+    sample = torch.randn(b, 4, f, h, w, generator=g)
+    text = torch.randn(b, 77, 768, generator=g)
+    feats = [torch.randn(b, C, f, h >> l, w >> l, generator=g) for l, C in enumerate(channels)]
+    trajs = [torch.randn(b, C, f, h >> l, w >> l, generator=g) for l, C in enumerate(channels)] if traj else None
+    return sample, text, feats, trajs
+
+
+@pytest.mark.parametrize("mode", ["bf16", "tf32", "reference"])
+@pytest.mark.parametrize("obj", [False, True])
+def test_tiny_unet_call_sequence(recorder, mode, obj):
+    o_unet = helpers.build_oracle_unet(tiny=True, obj=obj)
+    unet = helpers.build_product_unet(o_unet, tiny=True, obj=obj, device="cpu")
+    sample, text, feats, trajs = _inputs(traj=obj)
+    kw = {"traj_features": trajs} if obj else {}
+    with engine.precision(mode):
+        out = unet(sample, 961, text, pose_embedding_features=feats, **kw).sample
+    assert out.shape == sample.shape and out.dtype == torch.float32
+    names = set(recorder.names())
+    if mode == "bf16":
+        assert "fmc_gemm_bf16" in names and "fmc_spatial_attn_bf16" in names and "fmc_groupnorm_bf16" in names
+        assert not any(n in names for n in ("fmc_gemm_tf32", "fmc_attention_f32", "fmc_groupnorm_f32"))
+    else:
+        # reference precision: NO bf16 kernel may appear anywhere in the step
+        assert not any(n.endswith("_bf16") or n.endswith("_vf16") for n in names), sorted(names)
+        assert {"fmc_gemm_tf32", "fmc_attention_f32", "fmc_groupnorm_f32", "fmc_layernorm_f32",
+                "fmc_im2col3x3_f32"} <= names
+        splits = {a[16] for n, a in recorder.calls if n == "fmc_gemm_tf32"}
+        assert splits == ({3} if mode == "reference" else {1})
+        assert ("fmc_split_tf32" in names) == (mode == "reference")
+
+
+@pytest.mark.parametrize("mode", ["bf16", "reference"])
+def test_encoders_call_sequence(recorder, mode):
+    from synfmc_b200 import synth
+    from synfmc_b200.fmc.util import get_traj_features_v2
+    channels = (320, 640, 1280, 1280)
+    enc = helpers.build_product_pose_encoder(helpers.build_oracle_pose_encoder(channels), channels, device="cpu")
+    omcm = helpers.build_product_omcm(helpers.build_oracle_omcm(channels), channels, device="cpu")
+    infos, masks = synth.synth_objects(1, 2, 64, 64, 2, seed=1)
+    with engine.precision(mode):
+        feats = enc(torch.randn(1, 6, 2, 64, 64))
+        trajs = get_traj_features_v2(infos, masks, omcm, False, 0.0, None, "cpu", torch.float32)
+    assert [tuple(f.shape) for f in feats] == [(2, 320, 8, 8), (2, 640, 4, 4), (2, 1280, 2, 2), (2, 1280, 1, 1)]
+    assert [tuple(t.shape) for t in trajs] == [(1, 320, 2, 8, 8), (1, 640, 2, 4, 4), (1, 1280, 2, 2, 2), (1, 1280, 2, 1, 1)]
+    names = set(recorder.names())
+    if mode == "reference":
+        assert not any(n.endswith("_bf16") for n in names), sorted(names)
+        assert "fmc_mask_modulate_f32" in names and "fmc_traj_scatter_f32" in names
+
+
+def test_plans_follow_parameter_changes(recorder):
+    """in-place parameter updates, submodule load_state_dict and processor edits must drop the folded
+    weights (and the generation CUDA graphs are keyed on must move)."""
+    o_unet = helpers.build_oracle_unet(tiny=True)
+    unet = helpers.build_product_unet(o_unet, tiny=True, device="cpu")
+    sample, text, feats, _ = _inputs()
+    unet(sample, 961, text, pose_embedding_features=feats)
+    gen0 = engine.generation(unet)
+    attn = unet.down_blocks[0].attentions[0].transformer_blocks[0].attn1
+    plan0 = unet.down_blocks[0].attentions[0]._plan
+    unet(sample, 961, text, pose_embedding_features=feats)
+    assert unet.down_blocks[0].attentions[0]._plan is plan0 and engine.generation(unet) == gen0  # nothing changed
+    with torch.no_grad():
+        attn.to_q.weight.mul_(1.5)                                   # optimizer.step()-style in-place update
+    unet(sample, 961, text, pose_embedding_features=feats)
+    assert unet.down_blocks[0].attentions[0]._plan is not plan0 and engine.generation(unet) == gen0 + 1
+    plan1 = unet.down_blocks[0].attentions[0]._plan
+    attn.load_state_dict(attn.state_dict())                          # submodule load_state_dict
+    unet(sample, 961, text, pose_embedding_features=feats)
+    assert unet.down_blocks[0].attentions[0]._plan is not plan1
+    plan2 = unet.down_blocks[0].attentions[0]._plan
+    attn.processor.lora_scale = 0.5                                  # processor scalar edit
+    unet(sample, 961, text, pose_embedding_features=feats)
+    assert unet.down_blocks[0].attentions[0]._plan is not plan2
+
+
+def test_spatial_pose_processors_are_refused(recorder):
+    """add_spatial=True would install pose-adaptor processors the spatial kernels ignore -- refuse."""
+    o_unet = helpers.build_oracle_unet(tiny=True)
+    unet = helpers.build_product_unet(o_unet, tiny=True, device="cpu")
+    kw = dict(helpers.ATTN_PROC_KWARGS, add_spatial=True)
+    unet.set_all_attn_processor(add_spatial_lora=True, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
+                                motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
+                                pose_feature_dimensions=[320, 640], **kw)
+    unet.requires_grad_(False)
+    sample, text, feats, _ = _inputs()
+    with pytest.raises(NotImplementedError, match="spatial"):
+        unet(sample, 961, text, pose_embedding_features=feats)
+
+
+def test_training_mode_fails_loudly():
+    """under autograd with trainable parameters the forward-only product must raise a clear error
+    instead of returning a tensor without grad_fn (train_cam_ctrl.py:586-648 would die later in loss.backward())."""
+    from synfmc_b200.fmc.models.pose_adaptor import CameraPoseEncoder, PoseAdaptor
+    o_unet = helpers.build_oracle_unet(tiny=True)
+    unet = helpers.build_product_unet(o_unet, tiny=True, device="cpu")
+    enc = CameraPoseEncoder(channels=[320, 640], **helpers.POSE_ENCODER_KWARGS)
+    unet.requires_grad_(False)
+    enc.requires_grad_(True)   # the CMC trainer trains the pose encoder (train_cam_ctrl.py:259-284)
+    wrapper = PoseAdaptor(unet, enc)
+    sample, text, feats, _ = _inputs()
+    with pytest.raises(RuntimeError, match="forward pass only"):
+        wrapper(sample, torch.tensor([961]), text, torch.zeros(2, 6, 4, 64, 64))
+    for n, p in unet.named_parameters():
+        if "merge" in n:
+            p.requires_grad_(True)
+    with pytest.raises(RuntimeError, match="forward pass only"):
+        unet(sample, 961, text, pose_embedding_features=feats)
+    unet.requires_grad_(False)
+    with pytest.raises(RuntimeError, match="forward pass only"):
+        unet(sample.requires_grad_(True), 961, text, pose_embedding_features=feats)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA tensors only"):  # no_grad: passes the guard, hits the CPU refusal
+        unet(sample, 961, text, pose_embedding_features=feats)
