@@ -230,7 +230,7 @@ def summarise_trace(trace, steps, peaks):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(top.split(" ")[0])
+        traffic = json.load(open(tpath)).get(top.split(" ")[0])  # dram bytes per launch (ncu), see the file's _source
     roofline = {"kernel": top, "bound": bound, "achieved": round(achieved, 1), "peak": peak, "unit": unit,
                 "frac": round(achieved / peak, 4), "traffic": traffic,
                 "peak_source": f"{peaks['source']} MEASURED_PEAKS.json, sustained figure (kernel timed inside a long step)",
@@ -240,57 +240,63 @@ def summarise_trace(trace, steps, peaks):
 
 
 # ------------------------------------------------------------------------------------------------ CPU oracle legs
-def oracle_half_steps():
-    """Generator: each next() runs and times the fp32 CPU oracle (oracle/, a restatement of the reference PyTorch
-    path; the reference itself needs diffusers==0.24.0 which is not installable offline) on ONE of the two CFG halves
-    of a step: a U-Net forward with batch 1 at 320x512x16f incl. the object-feature injection.  A step = 2 halves."""
+def oracle_steps():
+    """Generator: each next() runs and times ONE WHOLE denoise step of the fp32 CPU oracle (oracle/, a restatement of the
+    reference PyTorch path; the reference itself needs diffusers==0.24.0 which is not installable offline): the two CFG
+    halves of the step -- unconditional text + zeroed object features, conditional text + object features
+    (pipeline_animation_cm_om.py:671-676) -- as two U-Net forwards of batch 1 at 320x512x16f (one batch-2 forward
+    materialises a 6.7 GB score tensor per level-0 attention; two batch-1 forwards are the same arithmetic), plus the CFG
+    combine and DDIM update."""
     import torch
     from oracle import harness
+    from oracle.diffusers_restated import DDIMScheduler
     torch.set_num_threads(os.cpu_count() or 1)
     _, _, _, _, latents, text = synth_clip(0)
     unet = harness.build_oracle_unet(tiny=False, obj=True)
+    sched = DDIMScheduler()
+    sched.set_timesteps(SCHEDULE_STEPS)
     g = torch.Generator().manual_seed(0)
     hh, ww = H // 8, W // 8
     # the encoders run once per clip outside the step; random features of the right shape stand in for them here
     feats = [torch.randn(1, c, FRAMES, hh >> l, ww >> l, generator=g) for l, c in enumerate(CHANNELS)]
     trajs = [0.5 * torch.randn(1, c, FRAMES, hh >> l, ww >> l, generator=g) for l, c in enumerate(CHANNELS)]
+    zeros = [torch.zeros_like(t) for t in trajs]
     with torch.no_grad():
         while True:
             t0 = time.perf_counter()
-            unet(latents, 961, text[1:], pose_embedding_features=feats, traj_features=trajs)
+            e_u = unet(latents, 961, text[:1], pose_embedding_features=feats, traj_features=zeros).sample
+            e_c = unet(latents, 961, text[1:], pose_embedding_features=feats, traj_features=trajs).sample
+            eps = e_u + GUIDANCE * (e_c - e_u)
+            sched.step(eps, 961, latents)
             yield time.perf_counter() - t0
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's CPU path (fp32 oracle port) on this host's cores, rank 0 only.  Every
-    step is a bounded sample (one CFG half, doubled); if the host is too slow for W + K samples inside the time budget
-    the warm-ups are cut first, then the number of timed steps (reported in `steps` / `sample`)."""
+    """`--impl reference`: the reference's CPU path (fp32 oracle port) on this host's cores, rank 0 only.  A step is one
+    WHOLE denoise step (both CFG halves); the arm is bounded by a wall-clock budget: warm-ups are cut first, then the
+    number of timed steps -- `steps` / `warmup` in the line are what was actually run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     cores = os.cpu_count() or 1
-    budget_s = 420.0
+    budget_s = float(os.environ.get("FMC_REFERENCE_BUDGET_S", "240"))
     t_start = time.perf_counter()
-    halves, warm_done = [], 0
-    for dt in oracle_half_steps():
-        elapsed = time.perf_counter() - t_start
-        remaining = budget_s - elapsed
-        if warm_done < args.warmup and not halves and remaining > (args.steps + args.warmup - warm_done - 1) * dt:
-            warm_done += 1
+    times, warm_done = [], 0
+    for dt in oracle_steps():
+        remaining = budget_s - (time.perf_counter() - t_start)
+        if not times and warm_done < min(args.warmup, 1) and remaining > 2 * dt:
+            warm_done += 1  # one untimed pass (thread pool / allocator warm-up) whenever a timed one still fits after it
             continue
-        if warm_done == 0 and not halves and remaining > dt:  # always at least one untimed pass when it fits
-            warm_done += 1
-            continue
-        halves.append(dt)
-        if len(halves) >= args.steps or remaining < dt:
+        times.append(dt)
+        if len(times) >= args.steps or remaining < dt:
             break
-    steps_done = len(halves)
-    sec_per_step = 2.0 * sum(halves) / steps_done
+    steps_done = len(times)
+    sec_per_step = sum(times) / steps_done
     value = 1.0 / sec_per_step
-    sample = (f"each step = 1 of its 2 CFG halves (oracle U-Net forward, batch 1, 320x512x16f, fp32, {cores} threads) "
-              f"timed and doubled; {steps_done} of the requested {args.steps} steps and {warm_done} of {args.warmup} "
-              f"warm-ups fit the {int(budget_s)} s budget")
+    sample = (f"whole denoise steps of the fp32 oracle port (2 U-Net forwards of batch 1 = the CFG pair, 320x512x16f, "
+              f"{cores} threads): {steps_done} timed step(s) and {warm_done} warm-up(s) of the requested {args.steps} + "
+              f"{args.warmup} fit the {int(budget_s)} s budget")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
             "steps": steps_done, "warmup": warm_done, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
@@ -429,11 +435,16 @@ def run_b200(args):
             "gpu_launches": gpu_launches, "cuda_graph": bool(pipe.use_cuda_graph), "clocks": clocks,
             "roofline": roofline, "kernels": table,
             "encoders_ms": round(encoders_ms, 2)}
+    # once per clip, outside the step: CameraEncoder 1.52 TFLOP + ObjectEncoder 1.34 TFLOP
+    line["kernels"]["encoders (once per clip: CameraEncoder + ObjectEncoder, all their kernels)"] = {
+        "ms_per_clip": round(encoders_ms, 2), "tflops": round(2.86 / (encoders_ms * 1e-3), 1)}
     if world == 1 and not args.no_cpu_baseline:
-        sec = 2.0 * next(oracle_half_steps())
+        gen = oracle_steps()
+        next(gen)  # untimed warm-up step (thread pool, allocator)
+        sec = next(gen)
         line["cpu_baseline"] = {"value": round(1.0 / sec, 6), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": "1 of the 2 CFG halves of one step (oracle U-Net forward, batch 1, "
-                                          "320x512x16f, fp32, all host threads), doubled; no warm-up"}
+                                "sample": "one whole denoise step of the fp32 oracle port (the CFG pair as 2 U-Net forwards "
+                                          "of batch 1, 320x512x16f, all host threads) after one untimed warm-up step"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -263,8 +263,6 @@ def test_product_against_reference_golden_vectors(cuda_device):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.skipif(not __import__("os").environ.get("FMC_TEST_UNVERIFIED"),
-                    reason="written after the round's GPU minutes were spent: enable with FMC_TEST_UNVERIFIED=1, ungate once seen green")
 def test_full_depth_unet_against_reference_golden(cuda_device):
     """CUDA path vs the output of the reference's own classes for the full-depth U-Net (4 levels, mid block, object
     features; tests/golden/make_golden_full.py) -- no oracle in between."""
