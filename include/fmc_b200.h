@@ -188,6 +188,15 @@ int fmc_cfg_ddim_step_f32(const float* eps_uncond, const float* eps_cond, float 
                           float* latents_out, float* eps_out, float alpha_t, float alpha_prev, long long n,
                           void* stream);
 
+/* Multidiff window average + DDIM update for long clips, fmc/pipelines/pipeline_animation.py:669-702: window k covers
+ * frames [k*stride, k*stride + L) with stride = L - multidiff_overlaps; per frame the (guided) predictions of the windows
+ * covering it are averaged in the reference's order (`noise_full[win] += noise_pred / count[win]`, window by window), then
+ * one DDIM (eta = 0) step updates the whole clip.  eps_windows [n_windows, (cfg ? 2b : b), C, L, HW] fp32, unconditional
+ * half first; latents / latents_out [b, C, F_total, HW] with F_total = (n_windows - 1) * stride + L. */
+int fmc_window_combine_ddim_f32(const float* eps_windows, int n_windows, int cfg, float guidance_scale,
+                                const float* latents, float* latents_out, int b, int C, int F_total, long long HW, int L,
+                                int stride, float alpha_t, float alpha_prev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Reference-precision mode (BASELINE config 1, "output parity vs reference" at 1e-3 rel): fp32 activations between
  * kernels, linears on tcgen05.mma.kind::tf32, attention / norms / glue in fp32 (csrc/precise.cu).  Each entry point

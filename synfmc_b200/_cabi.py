@@ -38,6 +38,7 @@ SIGNATURES = {
     "fmc_traj_scatter_unshuffle_bf16": [P, P, P, P, I, I, I, I, P],
     "fmc_mask_modulate_bf16": [P, P, P, P, P, I, I, I, I, I, I, P],
     "fmc_cfg_ddim_step_f32": [P, P, F, P, P, P, F, F, L, P],
+    "fmc_window_combine_ddim_f32": [P, I, I, F, P, P, I, I, I, L, I, I, F, F, P],
     # reference-precision mode (csrc/precise.cu)
     "fmc_gemm_tf32": [P, L, P, L, P, L, I, I, I, P, P, L, P, I, L, I, I, P],
     "fmc_split_tf32": [P, L, P, L, L, I, P],

@@ -384,6 +384,44 @@ cfg_ddim_kernel(const float* __restrict__ eps_u, const float* __restrict__ eps_c
   if (eps_out != nullptr) eps_out[idx] = eps;
 }
 
+// Multidiff window average + DDIM update (fmc/pipelines/pipeline_animation.py:669-702): the long clip is denoised as
+// n_windows overlapping windows of L frames (window k starts at frame k * stride); per frame the guided predictions of
+// the windows covering it are averaged -- `noise_full[window] += noise_pred / count[window]` in window order, as the
+// reference accumulates it -- and one DDIM (eta = 0) update is applied to the whole clip.
+// eps: [n_windows, (cfg ? 2 b : b), C, L, HW] fp32 (unconditional half first); latents: [b, C, F_total, HW].
+__global__ void __launch_bounds__(256)
+window_combine_ddim_kernel(const float* __restrict__ eps, int n_windows, int cfg, float guidance,
+                           const float* __restrict__ x, float* __restrict__ x_out, int b, int C, int F_total, long long HW,
+                           int L, int stride, float sqrt_a_t, float sqrt_1m_a_t, float sqrt_a_prev, float sqrt_1m_a_prev) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(b) * C * F_total * HW;
+  if (idx >= total) return;
+  const long long hw = idx % HW;
+  long long t = idx / HW;
+  const int f = static_cast<int>(t % F_total);
+  t /= F_total;
+  const int c = static_cast<int>(t % C);
+  const int bi = static_cast<int>(t / C);
+  // windows covering frame f: k * stride <= f < k * stride + L
+  int k_lo = f - L + 1 > 0 ? (f - L + 1 + stride - 1) / stride : 0;
+  int k_hi = f / stride;
+  if (k_hi > n_windows - 1) k_hi = n_windows - 1;
+  const float count = static_cast<float>(k_hi - k_lo + 1);
+  const long long win_elems = static_cast<long long>(cfg ? 2 * b : b) * C * L * HW;
+  const long long half = static_cast<long long>(b) * C * L * HW;
+  float acc = 0.f;
+  for (int k = k_lo; k <= k_hi; ++k) {
+    const long long off = ((static_cast<long long>(bi) * C + c) * L + (f - k * stride)) * HW + hw;
+    const float eu = __ldg(eps + k * win_elems + off);
+    const float e = cfg ? eu + guidance * (__ldg(eps + k * win_elems + half + off) - eu) : eu;
+    acc += e / count;
+  }
+  const float x0 = (x[idx] - sqrt_1m_a_t * acc) / sqrt_a_t;
+  x_out[idx] = sqrt_a_prev * x0 + sqrt_1m_a_prev * acc;
+}
+
 static inline unsigned blocks_for(long long n) { return static_cast<unsigned>((n + 255) / 256); }
 
 }  // namespace fmc
@@ -532,4 +570,22 @@ extern "C" int fmc_cfg_ddim_step_f32(const float* eps_uncond, const float* eps_c
       eps_uncond, eps_cond, guidance_scale, latents, latents_out, eps_out, sqrtf(alpha_t), sqrtf(1.f - alpha_t),
       sqrtf(alpha_prev), sqrtf(1.f - alpha_prev), n);
   return check_launch("cfg_ddim_kernel");
+}
+
+extern "C" int fmc_window_combine_ddim_f32(const float* eps_windows, int n_windows, int cfg, float guidance_scale,
+                                           const float* latents, float* latents_out, int b, int C, int F_total,
+                                           long long HW, int L, int stride, float alpha_t, float alpha_prev,
+                                           void* stream) {
+  FMC_REQUIRE(eps_windows && latents && latents_out, FMC_ERR_ARG, "fmc_window_combine_ddim_f32: null operand");
+  FMC_REQUIRE(n_windows >= 1 && L >= 1 && stride >= 1 && stride <= L && F_total == (n_windows - 1) * stride + L, FMC_ERR_SHAPE,
+              "fmc_window_combine_ddim_f32: %d windows of %d frames with stride %d do not tile %d frames", n_windows, L,
+              stride, F_total);
+  FMC_REQUIRE(alpha_t > 0.f && alpha_t <= 1.f && alpha_prev > 0.f && alpha_prev <= 1.f, FMC_ERR_ARG,
+              "fmc_window_combine_ddim_f32: alphas must be in (0, 1]");
+  const long long total = static_cast<long long>(b) * C * F_total * HW;
+  if (total == 0) return FMC_OK;
+  launch_k(window_combine_ddim_kernel, dim3(blocks_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), eps_windows,
+           n_windows, cfg, guidance_scale, latents, latents_out, b, C, F_total, HW, L, stride, sqrtf(alpha_t),
+           sqrtf(1.f - alpha_t), sqrtf(alpha_prev), sqrtf(1.f - alpha_prev));
+  return check_launch("window_combine_ddim_kernel");
 }

@@ -209,6 +209,11 @@ class CameraCtrlPipeline:
             pose_features = [CL(CL.from_reference(f).t[half].contiguous()) for f in pose_features]
             if traj_features is not None:  # the unconditional half carries zeros, i.e. no object features at all
                 traj_features = None if which == 0 else [CL(CL.from_reference(f).t[half].contiguous()) for f in traj_features]
+        if multidiff_total_steps > 1:
+            # slice the per-frame features into their windows ONCE per loop (the reference re-slices every step, :678-681)
+            pose_features = self._window_features(pose_features, L, multidiff_total_steps, multidiff_overlaps)
+            if traj_features is not None:
+                traj_features = self._window_features(traj_features, L, multidiff_total_steps, multidiff_overlaps)
         for i, t in enumerate(self.scheduler.timesteps.tolist()):
             if max_steps is not None and i >= max_steps:
                 break
@@ -221,6 +226,29 @@ class CameraCtrlPipeline:
             if callback is not None and i % callback_steps == 0:
                 callback(i, t, latents)
         return latents
+
+    @staticmethod
+    def _is_window_list(feats):
+        return isinstance(feats, (list, tuple)) and len(feats) > 0 and isinstance(feats[0], (list, tuple))
+
+    def _window_features(self, feats, L, n_windows, overlaps):
+        """4 features over all frames -> list (one entry per window) of 4 CL features over that window's L frames; a
+        per-window list (the reference's `pose_embedding` list form, pipeline_animation.py:644-651,678-679) passes through."""
+        if self._is_window_list(feats):
+            if len(feats) != n_windows:
+                raise ValueError(f"{len(feats)} per-window feature sets for {n_windows} windows")
+            return [[CL.from_reference(f) for f in w] for w in feats]
+        feats = [CL.from_reference(f) for f in feats]
+        return [[_slice_frames(f, k * (L - overlaps), L) for f in feats] for k in range(n_windows)]
+
+    def _window_eps(self, part, t, text_embeddings, feats, traj, do_cfg):
+        """CFG-doubled U-Net on one window: graph replay when possible, kernel by kernel otherwise."""
+        if (self.use_cuda_graph and _cabi.trace is None and not torch.is_tensor(t) and torch.is_tensor(text_embeddings)
+                and part.dtype == torch.float32):
+            return self._step_graph(part, text_embeddings, feats, traj, do_cfg).run(part, t, text_embeddings, feats, traj)
+        x_in = torch.cat([part] * 2) if do_cfg else part
+        kw = {"traj_features": traj} if self._accepts_traj else {}
+        return self.unet(x_in, t, encoder_hidden_states=text_embeddings, pose_embedding_features=feats, **kw).sample
 
     @torch.no_grad()
     def denoise_step(self, latents, t, text_embeddings, pose_features, video_length, traj_features=None,
@@ -259,32 +287,36 @@ class CameraCtrlPipeline:
                                                                                      traj)
             e_u, e_c = (eps[:b], eps[b:]) if do_cfg else (eps, None)
             return ops.cfg_ddim_step(e_u, e_c, guidance_scale, latents, a_t, a_prev)
-        window_eps = []
-        for k in range(multidiff_total_steps):
-            s = k * (L - multidiff_overlaps)
-            part = latents if multidiff_total_steps == 1 else latents[:, :, s:s + L].contiguous()
-            x_in = torch.cat([part] * 2) if do_cfg else part
-            feats = [_slice_frames(f, s, L) for f in pose_features]
+        if multidiff_total_steps == 1:
+            feats = [CL.from_reference(f) for f in pose_features]
+            x_in = torch.cat([latents] * 2) if do_cfg else latents
             kw = {"traj_features": traj_features} if self._accepts_traj else {}
             eps = self.unet(x_in, t, encoder_hidden_states=text_embeddings, pose_embedding_features=feats, **kw).sample
-            window_eps.append((s, eps))
-        if multidiff_total_steps == 1:
-            s, eps = window_eps[0]
             e_u, e_c = (eps[:b], eps[b:]) if do_cfg else (eps, None)
             return ops.cfg_ddim_step(e_u, e_c, guidance_scale, latents, a_t, a_prev)
-        # overlapping windows: average the guided predictions per frame (:673-699), then one DDIM update
-        noise = torch.zeros_like(latents)
-        count = torch.zeros_like(latents)
-        for s, eps in window_eps:
-            count[:, :, s:s + L] += 1
-        for s, eps in window_eps:
-            e = eps[:b] + guidance_scale * (eps[b:] - eps[:b]) if do_cfg else eps
-            noise[:, :, s:s + L] += e / count[:, :, s:s + L]
-        return ops.cfg_ddim_step(noise, None, 1.0, latents, a_t, a_prev)
+        # overlapping windows (:669-702): every window through the same captured graph, then ONE kernel that averages the
+        # guided predictions per frame in the reference's order and applies the DDIM update
+        n_win, stride = multidiff_total_steps, L - multidiff_overlaps
+        if latents.shape[2] != (n_win - 1) * stride + L:
+            raise ValueError(f"{latents.shape[2]} frames are not {n_win} windows of {L} with overlap {multidiff_overlaps}")
+        win_feats = self._window_features(pose_features, L, n_win, multidiff_overlaps)
+        win_traj = None
+        if self._accepts_traj and traj_features is not None:
+            win_traj = self._window_features(traj_features, L, n_win, multidiff_overlaps)
+        eps_all = torch.empty((n_win, (2 if do_cfg else 1) * b) + tuple(latents.shape[1:2]) + (L,) + tuple(latents.shape[3:]),
+                              device=latents.device, dtype=torch.float32)
+        for k in range(n_win):
+            part = latents[:, :, k * stride:k * stride + L].contiguous()
+            eps_all[k].copy_(self._window_eps(part, t, text_embeddings, win_feats[k],
+                                              None if win_traj is None else win_traj[k], do_cfg))
+        return ops.window_combine_ddim(eps_all, do_cfg, guidance_scale, latents, L, stride, a_t, a_prev)
 
     def _pose_features(self, pose_embedding, do_cfg):
         if isinstance(pose_embedding, list):
-            raise NotImplementedError("per-window pose-embedding lists: pass one embedding covering all frames")
+            # one embedding PER WINDOW (pipeline_animation.py:644-651): the only form the reference can run beyond 16 frames,
+            # because the CameraEncoder's positional encoding has max_len 16 (configs/cam.yaml:120)
+            assert all(x.ndim == 5 for x in pose_embedding)
+            return [self._pose_features(pe, do_cfg) for pe in pose_embedding]
         assert pose_embedding.ndim == 5
         feats = self.pose_encoder.encode_cl(unshuffle8_to_cl(pose_embedding.float()))
         if do_cfg:
@@ -320,7 +352,7 @@ class CameraCtrlPipeline:
         assert eta == 0.0 and num_videos_per_prompt == 1
         if traj_features is not None and not self._accepts_traj:
             raise TypeError("traj_features needs CameraObjCtrlPipeline")
-        device = pose_embedding.device
+        device = pose_embedding[0].device if isinstance(pose_embedding, list) else pose_embedding.device
         height = height or self.unet.config.sample_size * self.vae_scale_factor
         width = width or self.unet.config.sample_size * self.vae_scale_factor
         batch_size = latents.shape[0] if latents is not None else 1
@@ -338,8 +370,12 @@ class CameraCtrlPipeline:
                                        device, generator, latents)
         pose_features = self._pose_features(pose_embedding, do_cfg)
         traj = self._traj_features(traj_features, do_cfg)
-        if traj is not None:
-            assert multidiff_total_steps == 1  # pipeline_animation_cm_om.py:690
+        if traj is not None and multidiff_total_steps != 1 and not kwargs.get("windowed_objects"):
+            # pipeline_animation_cm_om.py:690 asserts a single window.  windowed_objects=True is this package's extension
+            # for BASELINE config 5 (64 frames with objects): the object features are sliced per window like the pose
+            # features of :680-681
+            raise AssertionError("CameraObjCtrlPipeline: multidiff_total_steps must be 1 (pass windowed_objects=True for the "
+                                 "per-window extension)")
         latents = self.denoise(latents, prompt_embeds.to(device), pose_features, single_len, traj_features=traj,
                                num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
                                multidiff_total_steps=multidiff_total_steps, multidiff_overlaps=multidiff_overlaps,

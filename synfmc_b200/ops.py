@@ -408,6 +408,22 @@ def cfg_ddim_step(eps_uncond, eps_cond, guidance_scale, latents, alpha_t, alpha_
     return (out, eps_out) if return_eps else out
 
 
+def window_combine_ddim(eps_windows, cfg, guidance_scale, latents, L, stride, alpha_t, alpha_prev):
+    """eps_windows [n_win, (2)b, C, L, h, w] fp32, latents [b, C, F_total, h, w] fp32 -> new latents (window-averaged
+    guided prediction + DDIM update, fmc_window_combine_ddim_f32)."""
+    _check_cuda(eps_windows, latents)
+    assert eps_windows.dtype == torch.float32 and latents.dtype == torch.float32
+    assert eps_windows.is_contiguous() and latents.is_contiguous()
+    n_win = eps_windows.shape[0]
+    b, C, F_total, h, w = latents.shape
+    assert eps_windows.shape[1:] == ((2 if cfg else 1) * b, C, L, h, w), (eps_windows.shape, latents.shape)
+    out = torch.empty_like(latents)
+    _cabi.call("fmc_window_combine_ddim_f32", eps_windows.data_ptr(), n_win, 1 if cfg else 0, float(guidance_scale),
+               latents.data_ptr(), out.data_ptr(), b, C, F_total, h * w, L, stride, float(alpha_t), float(alpha_prev),
+               _stream())
+    return out
+
+
 def conv3x3_supported(H, W, cin, cout, stride):
     """Geometry handled by fmc_conv3x3_bf16 (everything the FMC U-Net / encoders use at the BASELINE shapes)."""
     if stride not in (1, 2) or H % stride or W % stride or cin % 64 or cout % 32:

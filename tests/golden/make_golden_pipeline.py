@@ -192,6 +192,15 @@ def main():
     out["cam_latents"] = torch.stack([lat for _, _, lat in trace_c])
     out["cam_videos_stride8"] = res_c.videos[..., ::8, ::8].clone()
     out["cam_videos_shape"] = tuple(res_c.videos.shape)
+    # ---- the same windows with the pose embedding given as a per-window LIST (:644-651, :678-679): the only form the
+    # reference can run beyond 16 frames (the CameraEncoder's positional encoding has max_len 16).  Each window's
+    # embedding is encoded separately, so its temporal attention sees that window's 4 frames only.
+    trace_l = []
+    windows = [plucker6[:, :, 0:4].contiguous(), plucker6[:, :, 2:6].contiguous()]
+    pipe_c(prompt=inp["prompt"], pose_embedding=windows, video_length=4, height=inp["H"], width=inp["W"],
+           num_inference_steps=6, guidance_scale=7.5, latents=inp["latents6"].clone(), multidiff_total_steps=2,
+           multidiff_overlaps=2, callback=lambda i, t, lat: trace_l.append((int(i), int(t), lat.clone())))
+    out["cam_list_latents"] = torch.stack([lat for _, _, lat in trace_l])
     # ---- the training forward: get_traj_features_v2 with random nulling (python `random`, seeded) -> CamObjPoseAdaptor
     import random
     omcm = ref.adapter.Adapter(channels=list(inp["channels"]), **harness.OMCM_KWARGS)

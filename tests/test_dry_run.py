@@ -150,3 +150,44 @@ def test_training_mode_fails_loudly():
         unet(sample.requires_grad_(True), 961, text, pose_embedding_features=feats)
     with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA tensors only"):  # no_grad: passes the guard, hits the CPU refusal
         unet(sample, 961, text, pose_embedding_features=feats)
+
+
+@pytest.mark.parametrize("form", ["sliced", "list"])
+@pytest.mark.parametrize("obj", [False, True])
+def test_windowed_pipeline_call_sequence(recorder, form, obj):
+    """Multidiff windows (pipeline_animation.py:669-702): n_win U-Net passes per step + ONE window-average/DDIM kernel;
+    per-window pose lists are encoded window by window; the obj pipeline keeps the reference's single-window assert
+    unless windowed_objects=True."""
+    from synfmc_b200.fmc._blocks import DDIMScheduler
+    from synfmc_b200.fmc.pipelines.pipeline_animation import CameraCtrlPipeline
+    from synfmc_b200.fmc.pipelines.pipeline_animation_cm_om import CameraObjCtrlPipeline
+    channels = (320, 640)
+    o_unet = helpers.build_oracle_unet(tiny=True, obj=obj)
+    unet = helpers.build_product_unet(o_unet, tiny=True, obj=obj, device="cpu")
+    enc = helpers.build_product_pose_encoder(helpers.build_oracle_pose_encoder(channels), channels, device="cpu")
+    L, ov, n_win, H, W = 4, 2, 3, 64, 64
+    F_total = n_win * (L - ov) + ov
+    pose = torch.randn(1, 6, F_total, H, W)
+    if form == "list":
+        pose = [pose[:, :, k * (L - ov):k * (L - ov) + L].contiguous() for k in range(n_win)]
+    pipe = (CameraObjCtrlPipeline if obj else CameraCtrlPipeline)(None, None, None, unet, DDIMScheduler(), enc)
+    pipe.use_cuda_graph = False
+    kw = dict(height=H, width=W, num_inference_steps=5, guidance_scale=7.5, latents=torch.randn(1, 4, F_total, 8, 8),
+              prompt_embeds=torch.randn(2, 77, 768), multidiff_total_steps=n_win, multidiff_overlaps=ov, max_steps=2)
+    if obj:
+        kw["traj_features"] = [torch.randn(1, C, F_total, 8 >> l, 8 >> l) for l, C in enumerate(channels)]
+        with pytest.raises(AssertionError):          # pipeline_animation_cm_om.py:690
+            pipe(None, pose, L, **kw)
+        kw["windowed_objects"] = True
+    recorder.calls.clear()
+    encoded, encode_cl = [], enc.encode_cl
+    enc.encode_cl = lambda x: (encoded.append(x.shape[1]), encode_cl(x))[1]   # frames per CameraEncoder call
+    out = pipe(None, pose, L, **kw)
+    assert out.latents.shape == (1, 4, F_total, 8, 8)
+    names = recorder.names()
+    assert names.count("fmc_window_combine_ddim_f32") == 2 and "fmc_cfg_ddim_step_f32" not in names
+    combine = next(a for n, a in recorder.calls if n == "fmc_window_combine_ddim_f32")
+    assert combine[1] == n_win and combine[2] == 1 and combine[8] == F_total and combine[10] == L and combine[11] == L - ov
+    conv_in = [a for n, a in recorder.calls if n == "fmc_conv3x3_bf16" and a[8] == 64 and a[9] == 320]
+    assert len(conv_in) == 2 * n_win                # one U-Net pass per window per step
+    assert encoded == ([L] * n_win if form == "list" else [F_total])

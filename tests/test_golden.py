@@ -178,6 +178,26 @@ def test_cam_pipeline_multidiff_windows_match_reference(pgold, pinp):
     assert torch.allclose(_decode(got), pgold["cam_videos_stride8"], rtol=0, atol=1e-3)
 
 
+def test_cam_pipeline_per_window_pose_list_matches_reference(pgold, pinp):
+    """The same two windows with `pose_embedding` given as a per-window LIST (pipeline_animation.py:644-651,678-679) --
+    the only form the reference runs beyond 16 frames (pose-encoder PE max_len 16, configs/cam.yaml:120): each window's
+    embedding goes through the CameraEncoder on its own."""
+    from oracle.diffusers_restated import DDIMScheduler
+    from oracle.pipeline import denoise
+    from oracle.rays import to_plucker_embedding
+    text = _text_embeddings(pinp, negative=False)
+    unet = harness.build_oracle_unet(tiny=True, obj=False)
+    enc = harness.build_oracle_pose_encoder(pinp["channels"])
+    plucker6 = to_plucker_embedding(pinp["c2w6"], pinp["K6"], (pinp["H"], pinp["W"])).permute(0, 2, 1, 3, 4).contiguous()
+    windows = [plucker6[:, :, 0:4].contiguous(), plucker6[:, :, 2:6].contiguous()]
+    for steps in (1, 6):
+        got = denoise(unet, DDIMScheduler(), enc, pinp["latents6"].clone(), text, windows, 4, num_inference_steps=6,
+                      guidance_scale=7.5, multidiff_total_steps=2, multidiff_overlaps=2, max_steps=steps)
+        assert rel(got, pgold["cam_list_latents"][steps - 1]) < LOOP_TOL, steps
+    # and it is a different computation from slicing one 6-frame encoding (the temporal attention of the encoder)
+    assert rel(pgold["cam_list_latents"][5], pgold["cam_latents"][5]) > 1e-2
+
+
 def test_training_forward_matches_reference(pgold, pinp):
     """The training-side forward of both stages on a batch of two clips with per-sample timesteps [961, 41]:
     get_traj_features_v2 with random nulling (python `random` seeded: clip 0 loses its object features, clip 1 keeps

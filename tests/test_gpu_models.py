@@ -171,6 +171,72 @@ def test_cfg_denoise_loop(cuda_device):
     assert rel_l2(out.latents, want) < UNET_TOL
 
 
+@pytest.mark.parametrize("form", ["sliced", "list"])
+def test_multidiff_windows(cuda_device, form):
+    """Long clips as overlapping windows (pipeline_animation.py:669-702): 4 windows of 8 frames, overlap 6 -> 14 frames;
+    every window through the captured graph, one window-average + DDIM kernel; the pose embedding either covers all
+    frames (sliced per window) or is the reference's per-window list (:644-651)."""
+    from oracle.diffusers_restated import DDIMScheduler as ODDIM
+    from oracle.pipeline import denoise as o_denoise
+    from oracle.rays import to_plucker_embedding
+    from synfmc_b200 import synth
+    from synfmc_b200.fmc._blocks import DDIMScheduler
+    from synfmc_b200.fmc.pipelines.pipeline_animation import CameraCtrlPipeline
+    channels = (320, 640)
+    o_unet = helpers.build_oracle_unet(tiny=True)
+    p_unet = helpers.build_product_unet(o_unet, tiny=True, device=cuda_device)
+    o_enc = helpers.build_oracle_pose_encoder(channels)
+    p_enc = helpers.build_product_pose_encoder(o_enc, channels, device=cuda_device)
+    b, L, ov, n_win, H, W = 1, 8, 6, 4, 64, 96
+    F_total = n_win * (L - ov) + ov
+    K, c2w = synth.synth_camera(b, F_total, H, W, seed=8)
+    plucker = to_plucker_embedding(c2w, K, (H, W)).permute(0, 2, 1, 3, 4).contiguous()
+    pose = plucker if form == "sliced" else [plucker[:, :, k * (L - ov):k * (L - ov) + L].contiguous() for k in range(n_win)]
+    latents, text = synth.synth_step_inputs(b, F_total, H // 8, W // 8, cfg=True, seed=8)
+    want = o_denoise(o_unet, ODDIM(), o_enc, latents, text, pose, L, num_inference_steps=25, guidance_scale=7.5,
+                     multidiff_total_steps=n_win, multidiff_overlaps=ov, max_steps=2)
+    pipe = CameraCtrlPipeline(None, None, None, p_unet, DDIMScheduler(), p_enc)
+    dpose = pose.to(cuda_device) if form == "sliced" else [p.to(cuda_device) for p in pose]
+    outs = {}
+    for graph in (True, False):
+        pipe.use_cuda_graph = graph
+        outs[graph] = pipe(None, dpose, L, height=H, width=W, num_inference_steps=25, guidance_scale=7.5,
+                           latents=latents.to(cuda_device), prompt_embeds=text.to(cuda_device),
+                           multidiff_total_steps=n_win, multidiff_overlaps=ov, max_steps=2).latents
+    assert outs[True].shape == (b, 4, F_total, H // 8, W // 8)
+    assert torch.equal(outs[True], outs[False])
+    assert rel_l2(outs[True], want) < UNET_TOL
+
+
+def test_window_combine_ddim_kernel(cuda_device):
+    """fmc_window_combine_ddim_f32 against the reference's accumulation (pipeline_animation.py:673-702), bit for bit
+    up to the final DDIM arithmetic (1e-6)."""
+    from synfmc_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    b, C, L, ov, n_win, h, w = 2, 4, 16, 12, 5, 5, 7
+    stride, F_total = L - ov, n_win * (L - ov) + ov
+    eps = torch.randn(n_win, 2 * b, C, L, h, w, generator=g)
+    lat = torch.randn(b, C, F_total, h, w, generator=g)
+    a_t, a_prev, gs = 0.3, 0.5, 7.5
+    noise, count = torch.zeros_like(lat), torch.zeros_like(lat)
+    for k in range(n_win):
+        count[:, :, k * stride:k * stride + L] += 1
+    for k in range(n_win):
+        e = eps[k, :b] + gs * (eps[k, b:] - eps[k, :b])
+        noise[:, :, k * stride:k * stride + L] += e / count[:, :, k * stride:k * stride + L]
+    x0 = (lat - (1 - a_t) ** 0.5 * noise) / a_t ** 0.5
+    want = a_prev ** 0.5 * x0 + (1 - a_prev) ** 0.5 * noise
+    got = ops.window_combine_ddim(eps.to(cuda_device), True, gs, lat.to(cuda_device), L, stride, a_t, a_prev)
+    assert rel_l2(got, want) < 1e-6
+    got1 = ops.window_combine_ddim(eps[:, :b].contiguous().to(cuda_device), False, 1.0, lat.to(cuda_device), L, stride, a_t,
+                                   a_prev)
+    noise1 = torch.zeros_like(lat)
+    for k in range(n_win):
+        noise1[:, :, k * stride:k * stride + L] += eps[k, :b] / count[:, :, k * stride:k * stride + L]
+    want1 = a_prev ** 0.5 * (lat - (1 - a_t) ** 0.5 * noise1) / a_t ** 0.5 + (1 - a_prev) ** 0.5 * noise1
+    assert rel_l2(got1, want1) < 1e-6
+
+
 def test_cuda_graph_step_is_bit_identical_to_eager(cuda_device):
     """The captured-graph step (default) replays exactly the kernels of the kernel-by-kernel step: same latents bit for
     bit over 3 steps that cross the omcm_min_step boundary (two graphs: with / without object features), and again on
