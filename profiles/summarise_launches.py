@@ -47,7 +47,7 @@ if __name__ == "__main__":
                     o["launches"] += n
                     o["bytes"] += by
         res = {name: round(o["bytes"] / o["launches"]) for name, o in out.items()}
-        res["_source"] = (f"{path}: mean dram__bytes_read.sum + dram__bytes_write.sum per launch over every launch of the "
+        res["_source"] = (f"{sys.argv[1]}: mean dram__bytes_read.sum + dram__bytes_write.sum per launch over every launch of the "
                           "kernel in two bench steps, ncu --cache-control all (cold L2 before every kernel: an upper bound "
                           "of the traffic inside the running step)")
         json.dump(res, open(sys.argv[2], "w"), indent=1)

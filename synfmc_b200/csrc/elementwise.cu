@@ -226,7 +226,13 @@ plucker_plain_kernel(const float* __restrict__ K, const float* __restrict__ c2w,
   for (int j = 0; j < 6; ++j) o[j] = v[j];
 }
 
-// one thread per (frame, cell y, cell x, comp, dy): writes 8 consecutive channels (dx = 0..7) = one 16-byte store
+// one thread per (frame, cell y, cell x, dy): 8 pixels of one image row -> for each of the 6 components one 16-byte store
+// (channels comp*64 + dy*8 + 0..7).  Write-only and HBM bound once the per-pixel arithmetic is out of the way: everything
+// that does not depend on the pixel column is hoisted (1/fx, 1/fy, y, y^2 + 1, y R[k][1] + R[k][2]), the normalisation is
+// one rsqrt.approx and the direction d_k = r (x R[k][0] + c_k) -- ~20 instructions per pixel instead of ~150 with
+// IEEE division and sqrt (the first version was ISSUE bound: 18.4 us = 1.7 TB/s on 31.5 MB, profiles/r02_membound.md).
+// The result is rounded to bf16 (2^-9), far above the 2-ulp fp32 approximations; the fp32 entry point
+// fmc_plucker_f32 keeps the reference's exact operation order.
 __global__ void __launch_bounds__(256)
 plucker_unshuffle_kernel(const float* __restrict__ K, const float* __restrict__ c2w, __nv_bfloat16* __restrict__ out,
                          int BF, int H, int W) {
@@ -234,7 +240,7 @@ plucker_unshuffle_kernel(const float* __restrict__ K, const float* __restrict__ 
   pdl_wait();
   const int h8 = H >> 3, w8 = W >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(BF) * h8 * w8 * 8;  // x 8 dy; the 6 comps are produced together
+  const long long total = static_cast<long long>(BF) * h8 * w8 * 8;
   if (idx >= total) return;
   const int dy = static_cast<int>(idx & 7);
   long long t = idx >> 3;
@@ -242,17 +248,31 @@ plucker_unshuffle_kernel(const float* __restrict__ K, const float* __restrict__ 
   t /= w8;
   const int cy = static_cast<int>(t % h8);
   const int n = static_cast<int>(t / h8);
-  float v[8][6];
+  const float4 k4 = __ldg(reinterpret_cast<const float4*>(K) + n);          // fx, fy, cx, cy
+  const float4* Mp = reinterpret_cast<const float4*>(c2w) + n * 3;          // rows of [R | t]
+  const float4 m0 = __ldg(Mp), m1 = __ldg(Mp + 1), m2 = __ldg(Mp + 2);
+  const float inv_fx = 1.0f / k4.x, inv_fy = 1.0f / k4.y;
+  const float y = ((static_cast<float>(cy * 8 + dy) + 0.5f) - k4.w) * inv_fy;
+  const float yy1 = fmaf(y, y, 1.0f);
+  const float c0 = fmaf(y, m0.y, m0.z), c1 = fmaf(y, m1.y, m1.z), c2 = fmaf(y, m2.y, m2.z);
+  const float o0 = m0.w, o1 = m1.w, o2 = m2.w;
+  const float x0 = ((static_cast<float>(cx * 8) + 0.5f) - k4.z) * inv_fx;
+  float v[6][8];
 #pragma unroll
-  for (int dx = 0; dx < 8; ++dx) plucker_pixel(K + n * 4, c2w + n * 12, cx * 8 + dx, cy * 8 + dy, v[dx]);
-  __nv_bfloat16* cell = out + ((static_cast<long long>(n) * h8 + cy) * w8 + cx) * 384;
-#pragma unroll
-  for (int comp = 0; comp < 6; ++comp) {
-    float r[8];
-#pragma unroll
-    for (int dx = 0; dx < 8; ++dx) r[dx] = v[dx][comp];
-    *reinterpret_cast<uint4*>(cell + comp * 64 + dy * 8) = pack8(r);
+  for (int dx = 0; dx < 8; ++dx) {
+    const float x = fmaf(static_cast<float>(dx), inv_fx, x0);
+    const float r = rsqrtf(fmaf(x, x, yy1));
+    const float d0 = r * fmaf(x, m0.x, c0), d1 = r * fmaf(x, m1.x, c1), d2 = r * fmaf(x, m2.x, c2);
+    v[0][dx] = fmaf(o1, d2, -o2 * d1);
+    v[1][dx] = fmaf(o2, d0, -o0 * d2);
+    v[2][dx] = fmaf(o0, d1, -o1 * d0);
+    v[3][dx] = d0;
+    v[4][dx] = d1;
+    v[5][dx] = d2;
   }
+  __nv_bfloat16* cell = out + ((static_cast<long long>(n) * h8 + cy) * w8 + cx) * 384 + dy * 8;
+#pragma unroll
+  for (int comp = 0; comp < 6; ++comp) *reinterpret_cast<uint4*>(cell + comp * 64) = pack8(v[comp]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -304,6 +324,9 @@ traj_plain_kernel(const float* __restrict__ info, const float* __restrict__ mask
   mask_out[idx] = m;
 }
 
+// one thread per (frame, cell y, cell x, dy) = 8 pixels of one image row: the masks of every object are read as two
+// 16-byte loads, the winning (object, mask value) per pixel stays in registers, and each of the 13 channels leaves as
+// one 16-byte store (channels c*64 + dy*8 + 0..7); the combined mask as two 16-byte stores.  Arithmetic as traj_pixel.
 __global__ void __launch_bounds__(256)
 traj_unshuffle_kernel(const float* __restrict__ info, const float* __restrict__ masks, __nv_bfloat16* __restrict__ feat,
                       float* __restrict__ mask_out, int BF, int n_obj, int H, int W) {
@@ -320,24 +343,46 @@ traj_unshuffle_kernel(const float* __restrict__ info, const float* __restrict__ 
   t /= w8;
   const int cy = static_cast<int>(t % h8);
   const int n = static_cast<int>(t / h8);
-  float v[8][13];
-  const int py = cy * 8 + dy;
+  const long long pix0 = static_cast<long long>(cy * 8 + dy) * W + cx * 8;  // W % 8 == 0: 32-byte aligned
+  const float* mrow = masks + static_cast<long long>(n) * n_obj * HW + pix0;
+  int sel[8];
+  float m[8];
 #pragma unroll
   for (int dx = 0; dx < 8; ++dx) {
-    const long long pix = static_cast<long long>(py) * W + cx * 8 + dx;
-    float m;
-    traj_pixel(info + static_cast<long long>(n) * n_obj * 12, masks + static_cast<long long>(n) * n_obj * HW, n_obj, HW, pix,
-               v[dx], m);
-    mask_out[static_cast<long long>(n) * HW + pix] = m;
+    sel[dx] = -1;
+    m[dx] = 0.f;
   }
-  __nv_bfloat16* cell = feat + ((static_cast<long long>(n) * h8 + cy) * w8 + cx) * 832;
+  for (int o = 0; o < n_obj; ++o) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(mrow + o * HW));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(mrow + o * HW) + 1);
+    const float mo[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-  for (int c = 0; c < 13; ++c) {
+    for (int dx = 0; dx < 8; ++dx) {
+      if (mo[dx] > 0.f) {  // the LAST object with mask > 0 wins (fmc/util.py:178-182)
+        sel[dx] = o;
+        m[dx] = mo[dx];
+      }
+    }
+  }
+  float4* mo4 = reinterpret_cast<float4*>(mask_out + static_cast<long long>(n) * HW + pix0);
+  mo4[0] = make_float4(m[0], m[1], m[2], m[3]);
+  mo4[1] = make_float4(m[4], m[5], m[6], m[7]);
+  const float* inf = info + static_cast<long long>(n) * n_obj * 12;
+  __nv_bfloat16* cell = feat + ((static_cast<long long>(n) * h8 + cy) * w8 + cx) * 832 + dy * 8;
+#pragma unroll
+  for (int c = 0; c < 12; ++c) {
     float r[8];
 #pragma unroll
-    for (int dx = 0; dx < 8; ++dx) r[dx] = v[dx][c];
-    *reinterpret_cast<uint4*>(cell + c * 64 + dy * 8) = pack8(r);
+    for (int dx = 0; dx < 8; ++dx) {
+      const float iv = sel[dx] >= 0 ? __ldg(inf + sel[dx] * 12 + c) : 0.f;
+      r[dx] = __fmul_rn(__fmul_rn(iv, m[dx]), m[dx]);  // (expanded_obj_info * obj_mask) * mask_features (util.py:176,200)
+    }
+    *reinterpret_cast<uint4*>(cell + c * 64) = pack8(r);
   }
+  float r[8];
+#pragma unroll
+  for (int dx = 0; dx < 8; ++dx) r[dx] = __fmul_rn(m[dx], m[dx]);
+  *reinterpret_cast<uint4*>(cell + 12 * 64) = pack8(r);
 }
 
 // Mask modulation of an ObjectEncoder level (fmc/adapter.py:175-177): out[n, y, x, :] = x[n, y, x, :] * mask[n, ry[y], rx[x]]

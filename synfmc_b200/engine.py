@@ -9,7 +9,9 @@ Domain-LoRA folded into the projections (exact while LoRA is frozen),
 q/k heads zero-padded to a multiple of 16 columns, GEGLU rows interleaved for the fused epilogue, the CameraAdapter
 scale folded into qkv_merge.  The `run_*` functions issue the kernels of include/fmc_b200.h in order.
 """
+import operator
 import os
+import time
 
 import torch
 
@@ -74,18 +76,31 @@ def plan_key(device):
     return (torch.device(device), _precision)
 
 
+STRUCTURE_EPOCH = 0  # bumped by Attention.set_processor: the cached tensor / processor lists below are rebuilt
+
+
+def structure_changed():
+    global STRUCTURE_EPOCH
+    STRUCTURE_EPOCH += 1
+
+
+_version_of = operator.attrgetter("_version")
+
+
 def fingerprint(module):
     """Cheap identity of everything a module's plans were derived from: (storage address, in-place version) of every
-    parameter / buffer plus the processor scalars.  optimizer.step(), param.data.copy_(), load_state_dict on a
-    submodule and set_processor all change it (stale folded weights / stale CUDA graphs)."""
-    h = 0
-    for t in list(module.parameters()) + list(module.buffers()):
-        h = hash((h, t.data_ptr(), t._version))
-    for m in module.modules():
-        proc = getattr(m, "processor", None)
-        if proc is not None:
-            h = hash((h, id(proc), getattr(proc, "scale", None), getattr(proc, "lora_scale", None)))
-    return h
+    parameter / buffer plus the processor objects and their scalars.  optimizer.step(), param.data.copy_(),
+    load_state_dict on a submodule, .to(device) and set_processor all change it (stale folded weights / stale
+    CUDA graphs).  The module tree is walked once per structure epoch; a check is two C-level passes over ~1500 tensors."""
+    cache = module.__dict__.get("_fmc_fp_cache")
+    if cache is None or cache[0] != STRUCTURE_EPOCH:
+        tensors = list(module.parameters()) + list(module.buffers())
+        procs = [m.processor for m in module.modules() if getattr(m, "processor", None) is not None]
+        cache = (STRUCTURE_EPOCH, tensors, procs)
+        module.__dict__["_fmc_fp_cache"] = cache
+    _, tensors, procs = cache
+    return hash((tuple(map(_version_of, tensors)), tuple(map(torch.Tensor.data_ptr, tensors)),
+                 tuple((id(p), getattr(p, "scale", None), getattr(p, "lora_scale", None)) for p in procs)))
 
 
 def invalidate_plans(root):
@@ -102,9 +117,16 @@ def generation(root):
     return getattr(root, "_fmc_generation", 0)
 
 
-def refresh_plans(root):
-    """Called at the top of every forward of a top-level mirror module (U-Net, CameraPoseEncoder, Adapter): if any
-    parameter, buffer or processor setting changed since the plans were built, drop them."""
+def refresh_plans(root, min_interval_s=0.0):
+    """Called at the top of every forward of a top-level mirror module (U-Net, CameraPoseEncoder, Adapter) and at the
+    start of every denoising loop: if any parameter, buffer or processor setting changed since the plans were built, drop
+    them.  `min_interval_s`: the per-step call of the graph-replay path re-checks at most that often (a check is ~1 ms
+    of host time against a 30 ms step; loops re-check exactly at their start)."""
+    if min_interval_s > 0.0:
+        now = time.monotonic()
+        if now - getattr(root, "_fmc_checked_at", -1e9) < min_interval_s:
+            return
+        root._fmc_checked_at = now
     fp = fingerprint(root)
     if getattr(root, "_fmc_fingerprint", None) != fp:
         if getattr(root, "_fmc_fingerprint", None) is not None:
@@ -522,14 +544,27 @@ class TextCtx:
         if hit is None or len(hit[0]) != len(plans) or any(a is not b for a, b in zip(hit[0], plans)):
             hit = (plans, torch.cat([p.kv.w for p in plans], dim=0).contiguous())
             cache["text_kv"] = hit
-        if plans[0].kv.split:
-            allkv = ops.gemm_f32(self.rows, hit[1], split=plans[0].kv.split)
+        self._kv_weights, self._kv_split = hit[1], plans[0].kv.split
+        if self._kv_split:
+            allkv = ops.gemm_f32(self.rows, hit[1], split=self._kv_split)
         else:
             allkv = ops.gemm(self.rows, hit[1])
+        self._allkv = allkv
         off = 0
         for p in plans:
             self.kv[id(p)] = allkv[:, off:off + p.kv.N]
             off += p.kv.N
+
+    def reload(self, text):
+        """New text embeddings into the SAME device buffers (rows and the projected K | V): a captured CUDA graph that
+        reads them stays valid, and the projection runs once per text instead of once per denoising step."""
+        B, n, c = text.shape
+        assert B == self.batch and n == self.length and self.kv, "reload() needs a projected context of the same shape"
+        self.rows.view(B, TEXT_PAD, c)[:, :n].copy_(text)
+        if self._kv_split:
+            ops.gemm_f32(self.rows, self._kv_weights, out=self._allkv, split=self._kv_split)
+        else:
+            ops.gemm(self.rows, self._kv_weights, out=self._allkv)
 
     @staticmethod
     def of(x, batch, frames, device):

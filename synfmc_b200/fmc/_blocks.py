@@ -44,6 +44,8 @@ class Attention(_Holder):
         if hasattr(self, "processor") and isinstance(self.processor, nn.Module) and not isinstance(processor, nn.Module):
             self._modules.pop("processor")
         self.processor = processor
+        from .. import engine
+        engine.structure_changed()  # cached processor lists of engine.fingerprint are rebuilt
 
 
 class GEGLU(_Holder):

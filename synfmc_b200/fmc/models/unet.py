@@ -287,6 +287,17 @@ class UNet3DConditionModelPoseCond(UNet3DConditionModel):
         self.set_mm_attn_processor(build(list(self.mm_attn_processors.keys()), add_temporal, temporal_attn_names,
                                          add_motion_lora, motion_lora_rank, motion_lora_kwargs, True))
 
+    def text_context(self, encoder_hidden_states, device):
+        """encoder_hidden_states [B, 77, 768] -> engine.TextCtx with the K | V projections of all 16 text cross-attentions
+        done (one GEMM).  The text is constant over a denoising loop, so the pipeline builds this once and passes it as
+        `encoder_hidden_states` to every step instead of re-projecting inside each forward."""
+        engine.refresh_plans(self)
+        text = engine.TextCtx(encoder_hidden_states, device)
+        if self._transformers is None:
+            self._transformers = [m for m in self.modules() if m.__class__.__name__ == "Transformer2DModel"]
+        text.project_all(self._transformers, device, self._cat_cache)
+        return text
+
     # ---- device plan of the UNet-level layers ----
     def plan(self, device):
         if self._plan is None or self._plan["device"] != engine.plan_key(device):

@@ -47,7 +47,13 @@ def test_motion_module_with_camera_adapter(cuda_device):
             got = pm(x.to(cuda_device), None, None, None,
                      cross_attention_kwargs={"pose_feature": pose.to(cuda_device)}).to_reference()
         # the module output is input + branch; judge the branch (otherwise the residual hides errors)
-        assert rel_l2(got.cpu() - x, want - x) < MODULE_TOL, C
+        assert _report(f"motion module + CameraAdapter C={C} (branch)", rel_l2(got.cpu() - x, want - x)) < MODULE_TOL, C
+
+
+def _report(name, err):
+    """measured rel-L2 of the bf16 path vs the fp32 oracle, collected by `pytest -s` into profiles/ (DESIGN.md numerics)"""
+    print(f"[parity] {name}: rel-L2 = {err:.3e}")
+    return err
 
 
 def _unet_inputs(b, f, h, w, channels, seed=0, traj=False):
@@ -78,7 +84,7 @@ def test_tiny_unet_forward(cuda_device, obj):
     got = p_unet(sample.to(cuda_device), 961, text.to(cuda_device),
                  pose_embedding_features=[x.to(cuda_device) for x in feats], **kwd).sample
     assert got.shape == want.shape and got.dtype == torch.float32
-    assert rel_l2(got, want) < UNET_TOL
+    assert _report(f"tiny U-Net obj={obj}", rel_l2(got, want)) < UNET_TOL
     if obj:  # the injected object features must matter
         got0 = p_unet(sample.to(cuda_device), 961, text.to(cuda_device),
                       pose_embedding_features=[x.to(cuda_device) for x in feats], traj_features=None).sample
@@ -168,7 +174,7 @@ def test_cfg_denoise_loop(cuda_device):
     out = pipe(None, plucker.to(cuda_device), f, traj_features=[t.to(cuda_device) for t in trajs], height=H, width=W,
                num_inference_steps=25, guidance_scale=8.0, latents=latents.to(cuda_device),
                prompt_embeds=text.to(cuda_device), omcm_min_step=900, max_steps=3)
-    assert rel_l2(out.latents, want) < UNET_TOL
+    assert _report("3-step CFG denoise loop (tiny U-Net, cam + obj)", rel_l2(out.latents, want)) < UNET_TOL
 
 
 @pytest.mark.parametrize("form", ["sliced", "list"])
@@ -205,7 +211,7 @@ def test_multidiff_windows(cuda_device, form):
                            multidiff_total_steps=n_win, multidiff_overlaps=ov, max_steps=2).latents
     assert outs[True].shape == (b, 4, F_total, H // 8, W // 8)
     assert torch.equal(outs[True], outs[False])
-    assert rel_l2(outs[True], want) < UNET_TOL
+    assert _report(f"multidiff windows ({form})", rel_l2(outs[True], want)) < UNET_TOL
 
 
 def test_window_combine_ddim_kernel(cuda_device):
@@ -288,7 +294,7 @@ def test_config1_full_unet(cuda_device):
         want = OPA(o_unet, o_enc)(latents, torch.tensor([961]), text, plucker)
     got = PoseAdaptor(p_unet, p_enc)(latents.to(cuda_device), torch.tensor([961], device=cuda_device),
                                      text.to(cuda_device), plucker.to(cuda_device))
-    assert rel_l2(got, want) < UNET_TOL
+    assert _report("config 1 full U-Net + CameraEncoder, bf16 mode", rel_l2(got, want)) < UNET_TOL
 
 
 @pytest.mark.timeout(1800)
@@ -307,7 +313,7 @@ def test_config2_full_size_unet_forward(cuda_device):
     got = p_unet(sample.to(dev), 961, text.to(dev), pose_embedding_features=[x.to(dev) for x in feats],
                  traj_features=[x.to(dev) for x in trajs]).sample
     assert got.shape == want.shape == (1, 4, 16, 40, 64)
-    assert rel_l2(got, want) < UNET_TOL
+    assert _report("config 2 full-size U-Net forward (cam + 1 object), bf16 mode", rel_l2(got, want)) < UNET_TOL
 
 
 def test_product_against_reference_golden_vectors(cuda_device):
@@ -325,7 +331,7 @@ def test_product_against_reference_golden_vectors(cuda_device):
         kw = {"traj_features": [t.to(dev) for t in inp["traj_feats"]]} if obj else {}
         got = p_unet(inp["sample"].to(dev), 961, inp["text"].to(dev),
                      pose_embedding_features=[x.to(dev) for x in inp["pose_feats"]], **kw).sample
-        assert rel_l2(got, gold[key]) < UNET_TOL, key
+        assert _report(f"tiny U-Net vs reference golden {key}", rel_l2(got, gold[key])) < UNET_TOL, key
 
 
 @pytest.mark.timeout(900)
@@ -343,6 +349,6 @@ def test_full_depth_unet_against_reference_golden(cuda_device):
     feats = [x.to(dev) for x in inp["pose_feats"]]
     got = p_unet(inp["sample"].to(dev), 961, inp["text"].to(dev), pose_embedding_features=feats,
                  traj_features=[x.to(dev) for x in inp["traj_feats"]]).sample
-    assert rel_l2(got, gold["unet_obj_full"]) < UNET_TOL
+    assert _report("full-depth U-Net vs reference golden (obj)", rel_l2(got, gold["unet_obj_full"])) < UNET_TOL
     got = p_unet(inp["sample"].to(dev), 41, inp["text"].to(dev), pose_embedding_features=feats, traj_features=None).sample
-    assert rel_l2(got, gold["unet_obj_full_no_traj"]) < UNET_TOL
+    assert _report("full-depth U-Net vs reference golden (t=41, no obj)", rel_l2(got, gold["unet_obj_full_no_traj"])) < UNET_TOL

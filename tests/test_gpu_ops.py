@@ -13,7 +13,16 @@ import torch.nn.functional as Fn
 pytestmark = pytest.mark.gpu
 
 BF16_TOL = 4e-3
+FUSED_TOL = 6e-3  # kernels that chain two tensor-core stages through bf16 operands (projection -> attention)
 F32_TOL = 1e-5
+
+
+def within_one_bf16_ulp(got, want):
+    """Fraction of elements whose bf16 result is within ONE bf16 ulp of the exact (fp64) value -- SURVEY H1's per-kernel
+    form of the 1e-3 bound for a bf16-output kernel that is fp32 inside: the only error left is the output rounding."""
+    got, want = got.double().cpu(), want.double().cpu()
+    ulp = torch.exp2(torch.floor(torch.log2(want.abs().clamp_min(2.0 ** -120))) - 7)
+    return float(((got - want).abs() <= ulp).double().mean())
 
 
 def bf(x):
@@ -216,11 +225,14 @@ def test_temporal_qkv_attention_fused(ops, cuda_device, B, F, HW):
 
     def seq(t):  # [(B F HW), C] -> [(B HW), heads, F, d]
         return t.view(B, F, HW, heads, d).permute(0, 2, 3, 1, 4).reshape(B * HW, heads, F, d)
-    # the kernel rounds q, k, v to bf16 between the projection and the attention, like the un-fused chain
-    q, k, v = (bf(x @ w.t()).float() for w in (wq, wk, wv))
+    # fp32 statement of the reference lines, NO rounding mirrored from the kernel (which feeds q, k, v and the
+    # probabilities to the tensor cores as bf16 MMA operands: three roundings more than a single bf16-output op)
+    q, k, v = (x @ w.t() for w in (wq, wk, wv))
     o = Fn.scaled_dot_product_attention(seq(q), seq(k), seq(v))
     want = o.view(B, HW, heads, F, d).permute(0, 3, 1, 2, 4).reshape(rows, C)
-    assert rel(out, want) < BF16_TOL
+    err = rel(out, want)
+    print(f"[parity] fused temporal q|k|v + attention B={B} F={F} HW={HW}: rel-L2 vs fp32 = {err:.3e}")
+    assert err < FUSED_TOL
     torch.cuda.synchronize()
 
 
@@ -251,6 +263,36 @@ def test_layernorm_plain(ops, cuda_device, rows, C):
     x, g, b = randn(rows, C, seed=1), 1 + 0.1 * randn(C, seed=2), 0.1 * randn(C, seed=3)
     got = ops.layernorm(bf(x).to(cuda_device), g.to(cuda_device), b.to(cuda_device), 1e-5)
     assert rel(got, Fn.layer_norm(x, (C,), g, b, 1e-5)) < BF16_TOL
+
+
+@pytest.mark.parametrize("rows,C", [(2000, 320), (500, 640), (300, 1280)])
+def test_layernorm_is_exact_up_to_output_rounding(ops, cuda_device, rows, C):
+    """LayerNorm (+PE, + pose add) is fp32 inside: every bf16 output is within one bf16 ulp of the fp64 result."""
+    F, HW = 4, 5
+    x, g, b = randn(rows, C, seed=1, scale=2.0), 1 + 0.1 * randn(C, seed=2), 0.1 * randn(C, seed=3)
+    pe, add = randn(F, C, seed=4), randn(rows, C, seed=5)
+    out, out2 = ops.layernorm(bf(x).to(cuda_device), g.to(cuda_device), b.to(cuda_device), 1e-5, pe=pe.to(cuda_device),
+                              F=F, HW=HW, add=bf(add).to(cuda_device))
+    frame = (torch.arange(rows) // HW) % F
+    want = Fn.layer_norm(x.double(), (C,), g.double(), b.double(), 1e-5) + pe.double()[frame]
+    assert within_one_bf16_ulp(out, want) > 0.9999
+    # out2 = (LN + PE) + pose in fp32 from the un-rounded LN value, then one rounding
+    assert within_one_bf16_ulp(out2, want + add.double()) > 0.9999
+
+
+@pytest.mark.parametrize("images,HW,C,silu", [(4, 2560, 320, True), (4, 640, 640, False), (2, 160, 1280, True),
+                                              (2, 40, 2560, True), (2, 2560, 960, True)])
+def test_groupnorm_is_exact_up_to_output_rounding(ops, cuda_device, images, HW, C, silu):
+    """GroupNorm (+SiLU) at the step's shapes: within one bf16 ulp of the fp64 result (fp32 statistics and apply)."""
+    x = randn(images * HW, C, seed=1, scale=2.0) + 0.25
+    g, b = 1 + 0.1 * randn(C, seed=2), 0.1 * randn(C, seed=3)
+    got = ops.groupnorm(bf(x).to(cuda_device), g.to(cuda_device), b.to(cuda_device), 1e-5, images, HW, groups=32, silu=silu)
+    want = Fn.group_norm(x.view(images, HW, C).double().permute(0, 2, 1), 32, g.double(), b.double(), 1e-5)
+    if silu:
+        want = Fn.silu(want)
+    frac = within_one_bf16_ulp(got, want.permute(0, 2, 1).reshape(images * HW, C))
+    print(f"[parity] groupnorm images={images} HW={HW} C={C} silu={silu}: {frac:.6f} of outputs within 1 bf16 ulp of fp64")
+    assert frac > 0.999
 
 
 def test_layernorm_pe_pose(ops, cuda_device):
