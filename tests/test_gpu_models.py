@@ -2,9 +2,11 @@
 oracle on identical bf16-exact synthetic weights and inputs (the product is filled from the oracle's state dict with
 strict=True, which doubles as the state-dict key contract check).
 
-Tolerance: activations are bf16 between kernels, fp32 inside them; one bf16 rounding is ~1.7e-3 rel-L2 and a U-Net
-forward chains >100 of them, so module-level parity is held to 6e-3 and whole-U-Net / multi-step parity to 1.5e-2
-(DESIGN.md "numerics")."""
+Tolerances of the bf16 PRODUCTION mode: activations are bf16 between kernels, fp32 inside them; one bf16 rounding is
+~1.7e-3 rel-L2 and a U-Net forward chains >100 of them.  The bounds below sit just above what is measured (every test
+prints its number with `-s`; profiles/r02_parity_measured.txt) and are tied to the reference's own bf16 behaviour by
+test_bf16_mode_is_no_worse_than_torch_autocast_of_the_reference.  The north star's 1e-3 is carried by the
+reference-precision mode: tests/test_gpu_precise.py (config 1 measured 3.9e-5)."""
 import pytest
 import torch
 
@@ -13,8 +15,9 @@ from oracle.harness import rel_l2
 
 pytestmark = pytest.mark.gpu
 
-MODULE_TOL = 6e-3
-UNET_TOL = 1.5e-2
+MODULE_TOL = 6.5e-3   # one module (measured 5.5e-3 - 5.8e-3)
+UNET_TOL = 1.3e-2     # one U-Net forward, tiny or full size (measured 8.5e-3 - 1.04e-2)
+LOOP_TOL = 2.0e-2     # several denoising steps chained (measured 1.46e-2 after 3 CFG steps)
 
 
 def test_motion_module_with_camera_adapter(cuda_device):
@@ -89,6 +92,24 @@ def test_tiny_unet_forward(cuda_device, obj):
         got0 = p_unet(sample.to(cuda_device), 961, text.to(cuda_device),
                       pose_embedding_features=[x.to(cuda_device) for x in feats], traj_features=None).sample
         assert rel_l2(got0, want) > 5 * UNET_TOL
+
+
+def test_bf16_mode_is_no_worse_than_torch_autocast_of_the_reference(cuda_device):
+    """What "bf16" can mean for this path at all: the oracle (= the reference's eager PyTorch code) run under torch's own
+    bf16 autocast deviates from its fp32 run by ~1e-2 on this U-Net.  The CUDA bf16 mode must be at least as close to
+    the fp32 reference as that -- it keeps fp32 inside every kernel, autocast rounds after every op."""
+    o_unet = helpers.build_oracle_unet(tiny=True, obj=True)
+    p_unet = helpers.build_product_unet(o_unet, tiny=True, obj=True, device=cuda_device)
+    sample, text, feats, trajs = _unet_inputs(2, 8, 16, 24, (320, 640), seed=1, traj=True)
+    with torch.no_grad():
+        want = o_unet(sample, 961, text, pose_embedding_features=feats, traj_features=trajs).sample
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            auto = o_unet(sample, 961, text, pose_embedding_features=feats, traj_features=trajs).sample.float()
+    got = p_unet(sample.to(cuda_device), 961, text.to(cuda_device), pose_embedding_features=[x.to(cuda_device) for x in feats],
+                 traj_features=[t.to(cuda_device) for t in trajs]).sample
+    e_auto, e_ours = rel_l2(auto, want), rel_l2(got, want)
+    print(f"[parity] tiny U-Net: torch bf16 autocast of the reference path {e_auto:.3e}, CUDA bf16 mode {e_ours:.3e}")
+    assert e_ours < e_auto
 
 
 def test_tiny_unet_timestep_forms(cuda_device):
@@ -174,12 +195,12 @@ def test_cfg_denoise_loop(cuda_device):
     out = pipe(None, plucker.to(cuda_device), f, traj_features=[t.to(cuda_device) for t in trajs], height=H, width=W,
                num_inference_steps=25, guidance_scale=8.0, latents=latents.to(cuda_device),
                prompt_embeds=text.to(cuda_device), omcm_min_step=900, max_steps=3)
-    assert _report("3-step CFG denoise loop (tiny U-Net, cam + obj)", rel_l2(out.latents, want)) < UNET_TOL
+    assert _report("3-step CFG denoise loop (tiny U-Net, cam + obj)", rel_l2(out.latents, want)) < LOOP_TOL
 
 
 @pytest.mark.parametrize("form", ["sliced", "list"])
 def test_multidiff_windows(cuda_device, form):
-    """Long clips as overlapping windows (pipeline_animation.py:669-702): 4 windows of 8 frames, overlap 6 -> 14 frames;
+    """Long clips as overlapping windows (pipeline_animation.py:669-702): 3 windows of 8 frames, overlap 4 -> 16 frames;
     every window through the captured graph, one window-average + DDIM kernel; the pose embedding either covers all
     frames (sliced per window) or is the reference's per-window list (:644-651)."""
     from oracle.diffusers_restated import DDIMScheduler as ODDIM
@@ -193,7 +214,7 @@ def test_multidiff_windows(cuda_device, form):
     p_unet = helpers.build_product_unet(o_unet, tiny=True, device=cuda_device)
     o_enc = helpers.build_oracle_pose_encoder(channels)
     p_enc = helpers.build_product_pose_encoder(o_enc, channels, device=cuda_device)
-    b, L, ov, n_win, H, W = 1, 8, 6, 4, 64, 96
+    b, L, ov, n_win, H, W = 1, 8, 4, 3, 64, 96  # 16 frames: the sliced form runs the CameraEncoder over all of them
     F_total = n_win * (L - ov) + ov
     K, c2w = synth.synth_camera(b, F_total, H, W, seed=8)
     plucker = to_plucker_embedding(c2w, K, (H, W)).permute(0, 2, 1, 3, 4).contiguous()
@@ -314,6 +335,124 @@ def test_config2_full_size_unet_forward(cuda_device):
                  traj_features=[x.to(dev) for x in trajs]).sample
     assert got.shape == want.shape == (1, 4, 16, 40, 64)
     assert _report("config 2 full-size U-Net forward (cam + 1 object), bf16 mode", rel_l2(got, want)) < UNET_TOL
+
+
+@pytest.mark.timeout(1800)
+def test_config4_three_objects_full_size(cuda_device):
+    """BASELINE config 4's forward at full size: 3 overlapping Gaussian objects per frame (order-dependent scatter,
+    util.py:178-182) -> ObjectEncoder with mask modulation (adapter.py:154-192) -> feature injection into the full 4-level
+    U-Net (modified_modules.py:52-127) at 320x512x16f, t = 961, batch 1 -- CUDA path vs the fp32 CPU oracle."""
+    from oracle.util import get_traj_features_v2 as o_get
+    from synfmc_b200 import synth
+    from synfmc_b200.fmc.util import get_traj_features_v2
+    channels = (320, 640, 1280, 1280)
+    o_unet = helpers.build_oracle_unet(tiny=False, obj=True)
+    p_unet = helpers.build_product_unet(o_unet, tiny=False, obj=True, device=cuda_device)
+    o_m = helpers.build_oracle_omcm(channels)
+    p_m = helpers.build_product_omcm(o_m, channels, device=cuda_device)
+    b, f, H, W = 1, 16, 320, 512
+    infos, masks = synth.synth_objects(b, f, H, W, 3, seed=21, gaussian=True)
+    sample, text, feats, _ = _unet_inputs(b, f, H // 8, W // 8, channels, seed=12)
+    with torch.no_grad():
+        o_traj = o_get(infos, masks, o_m, False, 0.0, None, "cpu", torch.float32)
+        want = o_unet(sample, 961, text, pose_embedding_features=feats, traj_features=o_traj).sample
+    dev = cuda_device
+    p_traj = get_traj_features_v2(infos, masks, p_m, False, 0.0, None, dev, torch.float32)
+    for l, (g_, w_) in enumerate(zip(p_traj, o_traj)):
+        assert _report(f"config 4 ObjectEncoder feature {l} (3 objects, 320x512x16f)", rel_l2(g_, w_)) < UNET_TOL
+        assert bool(((w_ == 0) == (g_.cpu() == 0)).all()), l   # the mask-modulated support is identical
+    got = p_unet(sample.to(dev), 961, text.to(dev), pose_embedding_features=[x.to(dev) for x in feats],
+                 traj_features=p_traj).sample
+    assert _report("config 4 full-size U-Net forward with 3-object features", rel_l2(got, want)) < UNET_TOL
+
+
+@pytest.mark.timeout(2400)
+def test_config5_windows_full_size(cuda_device):
+    """BASELINE config 5's step at full spatial size (320x512), definition H5(i) = reference-faithful multidiff windows
+    (pipeline_animation.py:669-702) of 16 frames with overlap 12; here 2 windows = 20 frames (the fp32 oracle needs ~20 s
+    per U-Net forward at this size; the 64-frame / 13-window bookkeeping is covered by
+    test_config5_64_frames_window_bookkeeping).  Per-window pose-embedding LIST (:644-651 -- the CameraEncoder's PE has
+    max_len 16), 3 objects with the object features sliced per window (windowed_objects, this package's extension of
+    pipeline_animation_cm_om.py:690), CFG 8.0, one DDIM step."""
+    from oracle.diffusers_restated import DDIMScheduler as ODDIM
+    from oracle.pipeline import denoise as o_denoise
+    from oracle.rays import to_plucker_embedding
+    from oracle.util import get_traj_features_v2 as o_get
+    from synfmc_b200 import synth
+    from synfmc_b200.fmc._blocks import DDIMScheduler
+    from synfmc_b200.fmc.pipelines.pipeline_animation_cm_om import CameraObjCtrlPipeline
+    from synfmc_b200.fmc.util import get_traj_features_v2
+    channels = (320, 640, 1280, 1280)
+    o_unet = helpers.build_oracle_unet(tiny=False, obj=True)
+    p_unet = helpers.build_product_unet(o_unet, tiny=False, obj=True, device=cuda_device)
+    o_enc = helpers.build_oracle_pose_encoder(channels)
+    p_enc = helpers.build_product_pose_encoder(o_enc, channels, device=cuda_device)
+    o_m = helpers.build_oracle_omcm(channels)
+    p_m = helpers.build_product_omcm(o_m, channels, device=cuda_device)
+    b, L, ov, n_win, H, W = 1, 16, 12, 2, 320, 512
+    F_total = n_win * (L - ov) + ov
+    K, c2w = synth.synth_camera(b, F_total, H, W, seed=31)
+    plucker = to_plucker_embedding(c2w, K, (H, W)).permute(0, 2, 1, 3, 4).contiguous()
+    windows = [plucker[:, :, k * (L - ov):k * (L - ov) + L].contiguous() for k in range(n_win)]
+    infos, masks = synth.synth_objects(b, F_total, H, W, 3, seed=32, gaussian=True)
+    latents, text = synth.synth_step_inputs(b, F_total, H // 8, W // 8, cfg=True, seed=33)
+    with torch.no_grad():
+        o_traj = o_get(infos, masks, o_m, False, 0.0, None, "cpu", torch.float32)
+    want = o_denoise(o_unet, ODDIM(), o_enc, latents, text, windows, L, traj_features=o_traj, num_inference_steps=50,
+                     guidance_scale=8.0, multidiff_total_steps=n_win, multidiff_overlaps=ov, max_steps=1,
+                     windowed_objects=True)
+    dev = cuda_device
+    p_traj = get_traj_features_v2(infos, masks, p_m, False, 0.0, None, dev, torch.float32)
+    pipe = CameraObjCtrlPipeline(None, None, None, p_unet, DDIMScheduler(), p_enc)
+    out = pipe(None, [w_.to(dev) for w_ in windows], L, traj_features=p_traj, height=H, width=W, num_inference_steps=50,
+               guidance_scale=8.0, latents=latents.to(dev), prompt_embeds=text.to(dev), multidiff_total_steps=n_win,
+               multidiff_overlaps=ov, max_steps=1, windowed_objects=True)
+    assert out.latents.shape == (b, 4, F_total, H // 8, W // 8)
+    assert _report("config 5 windowed step at 320x512 (2 windows x 16 f, cam list + 3 objects, CFG)",
+                   rel_l2(out.latents, want)) < UNET_TOL
+
+
+def test_config5_64_frames_window_bookkeeping(cuda_device):
+    """64 frames = 13 windows of 16 with overlap 12 (config 5): the pipeline's windowed step (13 graph replays + the
+    window-average/DDIM kernel) equals the composition of 13 single-window U-Net calls averaged with torch indexing as the
+    reference writes it (pipeline_animation.py:673-702) -- a size-independent property, no CPU oracle involved."""
+    from synfmc_b200 import ops, synth
+    from synfmc_b200.engine import CL
+    from synfmc_b200.fmc._blocks import DDIMScheduler
+    from synfmc_b200.fmc.pipelines.pipeline_animation import CameraCtrlPipeline, ddim_alphas
+    channels = (320, 640)
+    o_unet = helpers.build_oracle_unet(tiny=True)
+    p_unet = helpers.build_product_unet(o_unet, tiny=True, device=cuda_device)
+    dev = cuda_device
+    b, L, ov, n_win, h, w = 1, 16, 12, 13, 8, 12
+    F_total = n_win * (L - ov) + ov
+    assert F_total == 64
+    latents, text = synth.synth_step_inputs(b, F_total, h, w, cfg=True, seed=41)
+    latents, text = latents.to(dev), text.to(dev)
+    g = torch.Generator().manual_seed(42)
+    feats = [CL(ops.to_channels_last(torch.randn(2 * b, C, F_total, h >> l, w >> l, generator=g).to(dev)))
+             for l, C in enumerate(channels)]
+    sched = DDIMScheduler()
+    sched.set_timesteps(50)
+    t = int(sched.timesteps[0])
+    pipe = CameraCtrlPipeline(None, None, None, p_unet, sched, None)
+    got = pipe.denoise_step(latents, t, text, feats, L, guidance_scale=8.0, multidiff_total_steps=n_win,
+                            multidiff_overlaps=ov)
+    noise, count = torch.zeros_like(latents), torch.zeros_like(latents)
+    preds = []
+    for k in range(n_win):
+        s = k * (L - ov)
+        count[:, :, s:s + L] += 1
+        wf = [CL(f.t[:, s:s + L].contiguous()) for f in feats]
+        eps = p_unet(torch.cat([latents[:, :, s:s + L]] * 2), t, text, pose_embedding_features=wf).sample
+        preds.append(eps[:b] + 8.0 * (eps[b:] - eps[:b]))
+    for k, e in enumerate(preds):
+        s = k * (L - ov)
+        noise[:, :, s:s + L] += e / count[:, :, s:s + L]
+    a_t, a_prev = ddim_alphas(sched, t)
+    want = a_prev ** 0.5 * (latents - (1 - a_t) ** 0.5 * noise) / a_t ** 0.5 + (1 - a_prev) ** 0.5 * noise
+    assert float(count.min()) == 1.0 and float(count.max()) == 4.0
+    assert rel_l2(got, want) < 1e-6
 
 
 def test_product_against_reference_golden_vectors(cuda_device):

@@ -284,7 +284,7 @@ def test_layernorm_is_exact_up_to_output_rounding(ops, cuda_device, rows, C):
                                               (2, 40, 2560, True), (2, 2560, 960, True)])
 def test_groupnorm_is_exact_up_to_output_rounding(ops, cuda_device, images, HW, C, silu):
     """GroupNorm (+SiLU) at the step's shapes: within one bf16 ulp of the fp64 result (fp32 statistics and apply)."""
-    x = randn(images * HW, C, seed=1, scale=2.0) + 0.25
+    x = bf(randn(images * HW, C, seed=1, scale=2.0) + 0.25).float()  # bf16-exact: both sides see the same numbers
     g, b = 1 + 0.1 * randn(C, seed=2), 0.1 * randn(C, seed=3)
     got = ops.groupnorm(bf(x).to(cuda_device), g.to(cuda_device), b.to(cuda_device), 1e-5, images, HW, groups=32, silu=silu)
     want = Fn.group_norm(x.view(images, HW, C).double().permute(0, 2, 1), 32, g.double(), b.double(), 1e-5)
