@@ -866,6 +866,224 @@ groupnorm_tma_kernel(const __grid_constant__ CUtensorMap tmx, const float* __res
   if (R > 1) cluster_wait_acquire();
 }
 
+// ------------------------------------------------------------------------------------------------
+// PERSISTENT form of the TMA-staged kernel (round 2).  The kernel above is bound by bytes in flight: a CTA has loads
+// outstanding only while it waits for its slab, then reduces / exchanges / applies with nothing in flight, and the CTAs
+// of a wave run those phases in lockstep.  Here a cluster is resident for the whole launch and walks work items
+// (image, channel chunk) with TWO slab buffers: the TMA load of item i+1 is issued before the reduction of item i
+// starts, so every CTA always has a slab in flight while it computes.  Arithmetic and reduction order are those of
+// groupnorm_tma_kernel -- the two produce identical bits (tests/test_gpu_ops.py::test_groupnorm_persistent_is_bit_identical).
+// grid = (R, n_clusters), cluster (R, 1, 1); item = blockIdx.y + it * gridDim.y over chunks * images items.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GNF_THREADS, 3)
+groupnorm_tma_persist_kernel(const __grid_constant__ CUtensorMap tmx, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out, long long ldo,
+                             int HW, int cpg, int CH, int rows_cta, int boxr, int nbox, int silu,
+                             const float* __restrict__ rowbias, long long ldrb, int rb_div, int chunks, int items,
+                             int slab_bytes) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t gnt_raw[];
+  __shared__ uint64_t bar[2];
+  __shared__ float red_s[2 * GNF_THREADS], red_q[2 * GNF_THREADS];
+  __shared__ float tot_s[2 * GNF_MAX_CH / 8], tot_q[2 * GNF_MAX_CH / 8];
+  __shared__ float2 part[8];
+  __shared__ float s_mean[8], s_rstd[8];
+  const int tid = threadIdx.x;
+  const int R = gridDim.x, rank = blockIdx.x;
+  const int row_begin = rank * rows_cta;
+  const int nrows = min(HW, row_begin + rows_cta) - row_begin;
+  const uint32_t slab0 = (smem_u32(gnt_raw) + 127u) & ~127u;
+  const uint32_t slab_stride = (static_cast<uint32_t>(slab_bytes) + 127u) & ~127u;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  const int VPR = CH >> 3;
+  const int rows_par = GNF_THREADS / VPR;
+  const int vc = tid % VPR, rsub = tid / VPR;
+  const bool active = rsub < rows_par;
+  const int ngc = CH / cpg;
+  const int mine = nrows - rsub;
+  const int nvalid = (active && mine > 0) ? (mine + rows_par - 1) / rows_par : 0;
+  const uint32_t sstep = static_cast<uint32_t>(rows_par * VPR * 16);
+
+  auto issue = [&](int item, int buf) {  // one elected thread of warp 0
+    const int chunk = item % chunks, img = item / chunks;
+    mbar_arrive_expect_tx(&bar[buf], static_cast<uint32_t>(nbox * boxr * CH * 2));
+    for (int b = 0; b < nbox; ++b) {
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+          ::"r"(slab0 + static_cast<uint32_t>(buf) * slab_stride + static_cast<uint32_t>(b * boxr * CH * 2)),
+          "l"(reinterpret_cast<uint64_t>(&tmx)), "r"(smem_u32(&bar[buf])), "r"(chunk * CH), "r"(row_begin + b * boxr),
+          "r"(img)
+          : "memory");
+    }
+  };
+  const int first = blockIdx.y, step = gridDim.y;
+  if (tid < 32 && first < items) {
+    if (elect_one()) issue(first, 0);
+  }
+  int it = 0;
+  for (int item = first; item < items; item += step, ++it) {
+    const int buf = it & 1;
+    const int chunk = item % chunks, img = item / chunks;
+    // prefetch the next item's slab into the other buffer: every thread finished reading it before the __syncthreads
+    // that ended the previous iteration
+    if (tid < 32 && item + step < items) {
+      if (elect_one()) issue(item + step, buf ^ 1);
+    }
+    const uint32_t my0 = slab0 + static_cast<uint32_t>(buf) * slab_stride + static_cast<uint32_t>((rsub * VPR + vc) * 16);
+    const int c0 = chunk * CH + vc * 8;
+    const int g_first = c0 / cpg;
+    const int split = min(8, (g_first + 1) * cpg - c0);
+    uint64_t rb2[4];
+    if (rowbias != nullptr) {
+      const float4* rp = reinterpret_cast<const float4*>(rowbias + (img / rb_div) * ldrb + c0);
+      const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+      rb2[0] = f2_pack(r0.x, r0.y); rb2[1] = f2_pack(r0.z, r0.w); rb2[2] = f2_pack(r1.x, r1.y); rb2[3] = f2_pack(r1.z, r1.w);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rb2[j] = 0ull;
+    }
+    mbar_wait(&bar[buf], static_cast<uint32_t>(it >> 1) & 1u);
+    {
+      uint64_t a2[4], b2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a2[j] = b2[j] = 0ull;
+#pragma unroll 4
+      for (int i = 0; i < nvalid; ++i) {
+        uint32_t w[4];
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(my0 + i * sstep));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t xr = f2_add(bf16x2_to_f2(w[j]), rb2[j]);
+          a2[j] = f2_add(a2[j], xr);
+          b2[j] = f2_fma(xr, xr, b2[j]);
+        }
+      }
+      float a[8], b[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f2_unpack(a2[j], a[2 * j], a[2 * j + 1]);
+        f2_unpack(b2[j], b[2 * j], b[2 * j + 1]);
+      }
+      float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < split) { s_lo += a[j]; q_lo += b[j]; } else { s_hi += a[j]; q_hi += b[j]; }
+      }
+      if (active) {
+        red_s[(vc * 2) * rows_par + rsub] = s_lo;
+        red_q[(vc * 2) * rows_par + rsub] = q_lo;
+        red_s[(vc * 2 + 1) * rows_par + rsub] = s_hi;
+        red_q[(vc * 2 + 1) * rows_par + rsub] = q_hi;
+      }
+    }
+    __syncthreads();
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int s = warp; s < 2 * VPR; s += GNF_THREADS / 32) {
+        float ss = 0.f, qq = 0.f;
+        for (int r = lane; r < rows_par; r += 32) {
+          ss += red_s[s * rows_par + r];
+          qq += red_q[s * rows_par + r];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          qq += __shfl_xor_sync(0xffffffffu, qq, o);
+        }
+        if (lane == 0) { tot_s[s] = ss; tot_q[s] = qq; }
+      }
+    }
+    __syncthreads();
+    if (tid < ngc) {
+      const int g = chunk * ngc + tid;
+      float ss = 0.f, qq = 0.f;
+      for (int s = 0; s < 2 * VPR; ++s) {
+        const int sc0 = chunk * CH + (s >> 1) * 8;
+        if (sc0 / cpg + (s & 1) == g) { ss += tot_s[s]; qq += tot_q[s]; }
+      }
+      part[tid] = make_float2(ss, qq);
+    }
+    if (R > 1) { cluster_arrive_release(); cluster_wait_acquire(); } else { __syncthreads(); }
+    if (tid < ngc) {
+      float ss = 0.f, qq = 0.f;
+      if (R > 1) {
+        const uint32_t mine_addr = smem_u32(&part[tid]);
+        float2 p[GNF_MAX_CLUSTER];
+#pragma unroll
+        for (int r = 0; r < GNF_MAX_CLUSTER; ++r)
+          p[r] = r < R ? ld_dsmem_f2(mapa_shared(mine_addr, static_cast<uint32_t>(r))) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < GNF_MAX_CLUSTER; ++r) {
+          if (r < R) { ss += p[r].x; qq += p[r].y; }
+        }
+      } else {
+        ss = part[tid].x; qq = part[tid].y;
+      }
+      const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
+      const float mean = ss * inv_n;
+      const float var = fmaxf(qq * inv_n - mean * mean, 0.f);
+      s_mean[tid] = mean;
+      s_rstd[tid] = rsqrtf(var + eps);
+    }
+    __syncthreads();
+    if (R > 1) cluster_arrive_release();  // my remote reads of every CTA's `part` are done
+
+    if (nvalid > 0) {
+      float sa[8], sb[8], rbf[8];
+#pragma unroll
+      for (int j = 0; j < 8; j += 4) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + j));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c0 + j));
+        sa[j] = g4.x; sa[j + 1] = g4.y; sa[j + 2] = g4.z; sa[j + 3] = g4.w;
+        sb[j] = b4.x; sb[j + 1] = b4.y; sb[j + 2] = b4.z; sb[j + 3] = b4.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f2_unpack(rb2[j], rbf[2 * j], rbf[2 * j + 1]);
+      const int gl = g_first - chunk * ngc;
+      const float m0 = s_mean[gl], r0 = s_rstd[gl];
+      const float m1 = split < 8 ? s_mean[gl + 1] : 0.f, r1 = split < 8 ? s_rstd[gl + 1] : 0.f;
+      uint64_t sa2[4], sb2[4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = (j < split ? r0 : r1) * sa[j];
+        sb[j] = fmaf(rbf[j] - (j < split ? m0 : m1), a, sb[j]);
+        sa[j] = a;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sa2[j] = f2_pack(sa[2 * j], sa[2 * j + 1]);
+        sb2[j] = f2_pack(sb[2 * j], sb[2 * j + 1]);
+      }
+      uint4* op = reinterpret_cast<uint4*>(out + (static_cast<long long>(img) * HW + row_begin + rsub) * ldo + c0);
+      const long long ostep = static_cast<long long>(rows_par) * ldo / 8;
+#pragma unroll 4
+      for (int i = 0; i < nvalid; ++i) {
+        uint32_t w[4], o[4];
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(my0 + i * sstep));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint64_t y2 = f2_fma(bf16x2_to_f2(w[j]), sa2[j], sb2[j]);
+          if (silu) y2 = silu_f2(y2);
+          o[j] = f2_to_bf16x2(y2);
+        }
+        op[i * ostep] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    // every CTA of the cluster has read my `part` (second cluster barrier) and every thread of this CTA is done with
+    // slab `buf`, s_mean / s_rstd and the reduction scratch before the next iteration overwrites them
+    if (R > 1) cluster_wait_acquire();
+    __syncthreads();
+  }
+}
+
 // Shape plan of the single-pass kernel: returns 0 when the shape does not fit (the three-kernel form takes it).
 struct GnFusedPlan {
   int ch, cluster, rows_cta, vmax;
@@ -946,6 +1164,65 @@ static int launch_gn_tma(const GnTmaPlan& pl, const void* x, long long ldx, cons
   FMC_CUDA_OK(cudaLaunchKernelEx(&cfg, groupnorm_tma_kernel, tmx, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo,
                                  HW, C / groups, pl.ch, pl.rows_cta, pl.boxr, pl.nbox, silu, rowbias, ldrb, rb_div));
   return check_launch("groupnorm_tma_kernel");
+}
+
+static int launch_gn_tma_persist(const GnTmaPlan& pl, const void* x, long long ldx, const float* gamma, const float* beta,
+                                 float eps, void* out, long long ldo, int images, int HW, int C, int groups, int silu,
+                                 const float* rowbias, long long ldrb, int rb_div, cudaStream_t stream) {
+  CUtensorMap tmx;
+  const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(HW), static_cast<uint64_t>(images)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(HW) * static_cast<uint64_t>(ldx) * 2};
+  const uint32_t box[3] = {static_cast<uint32_t>(pl.ch), static_cast<uint32_t>(pl.boxr), 1u};
+  const int rc = make_tmap_bf16(&tmx, x, 3, dims, strides, box, false);
+  if (rc != FMC_OK) return rc;
+  const int chunks = C / pl.ch;
+  const int items = chunks * images;
+  const int slab_stride = (pl.slab + 127) & ~127;
+  const size_t smem = static_cast<size_t>(2) * slab_stride + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FMC_CUDA_OK(cudaFuncSetAttribute(groupnorm_tma_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (GNT_MAX_SLAB + 128) + 128));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(GNF_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = pl.cluster;
+  attr[na].val.clusterDim.y = 1;
+  attr[na].val.clusterDim.z = 1;
+  ++na;
+  // resident clusters for this (cluster size, shared memory) configuration: cached per configuration
+  static int cached_key = -1, cached_clusters = 0;
+  const int key = pl.cluster * 1000000 + static_cast<int>(smem / 128);
+  if (key != cached_key) {
+    cfg.gridDim = dim3(pl.cluster, 1, 1);
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, groupnorm_tma_persist_kernel, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = device_sm_count() * 2 / pl.cluster;
+    }
+    cached_key = key;
+    cached_clusters = n;
+  }
+  const int nclusters = items < cached_clusters ? items : cached_clusters;
+  cfg.gridDim = dim3(pl.cluster, nclusters, 1);
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  FMC_CUDA_OK(cudaLaunchKernelEx(&cfg, groupnorm_tma_persist_kernel, tmx, gamma, beta, eps, static_cast<__nv_bfloat16*>(out),
+                                 ldo, HW, C / groups, pl.ch, pl.rows_cta, pl.boxr, pl.nbox, silu, rowbias, ldrb, rb_div,
+                                 chunks, items, pl.slab));
+  return check_launch("groupnorm_tma_persist_kernel");
 }
 
 static int gn_fused_mode() {
@@ -1119,8 +1396,13 @@ extern "C" int fmc_groupnorm_bf16(const void* x, long long ldx, const float* gam
   GnFusedPlan pl;
   GnTmaPlan tp;
   if (images <= 65535 && gn_fused_mode() >= 3 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-      gn_tma_plan(HW, C, groups, gn_fused_mode() == 4 ? GNF_MAX_CH : 80, &tp))
+      gn_tma_plan(HW, C, groups, gn_fused_mode() >= 4 ? GNF_MAX_CH : 80, &tp)) {
+    // mode 5: the persistent, double-buffered form (worth it only when a resident cluster gets several items)
+    if (gn_fused_mode() >= 5 && static_cast<long long>(C / tp.ch) * images * tp.cluster > 2LL * device_sm_count() * 3)
+      return launch_gn_tma_persist(tp, x, ldx, gamma, beta, eps, out, ldo, images, HW, C, groups, silu, rowbias, ldrb,
+                                   rb_div0, stream);
     return launch_gn_tma(tp, x, ldx, gamma, beta, eps, out, ldo, images, HW, C, groups, silu, rowbias, ldrb, rb_div0, stream);
+  }
   if (images <= 65535 && gn_fused_wanted(HW, C, groups, &pl)) {
     cudaError_t e;
     if (pl.vmax == 2) e = launch_gn_fused<2>(pl, x, ldx, gamma, beta, eps, out, ldo, images, HW, C, groups, silu, rowbias, ldrb, rb_div0, stream);

@@ -150,11 +150,11 @@ def require_no_grad(module, *tensors):
             "torch.no_grad(), or call .requires_grad_(False) on the module; training needs the reference path.")
 
 
-# 3x3 convolutions: "own" = fmc_conv3x3_bf16 (tcgen05 implicit GEMM) wherever its geometry allows, "cudnn" = torch /
-# cuDNN everywhere, "auto" (default) = the faster of the two as measured on B200 (profiles/r01_conv3x3.txt): cuDNN wins
-# the wide convolutions by 1.7-3x in round 1 (its kernels reuse the input window across the nine taps in shared
-# memory; ours re-fetches it per tap), ours wins the 4-channel conv_in by 3x.
-CONV3X3 = os.environ.get("FMC_CONV3X3", "auto")
+# 3x3 convolutions: the 4-channel conv_in (zero-padded to 64) runs on fmc_conv3x3_bf16, the tcgen05 implicit-GEMM kernel
+# of this library (3x faster than cuDNN there); the wide ones are a cuDNN library call through torch -- the in-tree kernel
+# is parity-clean on them but 1.7-3x slower (profiles/r01_conv3x3.txt), SURVEY 8f row 1 stays open.  One fixed policy, no
+# run-time backend switch.
+OWN_CONV_MAX_CIN = 64
 # FMC_SPATIAL_VF16=1: level-0 spatial self-attention with fp16 V / P and two-per-MUFU-op fp16x2 exponentials
 # (fmc_spatial_attn_vf16).  Correct (tests/test_gpu_ops.py::test_spatial_attention_fp16_v) but 8 % SLOWER than the bf16
 # kernel in round 1 -- the kernel turned out not to be MUFU bound (profiles/r01_spatial_attention_experiments.md).
@@ -442,7 +442,7 @@ class ConvPlan:
         elif self.linear is not None:
             res2d = residual.reshape(-1, self.cout) if residual is not None else None
             y = self.linear(x_img.reshape(-1, self.cin), residual=res2d).view(N, h, w, self.cout)
-        elif (self.fast3x3 and (CONV3X3 == "own" or (CONV3X3 == "auto" and self.cin <= 64))
+        elif (self.fast3x3 and self.cin <= OWN_CONV_MAX_CIN
               and ops.conv3x3_supported(h, w, self.cin, self.cout, self.stride[0])):
             y = ops.conv3x3(x_img, self.w2d, bias=self.b32, residual=residual, stride=self.stride[0])
         else:

@@ -295,6 +295,27 @@ def test_groupnorm_is_exact_up_to_output_rounding(ops, cuda_device, images, HW, 
     assert frac > 0.999
 
 
+@pytest.mark.parametrize("images,HW,C,silu,bias", [(32, 2560, 320, True, False), (32, 640, 640, True, True),
+                                                   (32, 2560, 640, False, False), (16, 1000, 320, True, True),
+                                                   (32, 640, 1920, True, False), (64, 640, 1280, False, False)])
+def test_groupnorm_persistent_is_bit_identical(ops, cuda_device, monkeypatch, images, HW, C, silu, bias):
+    """The persistent, double-buffered GroupNorm (FMC_GN_FUSED=5: resident clusters walking (image, chunk) items with the
+    next slab always in flight) keeps the arithmetic and reduction order of the one-item-per-cluster kernel (mode 4):
+    identical bits, at shapes large enough to take the persistent path (several items per resident cluster)."""
+    x = bf(randn(images * HW, C, seed=1, scale=1.5) + 0.2).to(cuda_device)
+    g, b = (1 + 0.1 * randn(C, seed=2)).to(cuda_device), (0.1 * randn(C, seed=3)).to(cuda_device)
+    rb = randn(images // 2, C, seed=4).to(cuda_device) if bias else None
+    outs = {}
+    for mode in ("4", "5"):
+        monkeypatch.setenv("FMC_GN_FUSED", mode)
+        outs[mode] = ops.groupnorm(x, g, b, 1e-5, images, HW, groups=32, silu=silu, rowbias=rb, rowbias_div=2 if bias else 1)
+    assert torch.equal(outs["4"], outs["5"])
+    xi = (x.float().view(images, HW, C) + (rb.repeat_interleave(2, 0)[:, None, :] if bias else 0)).permute(0, 2, 1)
+    want = Fn.group_norm(xi, 32, g, b, 1e-5)
+    want = Fn.silu(want) if silu else want
+    assert rel(outs["5"], want.permute(0, 2, 1).reshape(images * HW, C)) < BF16_TOL
+
+
 def test_layernorm_pe_pose(ops, cuda_device):
     """LN -> + pe[frame] (motion_module.py:319-321) and the x + pose_feature operand of qkv_merge
     (attention_processor.py:257)."""
