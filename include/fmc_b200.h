@@ -177,6 +177,14 @@ int fmc_traj_scatter_f32(const float* info, const float* masks, float* feat, flo
 int fmc_traj_scatter_unshuffle_bf16(const float* info, const float* masks, void* feat, float* mask_out, int BF,
                                     int n_obj, int H, int W, void* stream);
 
+/* Gaussian sphere masks on the device, fmc/data/dataset.py:5350-5403 (`use_sphere_mask`): circles[BF, n_obj, 3] = (cx, cy,
+ * r) of each object's minimum enclosing circle (r <= 0: object absent) -> masks[BF, n_obj, H, W] = exp(-0.5 (dist /
+ * (r/2))^2) / max * disc(int(cx), int(cy), int(r)).  _circles_unshuffle_bf16: fmc_traj_scatter_unshuffle_bf16 with these
+ * masks generated on the fly (no mask tensor is read; bit-identical to the two-step form). */
+int fmc_sphere_mask_f32(const float* circles, float* masks, int BF, int n_obj, int H, int W, void* stream);
+int fmc_traj_scatter_circles_unshuffle_bf16(const float* info, const float* circles, void* feat, float* mask_out, int BF,
+                                            int n_obj, int H, int W, void* stream);
+
 /* x * nearest-resized mask, fmc/adapter.py:175-177.  row_index[h] / col_index[w] map a level pixel to the
  * full-resolution mask pixel (composition of the iterated F.interpolate(mode='nearest') calls). */
 int fmc_mask_modulate_bf16(const void* x, const float* mask, const int* row_index, const int* col_index, void* out,

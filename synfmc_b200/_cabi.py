@@ -36,6 +36,8 @@ SIGNATURES = {
     "fmc_plucker_unshuffle_bf16": [P, P, P, I, I, I, P],
     "fmc_traj_scatter_f32": [P, P, P, P, I, I, I, I, P],
     "fmc_traj_scatter_unshuffle_bf16": [P, P, P, P, I, I, I, I, P],
+    "fmc_sphere_mask_f32": [P, P, I, I, I, I, P],
+    "fmc_traj_scatter_circles_unshuffle_bf16": [P, P, P, P, I, I, I, I, P],
     "fmc_mask_modulate_bf16": [P, P, P, P, P, I, I, I, I, I, I, P],
     "fmc_cfg_ddim_step_f32": [P, P, F, P, P, P, F, F, L, P],
     "fmc_window_combine_ddim_f32": [P, I, I, F, P, P, I, I, I, L, I, I, F, F, P],

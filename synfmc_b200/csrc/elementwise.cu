@@ -385,6 +385,122 @@ traj_unshuffle_kernel(const float* __restrict__ info, const float* __restrict__ 
   *reinterpret_cast<uint4*>(cell + 12 * 64) = pack8(r);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Gaussian sphere masks on the device (fmc/data/dataset.py:5350-5403, `use_sphere_mask`): the dataset
+// turns each object's segmentation mask into its minimum enclosing circle (centre, radius; cv2 on the host) and then into
+//     gaussian = exp(-0.5 (dist / sigma)^2), sigma = radius / 2;  gaussian /= gaussian.max();  gaussian *= disc
+// with the disc rasterised by cv2.circle(int(centre), int(radius), filled).  Everything after the circle is a closed
+// form of (cx, cy, r): generating it here removes the [n_obj, H, W] mask tensors from host memory, the H2D copy
+// (10 MB per object and clip at 320x512x16f) and -- in the fused form below -- the mask reads of the scatter kernel.
+// Disc test: (x - int(cx))^2 + (y - int(cy))^2 <= int(r)^2 (cv2's midpoint rasterisation may differ by single boundary
+// pixels; cv2 is not available offline to pin that).  `gaussian.max()` over the image is the value at the pixel nearest
+// to the centre.  r <= 0 marks an absent object (empty segmentation mask: the reference keeps the all-zero mask).
+// ---------------------------------------------------------------------------------------------------------------
+struct SphereObj {
+  float cx, cy, inv_s2, norm;  // inv_s2 = -0.5 / sigma^2, norm = 1 / gaussian.max()
+  int icx, icy, r2;            // r2 < 0: absent
+};
+__device__ __forceinline__ SphereObj sphere_obj(const float* __restrict__ c, int H, int W) {
+  SphereObj o;
+  const float cx = __ldg(c), cy = __ldg(c + 1), r = __ldg(c + 2);
+  o.cx = cx; o.cy = cy;
+  if (!(r > 0.f)) {
+    o.r2 = -1; o.icx = o.icy = 0; o.inv_s2 = 0.f; o.norm = 0.f;
+    return o;
+  }
+  const float sigma = r * 0.5f;
+  o.inv_s2 = -0.5f / (sigma * sigma);
+  o.icx = static_cast<int>(cx); o.icy = static_cast<int>(cy);
+  const int ir = static_cast<int>(r);
+  o.r2 = ir * ir;
+  const float nx = fminf(fmaxf(rintf(cx), 0.f), static_cast<float>(W - 1));
+  const float ny = fminf(fmaxf(rintf(cy), 0.f), static_cast<float>(H - 1));
+  const float dm2 = (nx - cx) * (nx - cx) + (ny - cy) * (ny - cy);
+  o.norm = 1.0f / expf(dm2 * o.inv_s2);
+  return o;
+}
+__device__ __forceinline__ float sphere_value(const SphereObj& o, int px, int py) {
+  const int dxi = px - o.icx, dyi = py - o.icy;
+  if (o.r2 < 0 || dxi * dxi + dyi * dyi > o.r2) return 0.f;
+  const float dx = static_cast<float>(px) - o.cx, dy = static_cast<float>(py) - o.cy;
+  return expf((dx * dx + dy * dy) * o.inv_s2) * o.norm;
+}
+
+// masks[bf, o, y, x] from circles[bf, o, 3] = (cx, cy, r)
+__global__ void __launch_bounds__(256)
+sphere_mask_kernel(const float* __restrict__ circles, float* __restrict__ masks, int BFn, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long HW = static_cast<long long>(H) * W;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= BFn * HW) return;
+  const int n = static_cast<int>(idx / HW);
+  const long long pix = idx % HW;
+  const SphereObj o = sphere_obj(circles + n * 3, H, W);
+  masks[idx] = sphere_value(o, static_cast<int>(pix % W), static_cast<int>(pix / W));
+}
+
+// The scatter + unshuffle kernel with the masks generated on the fly from the circles (no mask tensor anywhere).
+// Same selection rule and arithmetic as traj_unshuffle_kernel fed with sphere_mask_kernel's output (bit-identical).
+constexpr int TRAJ_MAX_OBJ = 8;
+__global__ void __launch_bounds__(256)
+traj_circles_unshuffle_kernel(const float* __restrict__ info, const float* __restrict__ circles,
+                              __nv_bfloat16* __restrict__ feat, float* __restrict__ mask_out, int BF, int n_obj, int H,
+                              int W) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int h8 = H >> 3, w8 = W >> 3;
+  const long long HW = static_cast<long long>(H) * W;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(BF) * h8 * w8 * 8;
+  if (idx >= total) return;
+  const int dy = static_cast<int>(idx & 7);
+  long long t = idx >> 3;
+  const int cx = static_cast<int>(t % w8);
+  t /= w8;
+  const int cy = static_cast<int>(t % h8);
+  const int n = static_cast<int>(t / h8);
+  const int py = cy * 8 + dy;
+  int sel[8];
+  float m[8];
+#pragma unroll
+  for (int dx = 0; dx < 8; ++dx) {
+    sel[dx] = -1;
+    m[dx] = 0.f;
+  }
+  for (int o = 0; o < n_obj; ++o) {
+    const SphereObj so = sphere_obj(circles + (static_cast<long long>(n) * n_obj + o) * 3, H, W);
+#pragma unroll
+    for (int dx = 0; dx < 8; ++dx) {
+      const float mo = sphere_value(so, cx * 8 + dx, py);
+      if (mo > 0.f) {
+        sel[dx] = o;
+        m[dx] = mo;
+      }
+    }
+  }
+  const long long pix0 = static_cast<long long>(py) * W + cx * 8;
+  float4* mo4 = reinterpret_cast<float4*>(mask_out + static_cast<long long>(n) * HW + pix0);
+  mo4[0] = make_float4(m[0], m[1], m[2], m[3]);
+  mo4[1] = make_float4(m[4], m[5], m[6], m[7]);
+  const float* inf = info + static_cast<long long>(n) * n_obj * 12;
+  __nv_bfloat16* cell = feat + ((static_cast<long long>(n) * h8 + cy) * w8 + cx) * 832 + dy * 8;
+#pragma unroll
+  for (int c = 0; c < 12; ++c) {
+    float r[8];
+#pragma unroll
+    for (int dx = 0; dx < 8; ++dx) {
+      const float iv = sel[dx] >= 0 ? __ldg(inf + sel[dx] * 12 + c) : 0.f;
+      r[dx] = __fmul_rn(__fmul_rn(iv, m[dx]), m[dx]);
+    }
+    *reinterpret_cast<uint4*>(cell + c * 64) = pack8(r);
+  }
+  float r[8];
+#pragma unroll
+  for (int dx = 0; dx < 8; ++dx) r[dx] = __fmul_rn(m[dx], m[dx]);
+  *reinterpret_cast<uint4*>(cell + 12 * 64) = pack8(r);
+}
+
 // Mask modulation of an ObjectEncoder level (fmc/adapter.py:175-177): out[n, y, x, :] = x[n, y, x, :] * mask[n, ry[y], rx[x]]
 // where ry / rx compose the iterated nearest-neighbour resizes down to this level (built on the host).
 __global__ void __launch_bounds__(256)
@@ -633,4 +749,25 @@ extern "C" int fmc_window_combine_ddim_f32(const float* eps_windows, int n_windo
            n_windows, cfg, guidance_scale, latents, latents_out, b, C, F_total, HW, L, stride, sqrtf(alpha_t),
            sqrtf(1.f - alpha_t), sqrtf(alpha_prev), sqrtf(1.f - alpha_prev));
   return check_launch("window_combine_ddim_kernel");
+}
+
+extern "C" int fmc_sphere_mask_f32(const float* circles, float* masks, int BF, int n_obj, int H, int W, void* stream) {
+  FMC_REQUIRE(circles && masks, FMC_ERR_ARG, "fmc_sphere_mask_f32: null operand");
+  const long long total = static_cast<long long>(BF) * n_obj * H * W;
+  if (total == 0) return FMC_OK;
+  FMC_REQUIRE(static_cast<long long>(BF) * n_obj < (1LL << 31), FMC_ERR_SHAPE, "fmc_sphere_mask_f32: too many objects");
+  launch_k(sphere_mask_kernel, dim3(blocks_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), circles, masks,
+           BF * n_obj, H, W);
+  return check_launch("sphere_mask_kernel");
+}
+
+extern "C" int fmc_traj_scatter_circles_unshuffle_bf16(const float* info, const float* circles, void* feat,
+                                                       float* mask_out, int BF, int n_obj, int H, int W, void* stream) {
+  FMC_REQUIRE(info && circles && feat && mask_out, FMC_ERR_ARG, "fmc_traj_scatter_circles_unshuffle_bf16: null operand");
+  FMC_REQUIRE(H % 8 == 0 && W % 8 == 0, FMC_ERR_SHAPE, "fmc_traj_scatter_circles_unshuffle_bf16: H=%d W=%d must be multiples of 8", H, W);
+  const long long total = static_cast<long long>(BF) * (H / 8) * (W / 8) * 8;
+  if (total == 0) return FMC_OK;
+  launch_k(traj_circles_unshuffle_kernel, dim3(blocks_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), info,
+           circles, static_cast<__nv_bfloat16*>(feat), mask_out, BF, n_obj, H, W);
+  return check_launch("traj_circles_unshuffle_kernel");
 }

@@ -47,6 +47,20 @@ def traj_features_cl(info, masks, omcm, null_clips=None):
     return [CL(o.view(B, Fn, *o.shape[1:])) for o in outs]
 
 
+def traj_features_from_circles(info, circles, omcm, H, W):
+    """Device-side form of the `use_sphere_mask` preprocessing (fmc/data/dataset.py:5350-5403) + get_traj_features_v2:
+    info [B, F, n, 12] and circles [B, F, n, 3] = (cx, cy, r) of every object's minimum enclosing circle (device fp32;
+    r <= 0 = absent) -> 4 CL features.  The Gaussian masks are generated inside the scatter kernel: no [n, H, W] mask
+    tensors on the host, no H2D copy of them, no mask reads."""
+    B, Fn, n, _ = circles.shape
+    if engine.precise():
+        masks = ops.sphere_masks(circles.reshape(B * Fn, n, 3), H, W)
+        return traj_features_cl(info, masks.view(B, Fn, n, H, W), omcm)
+    feat, mask = ops.traj_scatter_circles_unshuffle(info.reshape(B * Fn, n, 12), circles.reshape(B * Fn, n, 3), H, W)
+    outs = omcm.encode_cl(feat, mask)
+    return [CL(o.view(B, Fn, *o.shape[1:])) for o in outs]
+
+
 def get_traj_features_v2(obj_info_list_list, obj_mask_list_list, omcm, cfg_random_null_om, cfg_random_null_om_ratio,
                          is_cm_condition_null_list, local_rank, dtype):
     """Reference signature; returns 4 tensors [b, C_l, f, h_l, w_l] (fp32, reference layout)."""

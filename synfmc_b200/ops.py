@@ -382,6 +382,31 @@ def traj_scatter_unshuffle(info, masks):
     return feat, mask
 
 
+def sphere_masks(circles, H, W):
+    """circles [BF, n_obj, 3] = (cx, cy, r) fp32 -> Gaussian sphere masks [BF, n_obj, H, W] fp32 (fmc_sphere_mask_f32)."""
+    _check_cuda(circles)
+    circles = circles.contiguous().float()
+    BF, n_obj, _ = circles.shape
+    out = torch.empty((BF, n_obj, H, W), device=circles.device, dtype=torch.float32)
+    _cabi.call("fmc_sphere_mask_f32", circles.data_ptr(), out.data_ptr(), BF, n_obj, H, W, _stream())
+    return out
+
+
+def traj_scatter_circles_unshuffle(info, circles, H, W):
+    """info [BF, n_obj, 12], circles [BF, n_obj, 3] -> (feat [BF, H/8, W/8, 832] bf16, mask [BF, H, W] fp32): the object
+    scatter with the Gaussian sphere masks generated on the fly."""
+    _check_cuda(info, circles)
+    info = info.contiguous().float()
+    circles = circles.contiguous().float()
+    BF, n_obj, _ = circles.shape
+    assert info.shape == (BF, n_obj, 12)
+    feat = torch.empty((BF, H // 8, W // 8, 832), device=info.device, dtype=BF16)
+    mask = torch.empty((BF, H, W), device=info.device, dtype=torch.float32)
+    _cabi.call("fmc_traj_scatter_circles_unshuffle_bf16", info.data_ptr(), circles.data_ptr(), feat.data_ptr(),
+               mask.data_ptr(), BF, n_obj, H, W, _stream())
+    return feat, mask
+
+
 def mask_modulate(x, mask, row_index, col_index):
     """x [N, h, w, C] bf16 / fp32, mask [N, H, W] fp32, index maps int32 [h], [w]."""
     _check_cuda(x, mask)

@@ -109,6 +109,28 @@ def synth_objects(b, f, H, W, n_obj, seed=0, gaussian=True):
     return infos, masks
 
 
+def synth_circles(b, f, H, W, n_obj, seed=0):
+    """Object poses + minimum-enclosing circles (what the dataset's `use_sphere_mask` branch derives from the segmentation
+    masks, fmc/data/dataset.py:5359): info [b, f, n_obj, 12] fp32 and circles [b, f, n_obj, 3] = (cx, cy, r) fp32 with
+    sub-pixel centres on a random walk, radii 20 - 80 px, overlapping objects, and one absent object (r = 0) per clip
+    when n_obj > 1."""
+    g = _gen("circles", seed)
+    info = torch.randn(b, f, n_obj, 12, generator=g)
+    info[..., 3::4] *= 0.1
+    circles = torch.zeros(b, f, n_obj, 3)
+    for bi in range(b):
+        radius = 20 + 60 * torch.rand(n_obj, generator=g)
+        radius = torch.minimum(radius, torch.tensor(min(H, W) / 3.0))
+        c0 = torch.tensor([W / 2.0, H / 2.0]) + (torch.rand(n_obj, 2, generator=g) - 0.5) * float(radius.mean()) * 1.5
+        vel = (torch.rand(n_obj, 2, generator=g) - 0.5) * 6.0
+        for fi in range(f):
+            circles[bi, fi, :, :2] = c0 + vel * fi
+            circles[bi, fi, :, 2] = radius * (1.0 + 0.01 * fi)
+        if n_obj > 1:
+            circles[bi, f // 2, n_obj - 1, 2] = 0.0  # the object leaves the frame: empty segmentation mask
+    return info, circles
+
+
 def synth_step_inputs(b, f, h, w, cfg=True, seed=0, text_len=77, text_dim=768):
     """Latents ~ N(0,1) [b,4,f,h,w]; text embeddings ~ 0.5 N(0,1) (CLIP-like scale), uncond = a different draw."""
     g = _gen("step_inputs", seed)

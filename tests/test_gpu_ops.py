@@ -512,6 +512,28 @@ def test_traj_scatter_bit_exact(ops, cuda_device, n_obj, gaussian):
     assert torch.equal(un_mask.cpu(), maskf.reshape(b * f, H, W))
 
 
+@pytest.mark.parametrize("n_obj,H,W", [(1, 64, 96), (3, 128, 192), (3, 320, 512)])
+def test_sphere_masks_and_fused_scatter(ops, cuda_device, n_obj, H, W):
+    """On-device `use_sphere_mask` preprocessing (fmc/data/dataset.py:5350-5403): Gaussian disc masks from the minimum
+    enclosing circles vs the numpy restatement (fp64) -- values to fp32 accuracy, IDENTICAL support -- and the scatter
+    with the masks generated on the fly vs scatter(masks): bit-identical features and combined mask."""
+    from oracle.sphere_mask import sphere_masks as o_masks
+    from synfmc_b200 import synth
+    b, f = 1, 4
+    info, circles = synth.synth_circles(b, f, H, W, n_obj, seed=n_obj)
+    want = torch.from_numpy(o_masks(circles.numpy(), H, W)).view(b * f, n_obj, H, W)
+    got = ops.sphere_masks(circles.view(b * f, n_obj, 3).to(cuda_device), H, W)
+    assert torch.equal(got.cpu() > 0, want > 0)
+    assert float((got.cpu().double() - want).abs().max()) < 2e-6
+    assert float(got.max()) <= 1.0 and float(want.max()) == 1.0
+    if n_obj > 1:
+        assert float(got.view(b, f, n_obj, H, W)[0, f // 2, n_obj - 1].abs().max()) == 0.0  # absent object
+    d_info = info.view(b * f, n_obj, 12).to(cuda_device)
+    feat2, mask2 = ops.traj_scatter_unshuffle(d_info, got)
+    feat1, mask1 = ops.traj_scatter_circles_unshuffle(d_info, circles.view(b * f, n_obj, 3).to(cuda_device), H, W)
+    assert torch.equal(mask1, mask2) and torch.equal(feat1, feat2)
+
+
 def test_mask_modulate_iterated_nearest(ops, cuda_device):
     """fmc/adapter.py:175-177: the mask is resized level after level with F.interpolate(mode='nearest')."""
     from synfmc_b200.engine import nearest_index_chain
