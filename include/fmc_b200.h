@@ -205,6 +205,19 @@ int fmc_window_combine_ddim_f32(const float* eps_windows, int n_windows, int cfg
                                 const float* latents, float* latents_out, int b, int C, int F_total, long long HW, int L,
                                 int stride, float alpha_t, float alpha_prev, void* stream);
 
+/* Training-step tail on flat fp32 buffers (train_cam_ctrl.py:647-665, train_cam_obj_ctrl.py:843-862: scaler.unscale_ ->
+ * clip_grad_norm_ -> AdamW.step -- three passes over the trainable set in the reference), after the gradient all-reduce.
+ * fmc_grad_norm_f32: state[0] = L2 norm of grad * inv_scale, state[1] = inv_scale * min(1, max_norm / (norm + 1e-6)) (max_norm
+ * <= 0: no clipping), state[2] = 1 if any gradient is inf / nan; deterministic (two-stage sum, no atomics); workspace:
+ * fmc_grad_norm_workspace_floats() floats.  fmc_adamw_step_f32: torch.optim.AdamW (no amsgrad) on grad * state[1], skipped
+ * entirely when state[2] != 0 (GradScaler.step); state = NULL: plain step on the gradients as they are.  Nothing returns
+ * to the host, so both can sit in a captured graph. */
+int fmc_grad_norm_workspace_floats(void);
+int fmc_grad_norm_f32(const float* grad, long long n, float inv_scale, float max_norm, float* workspace, float* state,
+                      void* stream);
+int fmc_adamw_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int step, const float* state, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Reference-precision mode (BASELINE config 1, "output parity vs reference" at 1e-3 rel): fp32 activations between
  * kernels, linears on tcgen05.mma.kind::tf32, attention / norms / glue in fp32 (csrc/precise.cu).  Each entry point

@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Collective + optimizer half of the config-3 training step on N GPUs (one collective per step, the gradient
+all-reduce of the CMC trainable set, 218 M fp32 = 873 MB; config 4 / OMC: 152.5 M = 610 MB): bucketed NCCL all-reduce of
+the flat gradient buffer (synfmc_b200.train.GradAllReduce) + the fused unscale * clip * AdamW step (FusedAdamW).
+The backward kernels that would PRODUCE these gradients are not built, so the gradients here are
+synthetic and rank-dependent with a known sum -- what is measured is the collective and the optimizer, checked exactly.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29513 \
+        profiles/allreduce_bench.py [--params-m 218] [--bucket-mb 64]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--params-m", type=float, default=218.0)
+    ap.add_argument("--bucket-mb", type=int, default=64)
+    ap.add_argument("--reps", type=int, default=10)
+    args = ap.parse_args()
+    from synfmc_b200 import shard
+    from synfmc_b200.train import FlatParams, FusedAdamW, GradAllReduce
+    rank, world, local = shard.world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    shard.init(backend="nccl", device=dev)
+    n_tensors = 200
+    per = int(args.params_m * 1e6 / n_tensors) // 4 * 4
+    g = torch.Generator(device="cpu").manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(per, generator=g).to(dev)) for _ in range(n_tensors)]
+    flat = FlatParams(params)
+    red = GradAllReduce(flat, bucket_bytes=args.bucket_mb << 20)
+    opt = FusedAdamW(flat, lr=1e-4, max_grad_norm=1.0)
+    base = torch.randn(flat.numel, generator=g).to(dev)
+
+    def fill():
+        flat.grads.copy_(base).mul_(float(rank + 1))  # sum over ranks = base * world (world + 1) / 2
+
+    def timed(fn, reps):
+        shard.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total = 0.0
+        for _ in range(reps):
+            fill()
+            torch.cuda.synchronize()
+            shard.barrier()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            total += shard.max_over_ranks(e0.elapsed_time(e1), device=dev)
+        return total / reps
+    red.reduce_all()  # warm-up (NCCL communicator, buffers)
+    fill()
+    red.reduce_all()
+    torch.cuda.synchronize()
+    want = base * (world * (world + 1) / 2.0)
+    exact = bool(torch.allclose(flat.grads, want, rtol=1e-6, atol=0))
+    ms_ar = timed(lambda: red.reduce_all(), args.reps)
+    ms_opt = timed(lambda: opt.step(loss_scale=65536.0, world=world), args.reps)
+    ms_both = timed(lambda: (red.reduce_all(), opt.step(loss_scale=65536.0, world=world)), args.reps)
+    nbytes = flat.numel * 4
+    if rank == 0:
+        print(json.dumps({"what": "gradient all-reduce + fused AdamW on the flat trainable set", "n_gpus": world,
+                          "params_m": round(flat.numel / 1e6, 1), "grad_mb": round(nbytes / 1e6, 1),
+                          "buckets": len(red.buckets), "bucket_mb": args.bucket_mb,
+                          "allreduce_ms": round(ms_ar, 3),
+                          "allreduce_bus_gbs": round(2 * (world - 1) / world * nbytes / (ms_ar * 1e-3) / 1e9, 1) if world > 1 else None,
+                          "fused_norm_adamw_ms": round(ms_opt, 3),
+                          "optimizer_hbm_gbs": round(flat.numel * 32 / (ms_opt * 1e-3) / 1e9, 1),
+                          "allreduce_plus_optimizer_ms": round(ms_both, 3), "allreduced_sum_exact": exact,
+                          "found_inf": opt.found_inf(), "grad_norm": opt.last_norm()}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,8 @@ SIGNATURES = {
     "fmc_mask_modulate_bf16": [P, P, P, P, P, I, I, I, I, I, I, P],
     "fmc_cfg_ddim_step_f32": [P, P, F, P, P, P, F, F, L, P],
     "fmc_window_combine_ddim_f32": [P, I, I, F, P, P, I, I, I, L, I, I, F, F, P],
+    "fmc_grad_norm_f32": [P, L, F, F, P, P, P],
+    "fmc_adamw_step_f32": [P, P, P, P, L, F, F, F, F, F, I, P, P],
     # reference-precision mode (csrc/precise.cu)
     "fmc_gemm_tf32": [P, L, P, L, P, L, I, I, I, P, P, L, P, I, L, I, I, P],
     "fmc_split_tf32": [P, L, P, L, L, I, P],
@@ -80,6 +82,8 @@ def lib():
         handle.fmc_abi_version.argtypes = []
         handle.fmc_groupnorm_launches.restype = c_int
         handle.fmc_groupnorm_launches.argtypes = [c_int, c_int, c_int]
+        handle.fmc_grad_norm_workspace_floats.restype = c_int
+        handle.fmc_grad_norm_workspace_floats.argtypes = []
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the .so does not export what the header declares
             fn.restype = c_int
@@ -96,8 +100,8 @@ def lib():
 def _kernels_per_call(handle, name, args):
     if name == "fmc_groupnorm_bf16":
         return handle.fmc_groupnorm_launches(args[9], args[10], args[11])  # HW, C, groups
-    if name == "fmc_groupnorm_f32":
-        return 2  # statistics + apply
+    if name in ("fmc_groupnorm_f32", "fmc_grad_norm_f32"):
+        return 2  # statistics + apply / partial sums + finalize
     return 1
 launch_count = 0  # kernels of this library launched by this process (bench.py reports it as gpu_launches)
 trace = None      # when set to a list by bench.py: (name, args, start_event, end_event) per call, CUDA events on the

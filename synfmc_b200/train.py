@@ -1,0 +1,149 @@
+"""Training-step tail for the FMC trainers: what follows `loss.backward()` in
+train_cam_ctrl.py:647-665 / train_cam_obj_ctrl.py:843-862 -- DDP's gradient all-reduce, `scaler.unscale_`,
+`clip_grad_norm_`, `AdamW.step`, `zero_grad` -- on ONE flat fp32 buffer per role (values, gradients, two Adam moments):
+
+  * `FlatParams`      re-homes the trainable parameters (CMC: CameraEncoder + 20 qkv_merge = 218 M; OMC: the ObjectEncoder,
+                      152.5 M) into a flat buffer and makes every `p.grad` a view of a flat gradient buffer, so autograd
+                      accumulates straight into it;
+  * `GradAllReduce`   buckets the flat gradient (default 64 MiB: sized for launch latency and overlap, not link count --
+                      NVSwitch gives every GPU full bandwidth to every peer) and all-reduces each bucket with NCCL as
+                      soon as the last gradient of the bucket has been produced (post-accumulate-grad hooks), i.e.
+                      overlapped with the rest of backward; the mean's 1 / world is folded into the unscale factor;
+  * `FusedAdamW`      fmc_grad_norm_f32 + fmc_adamw_step_f32: one read of the gradients for the global norm, one fused
+                      unscale * clip * AdamW pass; the clip coefficient and the found-inf flag never leave the device.
+
+The BACKWARD kernels of the hot path do not exist yet: the mirror modules raise under autograd.  These
+classes are the collective + optimizer half of the training step, usable today with gradients from any source (the
+tests feed them torch-autograd gradients of small modules and compare with DDP-style mean + torch.optim.AdamW)."""
+import torch
+import torch.distributed as dist
+
+from . import _cabi, ops
+
+
+class FlatParams:
+    def __init__(self, params, device=None):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        device = torch.device(device) if device is not None else self.params[0].device
+        self.offsets, total = [], 0
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise TypeError("FlatParams keeps fp32 master parameters (the reference trains fp32 weights under autocast)")
+            self.offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4  # every parameter starts 16-byte aligned (float4 access in the kernels)
+        self.numel = total
+        self.values = torch.zeros(total, device=device, dtype=torch.float32)
+        self.grads = torch.zeros(total, device=device, dtype=torch.float32)
+        with torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                view = self.values[off:off + p.numel()].view(p.shape)
+                view.copy_(p.detach())
+                p.data = view
+        self.attach_grads()
+
+    def attach_grads(self):
+        """(Re-)point every `p.grad` at its slice of the flat gradient buffer (after a `zero_grad(set_to_none=True)`)."""
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.grads[off:off + p.numel()].view(p.shape)
+
+    def zero_grad(self):
+        self.grads.zero_()
+        self.attach_grads()
+
+
+class GradAllReduce:
+    """Bucketed, backward-overlapped all-reduce (SUM; the division by world size happens in FusedAdamW's unscale factor)."""
+
+    def __init__(self, flat, bucket_bytes=64 << 20, group=None):
+        self.flat, self.group = flat, group
+        per = max(4, bucket_bytes // 4 // 4 * 4)
+        # buckets are ranges of the flat buffer cut at parameter boundaries, filled from the END of the parameter list:
+        # backward produces the gradients of the last layers first
+        self.buckets, start = [], flat.numel
+        idx_end = len(flat.params)
+        i = len(flat.params) - 1
+        while i >= 0:
+            if start - flat.offsets[i] >= per or i == 0:
+                self.buckets.append((flat.offsets[i], start, range(i, idx_end)))
+                start, idx_end = flat.offsets[i], i
+            i -= 1
+        self.bucket_of = {}
+        for b, (_, _, idxs) in enumerate(self.buckets):
+            for j in idxs:
+                self.bucket_of[j] = b
+        self.pending, self.handles, self.hooks = [], [], []
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def install_hooks(self):
+        """Launch a bucket's all-reduce from inside backward, when its last gradient has been accumulated."""
+        self.reset()
+        for j, p in enumerate(self.flat.params):
+            self.hooks.append(p.register_post_accumulate_grad_hook(lambda _p, j=j: self._ready(j)))
+        return self
+
+    def reset(self):
+        self.pending = [len(idxs) for _, _, idxs in self.buckets]
+        self.handles = []
+
+    def _ready(self, j):
+        b = self.bucket_of[j]
+        self.pending[b] -= 1
+        if self.pending[b] == 0:
+            self._launch(b)
+
+    def _launch(self, b):
+        lo, hi, _ = self.buckets[b]
+        if self.world > 1:
+            self.handles.append(dist.all_reduce(self.flat.grads[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def reduce_all(self):
+        """Without hooks: all buckets now (last layers first)."""
+        self.reset()
+        for b in range(len(self.buckets)):
+            self._launch(b)
+        return self.wait()
+
+    def wait(self):
+        for h in self.handles:
+            h.wait()
+        self.reset()
+        return self.world
+
+
+class FusedAdamW:
+    """torch.optim.AdamW(lr, betas, eps, weight_decay) + GradScaler.unscale_ + clip_grad_norm_ on a FlatParams, as two
+    kernels (train_cam_ctrl.py:321-327, :647-655).  `step()` never synchronises; `last_norm()` / `found_inf()` read the
+    device-side state when the caller wants them (GradScaler.update needs found_inf once per step)."""
+
+    def __init__(self, flat, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0):
+        self.flat, self.lr, self.betas, self.eps, self.weight_decay = flat, lr, betas, eps, weight_decay
+        self.max_grad_norm = max_grad_norm
+        dev = flat.values.device
+        self.exp_avg = torch.zeros_like(flat.values)
+        self.exp_avg_sq = torch.zeros_like(flat.values)
+        self.state = torch.zeros(4, device=dev, dtype=torch.float32)  # norm, coefficient, found_inf
+        self.workspace = torch.zeros(_cabi.lib().fmc_grad_norm_workspace_floats(), device=dev, dtype=torch.float32)
+        self.steps = 0
+
+    def step(self, loss_scale=1.0, world=1, lr=None):
+        """One optimizer step on the gradients in `flat.grads` = SUM over `world` ranks of `loss_scale` * dL/dp."""
+        ops._check_cuda(self.flat.values, self.flat.grads)
+        f = self.flat
+        self.steps += 1
+        stream = ops._stream()
+        _cabi.call("fmc_grad_norm_f32", f.grads.data_ptr(), f.numel, 1.0 / (float(loss_scale) * world),
+                   float(self.max_grad_norm or 0.0), self.workspace.data_ptr(), self.state.data_ptr(), stream)
+        _cabi.call("fmc_adamw_step_f32", f.values.data_ptr(), f.grads.data_ptr(), self.exp_avg.data_ptr(),
+                   self.exp_avg_sq.data_ptr(), f.numel, float(self.lr if lr is None else lr), float(self.betas[0]),
+                   float(self.betas[1]), float(self.eps), float(self.weight_decay), self.steps, self.state.data_ptr(), stream)
+
+    def zero_grad(self, set_to_none=False):
+        self.flat.zero_grad()
+
+    def last_norm(self):
+        return float(self.state[0])
+
+    def found_inf(self):
+        return bool(self.state[2] != 0)

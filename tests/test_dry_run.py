@@ -191,3 +191,22 @@ def test_windowed_pipeline_call_sequence(recorder, form, obj):
     conv_in = [a for n, a in recorder.calls if n == "fmc_conv3x3_bf16" and a[8] == 64 and a[9] == 320]
     assert len(conv_in) == 2 * n_win                # one U-Net pass per window per step
     assert encoded == ([L] * n_win if form == "list" else [F_total])
+
+
+def test_circle_driven_object_path_call_sequence(recorder):
+    """object features straight from the objects' circles -- the fused sphere-mask scatter in bf16 mode
+    (no mask tensor), sphere masks -> bit-exact fp32 scatter in the reference-precision mode."""
+    from synfmc_b200 import synth
+    from synfmc_b200.fmc.util import traj_features_from_circles
+    channels = (320, 640, 1280, 1280)
+    omcm = helpers.build_product_omcm(helpers.build_oracle_omcm(channels), channels, device="cpu")
+    info, circles = synth.synth_circles(1, 2, 64, 64, 3, seed=1)
+    for mode, must, never in (("bf16", "fmc_traj_scatter_circles_unshuffle_bf16", "fmc_sphere_mask_f32"),
+                              ("reference", "fmc_sphere_mask_f32", "fmc_traj_scatter_circles_unshuffle_bf16")):
+        recorder.calls.clear()
+        with engine.precision(mode):
+            feats = traj_features_from_circles(info, circles, omcm, 64, 64)
+        assert [f.dims for f in feats] == [(1, 2, 8, 8, 320), (1, 2, 4, 4, 640), (1, 2, 2, 2, 1280), (1, 2, 1, 1, 1280)]
+        names = recorder.names()
+        assert must in names and never not in names
+        assert not any(n in ("fmc_traj_scatter_unshuffle_bf16",) for n in names)  # no mask tensor is ever read in bf16 mode
