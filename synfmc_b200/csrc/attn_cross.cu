@@ -311,10 +311,9 @@ template <int D>
 static int launch_ca(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CaParams& p,
                      cudaStream_t stream) {
   using Cfg = CaCfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per device: the attribute belongs to the (device, function) pair
+  if (first_use_on_this_device(&attr_devs)) {
     FMC_CUDA_OK(cudaFuncSetAttribute(cross_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   const int items = p.clips * p.heads * p.chunks;
   const int grid = items < device_sm_count() ? items : device_sm_count();

@@ -743,10 +743,9 @@ template <int D, bool VF16>
 static int launch_fa2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FaParams& p,
                       cudaStream_t stream) {
   using Cfg = Fa2Cfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per device: the attribute belongs to the (device, function) pair
+  if (first_use_on_this_device(&attr_devs)) {
     FMC_CUDA_OK(cudaFuncSetAttribute(spatial_attn2_kernel<D, VF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   const int items = p.images * p.heads * ((p.nq + 2 * FA_BM - 1) / (2 * FA_BM));
   const int grid = items < device_sm_count() ? items : device_sm_count();
@@ -758,10 +757,9 @@ template <int D>
 static int launch_fa(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FaParams& p,
                      cudaStream_t stream) {
   using Cfg = FaCfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per device: the attribute belongs to the (device, function) pair
+  if (first_use_on_this_device(&attr_devs)) {
     FMC_CUDA_OK(cudaFuncSetAttribute(spatial_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   const int items = p.images * p.heads * p.q_blocks;
   const int grid = items < device_sm_count() ? items : device_sm_count();

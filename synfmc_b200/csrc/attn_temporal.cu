@@ -283,10 +283,9 @@ temporal_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, TaParams p) {
 template <int D>
 static int launch_ta(const CUtensorMap& tm, const TaParams& p, cudaStream_t stream) {
   using Cfg = TaCfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per device: the attribute belongs to the (device, function) pair
+  if (first_use_on_this_device(&attr_devs)) {
     FMC_CUDA_OK(cudaFuncSetAttribute(temporal_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   const int items = p.B * p.tiles_per_b * p.heads;
   const int grid = items < device_sm_count() ? items : device_sm_count();

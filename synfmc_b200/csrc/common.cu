@@ -24,15 +24,28 @@ bool pdl_enabled() {
   return on;
 }
 
+int current_device_ordinal() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  return dev;
+}
+
 int device_sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  static int cached[64] = {0};
+  const int dev = current_device_ordinal() & 63;
+  if (cached[dev] == 0) {
+    int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-    cached = n;
+    cached[dev] = n;
   }
-  return cached;
+  return cached[dev];
+}
+
+bool first_use_on_this_device(unsigned long long* seen_mask) {
+  const unsigned long long bit = 1ull << (current_device_ordinal() & 63);
+  if (*seen_mask & bit) return false;
+  *seen_mask |= bit;
+  return true;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -50,7 +50,12 @@ inline int check_launch(const char* what) {
   return FMC_OK;
 }
 
-int device_sm_count();
+int device_sm_count();  // of the CURRENT device (cached per device ordinal)
+
+// true exactly once per (call site, current device): guards cudaFuncSetAttribute calls, which apply per device
+// (a process may drive several GPUs; one process per GPU is the normal deployment)
+bool first_use_on_this_device(unsigned long long* seen_mask);
+int current_device_ordinal();
 
 // Programmatic dependent launch: every kernel of this library starts with pdl_wait() (griddepcontrol.wait: all memory
 // of the preceding kernel is visible once it returns) and is launched with programmatic stream serialisation allowed,

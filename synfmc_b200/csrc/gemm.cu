@@ -759,11 +759,10 @@ template <int BN, bool GEGLU, int CL, bool CONV = false>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                         GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN, GEGLU, CL>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per device: the attribute belongs to the (device, function) pair
+  if (first_use_on_this_device(&attr_devs)) {
     FMC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tma_kernel<BN, GEGLU, CL, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   p.tiles_m = ceil_div(p.M, GEMM_BM);
   p.tiles_n = ceil_div(p.N, BN);
@@ -798,10 +797,9 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per device: the attribute belongs to the (device, function) pair
+  if (first_use_on_this_device(&attr_devs)) {
     FMC_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   p.tiles_m = ceil_div(p.M, GEMM_BM);
   p.tiles_n = ceil_div(p.N, BN);

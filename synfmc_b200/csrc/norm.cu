@@ -1179,10 +1179,9 @@ static int launch_gn_tma_persist(const GnTmaPlan& pl, const void* x, long long l
   const int items = chunks * images;
   const int slab_stride = (pl.slab + 127) & ~127;
   const size_t smem = static_cast<size_t>(2) * slab_stride + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per device: the attribute belongs to the (device, function) pair
+  if (first_use_on_this_device(&attr_devs)) {
     FMC_CUDA_OK(cudaFuncSetAttribute(groupnorm_tma_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (GNT_MAX_SLAB + 128) + 128));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(GNF_THREADS);
@@ -1197,7 +1196,7 @@ static int launch_gn_tma_persist(const GnTmaPlan& pl, const void* x, long long l
   ++na;
   // resident clusters for this (cluster size, shared memory) configuration: cached per configuration
   static int cached_key = -1, cached_clusters = 0;
-  const int key = pl.cluster * 1000000 + static_cast<int>(smem / 128);
+  const int key = (current_device_ordinal() & 63) * 100000000 + pl.cluster * 1000000 + static_cast<int>(smem / 128);
   if (key != cached_key) {
     cfg.gridDim = dim3(pl.cluster, 1, 1);
     cfg.attrs = attr;
@@ -1417,7 +1416,8 @@ extern "C" int fmc_groupnorm_bf16(const void* x, long long ldx, const float* gam
   const int threads = nvec * (nvec >= 512 ? 1 : 512 / nvec);  // whole rows per pass, <= 1024 threads
   const int rows_par = threads / nvec;
   const size_t smem = static_cast<size_t>(2) * rows_par * C * sizeof(float);
-  static size_t smem_set = 0;
+  static size_t smem_set_dev[64] = {0};
+  size_t& smem_set = smem_set_dev[current_device_ordinal() & 63];
   if (smem > 48 * 1024 && smem > smem_set) {
     FMC_CUDA_OK(cudaFuncSetAttribute(groupnorm_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));

@@ -284,10 +284,9 @@ static int launch_gemm_tf32(const CUtensorMap& a0, const CUtensorMap& a1, const 
   using Cfg = PGemmCfg<BN>;
   p.tiles_m = ceil_div(p.M, PG_BM);
   p.tiles_n = ceil_div(p.N, BN);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per device: the attribute belongs to the (device, function) pair
+  if (first_use_on_this_device(&attr_devs)) {
     FMC_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
@@ -456,10 +455,9 @@ attention_f32_kernel(AttnF32Params p) {
 template <int D>
 static int launch_attention_f32(const AttnF32Params& p, cudaStream_t stream) {
   const int smem = (32 * (D + 1) + 32 * D + 4 * D * 8 + 4 * 32 * 8) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per device: the attribute belongs to the (device, function) pair
+  if (first_use_on_this_device(&attr_devs)) {
     FMC_CUDA_OK(cudaFuncSetAttribute(attention_f32_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
   }
   FMC_CUDA_OK(launch_k(attention_f32_kernel<D>, dim3(ceil_div(p.nq, 32), p.heads, p.images), dim3(128), smem, stream, p));
   return check_launch("attention_f32_kernel");

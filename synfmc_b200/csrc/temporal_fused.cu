@@ -503,10 +503,9 @@ extern "C" int fmc_temporal_qkv_attn_bf16(const void* X, long long ldx, const vo
   p.O = static_cast<__nv_bfloat16*>(O);
   p.ldo = ldo;
   p.timeline = g_tf_timeline;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // per device: the attribute belongs to the (device, function) pair
+  if (first_use_on_this_device(&attr_devs)) {
     FMC_CUDA_OK(cudaFuncSetAttribute(temporal_qkv_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES));
-    attr_set = true;
   }
   const int items = B * p.tiles_per_b * TF_HEADS;
   const int grid = items < device_sm_count() ? items : device_sm_count();

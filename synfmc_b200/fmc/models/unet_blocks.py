@@ -29,6 +29,12 @@ def _spatial_kwargs_ok(kw):
     extra = set(kw or {}) - {"pose_feature", "scale"}
     if extra:
         raise TypeError(f"unexpected cross_attention_kwargs for the spatial attention: {sorted(extra)}")
+    if (kw or {}).get("scale") is not None:
+        # attention_processor.py:118: a call-time `scale` overrides the processor's lora_scale.  Domain-LoRA is folded into
+        # the projection weights once per plan with processor.lora_scale, so a per-call value cannot be honoured: refuse
+        # (set `processor.lora_scale` instead -- the plans follow it)
+        raise NotImplementedError("cross_attention_kwargs['scale'] (call-time LoRA scale) is not supported: set "
+                                  "processor.lora_scale, the folded weights are rebuilt automatically")
 
 
 class UNetMidBlock3DCrossAttn(nn.Module):
