@@ -45,7 +45,7 @@ def main():
     def timed(fn, reps):
         shard.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        total = 0.0
+        mine = []
         for _ in range(reps):
             fill()
             torch.cuda.synchronize()
@@ -54,8 +54,12 @@ def main():
             fn()
             e1.record()
             torch.cuda.synchronize()
-            total += shard.max_over_ranks(e0.elapsed_time(e1), device=dev)
-        return total / reps
+            mine.append(e0.elapsed_time(e1))
+        mine.sort()
+        # median over the repetitions on every rank (a descheduled host thread between the start event and the launch
+        # shows up as a multi-ms outlier: the first 8-GPU run reported 7 ms for the collective-free optimizer step whose
+        # own kernels take 1.6 ms), then the slowest rank
+        return shard.max_over_ranks(mine[len(mine) // 2], device=dev)
     red.reduce_all()  # warm-up (NCCL communicator, buffers)
     fill()
     red.reduce_all()
