@@ -205,6 +205,58 @@ int fmc_window_combine_ddim_f32(const float* eps_windows, int n_windows, int cfg
                                 const float* latents, float* latents_out, int b, int C, int F_total, long long HW, int L,
                                 int stride, float alpha_t, float alpha_prev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Backward of the hot path (csrc/backward.cu; train_cam_ctrl.py:586-665 `scaler.scale(loss).backward()`): activation
+ * gradients through the frozen U-Net, parameter gradients for the trainable subset.  bf16 tensors in the forward's
+ * layouts, fp32 arithmetic.  Linear layers: dX = dY W is fmc_gemm_bf16 against a transposed weight copy, dW = dY^T X is
+ * fmc_gemm_bf16 (FMC_GEMM_OUT_F32) on operands transposed by fmc_transpose_bf16, bias gradients are fmc_colsum_f32.
+ * --------------------------------------------------------------------------------------------------------------- */
+int fmc_transpose_bf16(const void* x, long long ldx, void* out, long long ldo, long long rows, int cols, void* stream);
+
+/* out[n] (+)= sum_m x[m, n] (x bf16 or fp32), deterministic two-stage; workspace: fmc_colsum_workspace_floats(rows, cols). */
+int fmc_colsum_workspace_floats(long long rows, int cols);
+int fmc_colsum_f32(const void* x, long long ldx, int x_is_bf16, float* out, float* workspace, long long rows, int cols,
+                   int accumulate, void* stream);
+
+/* LayerNorm backward (nn.LayerNorm of fmc/models/motion_module.py:289,297 and diffusers BasicTransformerBlock): x = the
+ * forward's input rows, dy = gradient of the LayerNorm output (a positional-encoding add passes it through unchanged).
+ * param_partials (optional): [fmc_layernorm_bwd_blocks(rows), 2, C] fp32, per-block sums of dy * xhat (d gamma) and dy
+ * (d beta); fold them with fmc_colsum_f32. */
+int fmc_layernorm_bwd_blocks(long long rows);
+int fmc_layernorm_bwd_bf16(const void* x, long long ldx, const void* dy, long long lddy, const float* gamma, float eps,
+                           void* dx, long long lddx, float* param_partials, long long rows, int C, void* stream);
+
+/* GroupNorm backward with the forward's options (per-image channel bias added before the norm, SiLU after it), frozen
+ * affine parameters; stats_ws: 4 * images * groups floats. */
+int fmc_groupnorm_bwd_bf16(const void* x, long long ldx, const void* dy, long long lddy, const float* gamma,
+                           const float* beta, float eps, void* dx, long long lddx, float* stats_ws, int images, int HW, int C,
+                           int groups, int silu, const float* rowbias, long long ldrb, int rowbias_div, void* stream);
+
+/* GEGLU on the interleaved projection layout of FMC_GEMM_GEGLU (16 value | 16 gate column blocks): the training forward
+ * keeps the projection (fmc_gemm_bf16 without the flag) and applies y = value * gelu_erf(gate) here; backward returns the
+ * gradient of the projection. */
+int fmc_geglu_fwd_bf16(const void* proj, long long ldp, void* y, long long ldy, long long rows, int H, void* stream);
+int fmc_geglu_bwd_bf16(const void* proj, long long ldp, const void* dy, long long lddy, void* dproj, long long lddp,
+                       long long rows, int H, void* stream);
+
+int fmc_relu_bwd_bf16(const void* y, const void* dy, void* dx, long long n, void* stream);
+/* backward of fmc_resize_nearest_bf16 for integer upsampling factors (oh % h == 0, ow % w == 0) */
+int fmc_resize_nearest_bwd_bf16(const void* dy, void* dx, int N, int h, int w, int oh, int ow, int C, void* stream);
+int fmc_avgpool2_bwd_bf16(const void* dy, void* dx, int N, int h, int w, int C, void* stream);
+
+/* Attention backward (spatial self / text cross / temporal; row addressing and kv groups as fmc_attention_f32, head
+ * layout as the bf16 forward: Q / K heads at col0 + h * head_stride, V / O / dO heads at col0 + h * head_dim).
+ * Probabilities are recomputed flash-style; lse / dsum: fp32 [q_rows, heads] scratch (row log-sum-exp and sum_c dO O).
+ * dK = dV = NULL skips the key / value gradients (text cross-attention: the text is frozen); they are implemented for
+ * self-attention (kv_div = 1, nq = nk).  dQ / dK / dV use the Q / K / V layouts, so they can alias one [token, q|k|v]
+ * gradient buffer (zero-initialised: padding columns are not written). */
+int fmc_attention_bwd_bf16(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
+                           const void* V, long long ldv, int v_col0, int head_stride, const void* O, long long ldo,
+                           const void* dO, long long lddo, void* dQ, long long lddq, int dq_col0, void* dK, long long lddk,
+                           int dk_col0, void* dV, long long lddv, int dv_col0, float* lse, float* dsum, int images,
+                           int heads, int head_dim, int nq, int nk, int kv_div, int kv_stride, int inner, float scale,
+                           void* stream);
+
 /* Training-step tail on flat fp32 buffers (train_cam_ctrl.py:647-665, train_cam_obj_ctrl.py:843-862: scaler.unscale_ ->
  * clip_grad_norm_ -> AdamW.step -- three passes over the trainable set in the reference), after the gradient all-reduce.
  * fmc_grad_norm_f32: state[0] = L2 norm of grad * inv_scale, state[1] = inv_scale * min(1, max_norm / (norm + 1e-6)) (max_norm

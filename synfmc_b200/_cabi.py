@@ -41,6 +41,18 @@ SIGNATURES = {
     "fmc_mask_modulate_bf16": [P, P, P, P, P, I, I, I, I, I, I, P],
     "fmc_cfg_ddim_step_f32": [P, P, F, P, P, P, F, F, L, P],
     "fmc_window_combine_ddim_f32": [P, I, I, F, P, P, I, I, I, L, I, I, F, F, P],
+    # backward (csrc/backward.cu)
+    "fmc_transpose_bf16": [P, L, P, L, L, I, P],
+    "fmc_colsum_f32": [P, L, I, P, P, L, I, I, P],
+    "fmc_layernorm_bwd_bf16": [P, L, P, L, P, F, P, L, P, L, I, P],
+    "fmc_groupnorm_bwd_bf16": [P, L, P, L, P, P, F, P, L, P, I, I, I, I, I, P, L, I, P],
+    "fmc_geglu_fwd_bf16": [P, L, P, L, L, I, P],
+    "fmc_geglu_bwd_bf16": [P, L, P, L, P, L, L, I, P],
+    "fmc_relu_bwd_bf16": [P, P, P, L, P],
+    "fmc_resize_nearest_bwd_bf16": [P, P, I, I, I, I, I, I, P],
+    "fmc_avgpool2_bwd_bf16": [P, P, I, I, I, I, P],
+    "fmc_attention_bwd_bf16": [P, L, I, P, L, I, P, L, I, I, P, L, P, L, P, L, I, P, L, I, P, L, I, P, P, I, I, I, I, I, I,
+                               I, I, F, P],
     "fmc_grad_norm_f32": [P, L, F, F, P, P, P],
     "fmc_adamw_step_f32": [P, P, P, P, L, F, F, F, F, F, I, P, P],
     # reference-precision mode (csrc/precise.cu)
@@ -84,6 +96,10 @@ def lib():
         handle.fmc_groupnorm_launches.argtypes = [c_int, c_int, c_int]
         handle.fmc_grad_norm_workspace_floats.restype = c_int
         handle.fmc_grad_norm_workspace_floats.argtypes = []
+        handle.fmc_colsum_workspace_floats.restype = c_int
+        handle.fmc_colsum_workspace_floats.argtypes = [c_longlong, c_int]
+        handle.fmc_layernorm_bwd_blocks.restype = c_int
+        handle.fmc_layernorm_bwd_blocks.argtypes = [c_longlong]
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the .so does not export what the header declares
             fn.restype = c_int
@@ -100,8 +116,10 @@ def lib():
 def _kernels_per_call(handle, name, args):
     if name == "fmc_groupnorm_bf16":
         return handle.fmc_groupnorm_launches(args[9], args[10], args[11])  # HW, C, groups
-    if name in ("fmc_groupnorm_f32", "fmc_grad_norm_f32"):
+    if name in ("fmc_groupnorm_f32", "fmc_grad_norm_f32", "fmc_groupnorm_bwd_bf16", "fmc_colsum_f32"):
         return 2  # statistics + apply / partial sums + finalize
+    if name == "fmc_attention_bwd_bf16":
+        return 2 if args[17] else 1  # dQ kernel (+ dK / dV kernel)
     return 1
 launch_count = 0  # kernels of this library launched by this process (bench.py reports it as gpu_launches)
 trace = None      # when set to a list by bench.py: (name, args, start_event, end_event) per call, CUDA events on the
