@@ -8,12 +8,14 @@ from .ops import BF16, _check_cuda, _ptr, _rows2d, _stream
 F32 = torch.float32
 
 
-def transpose(x):
-    """bf16 [rows, cols] (row-strided) -> contiguous [cols, rows]."""
+def transpose(x, pad_rows_to=1):
+    """bf16 [rows, cols] (row-strided) -> contiguous [cols, rows]; with pad_rows_to = 8 the result is [cols, ceil8(rows)]
+    with zero columns at the end (the K extent of a following GEMM must be a multiple of 8)."""
     _check_cuda(x)
     _rows2d(x)
     rows, cols = x.shape
-    out = torch.empty((cols, rows), device=x.device, dtype=BF16)
+    padded = (rows + pad_rows_to - 1) // pad_rows_to * pad_rows_to
+    out = (torch.empty if padded == rows else torch.zeros)((cols, padded), device=x.device, dtype=BF16)
     _cabi.call("fmc_transpose_bf16", x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols, _stream())
     return out
 
@@ -140,4 +142,4 @@ def linear_dgrad(dy, w_t, residual=None):
 
 def linear_wgrad(dy, x):
     """dW [N_out, K_in] (fp32) = dY^T X on the tensor cores: both operands transposed into K-major form first."""
-    return ops.gemm(transpose(dy), transpose(x), out_f32=True)
+    return ops.gemm(transpose(dy, 8), transpose(x, 8), out_f32=True)

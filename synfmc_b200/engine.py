@@ -135,9 +135,11 @@ def refresh_plans(root, min_interval_s=0.0):
 
 
 def require_no_grad(module, *tensors):
-    """The product implements the FORWARD of the hot path (backward is a later row).  Under autograd the
+    """Training goes through the trainers' entry points -- `PoseAdaptor` / `CamObjPoseAdaptor.forward` and
+    `get_traj_features_v2` run the forward on a tape and hand torch.autograd the backward kernels
+    (synfmc_b200/train_engine.py).  A DIRECT call of a U-Net / encoder module under autograd is not part of that: its
     result would silently carry no grad_fn and `loss.backward()` would fail far away with torch's generic message -- fail
-    here, loudly, instead (train_cam_ctrl.py:586-648 runs the wrapper with grad enabled)."""
+    here, loudly, instead."""
     if not torch.is_grad_enabled():
         return
     needs = [n for n, p in module.named_parameters() if p.requires_grad]
@@ -145,9 +147,10 @@ def require_no_grad(module, *tensors):
     if needs or tens:
         what = f"{len(needs)} parameters (first: {needs[0]})" if needs else f"{len(tens)} input tensor(s)"
         raise RuntimeError(
-            f"{type(module).__name__}: called with autograd enabled and {what} requiring grad, but synfmc_b200 implements "
-            "the forward pass only (no backward kernels yet: SURVEY.md section 8f row 2). Wrap inference in "
-            "torch.no_grad(), or call .requires_grad_(False) on the module; training needs the reference path.")
+            f"{type(module).__name__}: called directly with autograd enabled and {what} requiring grad; this entry point is "
+            "forward pass only. Training is supported through PoseAdaptor / CamObjPoseAdaptor.forward and "
+            "fmc.util.get_traj_features_v2 (as train_cam_ctrl.py / train_cam_obj_ctrl.py call them); for inference wrap "
+            "the call in torch.no_grad() or call .requires_grad_(False) on the module.")
 
 
 # 3x3 convolutions: the 4-channel conv_in (zero-padded to 64) runs on fmc_conv3x3_bf16, the tcgen05 implicit-GEMM kernel

@@ -86,8 +86,8 @@ class Adapter(nn.Module):
 
     def forward(self, x, mask_feat):
         """Reference signature (:154): x [(b f), 13, H, W], mask_feat [(b f), 1, H, W] -> 4 x [(b f), C_l, h_l, w_l]."""
-        ops.require_cuda(x)
         engine.require_no_grad(self, x, mask_feat)
+        ops.require_cuda(x)
         n, c, H, W = x.shape
         x_cl = unshuffle8_to_cl(x.float().view(n, c, 1, H, W)).view(n, H // 8, W // 8, c * 64)
         mask = mask_feat.float().reshape(n, H, W).contiguous() if mask_feat is not None else None

@@ -163,8 +163,8 @@ class CameraPoseEncoder(nn.Module):
 
     def forward(self, x):
         """Reference signature (:224-240): x [b, 6, f, H, W] -> 4 tensors [(b f), C_l, h_l, w_l] (fp32)."""
-        ops.require_cuda(x)
         engine.require_no_grad(self, x)
+        ops.require_cuda(x)
         return [cl_to_frames_nchw(f) for f in self.encode_cl(unshuffle8_to_cl(x.float()))]
 
 
@@ -176,6 +176,10 @@ class PoseAdaptor(nn.Module):
 
     def forward(self, noisy_latents, timesteps, encoder_hidden_states, pose_embedding):
         assert pose_embedding.ndim == 5
-        engine.require_no_grad(self, noisy_latents, encoder_hidden_states, pose_embedding)
+        from ... import train_engine
+        if train_engine.wants_training(self, noisy_latents, pose_embedding):
+            # training step (train_cam_ctrl.py:586-648): forward on the tape, backward kernels behind loss.backward()
+            return train_engine.pose_adaptor_train_forward(self.unet, self.pose_encoder, noisy_latents, timesteps,
+                                                           encoder_hidden_states, pose_embedding)
         feats = self.pose_encoder.encode_cl(unshuffle8_to_cl(pose_embedding.float()))
         return self.unet(noisy_latents, timesteps, encoder_hidden_states, pose_embedding_features=feats).sample

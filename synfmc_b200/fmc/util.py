@@ -47,6 +47,16 @@ def traj_features_cl(info, masks, omcm, null_clips=None):
     return [CL(o.view(B, Fn, *o.shape[1:])) for o in outs]
 
 
+def _scatter_inputs(info, masks, null_clips=None):
+    B, Fn, n, H, W = masks.shape
+    feat, mask = ops.traj_scatter_unshuffle(info.view(B * Fn, n, 12), masks.view(B * Fn, n, H, W))
+    if null_clips:
+        fv = feat.view(B, Fn, *feat.shape[1:])
+        for i in null_clips:
+            fv[i].zero_()
+    return feat, mask
+
+
 def traj_features_from_circles(info, circles, omcm, H, W):
     """Device-side form of the `use_sphere_mask` preprocessing (fmc/data/dataset.py:5350-5403) + get_traj_features_v2:
     info [B, F, n, 12] and circles [B, F, n, 3] = (cx, cy, r) of every object's minimum enclosing circle (device fp32;
@@ -69,4 +79,11 @@ def get_traj_features_v2(obj_info_list_list, obj_mask_list_list, omcm, cfg_rando
     null = []
     if cfg_random_null_om:
         null = [i for i in range(info.shape[0]) if not (random.random() > cfg_random_null_om_ratio)]
+    from .. import train_engine
+    if train_engine.wants_training(omcm):
+        # OMC training (train_cam_obj_ctrl.py:843): the ObjectEncoder runs on the tape; the returned features carry its graph
+        if engine.precise():
+            raise NotImplementedError("training runs in the bf16 mode")
+        feat, mask = _scatter_inputs(info, masks, null)
+        return train_engine.adapter_train_forward(omcm, feat, mask, info.shape[0], info.shape[1])
     return [f.to_reference() for f in traj_features_cl(info, masks, omcm, null)]

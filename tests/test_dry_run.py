@@ -127,19 +127,18 @@ def test_spatial_pose_processors_are_refused(recorder):
         unet(sample, 961, text, pose_embedding_features=feats)
 
 
-def test_training_mode_fails_loudly():
-    """under autograd with trainable parameters the forward-only product must raise a clear error
-    instead of returning a tensor without grad_fn (train_cam_ctrl.py:586-648 would die later in loss.backward())."""
+def test_direct_module_calls_under_autograd_fail_loudly():
+    """a mirror module called DIRECTLY under autograd with something requiring grad must raise a clear
+    error instead of returning a tensor without grad_fn.  (The trainers' entry points -- PoseAdaptor / CamObjPoseAdaptor /
+    get_traj_features_v2 -- do train: test_training_tape_plumbing, tests/test_gpu_training.py.)"""
     from synfmc_b200.fmc.models.pose_adaptor import CameraPoseEncoder, PoseAdaptor
     o_unet = helpers.build_oracle_unet(tiny=True)
     unet = helpers.build_product_unet(o_unet, tiny=True, device="cpu")
     enc = CameraPoseEncoder(channels=[320, 640], **helpers.POSE_ENCODER_KWARGS)
-    unet.requires_grad_(False)
-    enc.requires_grad_(True)   # the CMC trainer trains the pose encoder (train_cam_ctrl.py:259-284)
-    wrapper = PoseAdaptor(unet, enc)
     sample, text, feats, _ = _inputs()
+    enc.requires_grad_(True)
     with pytest.raises(RuntimeError, match="forward pass only"):
-        wrapper(sample, torch.tensor([961]), text, torch.zeros(2, 6, 4, 64, 64))
+        enc(torch.zeros(2, 6, 4, 64, 64))
     for n, p in unet.named_parameters():
         if "merge" in n:
             p.requires_grad_(True)
@@ -150,6 +149,9 @@ def test_training_mode_fails_loudly():
         unet(sample.requires_grad_(True), 961, text, pose_embedding_features=feats)
     with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA tensors only"):  # no_grad: passes the guard, hits the CPU refusal
         unet(sample, 961, text, pose_embedding_features=feats)
+    # the wrapper under autograd takes the training path -- which, like everything else, refuses CPU tensors
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        PoseAdaptor(unet, enc)(sample.detach(), torch.tensor([961]), text, torch.zeros(2, 6, 4, 64, 64))
 
 
 @pytest.mark.parametrize("form", ["sliced", "list"])
@@ -210,3 +212,59 @@ def test_circle_driven_object_path_call_sequence(recorder):
         names = recorder.names()
         assert must in names and never not in names
         assert not any(n in ("fmc_traj_scatter_unshuffle_bf16",) for n in names)  # no mask tensor is ever read in bf16 mode
+
+
+@pytest.mark.parametrize("stage", ["cmc", "omc"])
+def test_training_tape_plumbing(recorder, stage):
+    """Training forward + backward through the trainers' entry points (kernels replaced by the recorder): every trainable
+    parameter of the stage receives a gradient of its own shape through torch.autograd, the frozen U-Net none; the forward
+    issues no fused GEGLU / LN-folded / fused temporal kernel (their intermediates are needed by backward)."""
+    from synfmc_b200 import synth
+    from synfmc_b200.fmc.models.pose_adaptor import PoseAdaptor
+    from synfmc_b200.fmc.models.pose_obj_adaptor import CamObjPoseAdaptor
+    from synfmc_b200.fmc.util import get_traj_features_v2
+    channels = (320, 640)
+    obj = stage == "omc"
+    o_unet = helpers.build_oracle_unet(tiny=True, obj=obj)
+    unet = helpers.build_product_unet(o_unet, tiny=True, obj=obj, device="cpu")
+    enc = helpers.build_product_pose_encoder(helpers.build_oracle_pose_encoder(channels), channels, device="cpu")
+    omcm = helpers.build_product_omcm(helpers.build_oracle_omcm(channels), channels, device="cpu") if obj else None
+    if stage == "cmc":   # train_cam_ctrl.py:259-284: the pose encoder and the qkv_merge layers
+        enc.requires_grad_(True)
+        for n, p in unet.named_parameters():
+            if "merge" in n and "lora" not in n:
+                p.requires_grad_(True)
+    else:                # train_cam_obj_ctrl.py:386-391: the ObjectEncoder only
+        omcm.requires_grad_(True)
+    b, f, H, W = 1, 4, 64, 64
+    latents = torch.randn(b, 4, f, 8, 8)
+    text = torch.randn(b, 77, 768)
+    pose = torch.randn(b, 6, f, H, W)
+    t = torch.tensor([961])
+    if obj:
+        infos, masks = synth.synth_objects(b, f, H, W, 2, seed=1)
+        trajs = get_traj_features_v2(infos, masks, omcm, False, 0.0, None, "cpu", torch.float32)
+        assert [tuple(x.shape) for x in trajs] == [(1, 320, 4, 8, 8), (1, 640, 4, 4, 4)] and all(x.requires_grad for x in trajs)
+        out = CamObjPoseAdaptor(unet, enc)(latents, t, text, pose, trajs)
+    else:
+        out = PoseAdaptor(unet, enc)(latents, t, text, pose)
+    assert out.shape == latents.shape and out.requires_grad
+    names = set(recorder.names())
+    assert "fmc_gemm_ln_bf16" not in names and "fmc_temporal_qkv_attn_bf16" not in names and "fmc_geglu_fwd_bf16" in names
+    assert not any(a[15] & 1 for n, a in recorder.calls if n == "fmc_gemm_bf16")   # no fused-GEGLU GEMM in training
+    recorder.calls.clear()
+    out.square().mean().backward()
+    bnames = set(recorder.names())
+    assert {"fmc_attention_bwd_bf16", "fmc_layernorm_bwd_bf16", "fmc_groupnorm_bwd_bf16", "fmc_geglu_bwd_bf16",
+            "fmc_transpose_bf16"} <= bnames
+    trainable = [(n, p) for m in (unet, enc) + ((omcm,) if obj else ()) for n, p in m.named_parameters() if p.requires_grad]
+    assert trainable
+    for n, p in trainable:
+        # tiny U-Net: only its first down block has cross-attention, so only ObjectEncoder feature 0 is injected
+        # (modified_modules.py:52-127) and the deeper ObjectEncoder levels are off the graph, as under torch autograd
+        used = not obj or n.startswith(("conv_in", "zero_conv_in", "body.0.", "body.1.", "zero_conv_out_list.0."))
+        if used:
+            assert p.grad is not None and p.grad.shape == p.shape and p.grad.dtype == torch.float32, n
+        else:
+            assert p.grad is None, n
+    assert all(p.grad is None for p in unet.parameters() if not p.requires_grad)

@@ -36,6 +36,8 @@ def test_transpose_and_colsum(B, cuda_device):
     assert torch.equal(B.transpose(bf(x).to(cuda_device)).float().cpu(), x.t())
     view = bf(randn(777, 640, seed=2)).to(cuda_device)[:, 64:384]
     assert torch.equal(B.transpose(view).cpu(), view.cpu().t())
+    padded = B.transpose(bf(x[:301]).to(cuda_device), 8).float().cpu()
+    assert padded.shape == (328, 304) and torch.equal(padded[:, :301], x[:301].t()) and float(padded[:, 301:].abs().max()) == 0
     got = B.colsum(bf(x).to(cuda_device))
     assert rel(got, x.double().sum(0)) < 1e-6
     acc = torch.ones(328, device=cuda_device)

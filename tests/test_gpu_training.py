@@ -1,0 +1,179 @@
+"""Training forward + backward on the tape (synfmc_b200/train_engine.py) against torch autograd of the fp32 CPU oracle
+(= the reference's eager modules): gradients of the trainable subsets of both stages through the frozen U-Net.
+
+  CMC (train_cam_ctrl.py:259-284, :586-648): CameraEncoder + the CameraAdapter qkv_merge layers
+  OMC (train_cam_obj_ctrl.py:386-391, :843-862): the ObjectEncoder
+
+Tolerances: the backward runs on bf16 activations / gradients with fp32 accumulation; one gradient tensor is held to 8e-2
+rel-L2 (many are ~1e-2; the bound is for the small-norm ones at the far end of the chain), the whole trainable gradient
+vector to 3e-2, the cosine between the two flat gradients to 0.999."""
+import pytest
+import torch
+
+from oracle import harness as helpers
+from oracle.harness import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(named_pairs, what):
+    flat_g, flat_w = [], []
+    worst = (0.0, None)
+    for name, got, want in named_pairs:
+        assert got is not None, f"{what}: no gradient for {name}"
+        assert got.shape == want.shape, name
+        e = rel_l2(got, want)
+        if e > worst[0]:
+            worst = (e, name)
+        flat_g.append(got.detach().float().cpu().reshape(-1))
+        flat_w.append(want.detach().float().reshape(-1))
+    g, w = torch.cat(flat_g), torch.cat(flat_w)
+    total = float((g - w).norm() / w.norm())
+    cos = float(torch.dot(g, w) / (g.norm() * w.norm()))
+    print(f"[parity] {what}: {len(flat_g)} gradient tensors, whole-vector rel-L2 {total:.3e}, cosine {cos:.6f}, "
+          f"worst tensor {worst[1]} {worst[0]:.3e}")
+    assert total < 3e-2 and cos > 0.999 and worst[0] < 8e-2, (total, cos, worst)
+
+
+def test_motion_module_backward(cuda_device):
+    """CameraAdapter motion module (attention_processor.py:255-293, motion_module.py:349-373): gradients w.r.t. the input,
+    the pose feature and qkv_merge, at the three widths."""
+    from oracle.attention_processor import AttnProcessor as OA, PoseAdaptorAttnProcessor as OP
+    from oracle.motion_module import get_motion_module as o_get
+    from oracle.unet import FMC_UNET_ADDITIONAL_KWARGS as KW
+    from synfmc_b200 import ops, train_engine as te
+    from synfmc_b200.fmc.models.attention_processor import AttnProcessor, PoseAdaptorAttnProcessor
+    from synfmc_b200.fmc.models.motion_module import get_motion_module
+    from synfmc_b200.synth import round_bf16, synth_init_
+    dev = cuda_device
+    for C, (b, f, h, w) in ((320, (2, 16, 6, 10)), (640, (1, 16, 5, 4)), (1280, (1, 8, 3, 3))):
+        om = o_get(C, "Vanilla", dict(KW["motion_module_kwargs"]))
+        pm = get_motion_module(C, "Vanilla", dict(KW["motion_module_kwargs"]))
+        kw = dict(hidden_size=C, pose_feature_dim=C, query_condition=True, key_value_condition=True, scale=1.0)
+        bo = om.temporal_transformer.transformer_blocks[0].attention_blocks
+        bp = pm.temporal_transformer.transformer_blocks[0].attention_blocks
+        bo[0].set_processor(OP(**kw)); bo[1].set_processor(OA())
+        bp[0].set_processor(PoseAdaptorAttnProcessor(**kw)); bp[1].set_processor(AttnProcessor())
+        synth_init_(om, seed=C)
+        pm.load_state_dict(om.state_dict(), strict=True)
+        pm.to(dev).requires_grad_(False)
+        om.requires_grad_(False)
+        for m in (om, pm):
+            for n, p in m.named_parameters():
+                if "merge" in n:
+                    p.requires_grad_(True)
+        g = torch.Generator().manual_seed(C)
+        x = round_bf16(torch.randn(b, C, f, h, w, generator=g)).requires_grad_(True)
+        pose = round_bf16(torch.randn(b, C, f, h, w, generator=g)).requires_grad_(True)
+        dy = round_bf16(torch.randn(b, C, f, h, w, generator=g))
+        om(x, None, None, None, cross_attention_kwargs={"pose_feature": pose}).backward(dy)
+        tape = te.Tape()
+        xv = te.Var(ops.to_channels_last(x.detach().to(dev)).view(-1, C))
+        pv = te.Var(ops.to_channels_last(pose.detach().to(dev)).view(-1, C))
+        with torch.no_grad():
+            out = te.motion_module(tape, pm, xv, (b, f, h, w, C), pv, dev)
+            out.grad = ops.to_channels_last(dy.to(dev)).view(-1, C)
+            tape.backward()
+        dx = ops.from_channels_last(xv.grad.view(b, f, h, w, C))
+        dpose = ops.from_channels_last(pv.grad.view(b, f, h, w, C))
+        # judge the gradient of the BRANCH (the module is input + branch: dx = dy + branch gradient)
+        pairs = [("d input (branch)", dx.cpu() - dy, x.grad - dy), ("d pose", dpose, pose.grad)]
+        o_params = dict(om.named_parameters())
+        for n, p in pm.named_parameters():
+            if p.requires_grad:
+                pairs.append((n, tape.param_grads.get(p), o_params[n].grad))
+        _compare(pairs, f"motion module backward C={C}")
+
+
+def _cmc_trainable(unet, enc):
+    unet.requires_grad_(False)
+    enc.requires_grad_(True)
+    for n, p in unet.named_parameters():
+        if "merge" in n and "lora" not in n:
+            p.requires_grad_(True)
+
+
+@pytest.mark.timeout(900)
+def test_cmc_training_step_gradients(cuda_device):
+    """PoseAdaptor.forward + loss.backward() as train_cam_ctrl.py:586-648 runs them: tiny U-Net (every block type) with
+    LoRA + CameraAdapter processors, CameraEncoder on Pluecker rays; the gradients of all 150 + 2 trainable tensors."""
+    from oracle.pose_adaptor import PoseAdaptor as OPA
+    from oracle.rays import to_plucker_embedding
+    from synfmc_b200 import synth
+    from synfmc_b200.fmc.models.pose_adaptor import PoseAdaptor
+    channels = (320, 640)
+    o_unet = helpers.build_oracle_unet(tiny=True)
+    p_unet = helpers.build_product_unet(o_unet, tiny=True, device=cuda_device)
+    o_enc = helpers.build_oracle_pose_encoder(channels)
+    p_enc = helpers.build_product_pose_encoder(o_enc, channels, device=cuda_device)
+    _cmc_trainable(o_unet, o_enc)
+    _cmc_trainable(p_unet, p_enc)
+    b, f, H, W = 2, 8, 64, 96
+    K, c2w = synth.synth_camera(b, f, H, W, seed=6)
+    plucker = to_plucker_embedding(c2w, K, (H, W)).permute(0, 2, 1, 3, 4).contiguous()
+    latents, text = synth.synth_step_inputs(b, f, H // 8, W // 8, cfg=False, seed=6)
+    g = torch.Generator().manual_seed(9)
+    target = torch.randn(latents.shape, generator=g)
+    t = torch.tensor([961, 41])
+    loss_o = torch.nn.functional.mse_loss(OPA(o_unet, o_enc)(latents, t, text, plucker).float(), target)
+    loss_o.backward()
+    dev = cuda_device
+    pred = PoseAdaptor(p_unet, p_enc)(latents.to(dev), t.to(dev), text.to(dev), plucker.to(dev))
+    assert pred.requires_grad
+    loss_p = torch.nn.functional.mse_loss(pred.float(), target.to(dev))
+    loss_p.backward()
+    assert abs(float(loss_p) - float(loss_o)) < 2e-2 * abs(float(loss_o))
+    pairs = []
+    for (n, po), (n2, pp) in zip(list(o_unet.named_parameters()) + list(o_enc.named_parameters()),
+                                 list(p_unet.named_parameters()) + list(p_enc.named_parameters())):
+        assert n == n2
+        if po.requires_grad:
+            pairs.append((n, pp.grad, po.grad))
+        else:
+            assert pp.grad is None, n
+    _compare(pairs, "CMC training step (tiny U-Net + CameraEncoder)")
+
+
+@pytest.mark.timeout(900)
+def test_omc_training_step_gradients(cuda_device):
+    """train_cam_obj_ctrl.py:843-862: get_traj_features_v2 (3 overlapping Gaussian objects) -> ObjectEncoder (trainable) ->
+    CamObjPoseAdaptor -> loss.backward(); the gradients reach the ObjectEncoder through the frozen U-Net."""
+    from oracle.pose_adaptor import CamObjPoseAdaptor as OCA
+    from oracle.rays import to_plucker_embedding
+    from oracle.util import get_traj_features_v2 as o_get
+    from synfmc_b200 import synth
+    from synfmc_b200.fmc.models.pose_obj_adaptor import CamObjPoseAdaptor
+    from synfmc_b200.fmc.util import get_traj_features_v2
+    channels = (320, 640)
+    o_unet = helpers.build_oracle_unet(tiny=True, obj=True)
+    p_unet = helpers.build_product_unet(o_unet, tiny=True, obj=True, device=cuda_device)
+    o_enc = helpers.build_oracle_pose_encoder(channels)
+    p_enc = helpers.build_product_pose_encoder(o_enc, channels, device=cuda_device)
+    o_m = helpers.build_oracle_omcm(channels)
+    p_m = helpers.build_product_omcm(o_m, channels, device=cuda_device)
+    for m in (o_unet, o_enc, p_unet, p_enc):
+        m.requires_grad_(False)
+    o_m.requires_grad_(True)
+    p_m.requires_grad_(True)
+    b, f, H, W = 1, 8, 64, 96
+    K, c2w = synth.synth_camera(b, f, H, W, seed=7)
+    plucker = to_plucker_embedding(c2w, K, (H, W)).permute(0, 2, 1, 3, 4).contiguous()
+    infos, masks = synth.synth_objects(b, f, H, W, 3, seed=8, gaussian=True)
+    latents, text = synth.synth_step_inputs(b, f, H // 8, W // 8, cfg=False, seed=7)
+    g = torch.Generator().manual_seed(10)
+    target = torch.randn(latents.shape, generator=g)
+    t = torch.tensor([801])
+    o_traj = o_get(infos, masks, o_m, False, 0.0, None, "cpu", torch.float32)
+    torch.nn.functional.mse_loss(OCA(o_unet, o_enc)(latents, t, text, plucker, o_traj).float(), target).backward()
+    dev = cuda_device
+    p_traj = get_traj_features_v2(infos, masks, p_m, False, 0.0, None, dev, torch.float32)
+    pred = CamObjPoseAdaptor(p_unet, p_enc)(latents.to(dev), t.to(dev), text.to(dev), plucker.to(dev), p_traj)
+    torch.nn.functional.mse_loss(pred.float(), target.to(dev)).backward()
+    pairs = []
+    for (n, po), (n2, pp) in zip(o_m.named_parameters(), p_m.named_parameters()):
+        if po.grad is None or float(po.grad.abs().max()) == 0.0:
+            assert pp.grad is None or float(pp.grad.abs().max()) == 0.0, n   # levels whose feature is never injected
+            continue
+        pairs.append((n, pp.grad, po.grad))
+    assert len(pairs) >= 10
+    _compare(pairs, "OMC training step (tiny U-Net + ObjectEncoder)")
