@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""BASELINE configs 3 and 4: one TRAINING step per GPU on one clip 320x512x16f (the reference trains batch 1 per GPU,
+configs/cam.yaml:149), data-parallel over N GPUs with the gradient all-reduce as the only collective.
+
+  --stage cmc   train_cam_ctrl.py:586-665: PoseAdaptor forward (CameraEncoder + frozen U-Net with the CameraAdapter),
+                MSE loss, backward, all-reduce of the 218 M trainable parameters (CameraEncoder + 20 qkv_merge), AdamW
+  --stage omc   train_cam_obj_ctrl.py:843-866: 3 objects per clip -> ObjectEncoder (trainable, 152.5 M) -> CamObjPoseAdaptor
+
+One step = zero_grad, forward on the tape, loss, backward (bucket all-reduces launched from gradient hooks), fused
+unscale + clip + AdamW.  Timed with CUDA events, barrier + synchronize on both sides, max over ranks.
+
+    python profiles/train_step_bench.py --stage cmc --steps 3 --warmup 1
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29517 \
+        profiles/train_step_bench.py --stage cmc"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--stage", default="cmc", choices=["cmc", "omc"])
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    args = ap.parse_args()
+    from synfmc_b200 import shard, synth
+    from synfmc_b200.fmc.models.pose_adaptor import PoseAdaptor
+    from synfmc_b200.fmc.models.pose_obj_adaptor import CamObjPoseAdaptor
+    from synfmc_b200.fmc.util import get_traj_features_v2
+    from synfmc_b200.train import FlatParams, FusedAdamW, GradAllReduce
+    rank, world, local = shard.world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    shard.init(backend="nccl", device=dev)
+    pipe, omcm = bench.build_product(dev)
+    unet, enc = pipe.unet, pipe.pose_encoder
+    if args.stage == "cmc":
+        enc.requires_grad_(True)
+        for n, p in unet.named_parameters():
+            if "merge" in n and "lora" not in n:
+                p.requires_grad_(True)
+        trainable = [p for p in enc.parameters()] + [p for p in unet.parameters() if p.requires_grad]
+        wrapper = PoseAdaptor(unet, enc)
+    else:
+        omcm.requires_grad_(True)
+        trainable = list(omcm.parameters())
+        wrapper = CamObjPoseAdaptor(unet, enc)
+    flat = FlatParams(trainable)
+    red = GradAllReduce(flat, bucket_bytes=256 << 20).install_hooks()
+    opt = FusedAdamW(flat, lr=1e-4, max_grad_norm=1.0)
+    H, W, F = bench.H, bench.W, bench.FRAMES
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_free_inputs import plucker_embedding  # the product's own ray kernel: oracle/ stays out of the bench
+    K, c2w = synth.synth_camera(1, F, H, W, seed=300 + rank)
+    pose = plucker_embedding(K.to(dev), c2w.to(dev), H, W)            # [1, 6, F, H, W] built by fmc_plucker_f32
+    latents, text = synth.synth_step_inputs(1, F, H // 8, W // 8, cfg=False, seed=300 + rank)
+    latents, text = latents.to(dev), text.to(dev)
+    target = torch.randn(latents.shape, generator=torch.Generator().manual_seed(rank)).to(dev)
+    infos, masks = synth.synth_objects(1, F, H, W, 3, seed=300 + rank, gaussian=True) if args.stage == "omc" else (None, None)
+    t = torch.tensor([801], device=dev)
+    losses = []
+
+    def step():
+        opt.zero_grad()
+        red.reset()
+        if args.stage == "omc":
+            trajs = get_traj_features_v2(infos, masks, omcm, False, 0.0, None, dev, torch.float32)
+            pred = wrapper(latents, t, text, pose, trajs)
+        else:
+            pred = wrapper(latents, t, text, pose)
+        loss = torch.nn.functional.mse_loss(pred.float(), target)
+        loss.backward()
+        n = red.wait()
+        opt.step(loss_scale=1.0, world=n)
+        losses.append(loss.detach())
+    for _ in range(args.warmup):
+        step()
+    shard.barrier()
+    mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    shard.barrier()
+    ms = shard.max_over_ranks(e0.elapsed_time(e1), device=dev) / args.steps
+    ls = [float(x) for x in losses]
+    if rank == 0:
+        print(json.dumps({"metric": f"training steps/sec, {args.stage.upper()} stage, 1 clip 320x512x16f per GPU",
+                          "value": round(world / (ms * 1e-3), 4), "unit": "steps/s (clips/s)", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2), "scaling": "weak",
+                          "dtype": "bf16 activations / gradients, fp32 master weights", "data": "synthetic",
+                          "trainable_params_m": round(flat.numel / 1e6, 1), "allreduce_buckets": len(red.buckets),
+                          "peak_memory_gib": round(mem, 1), "losses": [round(x, 5) for x in ls],
+                          "grad_norm_last": opt.last_norm(), "found_inf": opt.found_inf()}), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -77,6 +77,8 @@ def plan_key(device):
 
 
 STRUCTURE_EPOCH = 0  # bumped by Attention.set_processor: the cached tensor / processor lists below are rebuilt
+OPTIMIZER_EPOCH = 0  # bumped by synfmc_b200.train.FusedAdamW.step: its kernels write parameters through raw pointers,
+                     # which torch's version counters do not see
 
 
 def structure_changed():
@@ -99,7 +101,7 @@ def fingerprint(module):
         cache = (STRUCTURE_EPOCH, tensors, procs)
         module.__dict__["_fmc_fp_cache"] = cache
     _, tensors, procs = cache
-    return hash((tuple(map(_version_of, tensors)), tuple(map(torch.Tensor.data_ptr, tensors)),
+    return hash((OPTIMIZER_EPOCH, tuple(map(_version_of, tensors)), tuple(map(torch.Tensor.data_ptr, tensors)),
                  tuple((id(p), getattr(p, "scale", None), getattr(p, "lora_scale", None)) for p in procs)))
 
 
@@ -109,6 +111,8 @@ def invalidate_plans(root):
     for m in root.modules():
         if hasattr(m, "_plan"):
             m._plan = None
+        if hasattr(m, "_tplan"):
+            m._tplan = None  # training plans (synfmc_b200/train_engine.py) hold device copies of the frozen weights too
     root._fmc_fingerprint = None
     root._fmc_generation = getattr(root, "_fmc_generation", 0) + 1
 

@@ -132,6 +132,8 @@ class FusedAdamW:
         ops._check_cuda(self.flat.values, self.flat.grads)
         f = self.flat
         self.steps += 1
+        from . import engine
+        engine.OPTIMIZER_EPOCH += 1  # inference plans derived from these parameters are stale from here on
         stream = ops._stream()
         _cabi.call("fmc_grad_norm_f32", f.grads.data_ptr(), f.numel, 1.0 / (float(loss_scale) * world),
                    float(self.max_grad_norm or 0.0), self.workspace.data_ptr(), self.state.data_ptr(), stream)

@@ -34,19 +34,24 @@ F32 = torch.float32
 # --------------------------------------------------------------------------------------------------------------
 class Var:
     """A tensor of the training graph (any layout) with an accumulated gradient."""
-    __slots__ = ("t", "grad", "needs_grad")
+    __slots__ = ("t", "grad", "needs_grad", "_owned")
 
     def __init__(self, t, needs_grad=True):
-        self.t, self.grad, self.needs_grad = t, None, needs_grad
+        self.t, self.grad, self.needs_grad, self._owned = t, None, needs_grad, False
 
     def accumulate(self, g):
+        """The first gradient is kept by reference (it may be shared with other Vars: an add hands the same tensor to both
+        inputs); a second one is summed into a buffer this Var owns -- never in place into a shared tensor."""
         if not self.needs_grad or g is None:
             return
         if self.grad is None:
-            self.grad = g
-        else:
-            a, b = self.grad.view(-1, self.grad.shape[-1]), g.reshape(-1, g.shape[-1])
+            self.grad, self._owned = g, False
+            return
+        a, b = self.grad.view(-1, self.grad.shape[-1]), g.reshape(-1, g.shape[-1])
+        if self._owned:
             ops.add(a, b, out=a)
+        else:
+            self.grad, self._owned = ops.add(a, b).view(self.grad.shape), True
 
 
 class Tape:
@@ -71,7 +76,7 @@ class Tape:
                 continue
             fn(*grads)
             for o in outputs:
-                o.grad = None  # free as we go
+                o.grad, o._owned = None, False  # free as we go
         self.nodes = []
 
 
@@ -92,14 +97,21 @@ class TrainLinear:
     backward with the fp32 gradients of the EFFECTIVE weight / bias (db_eff None without a bias) and responsible for mapping
     them onto the nn.Parameters; None = frozen layer (activation gradient only)."""
 
-    def __init__(self, w_eff, b_eff, device, sink=None):
-        self.w = engine._dev_bf16(w_eff, device)                       # [N, K]
+    def __init__(self, w_eff, b_eff, device, sink=None, live=None):
+        """`live`: callable returning the current (w_eff, b_eff) -- given for TRAINABLE layers, whose device copies are
+        rebuilt at every forward (the optimizer changes the parameters between steps); frozen layers are converted once."""
+        self.device, self.sink, self.live = device, sink, live
+        self._set(w_eff, b_eff)
+
+    def _set(self, w_eff, b_eff):
+        self.w = engine._dev_bf16(w_eff, self.device)                  # [N, K]
         self.w_t = self.w.t().contiguous()                             # [K, N]: the "weight" of the dgrad GEMM
-        self.b = engine._dev_f32(b_eff, device)
-        self.sink = sink
+        self.b = engine._dev_f32(b_eff, self.device)
         self.N, self.K = self.w.shape
 
     def __call__(self, tape, x, residual=None):
+        if self.live is not None:
+            self._set(*self.live())
         y = ops.gemm(x.t, self.w, bias=self.b, residual=residual.t if residual is not None else None)
         out = Var(y)
 
@@ -133,16 +145,20 @@ def param_sink(weight, bias, scale=1.0, row_order=None):
 
 def linear_of(lin, device, geglu=False):
     """nn.Linear / 1x1 nn.Conv2d -> TrainLinear (GEGLU: rows interleaved as the inference plan does)."""
-    w = lin.weight.detach().float().reshape(lin.weight.shape[0], -1)
-    b = lin.bias.detach().float() if lin.bias is not None else None
     order = None
     if geglu:
-        half = w.shape[0] // 2
+        half = lin.weight.shape[0] // 2
         idx = torch.arange(half).view(-1, 16)
-        order = torch.cat([idx, idx + half], dim=1).reshape(-1)
-        w, b = w[order], (b[order] if b is not None else None)
-        order = order.to(device)
-    return TrainLinear(w, b, device, sink=param_sink(lin.weight, lin.bias, row_order=order))
+        order = torch.cat([idx, idx + half], dim=1).reshape(-1).to(lin.weight.device)
+
+    def current():
+        w = lin.weight.detach().float().reshape(lin.weight.shape[0], -1)
+        b = lin.bias.detach().float() if lin.bias is not None else None
+        if order is not None:
+            w, b = w[order], (b[order] if b is not None else None)
+        return w, b
+    sink = param_sink(lin.weight, lin.bias, row_order=order.to(device) if order is not None else None)
+    return TrainLinear(*current(), device, sink=sink, live=current if sink is not None else None)
 
 
 def layernorm(tape, x, norm, pe=None, F=0, HW=0, add=None):
@@ -239,15 +255,23 @@ class TrainConv:
         self.conv = conv
         self.k = conv.kernel_size[0]
         self.linear = linear_of(conv, device) if self.k == 1 else None
+        self.device = device
+        self.trainable = _trainable(conv.weight, conv.bias)
         if self.linear is None:
-            self.w = conv.weight.detach().to(device=device, dtype=BF16).contiguous(memory_format=torch.channels_last)
-            self.b = conv.bias.detach().to(device=device, dtype=BF16) if conv.bias is not None else None
+            self._set()
+
+    def _set(self):
+        conv = self.conv
+        self.w = conv.weight.detach().to(device=self.device, dtype=BF16).contiguous(memory_format=torch.channels_last)
+        self.b = conv.bias.detach().to(device=self.device, dtype=BF16) if conv.bias is not None else None
 
     def __call__(self, tape, x, shape):
         """x: Var of rows [(N h w), Cin]; shape = (N, h, w) -> (Var rows [(N oh ow), Cout], (N, oh, ow))."""
         N, h, w = shape
         if self.linear is not None:
             return self.linear(tape, x), shape
+        if self.trainable:
+            self._set()  # the optimizer moved the weights since the last step
         cin = x.t.shape[1]
         xi = x.t.view(N, h, w, cin).permute(0, 3, 1, 2)
         y = torch.nn.functional.conv2d(xi, self.w, self.b, stride=self.conv.stride, padding=self.conv.padding)
@@ -330,10 +354,18 @@ class TrainAttention:
         def folded(name):
             return engine._fold_lora(lins[name].weight, getattr(proc, f"{name}_lora") if has_lora else None, ls)
         heads, d, hs = self.heads, self.d, self.hs
+        rescale = float(getattr(attn, "rescale_output_factor", 1.0))
+
+        def qkv_current():
+            return torch.cat([engine._pad_heads(folded("to_q"), heads, d, hs), engine._pad_heads(folded("to_k"), heads, d, hs),
+                              folded("to_v")], dim=0), None
+
+        def out_current():
+            ol = lins["to_out"]
+            return folded("to_out") / rescale, (ol.bias.detach().float() / rescale if ol.bias is not None else None)
         wq = engine._pad_heads(folded("to_q"), heads, d, hs)
         wk = engine._pad_heads(folded("to_k"), heads, d, hs)
         wv = folded("to_v")
-        rescale = float(getattr(attn, "rescale_output_factor", 1.0))
 
         def unpad(dw):  # [heads * hs, K] -> [heads * d, K]
             return dw.view(heads, hs, -1)[:, :d].reshape(heads * d, -1) if hs != d else dw
@@ -348,17 +380,20 @@ class TrainAttention:
             self.q = TrainLinear(wq, None, device)
             self.kv = TrainLinear(torch.cat([wk, wv], dim=0), None, device)
         else:
-            self.qkv = TrainLinear(torch.cat([wq, wk, wv], dim=0), None, device, sink=qkv_sink if train_proj else None)
+            self.qkv = TrainLinear(torch.cat([wq, wk, wv], dim=0), None, device, sink=qkv_sink if train_proj else None,
+                                   live=qkv_current if train_proj else None)
         out_lin = lins["to_out"]
-        self.out = TrainLinear(folded("to_out") / rescale,
-                               out_lin.bias.detach().float() / rescale if out_lin.bias is not None else None, device,
-                               sink=param_sink(out_lin.weight, out_lin.bias, scale=1.0 / rescale))
+        out_sink = param_sink(out_lin.weight, out_lin.bias, scale=1.0 / rescale)
+        self.out = TrainLinear(*out_current(), device, sink=out_sink, live=out_current if out_sink is not None else None)
         self.k0, self.v0 = self.heads * self.hs, 2 * self.heads * self.hs
         self.merge = None
         if isinstance(proc, (PoseAdaptorAttnProcessor, LORAPoseAdaptorAttnProcessor)):
             s = float(proc.scale)
-            self.merge = TrainLinear(proc.qkv_merge.weight.detach().float() * s, proc.qkv_merge.bias.detach().float() * s,
-                                     device, sink=param_sink(proc.qkv_merge.weight, proc.qkv_merge.bias, scale=s))
+
+            def merge_current():
+                return proc.qkv_merge.weight.detach().float() * s, proc.qkv_merge.bias.detach().float() * s
+            m_sink = param_sink(proc.qkv_merge.weight, proc.qkv_merge.bias, scale=s)
+            self.merge = TrainLinear(*merge_current(), device, sink=m_sink, live=merge_current if m_sink is not None else None)
 
     def self_attention(self, tape, x, images, n, inner=1):
         """x rows -> ctx rows.  inner = 1: `images` sequences of n contiguous tokens; inner = HW: temporal (images = B * HW,
