@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--stage", default="cmc", choices=["cmc", "omc"])
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--trace", action="store_true", help="one extra step with CUDA events around every library call: "
+                                                         "per-entry-point time table on stderr")
     args = ap.parse_args()
     from synfmc_b200 import shard, synth
     from synfmc_b200.fmc.models.pose_adaptor import PoseAdaptor
@@ -92,6 +94,25 @@ def main():
     shard.barrier()
     ms = shard.max_over_ranks(e0.elapsed_time(e1), device=dev) / args.steps
     ls = [float(x) for x in losses]
+    if args.trace and rank == 0:
+        from synfmc_b200 import _cabi
+        _cabi.trace = []
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        step()
+        t1.record()
+        torch.cuda.synchronize()
+        trace, _cabi.trace = _cabi.trace, None
+        agg = {}
+        for name, a, s0, s1 in trace:
+            d = agg.setdefault(name, [0, 0.0])
+            d[0] += 1
+            d[1] += s0.elapsed_time(s1)
+        total = sum(v[1] for v in agg.values())
+        print(f"# traced step: {t0.elapsed_time(t1):.1f} ms wall on the device, {total:.1f} ms inside library calls "
+              f"(the rest: cuDNN convolutions forward / backward, torch glue)", file=sys.stderr)
+        for name, (n, ms_) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"{ms_:9.2f} ms {n:6d} calls  {name}", file=sys.stderr)
     if rank == 0:
         print(json.dumps({"metric": f"training steps/sec, {args.stage.upper()} stage, 1 clip 320x512x16f per GPU",
                           "value": round(world / (ms * 1e-3), 4), "unit": "steps/s (clips/s)", "n_gpus": world,

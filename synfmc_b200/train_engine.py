@@ -67,7 +67,7 @@ class Tape:
         if param in self.param_grads:
             self.param_grads[param].add_(g)
         else:
-            self.param_grads[param] = g.clone() if g.data_ptr() == 0 else g
+            self.param_grads[param] = g.contiguous()
 
     def backward(self):
         for outputs, fn in reversed(self.nodes):

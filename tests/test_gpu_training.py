@@ -134,6 +134,41 @@ def test_cmc_training_step_gradients(cuda_device):
     _compare(pairs, "CMC training step (tiny U-Net + CameraEncoder)")
 
 
+@pytest.mark.timeout(1800)
+def test_config3_full_depth_gradients(cuda_device):
+    """BASELINE config 3's step on the FULL 4-level U-Net (all 16 Transformer2D + 20 motion modules, mid block) with the
+    full CameraEncoder, one clip at config 1's size (256x256x16f: the fp32 oracle's autograd keeps every attention matrix,
+    0.5 GB each at this size): all 152 trainable tensors (218 M parameters)."""
+    from oracle.pose_adaptor import PoseAdaptor as OPA
+    from oracle.rays import to_plucker_embedding
+    from synfmc_b200 import synth
+    from synfmc_b200.fmc.models.pose_adaptor import PoseAdaptor
+    channels = (320, 640, 1280, 1280)
+    o_unet = helpers.build_oracle_unet(tiny=False)
+    p_unet = helpers.build_product_unet(o_unet, tiny=False, device=cuda_device)
+    o_enc = helpers.build_oracle_pose_encoder(channels)
+    p_enc = helpers.build_product_pose_encoder(o_enc, channels, device=cuda_device)
+    _cmc_trainable(o_unet, o_enc)
+    _cmc_trainable(p_unet, p_enc)
+    b, f, H, W = 1, 16, 256, 256
+    K, c2w = synth.synth_camera(b, f, H, W, seed=16)
+    plucker = to_plucker_embedding(c2w, K, (H, W)).permute(0, 2, 1, 3, 4).contiguous()
+    latents, text = synth.synth_step_inputs(b, f, H // 8, W // 8, cfg=False, seed=16)
+    target = torch.randn(latents.shape, generator=torch.Generator().manual_seed(17))
+    t = torch.tensor([501])
+    torch.nn.functional.mse_loss(OPA(o_unet, o_enc)(latents, t, text, plucker).float(), target).backward()
+    dev = cuda_device
+    pred = PoseAdaptor(p_unet, p_enc)(latents.to(dev), t.to(dev), text.to(dev), plucker.to(dev))
+    torch.nn.functional.mse_loss(pred.float(), target.to(dev)).backward()
+    pairs = []
+    for (n, po), (n2, pp) in zip(list(o_unet.named_parameters()) + list(o_enc.named_parameters()),
+                                 list(p_unet.named_parameters()) + list(p_enc.named_parameters())):
+        if po.requires_grad:
+            pairs.append((n, pp.grad, po.grad))
+    assert len(pairs) >= 150
+    _compare(pairs, "config 3 gradients, full-depth U-Net + CameraEncoder at 256x256x16f")
+
+
 @pytest.mark.timeout(900)
 def test_omc_training_step_gradients(cuda_device):
     """train_cam_obj_ctrl.py:843-862: get_traj_features_v2 (3 overlapping Gaussian objects) -> ObjectEncoder (trainable) ->
