@@ -1,0 +1,574 @@
+// Spatial self-attention BACKWARD on the tensor cores (head_dim 40, the level-0 shape that dominates the training step:
+// 16 images x 8 heads x 2560 x 2560 per attention).  Flash style, probabilities recomputed; two kernels, both built like
+// the forward kernel of attn_spatial.cu (TMA producer warp, one tcgen05.mma issuer thread, TMEM allocator warp, four
+// softmax warps with one TMEM lane = one row per thread) and arranged so that EVERY MMA has the forward's operand forms --
+// A K-major from shared memory, B K-major for the score-type products, B MN-major for the accumulate-type products:
+//
+//   dQ kernel   per (image, head, 128 queries), two sweeps over the key tiles:
+//                 sweep 1:  S = Q K^T                          -> row log-sum-exp L (log2 units), D = sum_c dO O
+//                 sweep 2:  S = Q K^T,  dP = dO V^T             (score-type, TMEM columns 0 / 128)
+//                           dS = exp2(S c - L) (dP - D) scale   -> bf16 -> smem (the forward's P layout)
+//                           dQ += dS K                           (accumulate-type: B = K tile, MN-major)
+//   dK/dV kernel per (image, head, 128 keys), one sweep over the query tiles, on TRANSPOSED scores:
+//                 S^T = K Q^T,  dP^T = V dO^T                    (TMEM lane = key, column = query)
+//                 P^T = exp2(S^T c - L[query]),  dS^T = P^T (dP^T - D[query]) scale   -> bf16 -> smem
+//                 dV += P^T dO,  dK += dS^T Q                    (B = dO / Q tile, MN-major)
+//
+// The dO tiles come through a 3-D tensor map (d = 40, head, row) whose 64-wide box is zero-filled past column 40, so the
+// contraction over the padded head width (48) of dP = dO V^T sees zeros there whatever V holds in those columns; Q and K
+// heads are zero-padded to 48 by the projection itself.  L and D travel from the first kernel to the second through the
+// [row, head] fp32 scratch buffers of the entry point.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fmc {
+
+constexpr int AB_BM = 128;
+constexpr int AB_D = 40;
+constexpr int AB_DK = 48;
+constexpr int AB_THREADS = 256;
+constexpr int AB_TILE = AB_BM * 128;        // [128 rows x 64 bf16] SWIZZLE_128B tile
+constexpr int AB_PT = 2 * AB_BM * 128;      // [128 x 128] bf16 probability-type tile (two 64-column chunks)
+
+struct AbParams {
+  int heads, n, images, blocks;  // n tokens per image (queries == keys), blocks = ceil(n / 128)
+  int head_stride, q_col0, k_col0, v_col0;
+  float scale, scale_log2e;
+  const __nv_bfloat16* O;
+  const __nv_bfloat16* dO;
+  long long ldo, lddo;
+  __nv_bfloat16* dQ; long long lddq; int dq_col0;
+  __nv_bfloat16* dK; long long lddk; int dk_col0;
+  __nv_bfloat16* dV; long long lddv; int dv_col0;
+  float* lse;   // [rows, heads], log2 units
+  float* dsum;  // [rows, heads]
+};
+
+__device__ __forceinline__ float ab_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void ab_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+// row r of a [128 x 128] bf16 tile in the forward's P layout: 16-byte piece j (8 columns) of the row
+__device__ __forceinline__ uint32_t ab_piece_addr(uint32_t tile, int r, int piece) {
+  return tile + static_cast<uint32_t>(r) * 128u + static_cast<uint32_t>(piece >> 3) * AB_TILE +
+         (static_cast<uint32_t>((piece & 7) ^ (r & 7)) << 4);
+}
+
+// =====================================================================================================================
+// dQ kernel
+// =====================================================================================================================
+constexpr int ABQ_STAGES = 3;
+constexpr int ABQ_SMEM = 2 * AB_TILE + AB_PT + ABQ_STAGES * 2 * AB_TILE + 1024;
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmG, AbParams p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t q_full, q_empty, s_full, s_free, ds_ready, ds_free, dq_final, dq_free;
+  __shared__ uint64_t kv_full[ABQ_STAGES], kv_empty[ABQ_STAGES];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base, sG = sQ + AB_TILE, sDS = sG + AB_TILE, sKV = sDS + AB_PT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_items = p.images * p.heads * p.blocks;
+  const int T = p.blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmG);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&q_full, 1); mbar_init(&q_empty, 1);
+    mbar_init(&s_full, 1); mbar_init(&s_free, 4);
+    mbar_init(&ds_ready, 4); mbar_init(&ds_free, 1);
+    mbar_init(&dq_final, 1); mbar_init(&dq_free, 4);
+    for (int s = 0; s < ABQ_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t t = 0, it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int qb = item % p.blocks;
+        const int head = (item / p.blocks) % p.heads;
+        const int img = item / (p.blocks * p.heads);
+        const int row0 = img * p.n;
+        mbar_wait(&q_empty, (it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&q_full, 2 * AB_TILE);
+        tma_load_2d_a(sQ, &tmQ, &q_full, p.q_col0 + head * p.head_stride, row0 + qb * AB_BM);
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(sG), "l"(reinterpret_cast<uint64_t>(&tmG)), "r"(smem_u32(&q_full)), "r"(0), "r"(head),
+            "r"(row0 + qb * AB_BM) : "memory");
+        for (int u = 0; u < 2 * T; ++u, ++t) {
+          const int j = u < T ? u : u - T;
+          const int st = t % ABQ_STAGES;
+          mbar_wait(&kv_empty[st], ((t / ABQ_STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&kv_full[st], 2 * AB_TILE);
+          const uint32_t sK = sKV + st * 2 * AB_TILE;
+          tma_load_2d_a(sK, &tmK, &kv_full[st], p.k_col0 + head * p.head_stride, row0 + j * AB_BM);
+          tma_load_2d_a(sK + AB_TILE, &tmV, &kv_full[st], p.v_col0 + head * AB_D, row0 + j * AB_BM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(AB_BM, AB_BM);
+      constexpr uint32_t idesc_a = umma_idesc_bf16_bmn(AB_BM, AB_DK);
+      uint32_t t = 0, it = 0, nds = 0;
+      // dQ += dS(tile u) K(tile u): the K tile sits in stage `st`
+      auto issue_dq = [&](int st, bool first) {
+        mbar_wait(&ds_ready, nds & 1u);
+        tc_fence_after_sync();
+        const uint32_t sK = sKV + st * 2 * AB_TILE;
+#pragma unroll
+        for (int k = 0; k < AB_BM / 16; ++k) {
+          const uint64_t da = umma_desc_k_sw128(sDS + (k >> 2) * AB_TILE + (k & 3) * 32);
+          const uint64_t db = umma_desc_mn_sw128(sK + k * (16 * 128), AB_TILE, 1024);
+          umma_bf16_ss(tmem_base + 256u, da, db, idesc_a, (!first || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(&ds_free);
+        ++nds;
+      };
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        mbar_wait(&q_full, it & 1u);
+        tc_fence_after_sync();
+        int prev_st = -1;
+        for (int u = 0; u < 2 * T; ++u, ++t) {
+          const int st = t % ABQ_STAGES;
+          mbar_wait(&kv_full[st], (t / ABQ_STAGES) & 1u);
+          mbar_wait(&s_free, (t & 1u) ^ 1u);
+          tc_fence_after_sync();
+          const uint32_t sK = sKV + st * 2 * AB_TILE;
+#pragma unroll
+          for (int k = 0; k < AB_DK / 16; ++k)
+            umma_bf16_ss(tmem_base, umma_desc_k_sw128(sQ + k * 32), umma_desc_k_sw128(sK + k * 32), idesc_s, k > 0 ? 1u : 0u);
+          if (u >= T) {
+#pragma unroll
+            for (int k = 0; k < AB_DK / 16; ++k)
+              umma_bf16_ss(tmem_base + 128u, umma_desc_k_sw128(sG + k * 32), umma_desc_k_sw128(sK + AB_TILE + k * 32), idesc_s,
+                           k > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full);
+          if (u < T) {
+            umma_commit(&kv_empty[st]);
+          } else {
+            if (prev_st >= 0) {
+              issue_dq(prev_st, u == T + 1);
+            } else {
+              mbar_wait(&dq_free, (it & 1u) ^ 1u);  // the previous item's epilogue has read the dQ accumulator
+              tc_fence_after_sync();
+            }
+            prev_st = st;
+          }
+        }
+        issue_dq(prev_st, T == 1);
+        umma_commit(&q_empty);
+        umma_commit(&dq_final);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float c = p.scale_log2e;
+    uint32_t t = 0, it = 0, nds = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int qb = item % p.blocks;
+      const int head = (item / p.blocks) % p.heads;
+      const int img = item / (p.blocks * p.heads);
+      const int q_in_img = qb * AB_BM + r;
+      const bool row_ok = q_in_img < p.n;
+      const long long row = static_cast<long long>(img) * p.n + q_in_img;
+      // D = sum_c dO[row, c] O[row, c] straight from global memory (one row per thread, 80 bytes each)
+      float dsum = 0.f;
+      if (row_ok) {
+        const uint4* op = reinterpret_cast<const uint4*>(p.O + row * p.ldo + head * AB_D);
+        const uint4* gp = reinterpret_cast<const uint4*>(p.dO + row * p.lddo + head * AB_D);
+#pragma unroll
+        for (int v = 0; v < AB_D / 8; ++v) {
+          const uint4 a = __ldg(op + v), b = __ldg(gp + v);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dsum += bf16_lo(aw[e]) * bf16_lo(bw[e]) + bf16_hi(aw[e]) * bf16_hi(bw[e]);
+        }
+      }
+      float m = -INFINITY, l = 0.f, L2 = 0.f;
+      for (int u = 0; u < 2 * T; ++u, ++t) {
+        const int j = u < T ? u : u - T;
+        const int valid = p.n - j * AB_BM;
+        mbar_wait(&s_full, t & 1u);
+        tc_fence_after_sync();
+        if (u < T) {
+          // ---- sweep 1: online row maximum / sum in log2 units
+          float mx = -INFINITY;
+          uint32_t v[32];
+#pragma unroll 1
+          for (int c4 = 0; c4 < 4; ++c4) {
+            tmem_ld_x32(lane_addr + c4 * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float s = (c4 * 32 + i < valid) ? __uint_as_float(v[i]) * c : -INFINITY;
+              v[i] = __float_as_uint(s);
+              mx = fmaxf(mx, s);
+            }
+            const float m_new = fmaxf(m, mx);
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum += ab_exp2(__uint_as_float(v[i]) - m_new);
+            l = l * ab_exp2(m - m_new) + sum;
+            m = m_new;
+          }
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free);
+          if (u == T - 1) {
+            L2 = m + log2f(l);
+            if (row_ok) {
+              p.lse[row * p.heads + head] = L2;
+              p.dsum[row * p.heads + head] = dsum;
+            }
+          }
+        } else {
+          // ---- sweep 2: dS = exp2(S c - L) (dP - D) scale  -> bf16 -> smem, 32 columns at a time
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint32_t sv[32], dv[32], pk[16];
+            tmem_ld_x32(lane_addr + c4 * 32, sv);
+            tmem_ld_x32(lane_addr + 128u + c4 * 32, dv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const bool ok0 = c4 * 32 + i < valid, ok1 = c4 * 32 + i + 1 < valid;
+              const float p0 = ok0 ? ab_exp2(fmaf(__uint_as_float(sv[i]), c, -L2)) : 0.f;
+              const float p1 = ok1 ? ab_exp2(fmaf(__uint_as_float(sv[i + 1]), c, -L2)) : 0.f;
+              const float d0 = ok0 ? p0 * (__uint_as_float(dv[i]) - dsum) * p.scale : 0.f;
+              const float d1 = ok1 ? p1 * (__uint_as_float(dv[i + 1]) - dsum) * p.scale : 0.f;
+              pk[i >> 1] = pack_bf16x2(d0, d1);
+            }
+            if (c4 == 0) mbar_wait(&ds_free, (nds & 1u) ^ 1u);  // dQ MMA of the previous tile has read the dS tile
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              st_shared_v4(ab_piece_addr(sDS, r, c4 * 4 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free);  // S / dP consumed: the next tile's score MMAs may overwrite them
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ds_ready);
+          ++nds;
+        }
+      }
+      // ---- epilogue: dQ accumulator -> bf16 -> global (40 of the 48 columns)
+      mbar_wait(&dq_final, it & 1u);
+      tc_fence_after_sync();
+      __nv_bfloat16* dst_row = p.dQ + row * p.lddq + p.dq_col0 + head * p.head_stride;
+#pragma unroll 1
+      for (int cc = 0; cc < AB_DK / 16; ++cc) {
+        uint32_t o[16];
+        tmem_ld_x16(lane_addr + 256u + cc * 16, o);
+        tmem_ld_wait();
+        if (row_ok) {
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(__uint_as_float(o[2 * i]), __uint_as_float(o[2 * i + 1]));
+          uint4* dst = reinterpret_cast<uint4*>(dst_row + cc * 16);
+          if (cc * 16 + 8 <= AB_D) dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+          if (cc * 16 + 16 <= AB_D) dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dq_free);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================================
+// dK / dV kernel (transposed scores: TMEM lane = key, column = query)
+// =====================================================================================================================
+constexpr int ABK_STAGES = 2;
+constexpr int ABK_SMEM = 2 * AB_TILE + 2 * AB_PT + ABK_STAGES * 2 * AB_TILE + 1024;
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmG, AbParams p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t kv_full, kv_empty, s_full, s_free, pds_ready, pds_free, acc_final, acc_free;
+  __shared__ uint64_t q_full[ABK_STAGES], q_empty[ABK_STAGES];
+  __shared__ float vec_l[2][AB_BM], vec_d[2][AB_BM];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = smem_base, sV = sK + AB_TILE, sP = sV + AB_TILE, sDS = sP + AB_PT, sQG = sDS + AB_PT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_items = p.images * p.heads * p.blocks;
+  const int T = p.blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmG);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&kv_full, 1); mbar_init(&kv_empty, 1);
+    mbar_init(&s_full, 1); mbar_init(&s_free, 4);
+    mbar_init(&pds_ready, 4); mbar_init(&pds_free, 1);
+    mbar_init(&acc_final, 1); mbar_init(&acc_free, 4);
+    for (int s = 0; s < ABK_STAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t t = 0, it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int kb = item % p.blocks;
+        const int head = (item / p.blocks) % p.heads;
+        const int img = item / (p.blocks * p.heads);
+        const int row0 = img * p.n;
+        mbar_wait(&kv_empty, (it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&kv_full, 2 * AB_TILE);
+        tma_load_2d_a(sK, &tmK, &kv_full, p.k_col0 + head * p.head_stride, row0 + kb * AB_BM);
+        tma_load_2d_a(sV, &tmV, &kv_full, p.v_col0 + head * AB_D, row0 + kb * AB_BM);
+        for (int i = 0; i < T; ++i, ++t) {
+          const int st = t % ABK_STAGES;
+          mbar_wait(&q_empty[st], ((t / ABK_STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&q_full[st], 2 * AB_TILE);
+          const uint32_t sQ = sQG + st * 2 * AB_TILE;
+          tma_load_2d_a(sQ, &tmQ, &q_full[st], p.q_col0 + head * p.head_stride, row0 + i * AB_BM);
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+              ::"r"(sQ + AB_TILE), "l"(reinterpret_cast<uint64_t>(&tmG)), "r"(smem_u32(&q_full[st])), "r"(0), "r"(head),
+              "r"(row0 + i * AB_BM) : "memory");
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(AB_BM, AB_BM);
+      constexpr uint32_t idesc_a = umma_idesc_bf16_bmn(AB_BM, AB_DK);
+      uint32_t t = 0, it = 0, npd = 0;
+      // dV += P^T dO, dK += dS^T Q with the (Q, dO) tiles of stage `st`
+      auto issue_acc = [&](int st, bool first) {
+        mbar_wait(&pds_ready, npd & 1u);
+        tc_fence_after_sync();
+        const uint32_t sQ = sQG + st * 2 * AB_TILE, sG = sQ + AB_TILE;
+#pragma unroll
+        for (int k = 0; k < AB_BM / 16; ++k) {
+          const uint64_t da = umma_desc_k_sw128(sP + (k >> 2) * AB_TILE + (k & 3) * 32);
+          const uint64_t db = umma_desc_mn_sw128(sG + k * (16 * 128), AB_TILE, 1024);
+          umma_bf16_ss(tmem_base + 256u, da, db, idesc_a, (!first || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < AB_BM / 16; ++k) {
+          const uint64_t da = umma_desc_k_sw128(sDS + (k >> 2) * AB_TILE + (k & 3) * 32);
+          const uint64_t db = umma_desc_mn_sw128(sQ + k * (16 * 128), AB_TILE, 1024);
+          umma_bf16_ss(tmem_base + 320u, da, db, idesc_a, (!first || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&q_empty[st]);
+        umma_commit(&pds_free);
+        ++npd;
+      };
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        mbar_wait(&kv_full, it & 1u);
+        tc_fence_after_sync();
+        int prev_st = -1;
+        for (int i = 0; i < T; ++i, ++t) {
+          const int st = t % ABK_STAGES;
+          mbar_wait(&q_full[st], (t / ABK_STAGES) & 1u);
+          mbar_wait(&s_free, (t & 1u) ^ 1u);
+          tc_fence_after_sync();
+          const uint32_t sQ = sQG + st * 2 * AB_TILE, sG = sQ + AB_TILE;
+#pragma unroll
+          for (int k = 0; k < AB_DK / 16; ++k)  // S^T = K Q^T
+            umma_bf16_ss(tmem_base, umma_desc_k_sw128(sK + k * 32), umma_desc_k_sw128(sQ + k * 32), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < AB_DK / 16; ++k)  // dP^T = V dO^T (dO zero beyond column 40)
+            umma_bf16_ss(tmem_base + 128u, umma_desc_k_sw128(sV + k * 32), umma_desc_k_sw128(sG + k * 32), idesc_s,
+                         k > 0 ? 1u : 0u);
+          umma_commit(&s_full);
+          if (prev_st >= 0) {
+            issue_acc(prev_st, i == 1);
+          } else {
+            mbar_wait(&acc_free, (it & 1u) ^ 1u);
+            tc_fence_after_sync();
+          }
+          prev_st = st;
+        }
+        issue_acc(prev_st, T == 1);
+        umma_commit(&kv_empty);
+        umma_commit(&acc_final);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // key row of the tile
+    const int tid = threadIdx.x - 128;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float c = p.scale_log2e;
+    uint32_t t = 0, it = 0, npd = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int kb = item % p.blocks;
+      const int head = (item / p.blocks) % p.heads;
+      const int img = item / (p.blocks * p.heads);
+      const long long img_row0 = static_cast<long long>(img) * p.n;
+      for (int i = 0; i < T; ++i, ++t) {
+        // per-query log-sum-exp / D of this query tile (written by the dQ kernel): +inf masks queries past the image
+        const int buf = t & 1u;
+        {
+          const int qi = i * AB_BM + tid;
+          const bool ok = qi < p.n;
+          vec_l[buf][tid] = ok ? p.lse[(img_row0 + qi) * p.heads + head] : INFINITY;
+          vec_d[buf][tid] = ok ? p.dsum[(img_row0 + qi) * p.heads + head] : 0.f;
+        }
+        ab_bar_sync(1, 128);
+        mbar_wait(&s_full, t & 1u);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t sv[32], dv[32], pp[16], pd[16];
+          tmem_ld_x32(lane_addr + c4 * 32, sv);
+          tmem_ld_x32(lane_addr + 128u + c4 * 32, dv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const int col = c4 * 32 + e;
+            const float p0 = ab_exp2(fmaf(__uint_as_float(sv[e]), c, -vec_l[buf][col]));
+            const float p1 = ab_exp2(fmaf(__uint_as_float(sv[e + 1]), c, -vec_l[buf][col + 1]));
+            const float d0 = p0 * (__uint_as_float(dv[e]) - vec_d[buf][col]) * p.scale;
+            const float d1 = p1 * (__uint_as_float(dv[e + 1]) - vec_d[buf][col + 1]) * p.scale;
+            pp[e >> 1] = pack_bf16x2(p0, p1);
+            pd[e >> 1] = pack_bf16x2(d0, d1);
+          }
+          if (c4 == 0) mbar_wait(&pds_free, (npd & 1u) ^ 1u);  // the accumulate MMAs of the previous tile have read P^T / dS^T
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            st_shared_v4(ab_piece_addr(sP, r, c4 * 4 + g), pp[4 * g], pp[4 * g + 1], pp[4 * g + 2], pp[4 * g + 3]);
+            st_shared_v4(ab_piece_addr(sDS, r, c4 * 4 + g), pd[4 * g], pd[4 * g + 1], pd[4 * g + 2], pd[4 * g + 3]);
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pds_ready);
+        ++npd;
+      }
+      // ---- epilogue: dV (columns 256..), dK (columns 320..) -> bf16 -> global
+      mbar_wait(&acc_final, it & 1u);
+      tc_fence_after_sync();
+      const int k_in_img = kb * AB_BM + r;
+      const bool row_ok = k_in_img < p.n;
+      const long long row = img_row0 + k_in_img;
+      __nv_bfloat16* dv_row = p.dV + row * p.lddv + p.dv_col0 + head * AB_D;
+      __nv_bfloat16* dk_row = p.dK + row * p.lddk + p.dk_col0 + head * p.head_stride;
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {
+#pragma unroll 1
+        for (int cc = 0; cc < AB_DK / 16; ++cc) {
+          uint32_t o[16];
+          tmem_ld_x16(lane_addr + (which == 0 ? 256u : 320u) + cc * 16, o);
+          tmem_ld_wait();
+          if (row_ok) {
+            uint32_t w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) w[e] = pack_bf16x2(__uint_as_float(o[2 * e]), __uint_as_float(o[2 * e + 1]));
+            uint4* dst = reinterpret_cast<uint4*>((which == 0 ? dv_row : dk_row) + cc * 16);
+            if (cc * 16 + 8 <= AB_D) dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            if (cc * 16 + 16 <= AB_D) dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_free);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// host side: tensor maps + launches; returns FMC_OK or an error (the caller falls back to nothing: an error is an error)
+int attention_bwd_tc_d40(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0, const void* V,
+                         long long ldv, int v_col0, int head_stride, const void* O, long long ldo, const void* dO,
+                         long long lddo, void* dQ, long long lddq, int dq_col0, void* dK, long long lddk, int dk_col0,
+                         void* dV, long long lddv, int dv_col0, float* lse, float* dsum, int images, int heads, int n,
+                         float scale, cudaStream_t stream) {
+  const long long rows = static_cast<long long>(images) * n;
+  CUtensorMap tmQ, tmK, tmV, tmG;
+  const uint32_t box[2] = {64, 128};
+  auto map2d = [&](CUtensorMap* m, const void* base, long long ld) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(rows)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ld) * 2};
+    return make_tmap_bf16(m, base, 2, dims, strides, box, true);
+  };
+  int rc = map2d(&tmQ, Q, ldq);
+  if (rc != FMC_OK) return rc;
+  rc = map2d(&tmK, K, ldk);
+  if (rc != FMC_OK) return rc;
+  rc = map2d(&tmV, V, ldv);
+  if (rc != FMC_OK) return rc;
+  {
+    // dO as (d = 40, head, row): the 64-wide box is zero-filled past column 40 of the head
+    const uint64_t dims[3] = {static_cast<uint64_t>(AB_D), static_cast<uint64_t>(heads), static_cast<uint64_t>(rows)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(AB_D) * 2, static_cast<uint64_t>(lddo) * 2};
+    const uint32_t box3[3] = {64, 1, 128};
+    rc = make_tmap_bf16(&tmG, dO, 3, dims, strides, box3, true);
+    if (rc != FMC_OK) return rc;
+  }
+  AbParams p{};
+  p.heads = heads; p.n = n; p.images = images; p.blocks = ceil_div(n, AB_BM);
+  p.head_stride = head_stride; p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+  p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
+  p.O = static_cast<const __nv_bfloat16*>(O); p.dO = static_cast<const __nv_bfloat16*>(dO); p.ldo = ldo; p.lddo = lddo;
+  p.dQ = static_cast<__nv_bfloat16*>(dQ); p.lddq = lddq; p.dq_col0 = dq_col0;
+  p.dK = static_cast<__nv_bfloat16*>(dK); p.lddk = lddk; p.dk_col0 = dk_col0;
+  p.dV = static_cast<__nv_bfloat16*>(dV); p.lddv = lddv; p.dv_col0 = dv_col0;
+  p.lse = lse; p.dsum = dsum;
+  static unsigned long long attr_devs = 0;
+  if (first_use_on_this_device(&attr_devs)) {
+    FMC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ABQ_SMEM));
+    FMC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ABK_SMEM));
+  }
+  const int items = images * heads * p.blocks;
+  const int grid = items < device_sm_count() ? items : device_sm_count();
+  launch_k(attn_bwd_dq_tc_kernel, dim3(grid), dim3(AB_THREADS), ABQ_SMEM, stream, tmQ, tmK, tmV, tmG, p);
+  rc = check_launch("attn_bwd_dq_tc_kernel");
+  if (rc != FMC_OK) return rc;
+  launch_k(attn_bwd_dkv_tc_kernel, dim3(grid), dim3(AB_THREADS), ABK_SMEM, stream, tmQ, tmK, tmV, tmG, p);
+  return check_launch("attn_bwd_dkv_tc_kernel");
+}
+
+}  // namespace fmc

@@ -914,6 +914,13 @@ extern "C" int fmc_avgpool2_bwd_bf16(const void* dy, void* dx, int N, int h, int
   return check_launch("avgpool2_bwd_kernel");
 }
 
+namespace fmc {
+int attention_bwd_tc_d40(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0, const void* V,
+                         long long ldv, int v_col0, int head_stride, const void* O, long long ldo, const void* dO,
+                         long long lddo, void* dQ, long long lddq, int dq_col0, void* dK, long long lddk, int dk_col0,
+                         void* dV, long long lddv, int dv_col0, float* lse, float* dsum, int images, int heads, int n,
+                         float scale, cudaStream_t stream);
+}
 extern "C" int fmc_attention_bwd_bf16(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
                                       const void* V, long long ldv, int v_col0, int head_stride, const void* O,
                                       long long ldo, const void* dO, long long lddo, void* dQ, long long lddq, int dq_col0,
@@ -941,6 +948,14 @@ extern "C" int fmc_attention_bwd_bf16(const void* Q, long long ldq, int q_col0, 
   p.head_stride = head_stride; p.lse = lse; p.dsum = dsum;
   p.images = images; p.heads = heads; p.nq = nq; p.nk = nk; p.kv_div = kv_div; p.kv_stride = kv_stride; p.inner = inner;
   p.scale = scale;
+  // level-0 spatial self-attention (the bulk of the training step) runs on the tensor cores (attn_bwd_tc.cu);
+  // FMC_ATTN_BWD_SIMT=1 keeps the SIMT kernels below for A/B checks
+  const char* simt_env = getenv("FMC_ATTN_BWD_SIMT");
+  const bool force_simt = simt_env && simt_env[0] == '1';
+  if (head_dim == 40 && head_stride == 48 && inner == 1 && dK != nullptr && !force_simt && ldo % 8 == 0 && lddq % 8 == 0 &&
+      lddk % 8 == 0 && lddv % 8 == 0 && dq_col0 % 8 == 0 && dk_col0 % 8 == 0 && dv_col0 % 8 == 0)
+    return attention_bwd_tc_d40(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo, dQ, lddq,
+                                dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images, heads, nq, scale, stream);
   switch (head_dim) {
     case 40: return launch_attention_bwd<40>(p, dK != nullptr, stream);
     case 80: return launch_attention_bwd<80>(p, dK != nullptr, stream);

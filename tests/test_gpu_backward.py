@@ -157,6 +157,34 @@ def test_attention_bwd_spatial_self(B, cuda_device, d, images, n):
         assert float(got[:, :k0].view(-1, heads, hs)[:, :, d:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("images,n", [(3, 2560), (2, 129), (1, 128)])
+def test_attention_bwd_tensor_core_matches_simt(B, cuda_device, monkeypatch, images, n):
+    """head_dim 40 self-attention: the tcgen05 kernels (csrc/attn_bwd_tc.cu) against the SIMT kernels on the same buffers,
+    including the level-0 sequence length (2560) and ragged last tiles."""
+    from synfmc_b200 import ops
+    heads, d, hs = 8, 40, 48
+    qkv = torch.zeros(images * n, 2 * heads * hs + heads * d)
+    qkv[:, :heads * hs] = _pad_heads(randn(images * n, heads * d, seed=1), heads, d, hs)
+    qkv[:, heads * hs:2 * heads * hs] = _pad_heads(randn(images * n, heads * d, seed=2), heads, d, hs)
+    qkv[:, 2 * heads * hs:] = randn(images * n, heads * d, seed=3)
+    dev_qkv = bf(qkv).to(cuda_device)
+    k0, v0 = heads * hs, 2 * heads * hs
+    dev_o = torch.empty(images * n, heads * d, dtype=torch.bfloat16, device=cuda_device)
+    ops.spatial_attn(dev_qkv, 0, dev_qkv, k0, dev_qkv, v0, hs, dev_o, images, heads, d, n, n, 1, n, d ** -0.5)
+    dev_do = bf(randn(images * n, heads * d, seed=4)).to(cuda_device)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("FMC_ATTN_BWD_SIMT", mode)
+        dqkv = torch.zeros_like(dev_qkv)
+        B.attention_bwd(dev_qkv, 0, dev_qkv, k0, dev_qkv, v0, hs, dev_o, dev_do, dqkv, 0, dqkv, k0, dqkv, v0, images, heads, d,
+                        n, n, 1, n, 1, d ** -0.5)
+        torch.cuda.synchronize()
+        out[mode] = dqkv.float().cpu()
+    for lo, hi in ((0, k0), (k0, v0), (v0, qkv.shape[1])):
+        assert rel(out["0"][:, lo:hi], out["1"][:, lo:hi]) < BF16_TOL
+    assert float(out["0"][:, :v0].view(-1, 2 * heads, hs)[:, :, d:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("d,images,nq,kv_div", [(40, 4, 200, 2), (160, 4, 64, 4)])
 def test_attention_bwd_text_cross(B, cuda_device, d, images, nq, kv_div):
     """Text cross-attention: dQ only (the text embeddings are frozen), 77 keys inside 80-row kv groups."""
