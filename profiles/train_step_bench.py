@@ -103,8 +103,21 @@ def main():
         t1.record()
         torch.cuda.synchronize()
         trace, _cabi.trace = _cabi.trace, None
-        agg = {}
+        agg, shapes = {}, {}
         for name, a, s0, s1 in trace:
+            if name == "fmc_attention_bwd_bf16":  # split by shape: images x head_dim, nq x nk, inner, self / cross
+                name += (f"[img={a[-10]} d={a[-8]} nq={a[-7]} nk={a[-6]} inner={a[-3]} "
+                         f"{'self' if a[17] else 'dQ only'}]")
+            elif name == "fmc_gemm_bf16":  # M x N x K, fp32 output (weight gradients) flagged
+                shapes.setdefault(f"gemm M={a[6]} N={a[7]} K={a[8]} flags={a[15]}", [0, 0.0])
+                sh = shapes[f"gemm M={a[6]} N={a[7]} K={a[8]} flags={a[15]}"]
+                sh[0] += 1
+                sh[1] += s0.elapsed_time(s1)
+            elif name == "fmc_groupnorm_bwd_bf16":
+                key = f"groupnorm_bwd images={a[10]} HW={a[11]} C={a[12]}"
+                sh = shapes.setdefault(key, [0, 0.0])
+                sh[0] += 1
+                sh[1] += s0.elapsed_time(s1)
             d = agg.setdefault(name, [0, 0.0])
             d[0] += 1
             d[1] += s0.elapsed_time(s1)
@@ -112,6 +125,9 @@ def main():
         print(f"# traced step: {t0.elapsed_time(t1):.1f} ms wall on the device, {total:.1f} ms inside library calls "
               f"(the rest: cuDNN convolutions forward / backward, torch glue)", file=sys.stderr)
         for name, (n, ms_) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"{ms_:9.2f} ms {n:6d} calls  {name}", file=sys.stderr)
+        print("# by shape (top 25)", file=sys.stderr)
+        for name, (n, ms_) in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:25]:
             print(f"{ms_:9.2f} ms {n:6d} calls  {name}", file=sys.stderr)
     if rank == 0:
         print(json.dumps({"metric": f"training steps/sec, {args.stage.upper()} stage, 1 clip 320x512x16f per GPU",

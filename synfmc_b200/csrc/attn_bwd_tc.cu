@@ -1,5 +1,5 @@
-// Spatial self-attention BACKWARD on the tensor cores (head_dim 40, the level-0 shape that dominates the training step:
-// 16 images x 8 heads x 2560 x 2560 per attention).  Flash style, probabilities recomputed; two kernels, both built like
+// Spatial self-attention BACKWARD on the tensor cores (head_dim 40 and 80: levels 0 and 1, which dominate the training
+// step -- 16 images x 8 heads x 2560 x 2560 resp. 640 x 640 per attention).  Flash style, probabilities recomputed; two kernels, both built like
 // the forward kernel of attn_spatial.cu (TMA producer warp, one tcgen05.mma issuer thread, TMEM allocator warp, four
 // softmax warps with one TMEM lane = one row per thread) and arranged so that EVERY MMA has the forward's operand forms --
 // A K-major from shared memory, B K-major for the score-type products, B MN-major for the accumulate-type products:
@@ -14,9 +14,11 @@
 //                 P^T = exp2(S^T c - L[query]),  dS^T = P^T (dP^T - D[query]) scale   -> bf16 -> smem
 //                 dV += P^T dO,  dK += dS^T Q                    (B = dO / Q tile, MN-major)
 //
-// The dO tiles come through a 3-D tensor map (d = 40, head, row) whose 64-wide box is zero-filled past column 40, so the
-// contraction over the padded head width (48) of dP = dO V^T sees zeros there whatever V holds in those columns; Q and K
-// heads are zero-padded to 48 by the projection itself.  L and D travel from the first kernel to the second through the
+// The dO tiles come through a 3-D tensor map (d, head, row) whose 64-wide boxes are zero-filled past the head's last
+// column, so the contraction over the padded head width (48 for head_dim 40) of dP = dO V^T sees zeros there whatever V
+// holds in those columns; Q and K heads are zero-padded by the projection itself.  Operand tiles wider than 64 columns
+// (head_dim 80) are two SWIZZLE_128B chunks, AB_TILE bytes apart (K-major: chunk = k / 4; MN-major: LBO).  The dK/dV
+// kernel takes 64-query tiles at head_dim 80 so that its resident K / V tiles and a two-deep (Q, dO) ring fit.  L and D travel from the first kernel to the second through the
 // [row, head] fp32 scratch buffers of the entry point.
 #include <cuda_bf16.h>
 
@@ -26,8 +28,6 @@
 namespace fmc {
 
 constexpr int AB_BM = 128;
-constexpr int AB_D = 40;
-constexpr int AB_DK = 48;
 constexpr int AB_THREADS = 256;
 constexpr int AB_TILE = AB_BM * 128;        // [128 rows x 64 bf16] SWIZZLE_128B tile
 constexpr int AB_PT = 2 * AB_BM * 128;      // [128 x 128] bf16 probability-type tile (two 64-column chunks)
@@ -54,6 +54,11 @@ __device__ __forceinline__ float ab_exp2(float x) {
 __device__ __forceinline__ void ab_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+__device__ __forceinline__ void ab_tma_load_3d(uint32_t smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 // row r of a [128 x 128] bf16 tile in the forward's P layout: 16-byte piece j (8 columns) of the row
 __device__ __forceinline__ uint32_t ab_piece_addr(uint32_t tile, int r, int piece) {
   return tile + static_cast<uint32_t>(r) * 128u + static_cast<uint32_t>(piece >> 3) * AB_TILE +
@@ -63,9 +68,15 @@ __device__ __forceinline__ uint32_t ab_piece_addr(uint32_t tile, int r, int piec
 // =====================================================================================================================
 // dQ kernel
 // =====================================================================================================================
-constexpr int ABQ_STAGES = 3;
-constexpr int ABQ_SMEM = 2 * AB_TILE + AB_PT + ABQ_STAGES * 2 * AB_TILE + 1024;
+template <int D, int ABQ_STAGES>
+struct AbqCfg {
+  static constexpr int DK = (D + 15) / 16 * 16;
+  static constexpr int CH = (DK + 63) / 64;
+  static constexpr int OT = CH * AB_TILE;  // one operand tile: 128 rows x DK columns
+  static constexpr int SMEM = 2 * OT + AB_PT + ABQ_STAGES * 2 * OT + 1024;
+};
 
+template <int AB_D, int ABQ_STAGES>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmG, AbParams p) {
@@ -75,7 +86,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __shared__ uint64_t kv_full[ABQ_STAGES], kv_empty[ABQ_STAGES];
   __shared__ uint32_t tmem_base_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base, sG = sQ + AB_TILE, sDS = sG + AB_TILE, sKV = sDS + AB_PT;
+  using Cfg = AbqCfg<AB_D, ABQ_STAGES>;
+  constexpr int AB_DK = Cfg::DK, CH = Cfg::CH, OT = Cfg::OT;
+  const uint32_t sQ = smem_base, sG = sQ + OT, sDS = sG + OT, sKV = sDS + AB_PT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = p.images * p.heads * p.blocks;
   const int T = p.blocks;
@@ -107,20 +120,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int img = item / (p.blocks * p.heads);
         const int row0 = img * p.n;
         mbar_wait(&q_empty, (it & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&q_full, 2 * AB_TILE);
-        tma_load_2d_a(sQ, &tmQ, &q_full, p.q_col0 + head * p.head_stride, row0 + qb * AB_BM);
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-            ::"r"(sG), "l"(reinterpret_cast<uint64_t>(&tmG)), "r"(smem_u32(&q_full)), "r"(0), "r"(head),
-            "r"(row0 + qb * AB_BM) : "memory");
+        mbar_arrive_expect_tx(&q_full, 2 * OT);
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+          tma_load_2d_a(sQ + ch * AB_TILE, &tmQ, &q_full, p.q_col0 + head * p.head_stride + ch * 64, row0 + qb * AB_BM);
+          ab_tma_load_3d(sG + ch * AB_TILE, &tmG, &q_full, ch * 64, head, row0 + qb * AB_BM);
+        }
         for (int u = 0; u < 2 * T; ++u, ++t) {
           const int j = u < T ? u : u - T;
           const int st = t % ABQ_STAGES;
           mbar_wait(&kv_empty[st], ((t / ABQ_STAGES) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&kv_full[st], 2 * AB_TILE);
-          const uint32_t sK = sKV + st * 2 * AB_TILE;
-          tma_load_2d_a(sK, &tmK, &kv_full[st], p.k_col0 + head * p.head_stride, row0 + j * AB_BM);
-          tma_load_2d_a(sK + AB_TILE, &tmV, &kv_full[st], p.v_col0 + head * AB_D, row0 + j * AB_BM);
+          mbar_arrive_expect_tx(&kv_full[st], 2 * OT);
+          const uint32_t sK = sKV + st * 2 * OT;
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch) {
+            tma_load_2d_a(sK + ch * AB_TILE, &tmK, &kv_full[st], p.k_col0 + head * p.head_stride + ch * 64, row0 + j * AB_BM);
+            tma_load_2d_a(sK + OT + ch * AB_TILE, &tmV, &kv_full[st], p.v_col0 + head * AB_D + ch * 64, row0 + j * AB_BM);
+          }
         }
       }
     }
@@ -133,7 +149,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       auto issue_dq = [&](int st, bool first) {
         mbar_wait(&ds_ready, nds & 1u);
         tc_fence_after_sync();
-        const uint32_t sK = sKV + st * 2 * AB_TILE;
+        const uint32_t sK = sKV + st * 2 * OT;
 #pragma unroll
         for (int k = 0; k < AB_BM / 16; ++k) {
           const uint64_t da = umma_desc_k_sw128(sDS + (k >> 2) * AB_TILE + (k & 3) * 32);
@@ -153,15 +169,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           mbar_wait(&kv_full[st], (t / ABQ_STAGES) & 1u);
           mbar_wait(&s_free, (t & 1u) ^ 1u);
           tc_fence_after_sync();
-          const uint32_t sK = sKV + st * 2 * AB_TILE;
+          const uint32_t sK = sKV + st * 2 * OT;
 #pragma unroll
-          for (int k = 0; k < AB_DK / 16; ++k)
-            umma_bf16_ss(tmem_base, umma_desc_k_sw128(sQ + k * 32), umma_desc_k_sw128(sK + k * 32), idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < AB_DK / 16; ++k) {
+            const uint32_t off = (k >> 2) * AB_TILE + (k & 3) * 32;
+            umma_bf16_ss(tmem_base, umma_desc_k_sw128(sQ + off), umma_desc_k_sw128(sK + off), idesc_s, k > 0 ? 1u : 0u);
+          }
           if (u >= T) {
 #pragma unroll
-            for (int k = 0; k < AB_DK / 16; ++k)
-              umma_bf16_ss(tmem_base + 128u, umma_desc_k_sw128(sG + k * 32), umma_desc_k_sw128(sK + AB_TILE + k * 32), idesc_s,
+            for (int k = 0; k < AB_DK / 16; ++k) {
+              const uint32_t off = (k >> 2) * AB_TILE + (k & 3) * 32;
+              umma_bf16_ss(tmem_base + 128u, umma_desc_k_sw128(sG + off), umma_desc_k_sw128(sK + OT + off), idesc_s,
                            k > 0 ? 1u : 0u);
+            }
           }
           umma_commit(&s_full);
           if (u < T) {
@@ -309,23 +329,35 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // =====================================================================================================================
 // dK / dV kernel (transposed scores: TMEM lane = key, column = query)
 // =====================================================================================================================
-constexpr int ABK_STAGES = 2;
-constexpr int ABK_SMEM = 2 * AB_TILE + 2 * AB_PT + ABK_STAGES * 2 * AB_TILE + 1024;
+template <int D, int BQ, int STAGES>
+struct AbkCfg {
+  static constexpr int DK = (D + 15) / 16 * 16;
+  static constexpr int CH = (DK + 63) / 64;
+  static constexpr int OT = CH * AB_TILE;    // resident K / V tile: 128 rows x DK columns
+  static constexpr int QC = BQ * 128;        // one 64-column chunk of a BQ-row (Q / dO) tile
+  static constexpr int QT = CH * QC;         // Q / dO tile: BQ rows x DK columns
+  static constexpr int PT = (BQ / 64) * AB_TILE;  // P^T / dS^T tile: 128 keys x BQ queries
+  static constexpr int SMEM = 2 * OT + 2 * PT + STAGES * 2 * QT + 1024;
+  static_assert(256 + 2 * DK <= 512, "TMEM: S^T, dP^T, dV, dK");
+};
 
+template <int AB_D, int BQ, int ABK_STAGES>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmG, AbParams p) {
   pdl_launch_dependents();
+  using Cfg = AbkCfg<AB_D, BQ, ABK_STAGES>;
+  constexpr int AB_DK = Cfg::DK, CH = Cfg::CH, OT = Cfg::OT, QC = Cfg::QC, QT = Cfg::QT, PT = Cfg::PT;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t kv_full, kv_empty, s_full, s_free, pds_ready, pds_free, acc_final, acc_free;
   __shared__ uint64_t q_full[ABK_STAGES], q_empty[ABK_STAGES];
-  __shared__ float vec_l[2][AB_BM], vec_d[2][AB_BM];
+  __shared__ float vec_l[2][BQ], vec_d[2][BQ];
   __shared__ uint32_t tmem_base_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sK = smem_base, sV = sK + AB_TILE, sP = sV + AB_TILE, sDS = sP + AB_PT, sQG = sDS + AB_PT;
+  const uint32_t sK = smem_base, sV = sK + OT, sP = sV + OT, sDS = sP + PT, sQG = sDS + PT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = p.images * p.heads * p.blocks;
-  const int T = p.blocks;
+  const int T = (p.n + BQ - 1) / BQ;  // query tiles per image
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmG);
@@ -354,43 +386,46 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int img = item / (p.blocks * p.heads);
         const int row0 = img * p.n;
         mbar_wait(&kv_empty, (it & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&kv_full, 2 * AB_TILE);
-        tma_load_2d_a(sK, &tmK, &kv_full, p.k_col0 + head * p.head_stride, row0 + kb * AB_BM);
-        tma_load_2d_a(sV, &tmV, &kv_full, p.v_col0 + head * AB_D, row0 + kb * AB_BM);
+        mbar_arrive_expect_tx(&kv_full, 2 * OT);
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+          tma_load_2d_a(sK + ch * AB_TILE, &tmK, &kv_full, p.k_col0 + head * p.head_stride + ch * 64, row0 + kb * AB_BM);
+          tma_load_2d_a(sV + ch * AB_TILE, &tmV, &kv_full, p.v_col0 + head * AB_D + ch * 64, row0 + kb * AB_BM);
+        }
         for (int i = 0; i < T; ++i, ++t) {
           const int st = t % ABK_STAGES;
           mbar_wait(&q_empty[st], ((t / ABK_STAGES) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&q_full[st], 2 * AB_TILE);
-          const uint32_t sQ = sQG + st * 2 * AB_TILE;
-          tma_load_2d_a(sQ, &tmQ, &q_full[st], p.q_col0 + head * p.head_stride, row0 + i * AB_BM);
-          asm volatile(
-              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-              ::"r"(sQ + AB_TILE), "l"(reinterpret_cast<uint64_t>(&tmG)), "r"(smem_u32(&q_full[st])), "r"(0), "r"(head),
-              "r"(row0 + i * AB_BM) : "memory");
+          mbar_arrive_expect_tx(&q_full[st], 2 * QT);
+          const uint32_t sQ = sQG + st * 2 * QT;
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch) {
+            tma_load_2d_a(sQ + ch * QC, &tmQ, &q_full[st], p.q_col0 + head * p.head_stride + ch * 64, row0 + i * BQ);
+            ab_tma_load_3d(sQ + QT + ch * QC, &tmG, &q_full[st], ch * 64, head, row0 + i * BQ);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(AB_BM, AB_BM);
+      constexpr uint32_t idesc_s = umma_idesc_bf16(AB_BM, BQ);
       constexpr uint32_t idesc_a = umma_idesc_bf16_bmn(AB_BM, AB_DK);
       uint32_t t = 0, it = 0, npd = 0;
       // dV += P^T dO, dK += dS^T Q with the (Q, dO) tiles of stage `st`
       auto issue_acc = [&](int st, bool first) {
         mbar_wait(&pds_ready, npd & 1u);
         tc_fence_after_sync();
-        const uint32_t sQ = sQG + st * 2 * AB_TILE, sG = sQ + AB_TILE;
+        const uint32_t sQ = sQG + st * 2 * QT, sG = sQ + QT;
 #pragma unroll
-        for (int k = 0; k < AB_BM / 16; ++k) {
+        for (int k = 0; k < BQ / 16; ++k) {
           const uint64_t da = umma_desc_k_sw128(sP + (k >> 2) * AB_TILE + (k & 3) * 32);
-          const uint64_t db = umma_desc_mn_sw128(sG + k * (16 * 128), AB_TILE, 1024);
+          const uint64_t db = umma_desc_mn_sw128(sG + k * (16 * 128), QC, 1024);
           umma_bf16_ss(tmem_base + 256u, da, db, idesc_a, (!first || k > 0) ? 1u : 0u);
         }
 #pragma unroll
-        for (int k = 0; k < AB_BM / 16; ++k) {
+        for (int k = 0; k < BQ / 16; ++k) {
           const uint64_t da = umma_desc_k_sw128(sDS + (k >> 2) * AB_TILE + (k & 3) * 32);
-          const uint64_t db = umma_desc_mn_sw128(sQ + k * (16 * 128), AB_TILE, 1024);
-          umma_bf16_ss(tmem_base + 320u, da, db, idesc_a, (!first || k > 0) ? 1u : 0u);
+          const uint64_t db = umma_desc_mn_sw128(sQ + k * (16 * 128), QC, 1024);
+          umma_bf16_ss(tmem_base + 256u + AB_DK, da, db, idesc_a, (!first || k > 0) ? 1u : 0u);
         }
         umma_commit(&q_empty[st]);
         umma_commit(&pds_free);
@@ -405,14 +440,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           mbar_wait(&q_full[st], (t / ABK_STAGES) & 1u);
           mbar_wait(&s_free, (t & 1u) ^ 1u);
           tc_fence_after_sync();
-          const uint32_t sQ = sQG + st * 2 * AB_TILE, sG = sQ + AB_TILE;
+          const uint32_t sQ = sQG + st * 2 * QT, sG = sQ + QT;
 #pragma unroll
           for (int k = 0; k < AB_DK / 16; ++k)  // S^T = K Q^T
-            umma_bf16_ss(tmem_base, umma_desc_k_sw128(sK + k * 32), umma_desc_k_sw128(sQ + k * 32), idesc_s, k > 0 ? 1u : 0u);
+            umma_bf16_ss(tmem_base, umma_desc_k_sw128(sK + (k >> 2) * AB_TILE + (k & 3) * 32),
+                         umma_desc_k_sw128(sQ + (k >> 2) * QC + (k & 3) * 32), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < AB_DK / 16; ++k)  // dP^T = V dO^T (dO zero beyond column 40)
-            umma_bf16_ss(tmem_base + 128u, umma_desc_k_sw128(sV + k * 32), umma_desc_k_sw128(sG + k * 32), idesc_s,
-                         k > 0 ? 1u : 0u);
+          for (int k = 0; k < AB_DK / 16; ++k)  // dP^T = V dO^T (dO zero beyond the head's last column)
+            umma_bf16_ss(tmem_base + 128u, umma_desc_k_sw128(sV + (k >> 2) * AB_TILE + (k & 3) * 32),
+                         umma_desc_k_sw128(sG + (k >> 2) * QC + (k & 3) * 32), idesc_s, k > 0 ? 1u : 0u);
           umma_commit(&s_full);
           if (prev_st >= 0) {
             issue_acc(prev_st, i == 1);
@@ -442,8 +478,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int i = 0; i < T; ++i, ++t) {
         // per-query log-sum-exp / D of this query tile (written by the dQ kernel): +inf masks queries past the image
         const int buf = t & 1u;
-        {
-          const int qi = i * AB_BM + tid;
+        if (tid < BQ) {
+          const int qi = i * BQ + tid;
           const bool ok = qi < p.n;
           vec_l[buf][tid] = ok ? p.lse[(img_row0 + qi) * p.heads + head] : INFINITY;
           vec_d[buf][tid] = ok ? p.dsum[(img_row0 + qi) * p.heads + head] : 0.f;
@@ -452,7 +488,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         mbar_wait(&s_full, t & 1u);
         tc_fence_after_sync();
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
+        for (int c4 = 0; c4 < BQ / 32; ++c4) {
           uint32_t sv[32], dv[32], pp[16], pd[16];
           tmem_ld_x32(lane_addr + c4 * 32, sv);
           tmem_ld_x32(lane_addr + 128u + c4 * 32, dv);
@@ -482,7 +518,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         if (lane == 0) mbar_arrive(&pds_ready);
         ++npd;
       }
-      // ---- epilogue: dV (columns 256..), dK (columns 320..) -> bf16 -> global
+      // ---- epilogue: dV (columns 256..), dK (columns 256 + DK ..) -> bf16 -> global
       mbar_wait(&acc_final, it & 1u);
       tc_fence_after_sync();
       const int k_in_img = kb * AB_BM + r;
@@ -495,7 +531,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll 1
         for (int cc = 0; cc < AB_DK / 16; ++cc) {
           uint32_t o[16];
-          tmem_ld_x16(lane_addr + (which == 0 ? 256u : 320u) + cc * 16, o);
+          tmem_ld_x16(lane_addr + 256u + (which == 0 ? 0u : static_cast<uint32_t>(AB_DK)) + cc * 16, o);
           tmem_ld_wait();
           if (row_ok) {
             uint32_t w[8];
@@ -520,34 +556,37 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
 }
 
-// host side: tensor maps + launches; returns FMC_OK or an error (the caller falls back to nothing: an error is an error)
-int attention_bwd_tc_d40(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0, const void* V,
-                         long long ldv, int v_col0, int head_stride, const void* O, long long ldo, const void* dO,
-                         long long lddo, void* dQ, long long lddq, int dq_col0, void* dK, long long lddk, int dk_col0,
-                         void* dV, long long lddv, int dv_col0, float* lse, float* dsum, int images, int heads, int n,
-                         float scale, cudaStream_t stream) {
+// host side: tensor maps + launches
+template <int D, int QSTAGES, int BQ, int KSTAGES>
+static int attention_bwd_tc_launch(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
+                                   const void* V, long long ldv, int v_col0, int head_stride, const void* O, long long ldo,
+                                   const void* dO, long long lddo, void* dQ, long long lddq, int dq_col0, void* dK,
+                                   long long lddk, int dk_col0, void* dV, long long lddv, int dv_col0, float* lse, float* dsum,
+                                   int images, int heads, int n, float scale, cudaStream_t stream) {
+  using CfgQ = AbqCfg<D, QSTAGES>;
+  using CfgK = AbkCfg<D, BQ, KSTAGES>;
   const long long rows = static_cast<long long>(images) * n;
-  CUtensorMap tmQ, tmK, tmV, tmG;
-  const uint32_t box[2] = {64, 128};
-  auto map2d = [&](CUtensorMap* m, const void* base, long long ld) {
+  CUtensorMap tmQ, tmK, tmV, tmG, tmQb, tmGb;
+  auto map2d = [&](CUtensorMap* m, const void* base, long long ld, int box_rows) {
     const uint64_t dims[2] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(rows)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ld) * 2};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(box_rows)};
     return make_tmap_bf16(m, base, 2, dims, strides, box, true);
   };
-  int rc = map2d(&tmQ, Q, ldq);
+  // dO as (d, head, row): 64-wide boxes are zero-filled past the head's last column
+  auto map_do = [&](CUtensorMap* m, int box_rows) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(heads), static_cast<uint64_t>(rows)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(lddo) * 2};
+    const uint32_t box3[3] = {64, 1, static_cast<uint32_t>(box_rows)};
+    return make_tmap_bf16(m, dO, 3, dims, strides, box3, true);
+  };
+  int rc = map2d(&tmQ, Q, ldq, AB_BM);
+  if (rc == FMC_OK) rc = map2d(&tmK, K, ldk, AB_BM);
+  if (rc == FMC_OK) rc = map2d(&tmV, V, ldv, AB_BM);
+  if (rc == FMC_OK) rc = map_do(&tmG, AB_BM);
+  if (rc == FMC_OK) rc = map2d(&tmQb, Q, ldq, BQ);
+  if (rc == FMC_OK) rc = map_do(&tmGb, BQ);
   if (rc != FMC_OK) return rc;
-  rc = map2d(&tmK, K, ldk);
-  if (rc != FMC_OK) return rc;
-  rc = map2d(&tmV, V, ldv);
-  if (rc != FMC_OK) return rc;
-  {
-    // dO as (d = 40, head, row): the 64-wide box is zero-filled past column 40 of the head
-    const uint64_t dims[3] = {static_cast<uint64_t>(AB_D), static_cast<uint64_t>(heads), static_cast<uint64_t>(rows)};
-    const uint64_t strides[2] = {static_cast<uint64_t>(AB_D) * 2, static_cast<uint64_t>(lddo) * 2};
-    const uint32_t box3[3] = {64, 1, 128};
-    rc = make_tmap_bf16(&tmG, dO, 3, dims, strides, box3, true);
-    if (rc != FMC_OK) return rc;
-  }
   AbParams p{};
   p.heads = heads; p.n = n; p.images = images; p.blocks = ceil_div(n, AB_BM);
   p.head_stride = head_stride; p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
@@ -559,16 +598,35 @@ int attention_bwd_tc_d40(const void* Q, long long ldq, int q_col0, const void* K
   p.lse = lse; p.dsum = dsum;
   static unsigned long long attr_devs = 0;
   if (first_use_on_this_device(&attr_devs)) {
-    FMC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ABQ_SMEM));
-    FMC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ABK_SMEM));
+    FMC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<D, QSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQ::SMEM));
+    FMC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<D, BQ, KSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     CfgK::SMEM));
   }
   const int items = images * heads * p.blocks;
   const int grid = items < device_sm_count() ? items : device_sm_count();
-  launch_k(attn_bwd_dq_tc_kernel, dim3(grid), dim3(AB_THREADS), ABQ_SMEM, stream, tmQ, tmK, tmV, tmG, p);
+  launch_k(attn_bwd_dq_tc_kernel<D, QSTAGES>, dim3(grid), dim3(AB_THREADS), CfgQ::SMEM, stream, tmQ, tmK, tmV, tmG, p);
   rc = check_launch("attn_bwd_dq_tc_kernel");
   if (rc != FMC_OK) return rc;
-  launch_k(attn_bwd_dkv_tc_kernel, dim3(grid), dim3(AB_THREADS), ABK_SMEM, stream, tmQ, tmK, tmV, tmG, p);
+  launch_k(attn_bwd_dkv_tc_kernel<D, BQ, KSTAGES>, dim3(grid), dim3(AB_THREADS), CfgK::SMEM, stream, tmQb, tmK, tmV, tmGb, p);
   return check_launch("attn_bwd_dkv_tc_kernel");
+}
+
+// head_dim 40 (heads padded to 48) or 80; anything else is the caller's SIMT path
+int attention_bwd_tc(int head_dim, const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
+                     const void* V, long long ldv, int v_col0, int head_stride, const void* O, long long ldo, const void* dO,
+                     long long lddo, void* dQ, long long lddq, int dq_col0, void* dK, long long lddk, int dk_col0, void* dV,
+                     long long lddv, int dv_col0, float* lse, float* dsum, int images, int heads, int n, float scale,
+                     cudaStream_t stream) {
+  if (head_dim == 40)
+    return attention_bwd_tc_launch<40, 3, 128, 2>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
+                                                  dQ, lddq, dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images,
+                                                  heads, n, scale, stream);
+  if (head_dim == 80)
+    return attention_bwd_tc_launch<80, 2, 64, 2>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
+                                                 dQ, lddq, dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images,
+                                                 heads, n, scale, stream);
+  set_error("attention_bwd_tc: head_dim %d not in {40, 80}", head_dim);
+  return FMC_ERR_SHAPE;
 }
 
 }  // namespace fmc

@@ -766,6 +766,141 @@ static int launch_attention_bwd(const AttnBwdParams& p, bool want_dkv, cudaStrea
   return check_launch("attention_bwd_dkv_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Temporal self-attention backward for 16-frame sequences (every motion-module attention of the training configs):
+// one warp per (sequence, head), everything of the 16 x 16 problem on chip.  The four operand slices (Q, K, V, dO:
+// 16 rows x D) are staged in shared memory as bf16 with a 16-byte row pad; phase 1 has lane = (query i, half of the keys)
+// and computes S, P, dP, D_i = sum_j P_ij dP_ij (= sum_c dO_ic O_ic, so O is not read) and dS in fp32; phase 2 has
+// lane = (row, half of the channels) and forms dQ = dS K, dK = dS^T Q, dV = P^T dO in 20-channel chunks.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8f(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+template <int D, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+temporal16_attn_bwd_kernel(AttnBwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int F = 16, VPR = D / 8, PITCH = D * 2 + 16, TILE = F * PITCH, PS = 17;
+  constexpr int WARP_BYTES = 4 * TILE + 2 * F * PS * 4;
+  extern __shared__ __align__(16) uint8_t smem_t16[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = static_cast<long long>(blockIdx.x) * WARPS + warp;
+  if (w >= static_cast<long long>(p.images) * p.heads) return;  // warp-uniform; only __syncwarp below
+  const int seq = static_cast<int>(w / p.heads), head = static_cast<int>(w % p.heads);
+  const long long row0 = static_cast<long long>(seq / p.inner) * F * p.inner + (seq % p.inner);
+  uint8_t* sq = smem_t16 + warp * WARP_BYTES;
+  uint8_t* sk = sq + TILE;
+  uint8_t* sv = sk + TILE;
+  uint8_t* sg = sv + TILE;
+  float* sp = reinterpret_cast<float*>(sg + TILE);  // P  [16][17]
+  float* sd = sp + F * PS;                          // dS [16][17]
+  for (int idx = lane; idx < 4 * F * VPR; idx += 32) {
+    const int op = idx / (F * VPR), rem = idx % (F * VPR), t = rem / VPR, v = rem % VPR;
+    const long long row = row0 + static_cast<long long>(t) * p.inner;
+    const __nv_bfloat16* src = op == 0   ? p.Q + row * p.ldq + p.q_col0 + head * p.head_stride
+                               : op == 1 ? p.K + row * p.ldk + p.k_col0 + head * p.head_stride
+                               : op == 2 ? p.V + row * p.ldv + p.v_col0 + head * D
+                                         : p.dO + row * p.lddo + head * D;
+    *reinterpret_cast<uint4*>(sq + op * TILE + t * PITCH + v * 16) = __ldg(reinterpret_cast<const uint4*>(src) + v);
+  }
+  __syncwarp();
+  {
+    const int i = lane >> 1, j0 = (lane & 1) * 8;
+    float s[8], dp[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) s[jj] = dp[jj] = 0.f;
+#pragma unroll 1
+    for (int v = 0; v < VPR; ++v) {
+      float q8[8], g8[8];
+      unpack8f(*reinterpret_cast<const uint4*>(sq + i * PITCH + v * 16), q8);
+      unpack8f(*reinterpret_cast<const uint4*>(sg + i * PITCH + v * 16), g8);
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        float k8[8], v8[8];
+        unpack8f(*reinterpret_cast<const uint4*>(sk + (j0 + jj) * PITCH + v * 16), k8);
+        unpack8f(*reinterpret_cast<const uint4*>(sv + (j0 + jj) * PITCH + v * 16), v8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s[jj] = fmaf(q8[e], k8[e], s[jj]);
+          dp[jj] = fmaf(g8[e], v8[e], dp[jj]);
+        }
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) { s[jj] *= p.scale; mx = fmaxf(mx, s[jj]); }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) { s[jj] = __expf(s[jj] - mx); sum += s[jj]; }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    const float inv = 1.f / sum;
+    float dsum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) { s[jj] *= inv; dsum = fmaf(s[jj], dp[jj], dsum); }
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      sp[i * PS + j0 + jj] = s[jj];
+      sd[i * PS + j0 + jj] = s[jj] * (dp[jj] - dsum) * p.scale;
+    }
+  }
+  __syncwarp();
+  {
+    const int r = lane & 15, ch = lane >> 4;
+    const long long row = row0 + static_cast<long long>(r) * p.inner;
+    __nv_bfloat16* dq = p.dQ + row * p.lddq + p.dq_col0 + head * p.head_stride;
+    __nv_bfloat16* dk = p.dK + row * p.lddk + p.dk_col0 + head * p.head_stride;
+    __nv_bfloat16* dv = p.dV + row * p.lddv + p.dv_col0 + head * D;
+#pragma unroll 1
+    for (int which = 0; which < 3; ++which) {
+      const uint8_t* src = which == 0 ? sk : which == 1 ? sq : sg;  // dQ = dS K, dK = dS^T Q, dV = P^T dO
+      const float* coef = which == 2 ? sp : sd;
+      const int cstride_t = which == 0 ? 1 : PS, cstride_r = which == 0 ? PS : 1;  // coefficient of (own row r, other t)
+      __nv_bfloat16* dst = which == 0 ? dq : which == 1 ? dk : dv;
+#pragma unroll 1
+      for (int cc = 0; cc < D / 40; ++cc) {
+        const int c0 = ch * (D / 2) + cc * 20;
+        float acc[20];
+#pragma unroll
+        for (int e = 0; e < 20; ++e) acc[e] = 0.f;
+#pragma unroll 4
+        for (int t = 0; t < F; ++t) {
+          const float a = coef[r * cstride_r + t * cstride_t];
+          const uint2* sp2 = reinterpret_cast<const uint2*>(src + t * PITCH + c0 * 2);
+#pragma unroll
+          for (int v = 0; v < 5; ++v) {
+            const uint2 x = sp2[v];
+            acc[4 * v] = fmaf(a, bf16_lo(x.x), acc[4 * v]);
+            acc[4 * v + 1] = fmaf(a, bf16_hi(x.x), acc[4 * v + 1]);
+            acc[4 * v + 2] = fmaf(a, bf16_lo(x.y), acc[4 * v + 2]);
+            acc[4 * v + 3] = fmaf(a, bf16_hi(x.y), acc[4 * v + 3]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < 5; ++v)
+          reinterpret_cast<uint2*>(dst + c0)[v] =
+              make_uint2(pack_bf16x2(acc[4 * v], acc[4 * v + 1]), pack_bf16x2(acc[4 * v + 2], acc[4 * v + 3]));
+      }
+    }
+  }
+}
+
+template <int D, int WARPS>
+static int launch_temporal16_attn_bwd(const AttnBwdParams& p, cudaStream_t stream) {
+  constexpr int smem = WARPS * (4 * 16 * (D * 2 + 16) + 2 * 16 * 17 * 4);
+  static unsigned long long attr_devs = 0;
+  if (first_use_on_this_device(&attr_devs))
+    FMC_CUDA_OK(cudaFuncSetAttribute(temporal16_attn_bwd_kernel<D, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const long long warps = static_cast<long long>(p.images) * p.heads;
+  FMC_CUDA_OK(launch_k(temporal16_attn_bwd_kernel<D, WARPS>, dim3(static_cast<unsigned>((warps + WARPS - 1) / WARPS)),
+                       dim3(WARPS * 32), smem, stream, p));
+  return check_launch("temporal16_attn_bwd_kernel");
+}
+
 }  // namespace fmc
 
 using namespace fmc;
@@ -915,7 +1050,7 @@ extern "C" int fmc_avgpool2_bwd_bf16(const void* dy, void* dx, int N, int h, int
 }
 
 namespace fmc {
-int attention_bwd_tc_d40(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0, const void* V,
+int attention_bwd_tc(int head_dim, const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0, const void* V,
                          long long ldv, int v_col0, int head_stride, const void* O, long long ldo, const void* dO,
                          long long lddo, void* dQ, long long lddq, int dq_col0, void* dK, long long lddk, int dk_col0,
                          void* dV, long long lddv, int dv_col0, float* lse, float* dsum, int images, int heads, int n,
@@ -952,9 +1087,20 @@ extern "C" int fmc_attention_bwd_bf16(const void* Q, long long ldq, int q_col0, 
   // FMC_ATTN_BWD_SIMT=1 keeps the SIMT kernels below for A/B checks
   const char* simt_env = getenv("FMC_ATTN_BWD_SIMT");
   const bool force_simt = simt_env && simt_env[0] == '1';
-  if (head_dim == 40 && head_stride == 48 && inner == 1 && dK != nullptr && !force_simt && ldo % 8 == 0 && lddq % 8 == 0 &&
-      lddk % 8 == 0 && lddv % 8 == 0 && dq_col0 % 8 == 0 && dk_col0 % 8 == 0 && dv_col0 % 8 == 0)
-    return attention_bwd_tc_d40(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo, dQ, lddq,
+  const bool aligned8 = ldo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 && dq_col0 % 8 == 0 &&
+                        dk_col0 % 8 == 0 && dv_col0 % 8 == 0;
+  // 16-frame self-attention (every motion-module attention): one warp per (sequence, head), all on chip
+  if (nq == 16 && nk == 16 && dK != nullptr && !force_simt && aligned8) {
+    switch (head_dim) {
+      case 40: return launch_temporal16_attn_bwd<40, 8>(p, stream);
+      case 80: return launch_temporal16_attn_bwd<80, 8>(p, stream);
+      case 160: return launch_temporal16_attn_bwd<160, 4>(p, stream);
+      default: break;
+    }
+  }
+  if (((head_dim == 40 && head_stride == 48) || (head_dim == 80 && head_stride == 80)) && inner == 1 && dK != nullptr &&
+      !force_simt && aligned8)
+    return attention_bwd_tc(head_dim, Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo, dQ, lddq,
                                 dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images, heads, nq, scale, stream);
   switch (head_dim) {
     case 40: return launch_attention_bwd<40>(p, dK != nullptr, stream);

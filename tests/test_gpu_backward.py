@@ -157,12 +157,12 @@ def test_attention_bwd_spatial_self(B, cuda_device, d, images, n):
         assert float(got[:, :k0].view(-1, heads, hs)[:, :, d:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("images,n", [(3, 2560), (2, 129), (1, 128)])
-def test_attention_bwd_tensor_core_matches_simt(B, cuda_device, monkeypatch, images, n):
-    """head_dim 40 self-attention: the tcgen05 kernels (csrc/attn_bwd_tc.cu) against the SIMT kernels on the same buffers,
-    including the level-0 sequence length (2560) and ragged last tiles."""
+@pytest.mark.parametrize("d,images,n", [(40, 3, 2560), (40, 2, 129), (40, 1, 128), (80, 3, 640), (80, 2, 200), (80, 1, 65)])
+def test_attention_bwd_tensor_core_matches_simt(B, cuda_device, monkeypatch, d, images, n):
+    """head_dim 40 / 80 self-attention: the tcgen05 kernels (csrc/attn_bwd_tc.cu) against the SIMT kernels on the same
+    buffers, including the level-0 / level-1 sequence lengths (2560, 640) and ragged last tiles."""
     from synfmc_b200 import ops
-    heads, d, hs = 8, 40, 48
+    heads, hs = 8, (d + 15) // 16 * 16
     qkv = torch.zeros(images * n, 2 * heads * hs + heads * d)
     qkv[:, :heads * hs] = _pad_heads(randn(images * n, heads * d, seed=1), heads, d, hs)
     qkv[:, heads * hs:2 * heads * hs] = _pad_heads(randn(images * n, heads * d, seed=2), heads, d, hs)
@@ -182,7 +182,35 @@ def test_attention_bwd_tensor_core_matches_simt(B, cuda_device, monkeypatch, ima
         out[mode] = dqkv.float().cpu()
     for lo, hi in ((0, k0), (k0, v0), (v0, qkv.shape[1])):
         assert rel(out["0"][:, lo:hi], out["1"][:, lo:hi]) < BF16_TOL
-    assert float(out["0"][:, :v0].view(-1, 2 * heads, hs)[:, :, d:].abs().max()) == 0.0
+    if hs != d:
+        assert float(out["0"][:, :v0].view(-1, 2 * heads, hs)[:, :, d:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("d,Bc,HW", [(40, 1, 300), (80, 2, 33), (160, 1, 9)])
+def test_attention_bwd_temporal16_matches_simt(B, cuda_device, monkeypatch, d, Bc, HW):
+    """16-frame temporal self-attention: the one-warp-per-sequence kernel against the generic SIMT kernels."""
+    heads, hs, F = 8, (d + 15) // 16 * 16, 16
+    rows = Bc * F * HW
+    qkv = torch.zeros(rows, 2 * heads * hs + heads * d)
+    qkv[:, :heads * hs] = _pad_heads(randn(rows, heads * d, seed=1), heads, d, hs)
+    qkv[:, heads * hs:2 * heads * hs] = _pad_heads(randn(rows, heads * d, seed=2), heads, d, hs)
+    qkv[:, 2 * heads * hs:] = randn(rows, heads * d, seed=3)
+    dev_qkv = bf(qkv).to(cuda_device)
+    k0, v0 = heads * hs, 2 * heads * hs
+    dev_o = bf(randn(rows, heads * d, seed=5)).to(cuda_device)  # only the SIMT path reads O (D = sum dO O); see below
+    from synfmc_b200 import ops
+    ops.temporal_attn(dev_qkv, 0, k0, v0, hs, dev_o, Bc, F, HW, heads, d, d ** -0.5)
+    dev_do = bf(randn(rows, heads * d, seed=4)).to(cuda_device)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("FMC_ATTN_BWD_SIMT", mode)
+        dqkv = torch.zeros_like(dev_qkv)
+        B.attention_bwd(dev_qkv, 0, dev_qkv, k0, dev_qkv, v0, hs, dev_o, dev_do, dqkv, 0, dqkv, k0, dqkv, v0, Bc * HW, heads, d,
+                        F, F, 1, F, HW, d ** -0.5)
+        torch.cuda.synchronize()
+        out[mode] = dqkv.float().cpu()
+    for lo, hi in ((0, k0), (k0, v0), (v0, qkv.shape[1])):
+        assert rel(out["0"][:, lo:hi], out["1"][:, lo:hi]) < BF16_TOL
 
 
 @pytest.mark.parametrize("d,images,nq,kv_div", [(40, 4, 200, 2), (160, 4, 64, 4)])
@@ -208,7 +236,7 @@ def test_attention_bwd_text_cross(B, cuda_device, d, images, nq, kv_div):
     assert rel(got, q.grad) < BF16_TOL
 
 
-@pytest.mark.parametrize("d,Bc,F,HW", [(40, 2, 16, 60), (80, 1, 16, 20), (160, 1, 8, 9)])
+@pytest.mark.parametrize("d,Bc,F,HW", [(40, 2, 16, 60), (80, 1, 16, 20), (160, 1, 8, 9), (160, 1, 16, 9)])
 def test_attention_bwd_temporal(B, cuda_device, d, Bc, F, HW):
     """Temporal attention over the frame axis of channels-last rows (inner = HW)."""
     heads, hs, C = 8, (d + 15) // 16 * 16, 8 * d
