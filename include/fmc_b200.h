@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FMC_B200_ABI_VERSION 2
+#define FMC_B200_ABI_VERSION 3
 
 /* flags for fmc_gemm_bf16 */
 #define FMC_GEMM_GEGLU 1   /* W rows interleaved (16 value, 16 gate); C[M, N/2] = value * gelu_erf(gate) */
@@ -227,7 +227,9 @@ int fmc_layernorm_bwd_bf16(const void* x, long long ldx, const void* dy, long lo
                            void* dx, long long lddx, float* param_partials, long long rows, int C, void* stream);
 
 /* GroupNorm backward with the forward's options (per-image channel bias added before the norm, SiLU after it), frozen
- * affine parameters; stats_ws: 4 * images * groups floats. */
+ * affine parameters; stats_ws: fmc_groupnorm_bwd_workspace_floats(images, HW, groups) floats (per-chunk partial sums of
+ * the three passes: statistics, the two group means of the gradient, dx). */
+long long fmc_groupnorm_bwd_workspace_floats(int images, int HW, int groups);
 int fmc_groupnorm_bwd_bf16(const void* x, long long ldx, const void* dy, long long lddy, const float* gamma,
                            const float* beta, float eps, void* dx, long long lddx, float* stats_ws, int images, int HW, int C,
                            int groups, int silu, const float* rowbias, long long ldrb, int rowbias_div, void* stream);
@@ -263,7 +265,9 @@ int fmc_attention_bwd_bf16(const void* Q, long long ldq, int q_col0, const void*
  * <= 0: no clipping), state[2] = 1 if any gradient is inf / nan; deterministic (two-stage sum, no atomics); workspace:
  * fmc_grad_norm_workspace_floats() floats.  fmc_adamw_step_f32: torch.optim.AdamW (no amsgrad) on grad * state[1], skipped
  * entirely when state[2] != 0 (GradScaler.step); state = NULL: plain step on the gradients as they are.  Nothing returns
- * to the host, so both can sit in a captured graph. */
+ * to the host, so both can sit in a captured graph: fmc_grad_norm_f32 also counts the steps that were not skipped in
+ * state[3], and fmc_adamw_step_f32 with step = 0 takes the bias-correction step count from there (and, with lr < 0, the
+ * learning rate from state[4]) instead of from host arguments a graph would freeze.  state: 8 floats. */
 int fmc_grad_norm_workspace_floats(void);
 int fmc_grad_norm_f32(const float* grad, long long n, float inv_scale, float max_norm, float* workspace, float* state,
                       void* stream);

@@ -29,14 +29,18 @@ def main():
     ap.add_argument("--stage", default="cmc", choices=["cmc", "omc"])
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--graph", action="store_true", help="capture the whole step into a CUDA graph (train.GraphedStep) and time "
+                    "replays; the warm-up steps run eagerly before the capture")
+    ap.add_argument("--profile", action="store_true", help="one extra step under torch.profiler (CUPTI): top kernels by "
+                    "device time on stderr, cuDNN and torch kernels included")
     ap.add_argument("--trace", action="store_true", help="one extra step with CUDA events around every library call: "
                                                          "per-entry-point time table on stderr")
     args = ap.parse_args()
     from synfmc_b200 import shard, synth
     from synfmc_b200.fmc.models.pose_adaptor import PoseAdaptor
     from synfmc_b200.fmc.models.pose_obj_adaptor import CamObjPoseAdaptor
-    from synfmc_b200.fmc.util import get_traj_features_v2
-    from synfmc_b200.train import FlatParams, FusedAdamW, GradAllReduce
+    from synfmc_b200.fmc.util import get_traj_features_v2, pack_objects, traj_features_packed
+    from synfmc_b200.train import FlatParams, FusedAdamW, GradAllReduce, GraphedStep
     rank, world, local = shard.world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -66,6 +70,7 @@ def main():
     latents, text = latents.to(dev), text.to(dev)
     target = torch.randn(latents.shape, generator=torch.Generator().manual_seed(rank)).to(dev)
     infos, masks = synth.synth_objects(1, F, H, W, 3, seed=300 + rank, gaussian=True) if args.stage == "omc" else (None, None)
+    packed = pack_objects(infos, masks, dev) if infos is not None else None  # data loading: outside the (captured) step
     t = torch.tensor([801], device=dev)
     losses = []
 
@@ -73,17 +78,27 @@ def main():
         opt.zero_grad()
         red.reset()
         if args.stage == "omc":
-            trajs = get_traj_features_v2(infos, masks, omcm, False, 0.0, None, dev, torch.float32)
+            trajs = (traj_features_packed(*packed, omcm) if args.graph else
+                     get_traj_features_v2(infos, masks, omcm, False, 0.0, None, dev, torch.float32))
             pred = wrapper(latents, t, text, pose, trajs)
         else:
             pred = wrapper(latents, t, text, pose)
         loss = torch.nn.functional.mse_loss(pred.float(), target)
         loss.backward()
         n = red.wait()
-        opt.step(loss_scale=1.0, world=n)
-        losses.append(loss.detach())
-    for _ in range(args.warmup):
-        step()
+        opt.step(loss_scale=1.0, world=n, device_state=args.graph)
+        if not args.graph:
+            losses.append(loss.detach())
+        return loss.detach()
+    if args.graph:
+        eager = step
+        graphed = GraphedStep(eager, warmup=max(args.warmup, 2))
+
+        def step():
+            losses.append(graphed().clone())
+    else:
+        for _ in range(args.warmup):
+            step()
     shard.barrier()
     mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -113,6 +128,10 @@ def main():
                 sh = shapes[f"gemm M={a[6]} N={a[7]} K={a[8]} flags={a[15]}"]
                 sh[0] += 1
                 sh[1] += s0.elapsed_time(s1)
+            elif name == "fmc_layernorm_bwd_bf16":
+                sh = shapes.setdefault(f"layernorm_bwd rows={a[9]} C={a[10]} params={'yes' if a[8] else 'no'}", [0, 0.0])
+                sh[0] += 1
+                sh[1] += s0.elapsed_time(s1)
             elif name == "fmc_groupnorm_bwd_bf16":
                 key = f"groupnorm_bwd images={a[10]} HW={a[11]} C={a[12]}"
                 sh = shapes.setdefault(key, [0, 0.0])
@@ -129,11 +148,22 @@ def main():
         print("# by shape (top 25)", file=sys.stderr)
         for name, (n, ms_) in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:25]:
             print(f"{ms_:9.2f} ms {n:6d} calls  {name}", file=sys.stderr)
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        rows_ = sorted(((e.key, e.count, e.device_time_total / 1e3) for e in prof.key_averages() if e.device_time_total > 0
+                        and e.device_type == torch.autograd.DeviceType.CUDA), key=lambda r: -r[2])
+        print(f"# torch.profiler: {sum(r[2] for r in rows_):.1f} ms of kernels in the step", file=sys.stderr)
+        for name, n, ms_ in rows_[:45]:
+            print(f"{ms_:9.2f} ms {n:6d} x  {name[:150]}", file=sys.stderr)
     if rank == 0:
         print(json.dumps({"metric": f"training steps/sec, {args.stage.upper()} stage, 1 clip 320x512x16f per GPU",
                           "value": round(world / (ms * 1e-3), 4), "unit": "steps/s (clips/s)", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2), "scaling": "weak",
                           "dtype": "bf16 activations / gradients, fp32 master weights", "data": "synthetic",
+                          "cuda_graph": bool(args.graph), "optimizer_steps_on_device": opt.steps_taken(),
                           "trainable_params_m": round(flat.numel / 1e6, 1), "allreduce_buckets": len(red.buckets),
                           "peak_memory_gib": round(mem, 1), "losses": [round(x, 5) for x in ls],
                           "grad_norm_last": opt.last_norm(), "found_inf": opt.found_inf()}), flush=True)

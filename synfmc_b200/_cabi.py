@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FMC_B200_LIB") or os.path.join(_HERE, "libfmc_b200.so")
 
 P, I, L, F = c_void_p, c_int, c_longlong, c_float
-ABI_VERSION = 2  # FMC_B200_ABI_VERSION of include/fmc_b200.h
+ABI_VERSION = 3  # FMC_B200_ABI_VERSION of include/fmc_b200.h
 
 # name -> argtypes, in the order of include/fmc_b200.h
 SIGNATURES = {
@@ -96,6 +96,8 @@ def lib():
         handle.fmc_groupnorm_launches.argtypes = [c_int, c_int, c_int]
         handle.fmc_grad_norm_workspace_floats.restype = c_int
         handle.fmc_grad_norm_workspace_floats.argtypes = []
+        handle.fmc_groupnorm_bwd_workspace_floats.restype = c_longlong
+        handle.fmc_groupnorm_bwd_workspace_floats.argtypes = [c_int, c_int, c_int]
         handle.fmc_colsum_workspace_floats.restype = c_int
         handle.fmc_colsum_workspace_floats.argtypes = [c_longlong, c_int]
         handle.fmc_layernorm_bwd_blocks.restype = c_int
@@ -116,9 +118,13 @@ def lib():
 def _kernels_per_call(handle, name, args):
     if name == "fmc_groupnorm_bf16":
         return handle.fmc_groupnorm_launches(args[9], args[10], args[11])  # HW, C, groups
-    if name in ("fmc_groupnorm_f32", "fmc_grad_norm_f32", "fmc_groupnorm_bwd_bf16", "fmc_colsum_f32"):
+    if name in ("fmc_groupnorm_f32", "fmc_grad_norm_f32", "fmc_colsum_f32"):
         return 2  # statistics + apply / partial sums + finalize
+    if name == "fmc_groupnorm_bwd_bf16":
+        return 3  # statistics, gradient means, dx
     if name == "fmc_attention_bwd_bf16":
+        if args[17] and args[-7] == 16 and args[-6] == 16:
+            return 1  # 16-frame self-attention: one warp per sequence
         return 2 if args[17] else 1  # dQ kernel (+ dK / dV kernel)
     return 1
 launch_count = 0  # kernels of this library launched by this process (bench.py reports it as gpu_launches)

@@ -54,6 +54,12 @@ def layernorm_bwd(x, dy, gamma, eps=1e-5, want_params=False):
     return dx, both[:C], both[C:]
 
 
+def _gn_bwd_ws_floats(images, HW, groups):
+    if ops.DRY_RUN:
+        return 4 * images * ((HW + 31) // 32) * groups
+    return int(_cabi.lib().fmc_groupnorm_bwd_workspace_floats(images, HW, groups))
+
+
 def groupnorm_bwd(x, dy, gamma, beta, eps, images, HW, groups=32, silu=False, rowbias=None, rowbias_div=1):
     _check_cuda(x, dy)
     _rows2d(x)
@@ -61,7 +67,7 @@ def groupnorm_bwd(x, dy, gamma, beta, eps, images, HW, groups=32, silu=False, ro
     rows, C = x.shape
     assert rows == images * HW and dy.shape == x.shape
     dx = torch.empty((rows, C), device=x.device, dtype=BF16)
-    ws = torch.empty(4 * images * groups, device=x.device, dtype=F32)
+    ws = torch.empty(_gn_bwd_ws_floats(images, HW, groups), device=x.device, dtype=F32)
     _cabi.call("fmc_groupnorm_bwd_bf16", x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), gamma.data_ptr(),
                beta.data_ptr(), float(eps), dx.data_ptr(), dx.stride(0), ws.data_ptr(), images, HW, C, groups,
                1 if silu else 0, _ptr(rowbias), rowbias.stride(0) if rowbias is not None else 0, rowbias_div, _stream())

@@ -92,7 +92,7 @@ template <int NV>  // vectors of 8 channels per lane: C <= NV * 256
 __global__ void __launch_bounds__(LNB_WARPS * 32)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ dy, long long lddy,
                      const float* __restrict__ gamma, float eps, __nv_bfloat16* __restrict__ dx, long long lddx,
-                     float* __restrict__ pgrad, long long rows, int C) {
+                     float* __restrict__ pgrad, long long rows, int C, int rows_per_block) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float lnb_smem[];  // [LNB_WARPS][2][C] when pgrad != nullptr
@@ -109,8 +109,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const _
       dg[i][j] = db[i][j] = 0.f;
     }
   }
-  const long long row0 = static_cast<long long>(blockIdx.x) * LNB_ROWS_PER_BLOCK;
-  for (int rr = warp; rr < LNB_ROWS_PER_BLOCK; rr += LNB_WARPS) {
+  const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  for (int rr = warp; rr < rows_per_block; rr += LNB_WARPS) {
     const long long row = row0 + rr;
     if (row >= rows) break;
     float xv[NV][8], gv[NV][8];
@@ -203,104 +203,136 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const _
 // GroupNorm (+ per-image channel bias before the norm, + SiLU after it) backward, frozen affine parameters:
 //   u = x + rb;  xhat = (u - mu) rstd;  z = xhat gamma + beta;  y = silu(z) | z
 //   dz = dy silu'(z);  g = dz gamma;  dx = rstd (g - mean_g(g) - xhat mean_g(g xhat))     (means over the group)
-// stats kernel: one block per (image, group): mu, rstd, then the two group means.  apply kernel: elementwise.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_grad(float z) {
   const float s = 1.0f / (1.0f + expf(-z));
   return s * (1.0f + z * (1.0f - s));
 }
+// Three passes over (image, row chunk) blocks, all with the same thread mapping -- a thread owns one 8-channel vector
+// (fixed channels, so the per-channel constants sit in registers) and every RL-th row of the chunk, 16-byte loads:
+//   pass 0: per-group chunk partials of sum u, sum u^2            -> part0[image, chunk, group, 2]
+//   pass 1: mean / rstd from part0, then sum g, sum g xhat        -> part1
+//   pass 2: both group means from the partials, then dx
+// Partials are folded in a fixed order (deterministic, no atomics), the chunk totals in double.
+constexpr int GNB_ROWS = 32;
+struct GnbParams {
+  const __nv_bfloat16 *x, *dy;
+  __nv_bfloat16* dx;
+  long long ldx, lddy, lddx, ldrb;
+  const float *gamma, *beta, *rowbias;
+  float *part0, *part1;
+  float eps;
+  int images, HW, C, groups, silu, rb_div, chunks, chunk_rows;
+};
+
+template <int PASS>
 __global__ void __launch_bounds__(256)
-groupnorm_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ dy,
-                           long long lddy, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                           float4* __restrict__ stats, int HW, int C, int groups, int silu,
-                           const float* __restrict__ rowbias, long long ldrb, int rb_div) {
+groupnorm_bwd_pass_kernel(GnbParams p) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float red[2][8];
-  __shared__ float bc[2];
-  const int img = blockIdx.x / groups, grp = blockIdx.x % groups;
-  const int cg = C / groups;
-  const long long base = static_cast<long long>(img) * HW;
-  const float* rb = rowbias != nullptr ? rowbias + static_cast<long long>(img / rb_div) * ldrb + grp * cg : nullptr;
-  const int total = HW * cg;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float mean = 0.f, rstd = 0.f;
-  for (int pass = 0; pass < 3; ++pass) {
-    float a = 0.f, b = 0.f;
-    for (int i = threadIdx.x; i < total; i += 256) {
-      const int r = i / cg, c = i - r * cg;
-      float u = bf2f(x[(base + r) * ldx + grp * cg + c]);
-      if (rb != nullptr) u += __ldg(rb + c);
-      if (pass == 0) {
-        a += u;
-      } else if (pass == 1) {
-        a += (u - mean) * (u - mean);
-      } else {
-        const float xh = (u - mean) * rstd;
-        const float gmm = __ldg(gamma + grp * cg + c);
-        float d = bf2f(dy[(base + r) * lddy + grp * cg + c]);
-        if (silu) d *= silu_grad(xh * gmm + __ldg(beta + grp * cg + c));
-        const float g = d * gmm;
-        a += g;
-        b += g * xh;
+  extern __shared__ float gnb_part[];  // [RL][C][2] per-channel sums of this block (passes 0, 1)
+  __shared__ double red[4][8][64];
+  __shared__ float s_mean[64], s_rstd[64], s_a[64], s_b[64];
+  const int tid = threadIdx.x;
+  const int img = blockIdx.y, chunk = blockIdx.x;
+  const int C = p.C, groups = p.groups, cg = C / groups, nvec = C >> 3;
+  const int VT = nvec < 256 ? nvec : 256, RL = 256 / VT;
+  const double inv_n = 1.0 / (static_cast<double>(p.HW) * cg);
+  if (PASS >= 1) {
+    const int nslice = 256 / groups > 8 ? 8 : 256 / groups;
+    const int g = tid % groups, sl = tid / groups;
+    if (sl < nslice) {
+      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+      for (int ch = sl; ch < p.chunks; ch += nslice) {
+        const long long o = ((static_cast<long long>(img) * p.chunks + ch) * groups + g) * 2;
+        a0 += p.part0[o];
+        a1 += p.part0[o + 1];
+        if (PASS == 2) {
+          b0 += p.part1[o];
+          b1 += p.part1[o + 1];
+        }
       }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-    if (lane == 0) {
-      red[0][warp] = a;
-      red[1][warp] = b;
+      red[0][sl][g] = a0; red[1][sl][g] = a1; red[2][sl][g] = b0; red[3][sl][g] = b1;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      float ta = 0.f, tb = 0.f;
-      for (int w = 0; w < 8; ++w) {
-        ta += red[0][w];
-        tb += red[1][w];
-      }
-      bc[0] = ta / static_cast<float>(total);
-      bc[1] = tb / static_cast<float>(total);
+    if (tid < groups) {
+      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+      for (int q = 0; q < nslice; ++q) { a0 += red[0][q][tid]; a1 += red[1][q][tid]; b0 += red[2][q][tid]; b1 += red[3][q][tid]; }
+      const double mean = a0 * inv_n;
+      const double var = a1 * inv_n - mean * mean;
+      s_mean[tid] = static_cast<float>(mean);
+      s_rstd[tid] = 1.0f / sqrtf(static_cast<float>(var > 0.0 ? var : 0.0) + p.eps);
+      s_a[tid] = static_cast<float>(b0 * inv_n);
+      s_b[tid] = static_cast<float>(b1 * inv_n);
     }
-    __syncthreads();
-    if (pass == 0) mean = bc[0];
-    else if (pass == 1) rstd = 1.0f / sqrtf(bc[0] + eps);
-    else if (threadIdx.x == 0) stats[blockIdx.x] = make_float4(mean, rstd, bc[0], bc[1]);
     __syncthreads();
   }
-}
-__global__ void __launch_bounds__(256)
-groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ dy,
-                           long long lddy, const float* __restrict__ gamma, const float* __restrict__ beta,
-                           const float4* __restrict__ stats, __nv_bfloat16* __restrict__ dx, long long lddx, long long rows,
-                           int HW, int C, int groups, int silu, const float* __restrict__ rowbias, long long ldrb, int rb_div) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int nvec = C >> 3;
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (idx >= rows * nvec) return;
-  const long long r = idx / nvec;
-  const int vi = static_cast<int>(idx % nvec);
-  const int img = static_cast<int>(r / HW);
-  const int cg = C / groups;
-  float xv[8], dv[8], o8[8];
-  unpack8b(__ldg(reinterpret_cast<const uint4*>(x + r * ldx) + vi), xv);
-  unpack8b(__ldg(reinterpret_cast<const uint4*>(dy + r * lddy) + vi), dv);
+  const int r0 = chunk * p.chunk_rows, r1 = min(p.HW, r0 + p.chunk_rows);
+  const long long base = static_cast<long long>(img) * p.HW;
+  const int vi0 = tid % VT, rl = tid / VT;
+  if (rl < RL) {
+    for (int vi = vi0; vi < nvec; vi += VT) {
+      float gm[8], bt[8], rb[8], mu[8], rs[8], ga[8], gb[8], a[8], b[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = vi * 8 + j;
-    const float4 st = __ldg(stats + img * groups + c / cg);
-    float u = xv[j];
-    if (rowbias != nullptr) u += __ldg(rowbias + static_cast<long long>(img / rb_div) * ldrb + c);
-    const float xh = (u - st.x) * st.y;
-    const float gmm = __ldg(gamma + c);
-    float d = dv[j];
-    if (silu) d *= silu_grad(xh * gmm + __ldg(beta + c));
-    o8[j] = st.y * (d * gmm - st.z - xh * st.w);
+      for (int j = 0; j < 8; ++j) {
+        const int c = vi * 8 + j, g = c / cg;
+        rb[j] = p.rowbias != nullptr ? __ldg(p.rowbias + static_cast<long long>(img / p.rb_div) * p.ldrb + c) : 0.f;
+        a[j] = b[j] = 0.f;
+        if (PASS >= 1) {
+          gm[j] = __ldg(p.gamma + c); bt[j] = __ldg(p.beta + c);
+          mu[j] = s_mean[g]; rs[j] = s_rstd[g];
+        }
+        if (PASS == 2) { ga[j] = s_a[g]; gb[j] = s_b[g]; }
+      }
+      for (int r = r0 + rl; r < r1; r += RL) {
+        float xv[8], dv[8], o8[8];
+        unpack8b(__ldg(reinterpret_cast<const uint4*>(p.x + (base + r) * p.ldx) + vi), xv);
+        if (PASS >= 1) unpack8b(__ldg(reinterpret_cast<const uint4*>(p.dy + (base + r) * p.lddy) + vi), dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float u = xv[j] + rb[j];
+          if (PASS == 0) {
+            a[j] += u;
+            b[j] = fmaf(u, u, b[j]);
+          } else {
+            const float xh = (u - mu[j]) * rs[j];
+            float d = dv[j];
+            if (p.silu) d *= silu_grad(fmaf(xh, gm[j], bt[j]));
+            const float g = d * gm[j];
+            if (PASS == 1) {
+              a[j] += g;
+              b[j] = fmaf(g, xh, b[j]);
+            } else {
+              o8[j] = rs[j] * (g - ga[j] - xh * gb[j]);
+            }
+          }
+        }
+        if (PASS == 2) *(reinterpret_cast<uint4*>(p.dx + (base + r) * p.lddx) + vi) = pack8b(o8);
+      }
+      if (PASS < 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          gnb_part[(static_cast<size_t>(rl) * C + vi * 8 + j) * 2] = a[j];
+          gnb_part[(static_cast<size_t>(rl) * C + vi * 8 + j) * 2 + 1] = b[j];
+        }
+      }
+    }
   }
-  *(reinterpret_cast<uint4*>(dx + r * lddx) + vi) = pack8b(o8);
+  if (PASS < 2) {
+    __syncthreads();
+    float* out = PASS == 0 ? p.part0 : p.part1;
+    for (int g = tid; g < groups; g += 256) {
+      float sa = 0.f, sb = 0.f;
+      for (int q = 0; q < RL; ++q)
+        for (int c = g * cg; c < (g + 1) * cg; ++c) {
+          sa += gnb_part[(static_cast<size_t>(q) * C + c) * 2];
+          sb += gnb_part[(static_cast<size_t>(q) * C + c) * 2 + 1];
+        }
+      const long long o = ((static_cast<long long>(img) * p.chunks + chunk) * groups + g) * 2;
+      out[o] = sa;
+      out[o + 1] = sb;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -954,7 +986,12 @@ extern "C" int fmc_layernorm_bwd_bf16(const void* x, long long ldx, const void* 
   FMC_REQUIRE(C % 8 == 0 && C <= 1280 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0, FMC_ERR_SHAPE,
               "fmc_layernorm_bwd_bf16: C=%d must be a multiple of 8, at most 1280", C);
   if (rows == 0) return FMC_OK;
-  const int blocks = fmc_layernorm_bwd_blocks(rows);
+  // with parameter partials the block count is part of the interface (fmc_layernorm_bwd_blocks); without them the rows
+  // per block shrink until the grid covers the SMs a few times over (rows = 640 .. 2560 at the deep levels)
+  int rpb = LNB_ROWS_PER_BLOCK;
+  if (param_partials == nullptr)
+    while (rpb > LNB_WARPS && (rows + rpb - 1) / rpb < 4ll * device_sm_count()) rpb >>= 1;
+  const int blocks = static_cast<int>((rows + rpb - 1) / rpb);
   const size_t smem = param_partials != nullptr ? static_cast<size_t>(LNB_WARPS) * 2 * C * sizeof(float) : 0;
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* db = static_cast<const __nv_bfloat16*>(dy);
@@ -964,15 +1001,19 @@ extern "C" int fmc_layernorm_bwd_bf16(const void* x, long long ldx, const void* 
     if (first_use_on_this_device(&devs))
       FMC_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LNB_WARPS * 2 * 512 * 4));
     launch_k(layernorm_bwd_kernel<2>, dim3(blocks), dim3(LNB_WARPS * 32), smem, stream, xb, ldx, db, lddy, gamma, eps, ob, lddx,
-             param_partials, rows, C);
+             param_partials, rows, C, rpb);
   } else {
     static unsigned long long devs = 0;
     if (first_use_on_this_device(&devs))
       FMC_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, LNB_WARPS * 2 * 1280 * 4));
     launch_k(layernorm_bwd_kernel<5>, dim3(blocks), dim3(LNB_WARPS * 32), smem, stream, xb, ldx, db, lddy, gamma, eps, ob, lddx,
-             param_partials, rows, C);
+             param_partials, rows, C, rpb);
   }
   return check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" long long fmc_groupnorm_bwd_workspace_floats(int images, int HW, int groups) {
+  return 4ll * images * ((HW + GNB_ROWS - 1) / GNB_ROWS) * groups;
 }
 
 extern "C" int fmc_groupnorm_bwd_bf16(const void* x, long long ldx, const void* dy, long long lddy, const float* gamma,
@@ -981,20 +1022,42 @@ extern "C" int fmc_groupnorm_bwd_bf16(const void* x, long long ldx, const void* 
                                       int rowbias_div, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FMC_REQUIRE(x && dy && gamma && beta && dx && stats_ws, FMC_ERR_ARG, "fmc_groupnorm_bwd_bf16: null operand");
-  FMC_REQUIRE(groups > 0 && C % groups == 0 && C % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0, FMC_ERR_SHAPE,
-              "fmc_groupnorm_bwd_bf16: C=%d groups=%d", C, groups);
+  FMC_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && C % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0,
+              FMC_ERR_SHAPE, "fmc_groupnorm_bwd_bf16: C=%d groups=%d", C, groups);
   if (images == 0 || HW == 0) return FMC_OK;
-  const int div = rowbias_div > 0 ? rowbias_div : 1;
-  float4* stats = reinterpret_cast<float4*>(stats_ws);
-  launch_k(groupnorm_bwd_stats_kernel, dim3(images * groups), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(x), ldx,
-           static_cast<const __nv_bfloat16*>(dy), lddy, gamma, beta, eps, stats, HW, C, groups, silu, rowbias, ldrb, div);
-  int rc = check_launch("groupnorm_bwd_stats_kernel");
+  FMC_REQUIRE(images <= 65535, FMC_ERR_SHAPE, "fmc_groupnorm_bwd_bf16: grid limit (images=%d)", images);
+  GnbParams p;
+  p.x = static_cast<const __nv_bfloat16*>(x); p.dy = static_cast<const __nv_bfloat16*>(dy);
+  p.dx = static_cast<__nv_bfloat16*>(dx);
+  p.ldx = ldx; p.lddy = lddy; p.lddx = lddx; p.ldrb = ldrb;
+  p.gamma = gamma; p.beta = beta; p.rowbias = rowbias; p.eps = eps;
+  p.images = images; p.HW = HW; p.C = C; p.groups = groups; p.silu = silu; p.rb_div = rowbias_div > 0 ? rowbias_div : 1;
+  // chunks: enough (image, chunk) blocks for two per SM, but at least GNB_ROWS rows each (the per-thread channel constants
+  // and the fold of the partials are paid once per block); the workspace bound ceil(HW / GNB_ROWS) chunks always covers it
+  const int max_chunks = (HW + GNB_ROWS - 1) / GNB_ROWS;
+  int want = (2 * device_sm_count() + images - 1) / images;
+  want = want < 1 ? 1 : (want > max_chunks ? max_chunks : want);
+  p.chunk_rows = ((HW + want - 1) / want + 7) / 8 * 8;
+  p.chunks = (HW + p.chunk_rows - 1) / p.chunk_rows;
+  p.part0 = stats_ws;
+  p.part1 = stats_ws + 2ll * images * p.chunks * groups;
+  const int nvec = C / 8, VT = nvec < 256 ? nvec : 256, RL = 256 / VT;
+  const int smem = RL * C * 2 * static_cast<int>(sizeof(float));
+  FMC_REQUIRE(smem <= 96 * 1024, FMC_ERR_SHAPE, "fmc_groupnorm_bwd_bf16: C=%d too wide", C);
+  static unsigned long long devs = 0;
+  if (first_use_on_this_device(&devs)) {
+    FMC_CUDA_OK(cudaFuncSetAttribute(groupnorm_bwd_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    FMC_CUDA_OK(cudaFuncSetAttribute(groupnorm_bwd_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  }
+  const dim3 grid(p.chunks, images);
+  launch_k(groupnorm_bwd_pass_kernel<0>, grid, dim3(256), smem, stream, p);
+  int rc = check_launch("groupnorm_bwd_pass_kernel<0>");
   if (rc != FMC_OK) return rc;
-  const long long rows = static_cast<long long>(images) * HW;
-  launch_k(groupnorm_bwd_apply_kernel, dim3(bblocks(rows * (C / 8))), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(x),
-           ldx, static_cast<const __nv_bfloat16*>(dy), lddy, gamma, beta, static_cast<const float4*>(stats),
-           static_cast<__nv_bfloat16*>(dx), lddx, rows, HW, C, groups, silu, rowbias, ldrb, div);
-  return check_launch("groupnorm_bwd_apply_kernel");
+  launch_k(groupnorm_bwd_pass_kernel<1>, grid, dim3(256), smem, stream, p);
+  rc = check_launch("groupnorm_bwd_pass_kernel<1>");
+  if (rc != FMC_OK) return rc;
+  launch_k(groupnorm_bwd_pass_kernel<2>, grid, dim3(256), 0, stream, p);
+  return check_launch("groupnorm_bwd_pass_kernel<2>");
 }
 
 extern "C" int fmc_geglu_fwd_bf16(const void* proj, long long ldp, void* y, long long ldy, long long rows, int H,

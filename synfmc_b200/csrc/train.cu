@@ -89,6 +89,7 @@ grad_norm_finalize_kernel(const float* __restrict__ partial, const float* __rest
     state[0] = norm;
     state[1] = inv_scale * clip;
     state[2] = found_inf ? 1.f : 0.f;
+    if (!found_inf) state[3] += 1.f;  // optimizer steps taken so far (fmc_adamw_step_f32 with step = 0 reads it)
   }
 }
 
@@ -96,11 +97,17 @@ grad_norm_finalize_kernel(const float* __restrict__ partial, const float* __rest
 __global__ void __launch_bounds__(256)
 adamw_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                   long long n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float rsqrt_bc2,
-                  const float* __restrict__ state) {
+                  const float* __restrict__ state, int device_step) {
   pdl_launch_dependents();
   pdl_wait();
   const float coef = state != nullptr ? __ldg(state + 1) : 1.0f;
   if (state != nullptr && __ldg(state + 2) != 0.f) return;
+  if (device_step) {  // step count (and, for lr < 0, the learning rate) live on the device: the call can sit in a CUDA graph
+    const float t = __ldg(state + 3);
+    bc1 = 1.0f - exp2f(t * log2f(beta1));
+    rsqrt_bc2 = rsqrtf(1.0f - exp2f(t * log2f(beta2)));
+    if (lr < 0.f) lr = __ldg(state + 4);
+  }
   const long long i4 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long base = i4 << 2;
   if (base >= n) return;
@@ -166,14 +173,16 @@ extern "C" int fmc_adamw_step_f32(float* param, const float* grad, float* exp_av
   FMC_REQUIRE(param && grad && exp_avg && exp_avg_sq, FMC_ERR_ARG, "fmc_adamw_step_f32: null operand");
   FMC_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
                 reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0, FMC_ERR_SHAPE, "fmc_adamw_step_f32: buffers must be 16-byte aligned");
-  FMC_REQUIRE(step >= 1 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, FMC_ERR_ARG,
-              "fmc_adamw_step_f32: step must be >= 1 and the betas in [0, 1)");
+  FMC_REQUIRE(step >= 0 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, FMC_ERR_ARG,
+              "fmc_adamw_step_f32: step must be >= 0 and the betas in [0, 1)");
+  FMC_REQUIRE(step >= 1 || state != nullptr, FMC_ERR_ARG, "fmc_adamw_step_f32: step = 0 reads the step count from state[3]");
+  FMC_REQUIRE(lr >= 0.f || step == 0, FMC_ERR_ARG, "fmc_adamw_step_f32: lr < 0 (read state[4]) needs step = 0");
   if (n == 0) return FMC_OK;
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  const double bc1 = step >= 1 ? 1.0 - pow(static_cast<double>(beta1), step) : 1.0;
+  const double bc2 = step >= 1 ? 1.0 - pow(static_cast<double>(beta2), step) : 1.0;
   const long long vecs = (n + 3) / 4;
   launch_k(adamw_step_kernel, dim3(static_cast<unsigned>((vecs + 255) / 256)), dim3(256), 0, stream, param, grad, exp_avg,
            exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1), static_cast<float>(1.0 / sqrt(bc2)),
-           state);
+           state, step == 0 ? 1 : 0);
   return check_launch("adamw_step_kernel");
 }

@@ -79,7 +79,15 @@ def get_traj_features_v2(obj_info_list_list, obj_mask_list_list, omcm, cfg_rando
     null = []
     if cfg_random_null_om:
         null = [i for i in range(info.shape[0]) if not (random.random() > cfg_random_null_om_ratio)]
+    return traj_features_packed(info, masks, omcm, null)
+
+
+def traj_features_packed(info, masks, omcm, null_clips=None):
+    """get_traj_features_v2 on objects already packed by `pack_objects` (dense device tensors): the part of the call that
+    is device work only, so a captured training step (train.GraphedStep) can contain it while the packing stays with the
+    data loading."""
     from .. import train_engine
+    null = list(null_clips or [])
     if train_engine.wants_training(omcm):
         # OMC training (train_cam_obj_ctrl.py:843): the ObjectEncoder runs on the tape; the returned features carry its graph
         if engine.precise():

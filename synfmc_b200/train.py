@@ -12,9 +12,12 @@ train_cam_ctrl.py:647-665 / train_cam_obj_ctrl.py:843-862 -- DDP's gradient all-
   * `FusedAdamW`      fmc_grad_norm_f32 + fmc_adamw_step_f32: one read of the gradients for the global norm, one fused
                       unscale * clip * AdamW pass; the clip coefficient and the found-inf flag never leave the device.
 
-The BACKWARD kernels of the hot path do not exist yet: the mirror modules raise under autograd.  These
-classes are the collective + optimizer half of the training step, usable today with gradients from any source (the
-tests feed them torch-autograd gradients of small modules and compare with DDP-style mean + torch.optim.AdamW)."""
+  * `GraphedStep`     captures one WHOLE training step (zero_grad, forward on the tape of train_engine.py, loss, backward,
+                      bucket all-reduces, optimizer) into a CUDA graph: the step is ~4000 kernels of 5-50 us, more than
+                      Python can launch in the time the GPU needs for them.
+
+The gradients come from the backward kernels behind train_engine.py or from any other source (the
+tests also feed these classes torch-autograd gradients of small modules and compare with DDP-style mean + AdamW)."""
 import torch
 import torch.distributed as dist
 
@@ -123,12 +126,21 @@ class FusedAdamW:
         dev = flat.values.device
         self.exp_avg = torch.zeros_like(flat.values)
         self.exp_avg_sq = torch.zeros_like(flat.values)
-        self.state = torch.zeros(4, device=dev, dtype=torch.float32)  # norm, coefficient, found_inf
+        # norm, coefficient, found_inf, steps taken (counted on the device), learning rate (device-side copy), 3 spare
+        self.state = torch.zeros(8, device=dev, dtype=torch.float32)
+        self.state[4] = lr
         self.workspace = torch.zeros(_cabi.lib().fmc_grad_norm_workspace_floats(), device=dev, dtype=torch.float32)
         self.steps = 0
 
-    def step(self, loss_scale=1.0, world=1, lr=None):
-        """One optimizer step on the gradients in `flat.grads` = SUM over `world` ranks of `loss_scale` * dL/dp."""
+    def set_lr(self, lr):
+        """Learning rate for the following steps; also updates the device-side copy a captured step reads."""
+        self.lr = lr
+        self.state[4:5].fill_(lr)
+
+    def step(self, loss_scale=1.0, world=1, lr=None, device_state=False):
+        """One optimizer step on the gradients in `flat.grads` = SUM over `world` ranks of `loss_scale` * dL/dp.
+        `device_state`: bias-correction step count and learning rate are read from the device (state[3], state[4]) instead
+        of being passed as launch arguments -- what a captured step (GraphedStep) needs, since a graph freezes arguments."""
         ops._check_cuda(self.flat.values, self.flat.grads)
         f = self.flat
         self.steps += 1
@@ -138,14 +150,53 @@ class FusedAdamW:
         _cabi.call("fmc_grad_norm_f32", f.grads.data_ptr(), f.numel, 1.0 / (float(loss_scale) * world),
                    float(self.max_grad_norm or 0.0), self.workspace.data_ptr(), self.state.data_ptr(), stream)
         _cabi.call("fmc_adamw_step_f32", f.values.data_ptr(), f.grads.data_ptr(), self.exp_avg.data_ptr(),
-                   self.exp_avg_sq.data_ptr(), f.numel, float(self.lr if lr is None else lr), float(self.betas[0]),
-                   float(self.betas[1]), float(self.eps), float(self.weight_decay), self.steps, self.state.data_ptr(), stream)
+                   self.exp_avg_sq.data_ptr(), f.numel, -1.0 if device_state else float(self.lr if lr is None else lr),
+                   float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
+                   0 if device_state else self.steps, self.state.data_ptr(), stream)
 
     def zero_grad(self, set_to_none=False):
         self.flat.zero_grad()
+
+    def steps_taken(self):
+        """Optimizer steps that were not skipped for inf / nan gradients, as counted on the device."""
+        return int(self.state[3])
 
     def last_norm(self):
         return float(self.state[0])
 
     def found_inf(self):
         return bool(self.state[2] != 0)
+
+
+class GraphedStep:
+    """One whole training step as a CUDA graph.
+
+    `fn()` runs the step -- `opt.zero_grad(); red.reset(); pred = wrapper(...); loss = ...; loss.backward(); n = red.wait();
+    opt.step(world=n, device_state=True)` -- and returns the tensors to keep (the loss).  It must read its inputs from
+    tensors whose storage does not change (refill them with `copy_` between replays), must not read device values on
+    the host, and must call the optimizer with `device_state=True` (step count and learning rate live on the device;
+    `FusedAdamW.set_lr` changes the rate without re-capturing).  `warmup` eager steps run first on a side stream -- they
+    build every plan and workspace and ARE training steps -- then the step is captured; every call replays it.  The NCCL
+    all-reduces launched by the gradient hooks during capture are part of the graph (torch's process group captures)."""
+
+    def __init__(self, fn, warmup=3):
+        if not torch.cuda.is_available():
+            raise RuntimeError("GraphedStep captures a CUDA graph: no CUDA device (there is no CPU path)")
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.warmup_steps = warmup
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+
+    def __call__(self):
+        from . import engine
+        self.graph.replay()
+        engine.OPTIMIZER_EPOCH += 1  # the captured optimizer moved the parameters: inference plans derived from them are stale
+        return self.out

@@ -212,3 +212,63 @@ def test_omc_training_step_gradients(cuda_device):
         pairs.append((n, pp.grad, po.grad))
     assert len(pairs) >= 10
     _compare(pairs, "OMC training step (tiny U-Net + ObjectEncoder)")
+
+
+@pytest.mark.timeout(900)
+def test_graphed_training_step_matches_eager(cuda_device):
+    """train.GraphedStep: the whole CMC step (zero_grad, tape forward, loss, backward, fused AdamW with the step count on
+    the device) captured once and replayed gives the parameters eager stepping gives, step for step."""
+    import copy
+    from oracle.rays import to_plucker_embedding
+    from synfmc_b200 import synth
+    from synfmc_b200.fmc.models.pose_adaptor import PoseAdaptor
+    from synfmc_b200.train import FlatParams, FusedAdamW, GraphedStep
+    channels = (320, 640)
+    dev = cuda_device
+    o_unet = helpers.build_oracle_unet(tiny=True)
+    o_enc = helpers.build_oracle_pose_encoder(channels)
+    b, f, H, W = 1, 8, 64, 96
+    K, c2w = synth.synth_camera(b, f, H, W, seed=6)
+    plucker = to_plucker_embedding(c2w, K, (H, W)).permute(0, 2, 1, 3, 4).contiguous().to(dev)
+    latents, text = synth.synth_step_inputs(b, f, H // 8, W // 8, cfg=False, seed=6)
+    latents, text = latents.to(dev), text.to(dev)
+    target = torch.randn(latents.shape, generator=torch.Generator().manual_seed(9)).to(dev)
+    t = torch.tensor([441], device=dev)
+    results = {}
+    for mode in ("eager", "graph"):
+        unet = helpers.build_product_unet(o_unet, tiny=True, device=dev)
+        enc = helpers.build_product_pose_encoder(o_enc, channels, device=dev)
+        _cmc_trainable(unet, enc)
+        wrapper = PoseAdaptor(unet, enc)
+        flat = FlatParams(list(enc.parameters()) + [p for p in unet.parameters() if p.requires_grad])
+        opt = FusedAdamW(flat, lr=1e-3, max_grad_norm=1.0)
+        start = flat.values.clone()
+
+        def step():
+            opt.zero_grad()
+            loss = torch.nn.functional.mse_loss(wrapper(latents, t, text, plucker).float(), target)
+            loss.backward()
+            opt.step(device_state=(mode == "graph"))
+            return loss.detach()
+        losses = []
+        if mode == "eager":
+            for _ in range(4):
+                losses.append(float(step()))
+        else:
+            graphed = GraphedStep(step, warmup=2)
+            for _ in range(2):
+                losses.append(float(graphed()))
+        assert opt.steps_taken() == 4 and not opt.found_inf()
+        results[mode] = (flat.values - start, losses)
+    d_e, l_e = results["eager"]
+    d_g, l_g = results["graph"]
+    # Adam turns every gradient into a step of about lr, whatever its size: bf16-level differences between two runs (cuDNN
+    # picks its convolution algorithms per run) move individual small-gradient weights by up to 2 lr, so the two
+    # 4-step parameter displacements are compared as vectors, not element by element
+    cos = float(torch.dot(d_e, d_g) / (d_e.norm() * d_g.norm()))
+    ratio = float(d_g.norm() / d_e.norm())
+    print(f"[parity] graphed vs eager training, 4 steps: losses {l_e} / {l_g}, displacement cosine {cos:.4f}, "
+          f"norm ratio {ratio:.4f}")
+    assert l_e[0] > l_e[-1]                                   # it trains
+    assert abs(l_e[-1] - l_g[-1]) < 3e-2 * abs(l_e[-1])       # the 4th step of both runs
+    assert cos > 0.9 and 0.9 < ratio < 1.1
