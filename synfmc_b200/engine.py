@@ -530,6 +530,18 @@ def nearest_index_chain(sizes):
     return maps
 
 
+_INDEX_CACHE = {}
+
+
+def nearest_index_on(sizes, device):
+    """Last map of `nearest_index_chain(sizes)` on `device`, cached per (sizes, device): a pure function of the sizes, and
+    a captured step (train.GraphedStep) cannot copy from pageable host memory."""
+    key = (tuple(int(v) for v in sizes), str(device))
+    if key not in _INDEX_CACHE:
+        _INDEX_CACHE[key] = nearest_index_chain(list(sizes))[-1].to(device)
+    return _INDEX_CACHE[key]
+
+
 # --------------------------------------------------------------------------------------------------------------
 # text context shared by every cross-attention of one U-Net call
 # --------------------------------------------------------------------------------------------------------------

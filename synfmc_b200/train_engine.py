@@ -689,8 +689,8 @@ def adapter_forward(tape, omcm, x_cl, mask):
             x, shape = p["zero_out"][i](tape, x, shape)
         sizes_h.append(shape[1])
         sizes_w.append(shape[2])
-        ry = engine.nearest_index_chain(sizes_h)[-1].to(device)
-        rx = engine.nearest_index_chain(sizes_w)[-1].to(device)
+        ry = engine.nearest_index_on(sizes_h, device)
+        rx = engine.nearest_index_on(sizes_w, device)
         x = mask_modulate(tape, x, shape, mask, ry, rx)
         feats.append(x)
     return feats

@@ -1,0 +1,61 @@
+"""Pins the two pipeline-edge restatements (oracle/vae.py, oracle/clip_text.py) to independent
+implementations that ARE installed: transformers' own CLIPTextModel (the very dependency the reference calls) and
+torchtitan's copy of the CompVis/LDM autoencoder (the architecture diffusers' AutoencoderKL ports)."""
+import pytest
+import torch
+
+
+def test_clip_text_restatement_matches_transformers():
+    transformers = pytest.importorskip("transformers")
+    from oracle.clip_text import CLIPTextModel as Oracle
+    cfg = transformers.CLIPTextConfig(vocab_size=1000, hidden_size=128, intermediate_size=512, num_hidden_layers=3,
+                                      num_attention_heads=4, max_position_embeddings=77, hidden_act="quick_gelu")
+    torch.manual_seed(0)
+    ref = transformers.CLIPTextModel(cfg).eval()
+    with torch.no_grad():  # the default init leaves LayerNorm at identity and biases at zero: move everything
+        for p in ref.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    ora = Oracle(1000, 77, 128, 3, 4, 512, cfg.layer_norm_eps)
+    state = {k: v for k, v in ref.state_dict().items() if "position_ids" not in k}
+    missing, unexpected = ora.load_state_dict(state, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    ids = torch.randint(0, 1000, (2, 77), generator=torch.Generator().manual_seed(1))
+    ids[:, -1] = 999  # eos = highest id (the pooled output is not used, but transformers locates it)
+    with torch.no_grad():
+        want = ref(ids)[0]
+        got = ora(ids)[0]
+    assert float((got - want).abs().max()) < 1e-5 * max(1.0, float(want.abs().max()))
+
+
+def test_vae_restatement_matches_the_ldm_autoencoder():
+    ae = pytest.importorskip("torchtitan.experiments.flux.model.autoencoder")
+    from oracle.vae import AutoencoderKL, ldm_state_to_diffusers
+    ch, mult, z = 32, [1, 2, 4, 4], 4
+    torch.manual_seed(0)
+    enc = ae.Encoder(resolution=32, in_channels=3, ch=ch, ch_mult=mult, num_res_blocks=2, z_channels=z).eval()
+    dec = ae.Decoder(ch=ch, out_ch=3, ch_mult=mult, num_res_blocks=2, in_channels=3, resolution=32, z_channels=z).eval()
+    with torch.no_grad():
+        for m in (enc, dec):
+            for p in m.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+    vae = AutoencoderKL(block_out_channels=tuple(ch * m for m in mult), latent_channels=z).eval()
+    state = {f"encoder.{k}": v for k, v in enc.state_dict().items()}
+    state.update({f"decoder.{k}": v for k, v in dec.state_dict().items()})
+    missing, unexpected = vae.load_state_dict(ldm_state_to_diffusers(state), strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith(("quant_conv", "post_quant_conv")) for k in missing), missing
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 3, 40, 24, generator=g)
+    zin = torch.randn(2, z, 5, 3, generator=g)
+    with torch.no_grad():
+        assert float((vae.encoder(x) - enc(x)).abs().max()) < 1e-5 * max(1.0, float(enc(x).abs().max()))
+        assert float((vae.decoder(zin) - dec(zin)).abs().max()) < 1e-5 * max(1.0, float(dec(zin).abs().max()))
+
+
+def test_vae_gaussian_posterior():
+    from oracle.vae import DiagonalGaussianDistribution
+    m = torch.randn(1, 8, 3, 3, generator=torch.Generator().manual_seed(3)) * 40
+    d = DiagonalGaussianDistribution(m)
+    assert float(d.logvar.max()) <= 20.0 and float(d.logvar.min()) >= -30.0
+    noise = torch.randn(1, 4, 3, 3, generator=torch.Generator().manual_seed(4))
+    assert torch.equal(d.sample(noise=noise), d.mean + torch.exp(0.5 * d.logvar) * noise)
