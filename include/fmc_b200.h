@@ -325,6 +325,43 @@ int fmc_timestep_embedding_f32(const float* t, float* out, int B, int dim, void*
 int fmc_mask_modulate_f32(const float* x, const float* mask, const int* row_index, const int* col_index, float* out,
                           int N, int h, int w, int C, int H, int W, void* stream);
 
+/* ---- pipeline edges: VAE decode / encode and the CLIP text encoder -----------------------------------
+ * Their convolutions, linears, GroupNorm and LayerNorm run on the entry points above; these are the remaining pieces.
+ * `is_f32` / `out_is_f32`: activation dtype of the call (0 = bf16, the product mode; 1 = fp32, reference-precision mode). */
+
+/* out[r, :] = softmax(scale * scores[r, :]) over n columns (n % 4 == 0, n <= 4096); scores fp32 (fmc_gemm_bf16 with
+ * FMC_GEMM_OUT_F32).  Replaces get_attention_scores' softmax of the diffusers Attention in the VAE mid block (1 head of
+ * 512 over h*w tokens), called from vae.decode at fmc/pipelines/pipeline_animation.py:472 and vae.encode at
+ * train_cam_ctrl.py:544. */
+int fmc_softmax_rows(const float* scores, long long lds, void* out, long long ldo, int out_is_f32, long long rows, int n,
+                     float scale, void* stream);
+
+/* Multi-head self-attention for short sequences (<= 128 tokens, head_dim in {32, 64, 96, 128}), causal or not, on the
+ * fused projection buffer [tokens, ld] with q / k / v at their column offsets and heads head_dim apart; out [tokens, ldo].
+ * Replaces transformers CLIPAttention (causal mask, 77 tokens, 12 heads of 64) behind self.text_encoder(...) at
+ * fmc/pipelines/pipeline_animation.py:506-510, :546-550 and train_cam_ctrl.py:557-561. */
+int fmc_small_mha(const void* qkv, long long ld, int q_col0, int k_col0, int v_col0, void* out, long long ldo, int is_f32,
+                  int seqs, int tokens_per_seq, int heads, int head_dim, float scale, int causal, void* stream);
+
+/* out = x * sigmoid(1.702 x): transformers `quick_gelu`, the activation of CLIPMLP. */
+int fmc_quick_gelu(const void* x, long long ldx, void* out, long long ldo, int is_f32, long long rows, int cols, void* stream);
+
+/* out[b t, :] = token_table[ids[b t], :] + position_table[t, :] (fp32 tables, ids int64 clamped into the vocabulary):
+ * transformers CLIPTextEmbeddings.forward. */
+int fmc_embed_tokens(const long long* ids, const float* token_table, const float* position_table, void* out, long long ldo,
+                     int out_is_f32, long long tokens, int tokens_per_seq, int C, int vocab, void* stream);
+
+/* diffusers DiagonalGaussianDistribution.sample on channels-last moment rows [N HW, ldm] (mean | logvar, z channels each):
+ * out [N, z, HW] fp32 = (mean + exp(0.5 clamp(logvar, -30, 20)) * noise) * out_scale; noise in the output layout, NULL =
+ * the distribution's mode.  `vae.encode(x).latent_dist.sample() * 0.18215` of train_cam_ctrl.py:544-545 in one pass. */
+int fmc_vae_sample_f32(const void* moments, long long ldm, int is_f32, const float* noise, float* out, int N, int z,
+                       long long HW, float out_scale, void* stream);
+
+/* Channels-last image rows [(b f) HW, ldc] -> video [b, C, f, HW] fp32 = clamp(x * mul + add, lo, hi): the rearrange +
+ * `(video / 2 + 0.5).clamp(0, 1)` + `.float()` tail of decode_latents, fmc/pipelines/pipeline_animation.py:474-477. */
+int fmc_cl_to_video_f32(const void* x, long long ldc, int is_f32, float* out, int B, int C, int F, long long HW, float mul,
+                        float add, float lo, float hi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,13 @@ SIGNATURES = {
     "fmc_transpose_bf16": [P, L, P, L, L, I, P],
     "fmc_colsum_f32": [P, L, I, P, P, L, I, I, P],
     "fmc_layernorm_bwd_bf16": [P, L, P, L, P, F, P, L, P, L, I, P],
+    # pipeline edges (csrc/edge.cu)
+    "fmc_softmax_rows": [P, L, P, L, I, L, I, F, P],
+    "fmc_small_mha": [P, L, I, I, I, P, L, I, I, I, I, I, F, I, P],
+    "fmc_quick_gelu": [P, L, P, L, I, L, I, P],
+    "fmc_embed_tokens": [P, P, P, P, L, I, L, I, I, I, P],
+    "fmc_vae_sample_f32": [P, L, I, P, P, I, I, L, F, P],
+    "fmc_cl_to_video_f32": [P, L, I, P, I, I, I, L, F, F, F, F, P],
     "fmc_groupnorm_bwd_bf16": [P, L, P, L, P, P, F, P, L, P, I, I, I, I, I, P, L, I, P],
     "fmc_geglu_fwd_bf16": [P, L, P, L, L, I, P],
     "fmc_geglu_bwd_bf16": [P, L, P, L, P, L, L, I, P],

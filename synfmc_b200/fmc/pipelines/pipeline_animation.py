@@ -177,6 +177,9 @@ class CameraCtrlPipeline:
     def decode_latents(self, latents):
         if self.vae is None:
             raise RuntimeError("no VAE attached: read `.latents` from the output instead of `.videos`")
+        if hasattr(self.vae, "decode_video"):
+            # the B200 VAE (synfmc_b200/edge/autoencoder_kl.py): all frames of a clip per pass, rearrange + /2 + 0.5 + clamp fused
+            return self.vae.decode_video(latents, scaling_factor=0.18215).cpu()
         f = latents.shape[2]
         latents = (1 / 0.18215 * latents).permute(0, 2, 1, 3, 4).flatten(0, 1)
         frames = [self.vae.decode(latents[i:i + 1]).sample for i in range(latents.shape[0])]

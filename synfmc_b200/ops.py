@@ -490,3 +490,82 @@ def conv2d_cl(x, weight, bias, stride=1, padding=1):
                                              weight.shape[1] * weight.shape[2] * weight.shape[3]), e0, e1))
     y = y.permute(0, 2, 3, 1)
     return y if y.is_contiguous() else y.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# pipeline edges (csrc/edge.cu): VAE + CLIP text encoder pieces
+# --------------------------------------------------------------------------------------------------------------
+def softmax_rows(scores, scale, out_dtype=BF16):
+    """softmax(scale * scores) per row; scores fp32 [rows, n] (n % 4 == 0, n <= 4096) -> bf16 / fp32 probabilities."""
+    _check_cuda(scores)
+    _rows2d(scores, F32)
+    rows, n = scores.shape
+    out = torch.empty((rows, n), device=scores.device, dtype=out_dtype)
+    _cabi.call("fmc_softmax_rows", scores.data_ptr(), scores.stride(0), out.data_ptr(), out.stride(0),
+               1 if out_dtype == F32 else 0, rows, n, float(scale), _stream())
+    return out
+
+
+def small_mha(qkv, q_col0, k_col0, v_col0, seqs, tokens_per_seq, heads, head_dim, scale, causal):
+    """Multi-head self-attention on the fused projection rows [seqs * tokens_per_seq, >= 3 * heads * head_dim]."""
+    _check_cuda(qkv)
+    dt = _act(qkv)
+    _rows2d(qkv, dt)
+    assert qkv.shape[0] == seqs * tokens_per_seq
+    out = torch.empty((qkv.shape[0], heads * head_dim), device=qkv.device, dtype=dt)
+    _cabi.call("fmc_small_mha", qkv.data_ptr(), qkv.stride(0), q_col0, k_col0, v_col0, out.data_ptr(), out.stride(0),
+               1 if dt == F32 else 0, seqs, tokens_per_seq, heads, head_dim, float(scale), 1 if causal else 0, _stream())
+    return out
+
+
+def quick_gelu(x, out=None):
+    _check_cuda(x)
+    dt = _act(x)
+    _rows2d(x, dt)
+    if out is None:
+        out = torch.empty_like(x)
+    _cabi.call("fmc_quick_gelu", x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), 1 if dt == F32 else 0, x.shape[0],
+               x.shape[1], _stream())
+    return out
+
+
+def embed_tokens(ids, token_table, position_table, out_dtype=BF16):
+    """ids int64 [B, T]; fp32 tables [vocab, C], [>= T, C] -> rows [B * T, C]."""
+    _check_cuda(ids, token_table, position_table)
+    assert ids.dtype == torch.int64 and ids.ndim == 2 and ids.is_contiguous()
+    _rows2d(token_table, F32)
+    _rows2d(position_table, F32)
+    assert token_table.is_contiguous() and position_table.is_contiguous()
+    B, T = ids.shape
+    vocab, C = token_table.shape
+    assert position_table.shape[0] >= T and position_table.shape[1] == C
+    out = torch.empty((B * T, C), device=ids.device, dtype=out_dtype)
+    _cabi.call("fmc_embed_tokens", ids.data_ptr(), token_table.data_ptr(), position_table.data_ptr(), out.data_ptr(),
+               out.stride(0), 1 if out_dtype == F32 else 0, B * T, T, C, vocab, _stream())
+    return out
+
+
+def vae_sample(moments, N, z, HW, noise=None, out_scale=1.0):
+    """moments rows [N * HW, 2 z] (channels-last, mean | logvar) -> [N, z, HW] fp32; noise [N, z, HW] fp32 or None (mode)."""
+    _check_cuda(moments, noise)
+    dt = _act(moments)
+    _rows2d(moments, dt)
+    assert moments.shape == (N * HW, 2 * z)
+    if noise is not None:
+        assert noise.dtype == F32 and noise.is_contiguous() and noise.numel() == N * z * HW
+    out = torch.empty((N, z, HW), device=moments.device, dtype=F32)
+    _cabi.call("fmc_vae_sample_f32", moments.data_ptr(), moments.stride(0), 1 if dt == F32 else 0, _ptr(noise), out.data_ptr(),
+               N, z, HW, float(out_scale), _stream())
+    return out
+
+
+def cl_to_video(x, B, C, F, HW, mul=1.0, add=0.0, lo=-3.0e38, hi=3.0e38):
+    """channels-last rows [(B F) HW, >= C] -> [B, C, F, HW] fp32 = clamp(x * mul + add, lo, hi)."""
+    _check_cuda(x)
+    dt = _act(x)
+    _rows2d(x, dt)
+    assert x.shape[0] == B * F * HW and x.shape[1] >= C
+    out = torch.empty((B, C, F, HW), device=x.device, dtype=torch.float32)
+    _cabi.call("fmc_cl_to_video_f32", x.data_ptr(), x.stride(0), 1 if dt == F32 else 0, out.data_ptr(), B, C, F, HW, float(mul),
+               float(add), float(lo), float(hi), _stream())
+    return out
