@@ -13,6 +13,8 @@ path: tcgen05 implicit GEMM up to 64 input channels, cuDNN for the wide ones); 1
 fmc_gemm_bf16 with the residual in the epilogue; the mid-block attention (1 head of 512 over h*w tokens, per image) = GEMM
 (fp32 scores) -> fmc_softmax_rows -> GEMM; nearest 2x upsample = fmc_resize_nearest_bf16; the posterior sample and the
 decoder's output conversion + clamp are fused single passes (fmc_vae_sample_f32, fmc_cl_to_video_f32)."""
+import contextlib
+
 import torch
 from torch import nn
 
@@ -20,6 +22,11 @@ from .. import bwd_ops, engine, ops
 from ..fmc._blocks import _Holder
 
 BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _device_ctx(device):
+    """make the tensor's GPU current for the calls below (the kernels launch on the current device's current stream)"""
+    return torch.cuda.device(device) if torch.device(device).type == "cuda" else contextlib.nullcontext()
 
 
 class _Resnet(_Holder):
@@ -241,7 +248,7 @@ class AutoencoderKL(nn.Module):
         return ops.to_channels_last(x.reshape(N, C, 1, H, W), dtype=engine.act_dtype()).view(N, H, W, C)
 
     def _decode_cl(self, z):
-        with torch.cuda.device(z.device):
+        with _device_ctx(z.device):
             plans = self._plan(z.device)
             dec = self.decoder
             x = plans[id(self.post_quant_conv)](self._to_cl(z))
@@ -261,7 +268,7 @@ class AutoencoderKL(nn.Module):
         """z [N, latent, h, w] -> .sample [N, 3, 8h, 8w] fp32 (the reference calls this one frame at a time)."""
         y = self._decode_cl(z)
         N, H, W, C = y.shape
-        with torch.cuda.device(z.device):
+        with _device_ctx(z.device):
             sample = ops.cl_to_video(y.reshape(-1, C), N, C, 1, H * W).view(N, C, H, W)
         return _Output(sample=sample) if return_dict else (sample,)
 
@@ -275,7 +282,7 @@ class AutoencoderKL(nn.Module):
         frames = (latents.float() * (1.0 / sf)).permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
         chunk = chunk or f
         out = torch.empty((b, self.config.out_channels, f, 8 * h, 8 * w), device=latents.device, dtype=F32)
-        with torch.cuda.device(latents.device):
+        with _device_ctx(latents.device):
             for bi in range(b):
                 for f0 in range(0, f, chunk):
                     n = min(chunk, f - f0)
@@ -288,7 +295,7 @@ class AutoencoderKL(nn.Module):
     @torch.no_grad()
     def encode(self, x, return_dict=True):
         """x [N, 3, H, W] in [-1, 1] -> .latent_dist (sample() / mode() give [N, latent, H/8, W/8] fp32)."""
-        with torch.cuda.device(x.device):
+        with _device_ctx(x.device):
             plans = self._plan(x.device)
             enc = self.encoder
             h = plans[id(enc.conv_in)](self._to_cl(x))

@@ -10,6 +10,8 @@ Execution on rows [(batch tokens), width]: token + position gather = fmc_embed_t
 q|k|v as ONE GEMM (the d^-1/2 query scale folded into the q rows of the weight), causal 12-head attention over 77 tokens =
 fmc_small_mha, out-projection GEMM with the residual in its epilogue, fc1 GEMM -> fmc_quick_gelu -> fc2 GEMM (+ residual);
 final LayerNorm.  The tokenizer (string processing on the host) stays transformers' own."""
+import contextlib
+
 import torch
 from torch import nn
 
@@ -17,6 +19,11 @@ from .. import engine, ops
 from ..fmc._blocks import _Holder
 
 BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _device_ctx(device):
+    """make the tensor's GPU current for the calls below (the kernels launch on the current device's current stream)"""
+    return torch.cuda.device(device) if torch.device(device).type == "cuda" else contextlib.nullcontext()
 
 
 class _Attn(_Holder):
@@ -139,7 +146,7 @@ class CLIPTextModel(nn.Module):
         if T > cfg.max_position_embeddings or T > 128:
             raise ValueError(f"{T} tokens: the position table holds {cfg.max_position_embeddings}")
         heads, C = cfg.num_attention_heads, cfg.hidden_size
-        with torch.cuda.device(input_ids.device):
+        with _device_ctx(input_ids.device):
             p = self._plan(input_ids.device)
             x = ops.embed_tokens(input_ids.to(torch.int64).contiguous(), p["tok"], p["pos"])
             for lp in p["layers"]:

@@ -268,3 +268,43 @@ def test_training_tape_plumbing(recorder, stage):
         else:
             assert p.grad is None, n
     assert all(p.grad is None for p in unet.parameters() if not p.requires_grad)
+
+
+def test_edge_models_call_sequence(recorder):
+    """SURVEY 8 f3 host logic: VAE decode / encode / decode_video and the CLIP text encoder issue the expected entry points
+    with convertible arguments; the reference-precision mode is refused for both (bf16-mode components)."""
+    from synfmc_b200.edge import AutoencoderKL, CLIPTextModel
+    vae = AutoencoderKL(block_out_channels=(32, 64, 64, 64))
+    out = vae.decode(torch.randn(2, 4, 4, 4)).sample
+    assert out.shape == (2, 3, 32, 32) and out.dtype == torch.float32
+    names = recorder.names()
+    assert {"fmc_groupnorm_bf16", "fmc_gemm_bf16", "fmc_softmax_rows", "fmc_transpose_bf16", "fmc_resize_nearest_bf16",
+            "fmc_cl_to_video_f32"} <= set(names)
+    assert names.count("fmc_softmax_rows") == 2 and names.count("fmc_resize_nearest_bf16") == 3
+    assert vae.decode_video(torch.randn(1, 4, 3, 4, 4), chunk=2).shape == (1, 3, 3, 32, 32)
+    dist = vae.encode(torch.randn(1, 3, 32, 32)).latent_dist
+    assert dist.sample(noise=torch.randn(1, 4, 4, 4), scale=0.18215).shape == (1, 4, 4, 4) and dist.mode().shape == (1, 4, 4, 4)
+    assert "fmc_vae_sample_f32" in recorder.names()
+    clip = CLIPTextModel(vocab_size=100, hidden_size=64, num_hidden_layers=2, num_attention_heads=2, intermediate_size=128)
+    del recorder.calls[:]
+    hidden = clip(torch.randint(0, 100, (2, 77)))[0]
+    assert hidden.shape == (2, 77, 64) and hidden.dtype == torch.float32
+    names = recorder.names()
+    assert names[0] == "fmc_embed_tokens" and names.count("fmc_small_mha") == 2 and names.count("fmc_quick_gelu") == 2
+    assert names.count("fmc_layernorm_bf16") == 5 and names.count("fmc_gemm_bf16") == 8
+    mha = [a for n, a in recorder.calls if n == "fmc_small_mha"][0]
+    assert mha[8:14] == (2, 77, 2, 32, 1.0, 1)   # sequences, tokens, heads, head_dim, scale (folded into q), causal
+    with engine.precision("reference"):
+        with pytest.raises(NotImplementedError):
+            vae.decode(torch.randn(1, 4, 4, 4))
+        with pytest.raises(NotImplementedError):
+            clip(torch.randint(0, 100, (1, 77)))
+
+
+def test_edge_models_refuse_cpu_tensors_without_the_dry_run():
+    from synfmc_b200.edge import AutoencoderKL, CLIPTextModel
+    with pytest.raises(Exception, match="CUDA"):
+        AutoencoderKL(block_out_channels=(32, 32, 32, 32)).decode(torch.randn(1, 4, 4, 4))
+    with pytest.raises(Exception, match="CUDA"):
+        CLIPTextModel(vocab_size=10, hidden_size=64, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64)(
+            torch.zeros(1, 77, dtype=torch.long))
