@@ -362,6 +362,23 @@ int fmc_vae_sample_f32(const void* moments, long long ldm, int is_f32, const flo
 int fmc_cl_to_video_f32(const void* x, long long ldc, int is_f32, float* out, int B, int C, int F, long long HW, float mul,
                         float add, float lo, float hi, void* stream);
 
+/* ---- relative-pose algebra on the device (fp64 like the reference's numpy) ------------------------------
+ * A pose is a row-major 3x4 block [R | T] at the head of a record of `stride` doubles (12: 3x4 storage, 16: 4x4).
+ * fmc_pose_relative_to_first_f64: create_relative_matrix_of_cam_list, fmc/data/utils.py:148-163 -- out[clip, f] =
+ *   [R_f^T R_0 | R_f^T (T_0 - T_f) / scale_T], out[clip, 0] = eye(3, 4) exactly.
+ * fmc_pose_absolute_from_relative_f64: create_absolute_matrix_from_ref_cam_list, :167-183 -- out[clip, f] = rows 0..2 of
+ *   first[clip] (4x4) @ inv([rel[clip, f] with T * scale_T; 0 0 0 1]), out[clip, 0] = first[clip] rows 0..2 (the reference
+ *   asserts 16 frames; any count works here).
+ * fmc_pose_objects_relative_f64: create_relative_matrix_of_two_torch_matrix, :185-200 -- n object poses per camera pose,
+ *   out[set, i] = [R_i^T R_cam | R_i^T (T_cam - T_obj0) / scale_T]: the translation of OBJECT 0 of the set is the one
+ *   subtracted for every object, which is what the reference's stacked np.dot(...)[..., 0, 0] evaluates to. */
+int fmc_pose_relative_to_first_f64(const double* poses, long long pose_stride, double* out, int clips, int frames,
+                                   double scale_T, void* stream);
+int fmc_pose_absolute_from_relative_f64(const double* first, const double* rel, double* out, int clips, int frames,
+                                        double scale_T, void* stream);
+int fmc_pose_objects_relative_f64(const double* cam, long long cam_stride, const double* obj, long long obj_stride, double* out,
+                                  int sets, int n, double scale_T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

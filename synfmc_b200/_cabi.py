@@ -2,13 +2,13 @@
 entry point is absent the import of any op fails loudly -- there is no fallback path."""
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # FMC_B200_LIB: A/B kernel experiments load another build of the same library (profiles/variants/*.so)
 LIB_PATH = os.environ.get("FMC_B200_LIB") or os.path.join(_HERE, "libfmc_b200.so")
 
-P, I, L, F = c_void_p, c_int, c_longlong, c_float
+P, I, L, F, D = c_void_p, c_int, c_longlong, c_float, c_double
 ABI_VERSION = 3  # FMC_B200_ABI_VERSION of include/fmc_b200.h
 
 # name -> argtypes, in the order of include/fmc_b200.h
@@ -45,6 +45,10 @@ SIGNATURES = {
     "fmc_transpose_bf16": [P, L, P, L, L, I, P],
     "fmc_colsum_f32": [P, L, I, P, P, L, I, I, P],
     "fmc_layernorm_bwd_bf16": [P, L, P, L, P, F, P, L, P, L, I, P],
+    # relative poses (csrc/pose.cu)
+    "fmc_pose_relative_to_first_f64": [P, L, P, I, I, D, P],
+    "fmc_pose_absolute_from_relative_f64": [P, P, P, I, I, D, P],
+    "fmc_pose_objects_relative_f64": [P, L, P, L, P, I, I, D, P],
     # pipeline edges (csrc/edge.cu)
     "fmc_softmax_rows": [P, L, P, L, I, L, I, F, P],
     "fmc_small_mha": [P, L, I, I, I, P, L, I, I, I, I, I, F, I, P],

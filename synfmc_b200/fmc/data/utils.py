@@ -61,3 +61,64 @@ def create_relative_matrix_of_two_torch_matrix(RT1, RT2, scale_T=1):
     out[:, :, :3] = r_t @ cam[:, :3]
     out[:, :, 3] = (-(r_t @ t_obj0) + r_t @ cam[:, 3]) / scale_T
     return out.reshape(out.shape[0], -1)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Device forms: the same three functions on poses that already live on the GPU, batched over clips /
+# frames, fp64 like the numpy originals (csrc/pose.cu).  Results stay on the device and feed `ops.plucker*` /
+# `fmc.util.pack_objects` without a round trip through numpy.
+# --------------------------------------------------------------------------------------------------------------
+def _poses_f64(x, what):
+    from ... import ops
+    ops.require_cuda(x)
+    if x.dtype != torch.float64 or x.shape[-1] != 4 or x.shape[-2] not in (3, 4):
+        raise ValueError(f"{what}: float64 poses [..., 3 or 4, 4] expected, got {tuple(x.shape)} {x.dtype}")
+    return x.contiguous()
+
+
+def relative_poses_to_first_frame(cams, scale_T=1.0):
+    """create_relative_matrix_of_cam_list for a batch: cams [clips, frames, 3|4, 4] float64 (device) -> [clips, frames, 12]."""
+    from ... import _cabi, ops
+    cams = _poses_f64(cams, "relative_poses_to_first_frame")
+    clips, frames, rows, _ = cams.shape
+    out = torch.empty((clips, frames, 12), device=cams.device, dtype=torch.float64)
+    ops._check_cuda(cams)
+    _cabi.call("fmc_pose_relative_to_first_f64", cams.data_ptr(), rows * 4, out.data_ptr(), clips, frames, float(scale_T),
+               ops._stream())
+    return out
+
+
+def absolute_poses_from_relative(first, rel, scale_T=1.0):
+    """create_absolute_matrix_from_ref_cam_list for a batch: first [clips, 4, 4], rel [clips, frames, 12] (or [..., 3, 4])
+    float64 (device) -> [clips, frames, 3, 4]."""
+    from ... import _cabi, ops
+    ops.require_cuda(first)
+    if first.dtype != torch.float64 or tuple(first.shape[-2:]) != (4, 4):
+        raise ValueError("absolute_poses_from_relative: first must be float64 [clips, 4, 4]")
+    first = first.contiguous()
+    clips = first.shape[0]
+    rel = rel.reshape(clips, -1, 12).contiguous()
+    if rel.dtype != torch.float64:
+        raise ValueError("absolute_poses_from_relative: rel must be float64")
+    frames = rel.shape[1]
+    out = torch.empty((clips, frames, 3, 4), device=first.device, dtype=torch.float64)
+    ops._check_cuda(first, rel)
+    _cabi.call("fmc_pose_absolute_from_relative_f64", first.data_ptr(), rel.data_ptr(), out.data_ptr(), clips, frames,
+               float(scale_T), ops._stream())
+    return out
+
+
+def relative_object_poses(cams, objs, scale_T=1.0):
+    """create_relative_matrix_of_two_torch_matrix for a batch of (camera pose, n object poses) sets -- typically one set per
+    frame: cams [sets, 3|4, 4], objs [sets, n, 3|4, 4] float64 (device) -> [sets, n, 12], the `obj_info` rows of
+    get_traj_features_v2 (the reference's object-0 translation quirk included, see the host function above)."""
+    from ... import _cabi, ops
+    cams = _poses_f64(cams, "relative_object_poses")
+    objs = _poses_f64(objs, "relative_object_poses")
+    sets, n = objs.shape[0], objs.shape[1]
+    assert cams.shape[0] == sets
+    out = torch.empty((sets, n, 12), device=cams.device, dtype=torch.float64)
+    ops._check_cuda(cams, objs)
+    _cabi.call("fmc_pose_objects_relative_f64", cams.data_ptr(), cams.shape[-2] * 4, objs.data_ptr(), objs.shape[-2] * 4,
+               out.data_ptr(), sets, n, float(scale_T), ops._stream())
+    return out
