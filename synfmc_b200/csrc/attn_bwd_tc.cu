@@ -33,7 +33,8 @@ constexpr int AB_TILE = AB_BM * 128;        // [128 rows x 64 bf16] SWIZZLE_128B
 constexpr int AB_PT = 2 * AB_BM * 128;      // [128 x 128] bf16 probability-type tile (two 64-column chunks)
 
 struct AbParams {
-  int heads, n, images, blocks;  // n tokens per image (queries == keys), blocks = ceil(n / 128)
+  int heads, n, images, blocks;  // n query tokens per image, blocks = ceil(n / 128)
+  int nk, key_blocks, kv_div, kv_stride;  // keys per group; image i reads keys of group i / kv_div at row group * kv_stride
   int head_stride, q_col0, k_col0, v_col0;
   float scale, scale_log2e;
   const __nv_bfloat16* O;
@@ -91,7 +92,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const uint32_t sQ = smem_base, sG = sQ + OT, sDS = sG + OT, sKV = sDS + AB_PT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = p.images * p.heads * p.blocks;
-  const int T = p.blocks;
+  const int T = p.key_blocks;  // key tiles per sweep (self-attention: = blocks; text cross-attention: 1)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmG);
@@ -119,6 +120,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int head = (item / p.blocks) % p.heads;
         const int img = item / (p.blocks * p.heads);
         const int row0 = img * p.n;
+        const int kv_row0 = (img / p.kv_div) * p.kv_stride;
         mbar_wait(&q_empty, (it & 1u) ^ 1u);
         mbar_arrive_expect_tx(&q_full, 2 * OT);
 #pragma unroll
@@ -134,8 +136,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const uint32_t sK = sKV + st * 2 * OT;
 #pragma unroll
           for (int ch = 0; ch < CH; ++ch) {
-            tma_load_2d_a(sK + ch * AB_TILE, &tmK, &kv_full[st], p.k_col0 + head * p.head_stride + ch * 64, row0 + j * AB_BM);
-            tma_load_2d_a(sK + OT + ch * AB_TILE, &tmV, &kv_full[st], p.v_col0 + head * AB_D + ch * 64, row0 + j * AB_BM);
+            tma_load_2d_a(sK + ch * AB_TILE, &tmK, &kv_full[st], p.k_col0 + head * p.head_stride + ch * 64, kv_row0 + j * AB_BM);
+            tma_load_2d_a(sK + OT + ch * AB_TILE, &tmV, &kv_full[st], p.v_col0 + head * AB_D + ch * 64, kv_row0 + j * AB_BM);
           }
         }
       }
@@ -230,7 +232,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       float m = -INFINITY, l = 0.f, L2 = 0.f;
       for (int u = 0; u < 2 * T; ++u, ++t) {
         const int j = u < T ? u : u - T;
-        const int valid = p.n - j * AB_BM;
+        const int valid = p.nk - j * AB_BM;
         mbar_wait(&s_full, t & 1u);
         tc_fence_after_sync();
         if (u < T) {
@@ -562,13 +564,16 @@ static int attention_bwd_tc_launch(const void* Q, long long ldq, int q_col0, con
                                    const void* V, long long ldv, int v_col0, int head_stride, const void* O, long long ldo,
                                    const void* dO, long long lddo, void* dQ, long long lddq, int dq_col0, void* dK,
                                    long long lddk, int dk_col0, void* dV, long long lddv, int dv_col0, float* lse, float* dsum,
-                                   int images, int heads, int n, float scale, cudaStream_t stream) {
+                                   int images, int heads, int n, int nk, int kv_div, int kv_stride, float scale,
+                                   cudaStream_t stream) {
   using CfgQ = AbqCfg<D, QSTAGES>;
   using CfgK = AbkCfg<D, BQ, KSTAGES>;
   const long long rows = static_cast<long long>(images) * n;
+  const bool want_dkv = dK != nullptr;
+  const long long kv_rows = want_dkv ? rows : static_cast<long long>((images + kv_div - 1) / kv_div) * kv_stride;
   CUtensorMap tmQ, tmK, tmV, tmG, tmQb, tmGb;
-  auto map2d = [&](CUtensorMap* m, const void* base, long long ld, int box_rows) {
-    const uint64_t dims[2] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(rows)};
+  auto map2d = [&](CUtensorMap* m, const void* base, long long ld, int box_rows, long long nrows) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(nrows)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ld) * 2};
     const uint32_t box[2] = {64, static_cast<uint32_t>(box_rows)};
     return make_tmap_bf16(m, base, 2, dims, strides, box, true);
@@ -580,15 +585,16 @@ static int attention_bwd_tc_launch(const void* Q, long long ldq, int q_col0, con
     const uint32_t box3[3] = {64, 1, static_cast<uint32_t>(box_rows)};
     return make_tmap_bf16(m, dO, 3, dims, strides, box3, true);
   };
-  int rc = map2d(&tmQ, Q, ldq, AB_BM);
-  if (rc == FMC_OK) rc = map2d(&tmK, K, ldk, AB_BM);
-  if (rc == FMC_OK) rc = map2d(&tmV, V, ldv, AB_BM);
+  int rc = map2d(&tmQ, Q, ldq, AB_BM, rows);
+  if (rc == FMC_OK) rc = map2d(&tmK, K, ldk, AB_BM, kv_rows);
+  if (rc == FMC_OK) rc = map2d(&tmV, V, ldv, AB_BM, kv_rows);
   if (rc == FMC_OK) rc = map_do(&tmG, AB_BM);
-  if (rc == FMC_OK) rc = map2d(&tmQb, Q, ldq, BQ);
-  if (rc == FMC_OK) rc = map_do(&tmGb, BQ);
+  if (rc == FMC_OK && want_dkv) rc = map2d(&tmQb, Q, ldq, BQ, rows);
+  if (rc == FMC_OK && want_dkv) rc = map_do(&tmGb, BQ);
   if (rc != FMC_OK) return rc;
   AbParams p{};
   p.heads = heads; p.n = n; p.images = images; p.blocks = ceil_div(n, AB_BM);
+  p.nk = nk; p.key_blocks = ceil_div(nk, AB_BM); p.kv_div = kv_div; p.kv_stride = kv_stride;
   p.head_stride = head_stride; p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   p.O = static_cast<const __nv_bfloat16*>(O); p.dO = static_cast<const __nv_bfloat16*>(dO); p.ldo = ldo; p.lddo = lddo;
@@ -606,25 +612,26 @@ static int attention_bwd_tc_launch(const void* Q, long long ldq, int q_col0, con
   const int grid = items < device_sm_count() ? items : device_sm_count();
   launch_k(attn_bwd_dq_tc_kernel<D, QSTAGES>, dim3(grid), dim3(AB_THREADS), CfgQ::SMEM, stream, tmQ, tmK, tmV, tmG, p);
   rc = check_launch("attn_bwd_dq_tc_kernel");
-  if (rc != FMC_OK) return rc;
+  if (rc != FMC_OK || !want_dkv) return rc;
   launch_k(attn_bwd_dkv_tc_kernel<D, BQ, KSTAGES>, dim3(grid), dim3(AB_THREADS), CfgK::SMEM, stream, tmQb, tmK, tmV, tmGb, p);
   return check_launch("attn_bwd_dkv_tc_kernel");
 }
 
-// head_dim 40 (heads padded to 48) or 80; anything else is the caller's SIMT path
+// head_dim 40 (heads padded to 48) or 80; anything else is the caller's SIMT path.  dK = dV = NULL: dQ only, keys / values of
+// group image / kv_div at row group * kv_stride (text cross-attention: nk = 77 inside 80-row groups); else self-attention
 int attention_bwd_tc(int head_dim, const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
                      const void* V, long long ldv, int v_col0, int head_stride, const void* O, long long ldo, const void* dO,
                      long long lddo, void* dQ, long long lddq, int dq_col0, void* dK, long long lddk, int dk_col0, void* dV,
-                     long long lddv, int dv_col0, float* lse, float* dsum, int images, int heads, int n, float scale,
-                     cudaStream_t stream) {
+                     long long lddv, int dv_col0, float* lse, float* dsum, int images, int heads, int n, int nk, int kv_div,
+                     int kv_stride, float scale, cudaStream_t stream) {
   if (head_dim == 40)
     return attention_bwd_tc_launch<40, 3, 128, 2>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
                                                   dQ, lddq, dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images,
-                                                  heads, n, scale, stream);
+                                                  heads, n, nk, kv_div, kv_stride, scale, stream);
   if (head_dim == 80)
     return attention_bwd_tc_launch<80, 2, 64, 2>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
                                                  dQ, lddq, dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images,
-                                                 heads, n, scale, stream);
+                                                 heads, n, nk, kv_div, kv_stride, scale, stream);
   set_error("attention_bwd_tc: head_dim %d not in {40, 80}", head_dim);
   return FMC_ERR_SHAPE;
 }

@@ -1116,8 +1116,8 @@ namespace fmc {
 int attention_bwd_tc(int head_dim, const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0, const void* V,
                          long long ldv, int v_col0, int head_stride, const void* O, long long ldo, const void* dO,
                          long long lddo, void* dQ, long long lddq, int dq_col0, void* dK, long long lddk, int dk_col0,
-                         void* dV, long long lddv, int dv_col0, float* lse, float* dsum, int images, int heads, int n,
-                         float scale, cudaStream_t stream);
+                         void* dV, long long lddv, int dv_col0, float* lse, float* dsum, int images, int heads, int n, int nk,
+                         int kv_div, int kv_stride, float scale, cudaStream_t stream);
 }
 extern "C" int fmc_attention_bwd_bf16(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
                                       const void* V, long long ldv, int v_col0, int head_stride, const void* O,
@@ -1161,10 +1161,13 @@ extern "C" int fmc_attention_bwd_bf16(const void* Q, long long ldq, int q_col0, 
       default: break;
     }
   }
-  if (((head_dim == 40 && head_stride == 48) || (head_dim == 80 && head_stride == 80)) && inner == 1 && dK != nullptr &&
-      !force_simt && aligned8)
+  // spatial self-attention and (dQ only) text cross-attention at head_dim 40 / 80
+  if (((head_dim == 40 && head_stride == 48) || (head_dim == 80 && head_stride == 80)) && inner == 1 && !force_simt &&
+      ldo % 8 == 0 && lddq % 8 == 0 && dq_col0 % 8 == 0 && (dK == nullptr || aligned8) &&
+      static_cast<long long>(images) * nq < 0x7fffffffll)
     return attention_bwd_tc(head_dim, Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo, dQ, lddq,
-                                dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images, heads, nq, scale, stream);
+                            dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images, heads, nq, nk, kv_div, kv_stride,
+                            scale, stream);
   switch (head_dim) {
     case 40: return launch_attention_bwd<40>(p, dK != nullptr, stream);
     case 80: return launch_attention_bwd<80>(p, dK != nullptr, stream);

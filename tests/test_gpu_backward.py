@@ -213,7 +213,7 @@ def test_attention_bwd_temporal16_matches_simt(B, cuda_device, monkeypatch, d, B
         assert rel(out["0"][:, lo:hi], out["1"][:, lo:hi]) < BF16_TOL
 
 
-@pytest.mark.parametrize("d,images,nq,kv_div", [(40, 4, 200, 2), (160, 4, 64, 4)])
+@pytest.mark.parametrize("d,images,nq,kv_div", [(40, 4, 200, 2), (160, 4, 64, 4), (80, 4, 150, 2), (40, 6, 2560, 3)])
 def test_attention_bwd_text_cross(B, cuda_device, d, images, nq, kv_div):
     """Text cross-attention: dQ only (the text embeddings are frozen), 77 keys inside 80-row kv groups."""
     heads, hs, C, nk, stride = 8, (d + 15) // 16 * 16, 8 * d, 77, 80
