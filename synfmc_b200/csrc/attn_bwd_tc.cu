@@ -1,5 +1,5 @@
-// Spatial self-attention BACKWARD on the tensor cores (head_dim 40 and 80: levels 0 and 1, which dominate the training
-// step -- 16 images x 8 heads x 2560 x 2560 resp. 640 x 640 per attention).  Flash style, probabilities recomputed; two kernels, both built like
+// Spatial self-attention (and, dQ only, text cross-attention) BACKWARD on the tensor cores at head_dim 40 / 80 / 160 --
+// levels 0 and 1 dominate the training step: 16 images x 8 heads x 2560 x 2560 resp. 640 x 640 scores per attention.  Flash style, probabilities recomputed; two kernels, both built like
 // the forward kernel of attn_spatial.cu (TMA producer warp, one tcgen05.mma issuer thread, TMEM allocator warp, four
 // softmax warps with one TMEM lane = one row per thread) and arranged so that EVERY MMA has the forward's operand forms --
 // A K-major from shared memory, B K-major for the score-type products, B MN-major for the accumulate-type products:
@@ -168,6 +168,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         int prev_st = -1;
         for (int u = 0; u < 2 * T; ++u, ++t) {
           const int st = t % ABQ_STAGES;
+          if constexpr (ABQ_STAGES == 1) {
+            // one K / V stage (head_dim 160): the pending dQ MMA is what frees it, so it goes first (no overlap between
+            // the score MMAs of this tile and the softmax of the previous one; these shapes have two key tiles)
+            if (u > T) {
+              issue_dq(prev_st, u == T + 1);
+              prev_st = -2;
+            }
+          }
           mbar_wait(&kv_full[st], (t / ABQ_STAGES) & 1u);
           mbar_wait(&s_free, (t & 1u) ^ 1u);
           tc_fence_after_sync();
@@ -191,7 +199,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           } else {
             if (prev_st >= 0) {
               issue_dq(prev_st, u == T + 1);
-            } else {
+            } else if (prev_st == -1) {
               mbar_wait(&dq_free, (it & 1u) ^ 1u);  // the previous item's epilogue has read the dQ accumulator
               tc_fence_after_sync();
             }
@@ -340,7 +348,10 @@ struct AbkCfg {
   static constexpr int QT = CH * QC;         // Q / dO tile: BQ rows x DK columns
   static constexpr int PT = (BQ / 64) * AB_TILE;  // P^T / dS^T tile: 128 keys x BQ queries
   static constexpr int SMEM = 2 * OT + 2 * PT + STAGES * 2 * QT + 1024;
-  static_assert(256 + 2 * DK <= 512, "TMEM: S^T, dP^T, dV, dK");
+  static constexpr uint32_t COL_DP = BQ;        // TMEM columns: S^T [0, BQ) | dP^T [BQ, 2 BQ) | dV | dK
+  static constexpr uint32_t COL_DV = 2 * BQ;
+  static constexpr uint32_t COL_DK = 2 * BQ + DK;
+  static_assert(2 * BQ + 2 * DK <= 512, "TMEM: S^T, dP^T, dV, dK");
 };
 
 template <int AB_D, int BQ, int ABK_STAGES>
@@ -421,13 +432,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int k = 0; k < BQ / 16; ++k) {
           const uint64_t da = umma_desc_k_sw128(sP + (k >> 2) * AB_TILE + (k & 3) * 32);
           const uint64_t db = umma_desc_mn_sw128(sG + k * (16 * 128), QC, 1024);
-          umma_bf16_ss(tmem_base + 256u, da, db, idesc_a, (!first || k > 0) ? 1u : 0u);
+          umma_bf16_ss(tmem_base + Cfg::COL_DV, da, db, idesc_a, (!first || k > 0) ? 1u : 0u);
         }
 #pragma unroll
         for (int k = 0; k < BQ / 16; ++k) {
           const uint64_t da = umma_desc_k_sw128(sDS + (k >> 2) * AB_TILE + (k & 3) * 32);
           const uint64_t db = umma_desc_mn_sw128(sQ + k * (16 * 128), QC, 1024);
-          umma_bf16_ss(tmem_base + 256u + AB_DK, da, db, idesc_a, (!first || k > 0) ? 1u : 0u);
+          umma_bf16_ss(tmem_base + Cfg::COL_DK, da, db, idesc_a, (!first || k > 0) ? 1u : 0u);
         }
         umma_commit(&q_empty[st]);
         umma_commit(&pds_free);
@@ -449,7 +460,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                          umma_desc_k_sw128(sQ + (k >> 2) * QC + (k & 3) * 32), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < AB_DK / 16; ++k)  // dP^T = V dO^T (dO zero beyond the head's last column)
-            umma_bf16_ss(tmem_base + 128u, umma_desc_k_sw128(sV + (k >> 2) * AB_TILE + (k & 3) * 32),
+            umma_bf16_ss(tmem_base + Cfg::COL_DP, umma_desc_k_sw128(sV + (k >> 2) * AB_TILE + (k & 3) * 32),
                          umma_desc_k_sw128(sG + (k >> 2) * QC + (k & 3) * 32), idesc_s, k > 0 ? 1u : 0u);
           umma_commit(&s_full);
           if (prev_st >= 0) {
@@ -493,7 +504,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int c4 = 0; c4 < BQ / 32; ++c4) {
           uint32_t sv[32], dv[32], pp[16], pd[16];
           tmem_ld_x32(lane_addr + c4 * 32, sv);
-          tmem_ld_x32(lane_addr + 128u + c4 * 32, dv);
+          tmem_ld_x32(lane_addr + Cfg::COL_DP + c4 * 32, dv);
           tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
@@ -520,7 +531,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         if (lane == 0) mbar_arrive(&pds_ready);
         ++npd;
       }
-      // ---- epilogue: dV (columns 256..), dK (columns 256 + DK ..) -> bf16 -> global
+      // ---- epilogue: dV, dK accumulators -> bf16 -> global
       mbar_wait(&acc_final, it & 1u);
       tc_fence_after_sync();
       const int k_in_img = kb * AB_BM + r;
@@ -533,7 +544,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll 1
         for (int cc = 0; cc < AB_DK / 16; ++cc) {
           uint32_t o[16];
-          tmem_ld_x16(lane_addr + 256u + (which == 0 ? 0u : static_cast<uint32_t>(AB_DK)) + cc * 16, o);
+          tmem_ld_x16(lane_addr + (which == 0 ? Cfg::COL_DV : Cfg::COL_DK) + cc * 16, o);
           tmem_ld_wait();
           if (row_ok) {
             uint32_t w[8];
@@ -617,7 +628,7 @@ static int attention_bwd_tc_launch(const void* Q, long long ldq, int q_col0, con
   return check_launch("attn_bwd_dkv_tc_kernel");
 }
 
-// head_dim 40 (heads padded to 48) or 80; anything else is the caller's SIMT path.  dK = dV = NULL: dQ only, keys / values of
+// head_dim 40 (heads padded to 48), 80 or 160; anything else is the caller's SIMT path.  dK = dV = NULL: dQ only, keys / values of
 // group image / kv_div at row group * kv_stride (text cross-attention: nk = 77 inside 80-row groups); else self-attention
 int attention_bwd_tc(int head_dim, const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
                      const void* V, long long ldv, int v_col0, int head_stride, const void* O, long long ldo, const void* dO,
@@ -632,7 +643,11 @@ int attention_bwd_tc(int head_dim, const void* Q, long long ldq, int q_col0, con
     return attention_bwd_tc_launch<80, 2, 64, 2>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
                                                  dQ, lddq, dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images,
                                                  heads, n, nk, kv_div, kv_stride, scale, stream);
-  set_error("attention_bwd_tc: head_dim %d not in {40, 80}", head_dim);
+  if (head_dim == 160)
+    return attention_bwd_tc_launch<160, 1, 64, 2>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
+                                                  dQ, lddq, dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images,
+                                                  heads, n, nk, kv_div, kv_stride, scale, stream);
+  set_error("attention_bwd_tc: head_dim %d not in {40, 80, 160}", head_dim);
   return FMC_ERR_SHAPE;
 }
 

@@ -1161,8 +1161,9 @@ extern "C" int fmc_attention_bwd_bf16(const void* Q, long long ldq, int q_col0, 
       default: break;
     }
   }
-  // spatial self-attention and (dQ only) text cross-attention at head_dim 40 / 80
-  if (((head_dim == 40 && head_stride == 48) || (head_dim == 80 && head_stride == 80)) && inner == 1 && !force_simt &&
+  // spatial self-attention and (dQ only) text cross-attention
+  if (((head_dim == 40 && head_stride == 48) || (head_dim == 80 && head_stride == 80) ||
+       (head_dim == 160 && head_stride == 160)) && inner == 1 && !force_simt &&
       ldo % 8 == 0 && lddq % 8 == 0 && dq_col0 % 8 == 0 && (dK == nullptr || aligned8) &&
       static_cast<long long>(images) * nq < 0x7fffffffll)
     return attention_bwd_tc(head_dim, Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo, dQ, lddq,

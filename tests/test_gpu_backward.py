@@ -157,7 +157,7 @@ def test_attention_bwd_spatial_self(B, cuda_device, d, images, n):
         assert float(got[:, :k0].view(-1, heads, hs)[:, :, d:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("d,images,n", [(40, 3, 2560), (40, 2, 129), (40, 1, 128), (80, 3, 640), (80, 2, 200), (80, 1, 65)])
+@pytest.mark.parametrize("d,images,n", [(40, 3, 2560), (40, 2, 129), (40, 1, 128), (80, 3, 640), (80, 2, 200), (80, 1, 65), (160, 3, 160), (160, 2, 40), (160, 1, 300)])
 def test_attention_bwd_tensor_core_matches_simt(B, cuda_device, monkeypatch, d, images, n):
     """head_dim 40 / 80 self-attention: the tcgen05 kernels (csrc/attn_bwd_tc.cu) against the SIMT kernels on the same
     buffers, including the level-0 / level-1 sequence lengths (2560, 640) and ragged last tiles."""
