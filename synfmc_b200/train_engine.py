@@ -105,7 +105,9 @@ class TrainLinear:
 
     def _set(self, w_eff, b_eff):
         self.w = engine._dev_bf16(w_eff, self.device)                  # [N, K]
-        self.w_t = self.w.t().contiguous()                             # [K, N]: the "weight" of the dgrad GEMM
+        # [K, N]: the "weight" of the dgrad GEMM (trainable layers redo this every step: the own transpose kernel, not a
+        # strided torch copy)
+        self.w_t = bwd_ops.transpose(self.w) if self.w.is_cuda else self.w.t().contiguous()
         self.b = engine._dev_f32(b_eff, self.device)
         self.N, self.K = self.w.shape
 
