@@ -88,96 +88,129 @@ colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, 
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int LNB_WARPS = 8;
 constexpr int LNB_ROWS_PER_BLOCK = 64;
-template <int NV>  // vectors of 8 channels per lane: C <= NV * 256
+// NV: vectors of 8 channels per lane (C <= NV * 256); PARAMS: also accumulate d gamma / d beta (the accumulators cost 16 NV
+// registers, so the frozen-LayerNorm form is a separate instantiation); R: rows a warp has in flight at once (the loads and
+// the three shuffle reductions of R rows interleave -- a single row per warp leaves the memory system idle during its
+// reduction chains: ncu showed 12 % of the DRAM peak at 22 % occupancy before).
+template <int NV, bool PARAMS, int R>
 __global__ void __launch_bounds__(LNB_WARPS * 32)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ dy, long long lddy,
                      const float* __restrict__ gamma, float eps, __nv_bfloat16* __restrict__ dx, long long lddx,
                      float* __restrict__ pgrad, long long rows, int C, int rows_per_block) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float lnb_smem[];  // [LNB_WARPS][2][C] when pgrad != nullptr
+  extern __shared__ float lnb_smem[];  // [LNB_WARPS][2][C] when PARAMS
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 3;
+  const float inv_c = 1.0f / static_cast<float>(C);
   float gm[NV][8];
-  float dg[NV][8], db[NV][8];
+  float dg[PARAMS ? NV : 1][8], db[PARAMS ? NV : 1][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = i * 32 + lane;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       gm[i][j] = vi < nvec ? __ldg(gamma + vi * 8 + j) : 0.f;
-      dg[i][j] = db[i][j] = 0.f;
+      if (PARAMS) dg[i][j] = db[i][j] = 0.f;
     }
   }
   const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_block;
-  for (int rr = warp; rr < rows_per_block; rr += LNB_WARPS) {
-    const long long row = row0 + rr;
-    if (row >= rows) break;
-    float xv[NV][8], gv[NV][8];
-    float s = 0.f;
+  for (int rr = warp * R; rr < rows_per_block; rr += LNB_WARPS * R) {
+    if (row0 + rr >= rows) break;
+    float xv[R][NV][8], gv[R][NV][8];
+    float s[R], q[R], m1[R], m2[R], rstd[R];
+    bool live[R];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
-        unpack8b(__ldg(reinterpret_cast<const uint4*>(x + row * ldx) + vi), xv[i]);
-        unpack8b(__ldg(reinterpret_cast<const uint4*>(dy + row * lddy) + vi), gv[i]);
-      } else {
+    for (int k = 0; k < R; ++k) {
+      const long long row = row0 + rr + k;
+      live[k] = rr + k < rows_per_block && row < rows;
+      s[k] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xv[i][j] = gv[i][j] = 0.f;
-      }
+      for (int i = 0; i < NV; ++i) {
+        const int vi = i * 32 + lane;
+        if (live[k] && vi < nvec) {
+          unpack8b(__ldg(reinterpret_cast<const uint4*>(x + row * ldx) + vi), xv[k][i]);
+          unpack8b(__ldg(reinterpret_cast<const uint4*>(dy + row * lddy) + vi), gv[k][i]);
+        } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += xv[i][j];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / static_cast<float>(C);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xv[i][j] -= mean;
-          q += xv[i][j] * xv[i][j];
+          for (int j = 0; j < 8; ++j) xv[k][i][j] = gv[k][i][j] = 0.f;
         }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = 1.0f / sqrtf(q / static_cast<float>(C) + eps);
-    float m1 = 0.f, m2 = 0.f;
+    for (int k = 0; k < R; ++k)
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
+      for (int i = 0; i < NV; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        xv[i][j] *= rstd;                        // xhat
-        dg[i][j] += gv[i][j] * xv[i][j];         // d gamma
-        db[i][j] += gv[i][j];                    // d beta
-        gv[i][j] *= gm[i][j];                    // g = dy * gamma
-        m1 += gv[i][j];
-        m2 += gv[i][j] * xv[i][j];
+        for (int j = 0; j < 8; ++j) s[k] += xv[k][i][j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < R; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const float mean = s[k] * inv_c;
+      q[k] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = i * 32 + lane;
+        if (vi < nvec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            xv[k][i][j] -= mean;
+            q[k] = fmaf(xv[k][i][j], xv[k][i][j], q[k]);
+          }
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      m1 += __shfl_xor_sync(0xffffffffu, m1, o);
-      m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < R; ++k) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      rstd[k] = 1.0f / sqrtf(q[k] * inv_c + eps);
+      m1[k] = m2[k] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xv[k][i][j] *= rstd[k];                                 // xhat
+          if (PARAMS) {
+            dg[i][j] = fmaf(gv[k][i][j], xv[k][i][j], dg[i][j]);  // d gamma
+            db[i][j] += gv[k][i][j];                               // d beta
+          }
+          gv[k][i][j] *= gm[i][j];                                // g = dy * gamma
+          m1[k] += gv[k][i][j];
+          m2[k] = fmaf(gv[k][i][j], xv[k][i][j], m2[k]);
+        }
+      }
     }
-    m1 /= static_cast<float>(C);
-    m2 /= static_cast<float>(C);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
-        float o8[8];
+    for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o8[j] = rstd * (gv[i][j] - m1 - xv[i][j] * m2);
-        *(reinterpret_cast<uint4*>(dx + row * lddx) + vi) = pack8b(o8);
+      for (int k = 0; k < R; ++k) {
+        m1[k] += __shfl_xor_sync(0xffffffffu, m1[k], o);
+        m2[k] += __shfl_xor_sync(0xffffffffu, m2[k], o);
+      }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if (!live[k]) continue;
+      const long long row = row0 + rr + k;
+      const float a1 = m1[k] * inv_c, a2 = m2[k] * inv_c;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = i * 32 + lane;
+        if (vi < nvec) {
+          float o8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o8[j] = rstd[k] * (gv[k][i][j] - a1 - xv[k][i][j] * a2);
+          *(reinterpret_cast<uint4*>(dx + row * lddx) + vi) = pack8b(o8);
+        }
       }
     }
   }
-  if (pgrad != nullptr) {
+  if (PARAMS) {
     float* mine = lnb_smem + static_cast<size_t>(warp) * 2 * C;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -215,6 +248,12 @@ __device__ __forceinline__ float silu_grad(float z) {
 //   pass 2: both group means from the partials, then dx
 // Partials are folded in a fixed order (deterministic, no atomics), the chunk totals in double.
 constexpr int GNB_ROWS = 32;
+constexpr int GNB_U = 4;  // rows a thread has in flight per trip
+// d silu(z) / dz with the fast exponential / reciprocal (relative error ~1e-6, far below the bf16 output)
+__device__ __forceinline__ float silu_grad_fast(float z) {
+  const float s = __fdividef(1.0f, 1.0f + __expf(-z));
+  return s * fmaf(z, 1.0f - s, 1.0f);
+}
 struct GnbParams {
   const __nv_bfloat16 *x, *dy;
   __nv_bfloat16* dx;
@@ -284,30 +323,46 @@ groupnorm_bwd_pass_kernel(GnbParams p) {
         }
         if (PASS == 2) { ga[j] = s_a[g]; gb[j] = s_b[g]; }
       }
-      for (int r = r0 + rl; r < r1; r += RL) {
-        float xv[8], dv[8], o8[8];
-        unpack8b(__ldg(reinterpret_cast<const uint4*>(p.x + (base + r) * p.ldx) + vi), xv);
-        if (PASS >= 1) unpack8b(__ldg(reinterpret_cast<const uint4*>(p.dy + (base + r) * p.lddy) + vi), dv);
+      // GNB_U rows per trip: their loads are issued together (memory-level parallelism; one row per trip left the kernel
+      // latency-bound at 10 % of the DRAM peak), then the arithmetic of the rows runs on registers
+      for (int rb0 = r0 + rl; rb0 < r1; rb0 += RL * GNB_U) {
+        uint4 xq[GNB_U], dq[GNB_U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float u = xv[j] + rb[j];
-          if (PASS == 0) {
-            a[j] += u;
-            b[j] = fmaf(u, u, b[j]);
-          } else {
-            const float xh = (u - mu[j]) * rs[j];
-            float d = dv[j];
-            if (p.silu) d *= silu_grad(fmaf(xh, gm[j], bt[j]));
-            const float g = d * gm[j];
-            if (PASS == 1) {
-              a[j] += g;
-              b[j] = fmaf(g, xh, b[j]);
-            } else {
-              o8[j] = rs[j] * (g - ga[j] - xh * gb[j]);
-            }
+        for (int k = 0; k < GNB_U; ++k) {
+          const int r = rb0 + k * RL;
+          if (r < r1) {
+            xq[k] = __ldg(reinterpret_cast<const uint4*>(p.x + (base + r) * p.ldx) + vi);
+            if (PASS >= 1) dq[k] = __ldg(reinterpret_cast<const uint4*>(p.dy + (base + r) * p.lddy) + vi);
           }
         }
-        if (PASS == 2) *(reinterpret_cast<uint4*>(p.dx + (base + r) * p.lddx) + vi) = pack8b(o8);
+#pragma unroll
+        for (int k = 0; k < GNB_U; ++k) {
+          const int r = rb0 + k * RL;
+          if (r >= r1) break;
+          float xv[8], dv[8], o8[8];
+          unpack8b(xq[k], xv);
+          if (PASS >= 1) unpack8b(dq[k], dv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float u = xv[j] + rb[j];
+            if (PASS == 0) {
+              a[j] += u;
+              b[j] = fmaf(u, u, b[j]);
+            } else {
+              const float xh = (u - mu[j]) * rs[j];
+              float d = dv[j];
+              if (p.silu) d *= silu_grad_fast(fmaf(xh, gm[j], bt[j]));
+              const float g = d * gm[j];
+              if (PASS == 1) {
+                a[j] += g;
+                b[j] = fmaf(g, xh, b[j]);
+              } else {
+                o8[j] = rs[j] * (g - ga[j] - xh * gb[j]);
+              }
+            }
+          }
+          if (PASS == 2) *(reinterpret_cast<uint4*>(p.dx + (base + r) * p.lddx) + vi) = pack8b(o8);
+        }
       }
       if (PASS < 2) {
 #pragma unroll
@@ -987,28 +1042,33 @@ extern "C" int fmc_layernorm_bwd_bf16(const void* x, long long ldx, const void* 
               "fmc_layernorm_bwd_bf16: C=%d must be a multiple of 8, at most 1280", C);
   if (rows == 0) return FMC_OK;
   // with parameter partials the block count is part of the interface (fmc_layernorm_bwd_blocks); without them the rows
-  // per block shrink until the grid covers the SMs a few times over (rows = 640 .. 2560 at the deep levels)
+  // per block shrink until the grid covers the SMs several times over
+  const bool params = param_partials != nullptr;
   int rpb = LNB_ROWS_PER_BLOCK;
-  if (param_partials == nullptr)
-    while (rpb > LNB_WARPS && (rows + rpb - 1) / rpb < 4ll * device_sm_count()) rpb >>= 1;
+  if (!params)
+    while (rpb > 2 * LNB_WARPS && (rows + rpb - 1) / rpb < 8ll * device_sm_count()) rpb >>= 1;
   const int blocks = static_cast<int>((rows + rpb - 1) / rpb);
-  const size_t smem = param_partials != nullptr ? static_cast<size_t>(LNB_WARPS) * 2 * C * sizeof(float) : 0;
+  const size_t smem = params ? static_cast<size_t>(LNB_WARPS) * 2 * C * sizeof(float) : 0;
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* db = static_cast<const __nv_bfloat16*>(dy);
   __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(dx);
+#define FMC_LNB_LAUNCH(NV, PARAMS, R, SMEM_MAX)                                                                             \
+  do {                                                                                                                      \
+    static unsigned long long devs = 0;                                                                                     \
+    if (PARAMS && first_use_on_this_device(&devs))                                                                          \
+      FMC_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<NV, PARAMS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                       SMEM_MAX));                                                                          \
+    launch_k(layernorm_bwd_kernel<NV, PARAMS, R>, dim3(blocks), dim3(LNB_WARPS * 32), smem, stream, xb, ldx, db, lddy, gamma, \
+             eps, ob, lddx, param_partials, rows, C, rpb);                                                                  \
+  } while (0)
   if (C <= 512) {
-    static unsigned long long devs = 0;
-    if (first_use_on_this_device(&devs))
-      FMC_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LNB_WARPS * 2 * 512 * 4));
-    launch_k(layernorm_bwd_kernel<2>, dim3(blocks), dim3(LNB_WARPS * 32), smem, stream, xb, ldx, db, lddy, gamma, eps, ob, lddx,
-             param_partials, rows, C, rpb);
+    if (params) FMC_LNB_LAUNCH(2, true, 1, LNB_WARPS * 2 * 512 * 4);
+    else FMC_LNB_LAUNCH(2, false, 2, 0);
   } else {
-    static unsigned long long devs = 0;
-    if (first_use_on_this_device(&devs))
-      FMC_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, LNB_WARPS * 2 * 1280 * 4));
-    launch_k(layernorm_bwd_kernel<5>, dim3(blocks), dim3(LNB_WARPS * 32), smem, stream, xb, ldx, db, lddy, gamma, eps, ob, lddx,
-             param_partials, rows, C, rpb);
+    if (params) FMC_LNB_LAUNCH(5, true, 1, LNB_WARPS * 2 * 1280 * 4);
+    else FMC_LNB_LAUNCH(5, false, 1, 0);
   }
+#undef FMC_LNB_LAUNCH
   return check_launch("layernorm_bwd_kernel");
 }
 
@@ -1032,10 +1092,10 @@ extern "C" int fmc_groupnorm_bwd_bf16(const void* x, long long ldx, const void* 
   p.ldx = ldx; p.lddy = lddy; p.lddx = lddx; p.ldrb = ldrb;
   p.gamma = gamma; p.beta = beta; p.rowbias = rowbias; p.eps = eps;
   p.images = images; p.HW = HW; p.C = C; p.groups = groups; p.silu = silu; p.rb_div = rowbias_div > 0 ? rowbias_div : 1;
-  // chunks: enough (image, chunk) blocks for two per SM, but at least GNB_ROWS rows each (the per-thread channel constants
+  // chunks: enough (image, chunk) blocks for four per SM, but at least GNB_ROWS rows each (the per-thread channel constants
   // and the fold of the partials are paid once per block); the workspace bound ceil(HW / GNB_ROWS) chunks always covers it
   const int max_chunks = (HW + GNB_ROWS - 1) / GNB_ROWS;
-  int want = (2 * device_sm_count() + images - 1) / images;
+  int want = (4 * device_sm_count() + images - 1) / images;
   want = want < 1 ? 1 : (want > max_chunks ? max_chunks : want);
   p.chunk_rows = ((HW + want - 1) / want + 7) / 8 * 8;
   p.chunks = (HW + p.chunk_rows - 1) / p.chunk_rows;
