@@ -251,7 +251,11 @@ int fmc_avgpool2_bwd_bf16(const void* dy, void* dx, int N, int h, int w, int C, 
  * Probabilities are recomputed flash-style; lse / dsum: fp32 [q_rows, heads] scratch (row log-sum-exp and sum_c dO O).
  * dK = dV = NULL skips the key / value gradients (text cross-attention: the text is frozen); they are implemented for
  * self-attention (kv_div = 1, nq = nk).  dQ / dK / dV use the Q / K / V layouts, so they can alias one [token, q|k|v]
- * gradient buffer (zero-initialised: padding columns are not written). */
+ * gradient buffer (zero-initialised: padding columns are not written).
+ * One entry point, three kernel families chosen by shape (same results within bf16 rounding; FMC_ATTN_BWD_SIMT=1 in the
+ * environment forces the last one for A/B checks): tcgen05 kernels (csrc/attn_bwd_tc.cu) for inner = 1 at head_dim 40
+ * (head_stride 48) / 80 / 160 -- self-attention and the dQ-only cross form; one warp per (sequence, head) for nq = nk = 16
+ * self-attention (the temporal attentions; lse / dsum are not written there); CUDA-core kernels for everything else. */
 int fmc_attention_bwd_bf16(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
                            const void* V, long long ldv, int v_col0, int head_stride, const void* O, long long ldo,
                            const void* dO, long long lddo, void* dQ, long long lddq, int dq_col0, void* dK, long long lddk,

@@ -395,9 +395,20 @@ groupnorm_bwd_pass_kernel(GnbParams p) {
 //   forward  y[:, 16 b + j] = a gelu(g)                           (training forward: the projection is kept for backward)
 //   backward dproj[value] = dy gelu(g);  dproj[gate] = dy a gelu'(g),  gelu'(g) = Phi(g) + g phi(g)   (exact erf GELU)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_exact(float g) { return 0.5f * g * (1.0f + erff(g * 0.70710678118654752440f)); }
-__device__ __forceinline__ float gelu_exact_grad(float g) {
-  return 0.5f * (1.0f + erff(g * 0.70710678118654752440f)) + g * 0.39894228040143267794f * expf(-0.5f * g * g);
+// Phi(g) = (1 + erf(g / sqrt 2)) / 2 with erf from Abramowitz & Stegun 7.1.28 (|err| <= 3e-7; the form the fused GEGLU
+// epilogue of the inference GEMM uses, csrc/gemm.cu): 1 - erf(x) = (1 + a1 x + ... + a6 x^6)^-16 for x >= 0, the
+// negative tail formed without cancellation.  One MUFU (rcp) per value instead of the ~40 instructions of erff.
+__device__ __forceinline__ float normal_cdf_fast(float g) {
+  const float x = fabsf(g) * 0.70710678118654752440f;
+  float p = fmaf(x, 0.0000430638f, 0.0002765672f);
+  p = fmaf(x, p, 0.0001520143f);
+  p = fmaf(x, p, 0.0092705272f);
+  p = fmaf(x, p, 0.0422820123f);
+  p = fmaf(x, p, 0.0705230784f);
+  p = fmaf(x, p, 1.0f);
+  float r = rcp_fast(p);
+  r *= r; r *= r; r *= r; r *= r;  // (1 / p)^16 = 1 - erf(x)
+  return 0.5f * (g >= 0.f ? 2.0f - r : r);
 }
 __global__ void __launch_bounds__(256)
 geglu_fwd_kernel(const __nv_bfloat16* __restrict__ proj, long long ldp, __nv_bfloat16* __restrict__ y, long long ldy,
@@ -414,7 +425,7 @@ geglu_fwd_kernel(const __nv_bfloat16* __restrict__ proj, long long ldp, __nv_bfl
   unpack8b(__ldg(reinterpret_cast<const uint4*>(proj + r * ldp + blk * 32 + half * 8)), a);
   unpack8b(__ldg(reinterpret_cast<const uint4*>(proj + r * ldp + blk * 32 + 16 + half * 8)), g);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o8[j] = a[j] * gelu_exact(g[j]);
+  for (int j = 0; j < 8; ++j) o8[j] = a[j] * g[j] * normal_cdf_fast(g[j]);
   *(reinterpret_cast<uint4*>(y + r * ldy) + vi) = pack8b(o8);
 }
 __global__ void __launch_bounds__(256)
@@ -434,8 +445,9 @@ geglu_bwd_kernel(const __nv_bfloat16* __restrict__ proj, long long ldp, const __
   unpack8b(__ldg(reinterpret_cast<const uint4*>(dy + r * lddy) + vi), d);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    da[j] = d[j] * gelu_exact(g[j]);
-    dg[j] = d[j] * a[j] * gelu_exact_grad(g[j]);
+    const float cdf = normal_cdf_fast(g[j]);  // gelu = g Phi(g);  gelu' = Phi(g) + g phi(g)
+    da[j] = d[j] * g[j] * cdf;
+    dg[j] = d[j] * a[j] * fmaf(g[j] * 0.39894228040143267794f, __expf(-0.5f * g[j] * g[j]), cdf);
   }
   *reinterpret_cast<uint4*>(dproj + r * lddp + blk * 32 + half * 8) = pack8b(da);
   *reinterpret_cast<uint4*>(dproj + r * lddp + blk * 32 + 16 + half * 8) = pack8b(dg);
