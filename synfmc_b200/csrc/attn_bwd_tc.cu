@@ -337,6 +337,299 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 }
 
 // =====================================================================================================================
+// dQ kernel, ping-pong form: 64-key tiles, TWO softmax warpgroups on alternate tiles (each thread still owns one query row;
+// group g = tile parity).  The single-group kernel above has one warp per scheduler doing the exponentials and cannot
+// overlap a tile's MMAs with its softmax (one S / dP buffer): ncu showed tensor pipe 12 %, XU 34 %, issue 42 % at level 0.
+// Here S / dP are double-buffered in TMEM (2 x (64 + 64) columns + dQ), each group has its own dS tile in shared memory,
+// and the MMA thread alternates between the groups.  The row log-sum-exp of the first sweep is folded across the two
+// groups through shared memory.
+// =====================================================================================================================
+constexpr int ABP_BN = 64;
+constexpr int ABP_THREADS = 384;
+template <int D, int STAGES>
+struct AbpCfg {
+  static constexpr int DK = (D + 15) / 16 * 16;
+  static constexpr int CH = (DK + 63) / 64;
+  static constexpr int OT = CH * AB_TILE;            // Q / dO tile: 128 rows x DK columns
+  static constexpr int KC = ABP_BN * 128;            // one 64-column chunk of a 64-key tile
+  static constexpr int KT = CH * KC;                 // K / V tile: 64 keys x DK columns
+  static constexpr int DS = AB_BM * 128;             // dS tile of one group: 128 queries x 64 keys
+  static constexpr int SMEM = 2 * OT + 2 * DS + STAGES * 2 * KT + 1024;
+  static_assert(256 + DK <= 512, "TMEM: 2 x (S, dP) + dQ");
+};
+
+template <int AB_D, int STAGES>
+__global__ void __launch_bounds__(ABP_THREADS, 1)
+attn_bwd_dq_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmG, AbParams p) {
+  pdl_launch_dependents();
+  using Cfg = AbpCfg<AB_D, STAGES>;
+  constexpr int AB_DK = Cfg::DK, CH = Cfg::CH, OT = Cfg::OT, KC = Cfg::KC, KT = Cfg::KT, DS = Cfg::DS;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t q_full, q_empty, dq_final, dq_free;
+  __shared__ uint64_t s_full[2], s_free[2], ds_ready[2], ds_free[2];
+  __shared__ uint64_t kv_full[STAGES], kv_empty[STAGES];
+  __shared__ float fold_m[2][AB_BM], fold_l[2][AB_BM];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base, sG = sQ + OT, sDS = sG + OT, sKV = sDS + 2 * DS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_items = p.images * p.heads * p.blocks;
+  const int T = (p.nk + ABP_BN - 1) / ABP_BN;  // 64-key tiles per sweep
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmG);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&q_full, 1); mbar_init(&q_empty, 1);
+    mbar_init(&dq_final, 1); mbar_init(&dq_free, 4);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 4);
+      mbar_init(&ds_ready[g], 4); mbar_init(&ds_free[g], 1);
+    }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t t = 0, it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int qb = item % p.blocks;
+        const int head = (item / p.blocks) % p.heads;
+        const int img = item / (p.blocks * p.heads);
+        const int row0 = img * p.n;
+        const int kv_row0 = (img / p.kv_div) * p.kv_stride;
+        mbar_wait(&q_empty, (it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&q_full, 2 * OT);
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+          tma_load_2d_a(sQ + ch * AB_TILE, &tmQ, &q_full, p.q_col0 + head * p.head_stride + ch * 64, row0 + qb * AB_BM);
+          ab_tma_load_3d(sG + ch * AB_TILE, &tmG, &q_full, ch * 64, head, row0 + qb * AB_BM);
+        }
+        for (int u = 0; u < 2 * T; ++u, ++t) {
+          const int j = u < T ? u : u - T;
+          const int st = t % STAGES;
+          mbar_wait(&kv_empty[st], ((t / STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&kv_full[st], 2 * KT);
+          const uint32_t sK = sKV + st * 2 * KT;
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch) {
+            tma_load_2d_a(sK + ch * KC, &tmK, &kv_full[st], p.k_col0 + head * p.head_stride + ch * 64, kv_row0 + j * ABP_BN);
+            tma_load_2d_a(sK + KT + ch * KC, &tmV, &kv_full[st], p.v_col0 + head * AB_D + ch * 64, kv_row0 + j * ABP_BN);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(AB_BM, ABP_BN);
+      constexpr uint32_t idesc_a = umma_idesc_bf16_bmn(AB_BM, AB_DK);
+      uint32_t t = 0, it = 0;
+      uint32_t n_tile[2] = {0, 0};  // tiles handed to each group so far (barrier phases)
+      uint32_t n_ds[2] = {0, 0};    // dS tiles consumed from each group so far
+      // dQ += dS_g K(stage st)
+      auto issue_dq = [&](int g, int st, bool first) {
+        mbar_wait(&ds_ready[g], n_ds[g] & 1u);
+        tc_fence_after_sync();
+        const uint32_t sK = sKV + st * 2 * KT;
+#pragma unroll
+        for (int k = 0; k < ABP_BN / 16; ++k) {
+          const uint64_t da = umma_desc_k_sw128(sDS + g * DS + k * 32);
+          const uint64_t db = umma_desc_mn_sw128(sK + k * (16 * 128), KC, 1024);
+          umma_bf16_ss(tmem_base + 256u, da, db, idesc_a, (!first || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(&ds_free[g]);
+        ++n_ds[g];
+      };
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        mbar_wait(&q_full, it & 1u);
+        tc_fence_after_sync();
+        int prev_st = -1, prev_g = 0;
+        for (int u = 0; u < 2 * T; ++u, ++t) {
+          const int st = t % STAGES;
+          const int g = u & 1;
+          mbar_wait(&kv_full[st], (t / STAGES) & 1u);
+          mbar_wait(&s_free[g], (n_tile[g] & 1u) ^ 1u);
+          tc_fence_after_sync();
+          const uint32_t sK = sKV + st * 2 * KT;
+          const uint32_t col = tmem_base + static_cast<uint32_t>(g) * 128u;
+#pragma unroll
+          for (int k = 0; k < AB_DK / 16; ++k)
+            umma_bf16_ss(col, umma_desc_k_sw128(sQ + (k >> 2) * AB_TILE + (k & 3) * 32),
+                         umma_desc_k_sw128(sK + (k >> 2) * KC + (k & 3) * 32), idesc_s, k > 0 ? 1u : 0u);
+          if (u >= T) {
+#pragma unroll
+            for (int k = 0; k < AB_DK / 16; ++k)
+              umma_bf16_ss(col + 64u, umma_desc_k_sw128(sG + (k >> 2) * AB_TILE + (k & 3) * 32),
+                           umma_desc_k_sw128(sK + KT + (k >> 2) * KC + (k & 3) * 32), idesc_s, k > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[g]);
+          ++n_tile[g];
+          if (u < T) {
+            umma_commit(&kv_empty[st]);
+          } else {
+            if (prev_st >= 0) {
+              issue_dq(prev_g, prev_st, u == T + 1);
+            } else {
+              mbar_wait(&dq_free, (it & 1u) ^ 1u);  // the previous item's epilogue has read the dQ accumulator
+              tc_fence_after_sync();
+            }
+            prev_st = st;
+            prev_g = g;
+          }
+        }
+        issue_dq(prev_g, prev_st, T == 1);
+        umma_commit(&q_empty);
+        umma_commit(&dq_final);
+      }
+    }
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 2;  // softmax group: tiles with u & 1 == g
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g) * 128u;
+    const uint32_t dq_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 256u;
+    const uint32_t my_ds = sDS + g * DS;
+    const float c = p.scale_log2e;
+    uint32_t n_tile = 0, n_ds = 0, it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int qb = item % p.blocks;
+      const int head = (item / p.blocks) % p.heads;
+      const int img = item / (p.blocks * p.heads);
+      const int q_in_img = qb * AB_BM + r;
+      const bool row_ok = q_in_img < p.n;
+      const long long row = static_cast<long long>(img) * p.n + q_in_img;
+      float dsum = 0.f;
+      if (row_ok) {
+        const uint4* op = reinterpret_cast<const uint4*>(p.O + row * p.ldo + head * AB_D);
+        const uint4* gp = reinterpret_cast<const uint4*>(p.dO + row * p.lddo + head * AB_D);
+#pragma unroll
+        for (int v = 0; v < AB_D / 8; ++v) {
+          const uint4 a = __ldg(op + v), b = __ldg(gp + v);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dsum += bf16_lo(aw[e]) * bf16_lo(bw[e]) + bf16_hi(aw[e]) * bf16_hi(bw[e]);
+        }
+      }
+      float m = -INFINITY, l = 0.f;
+      // ---- sweep 1 (this group's tiles): online row maximum / sum in log2 units
+      for (int u = g; u < T; u += 2) {
+        const int valid = p.nk - u * ABP_BN;
+        mbar_wait(&s_full[g], n_tile & 1u);
+        ++n_tile;
+        tc_fence_after_sync();
+        float mx = -INFINITY;
+        uint32_t v[32];
+#pragma unroll 1
+        for (int c2 = 0; c2 < 2; ++c2) {
+          tmem_ld_x32(lane_addr + c2 * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float s = (c2 * 32 + i < valid) ? __uint_as_float(v[i]) * c : -INFINITY;
+            v[i] = __float_as_uint(s);
+            mx = fmaxf(mx, s);
+          }
+          const float m_new = fmaxf(m, mx);
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum += ab_exp2(__uint_as_float(v[i]) - m_new);
+          l = l * ab_exp2(m - m_new) + sum;
+          m = m_new;
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[g]);
+      }
+      // ---- fold (m, l) of the two groups (a group without a sweep-1 tile contributes (-inf, 0)); group 0 always has tile 0
+      fold_m[g][r] = m;
+      fold_l[g][r] = l;
+      ab_bar_sync(1, 256);
+      const float m0 = fold_m[0][r], m1 = fold_m[1][r];
+      const float mm = fmaxf(m0, m1);
+      const float lsum = fold_l[0][r] * ab_exp2(m0 - mm) + fold_l[1][r] * ab_exp2(m1 - mm);
+      const float L2 = mm + log2f(lsum);
+      if (g == 0 && row_ok) {
+        p.lse[row * p.heads + head] = L2;
+        p.dsum[row * p.heads + head] = dsum;
+      }
+      ab_bar_sync(2, 256);  // fold_* are rewritten by the next item only after both groups have read them
+      // ---- sweep 2 (this group's tiles): dS = exp2(S c - L) (dP - D) scale  -> bf16 -> this group's smem tile
+      for (int u = T + ((T & 1) == g ? 0 : 1); u < 2 * T; u += 2) {
+        const int valid = p.nk - (u - T) * ABP_BN;
+        mbar_wait(&s_full[g], n_tile & 1u);
+        ++n_tile;
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t sv[32], dv[32], pk[16];
+          tmem_ld_x32(lane_addr + c2 * 32, sv);
+          tmem_ld_x32(lane_addr + 64u + c2 * 32, dv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const bool ok0 = c2 * 32 + i < valid, ok1 = c2 * 32 + i + 1 < valid;
+            const float p0 = ok0 ? ab_exp2(fmaf(__uint_as_float(sv[i]), c, -L2)) : 0.f;
+            const float p1 = ok1 ? ab_exp2(fmaf(__uint_as_float(sv[i + 1]), c, -L2)) : 0.f;
+            const float d0 = ok0 ? p0 * (__uint_as_float(dv[i]) - dsum) * p.scale : 0.f;
+            const float d1 = ok1 ? p1 * (__uint_as_float(dv[i + 1]) - dsum) * p.scale : 0.f;
+            pk[i >> 1] = pack_bf16x2(d0, d1);
+          }
+          if (c2 == 0) mbar_wait(&ds_free[g], (n_ds & 1u) ^ 1u);  // the dQ MMA of this group's previous tile has read dS
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            st_shared_v4(ab_piece_addr(my_ds, r, c2 * 4 + e), pk[4 * e], pk[4 * e + 1], pk[4 * e + 2], pk[4 * e + 3]);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[g]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ds_ready[g]);
+        ++n_ds;
+      }
+      if (g == 0) {
+        // ---- epilogue (group 0): dQ accumulator -> bf16 -> global
+        mbar_wait(&dq_final, it & 1u);
+        tc_fence_after_sync();
+        __nv_bfloat16* dst_row = p.dQ + row * p.lddq + p.dq_col0 + head * p.head_stride;
+#pragma unroll 1
+        for (int cc = 0; cc < AB_DK / 16; ++cc) {
+          uint32_t o[16];
+          tmem_ld_x16(dq_addr + cc * 16, o);
+          tmem_ld_wait();
+          if (row_ok) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(__uint_as_float(o[2 * i]), __uint_as_float(o[2 * i + 1]));
+            uint4* dst = reinterpret_cast<uint4*>(dst_row + cc * 16);
+            if (cc * 16 + 8 <= AB_D) dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            if (cc * 16 + 16 <= AB_D) dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dq_free);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================================
 // dK / dV kernel (transposed scores: TMEM lane = key, column = query)
 // =====================================================================================================================
 template <int D, int BQ, int STAGES>
@@ -570,7 +863,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 }
 
 // host side: tensor maps + launches
-template <int D, int QSTAGES, int BQ, int KSTAGES>
+// QSTAGES: K / V ring depth of the dQ kernel; PP_STAGES > 0 selects the ping-pong dQ kernel (64-key tiles, two softmax
+// groups) with that ring depth -- FMC_ATTN_BWD_DQ1=1 in the environment keeps the single-group kernel for A/B runs
+template <int D, int QSTAGES, int BQ, int KSTAGES, int PP_STAGES>
 static int attention_bwd_tc_launch(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
                                    const void* V, long long ldv, int v_col0, int head_stride, const void* O, long long ldo,
                                    const void* dO, long long lddo, void* dQ, long long lddq, int dq_col0, void* dK,
@@ -583,6 +878,8 @@ static int attention_bwd_tc_launch(const void* Q, long long ldq, int q_col0, con
   const bool want_dkv = dK != nullptr;
   const long long kv_rows = want_dkv ? rows : static_cast<long long>((images + kv_div - 1) / kv_div) * kv_stride;
   CUtensorMap tmQ, tmK, tmV, tmG, tmQb, tmGb;
+  bool ping_pong = PP_STAGES > 0;
+  if (const char* e = getenv("FMC_ATTN_BWD_DQ1")) ping_pong = ping_pong && e[0] != '1';
   auto map2d = [&](CUtensorMap* m, const void* base, long long ld, int box_rows, long long nrows) {
     const uint64_t dims[2] = {static_cast<uint64_t>(ld), static_cast<uint64_t>(nrows)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ld) * 2};
@@ -599,6 +896,9 @@ static int attention_bwd_tc_launch(const void* Q, long long ldq, int q_col0, con
   int rc = map2d(&tmQ, Q, ldq, AB_BM, rows);
   if (rc == FMC_OK) rc = map2d(&tmK, K, ldk, AB_BM, kv_rows);
   if (rc == FMC_OK) rc = map2d(&tmV, V, ldv, AB_BM, kv_rows);
+  CUtensorMap tmK64, tmV64;  // 64-key boxes of the ping-pong dQ kernel (the dK / dV kernel keeps 128-key tiles)
+  if (rc == FMC_OK && ping_pong) rc = map2d(&tmK64, K, ldk, ABP_BN, kv_rows);
+  if (rc == FMC_OK && ping_pong) rc = map2d(&tmV64, V, ldv, ABP_BN, kv_rows);
   if (rc == FMC_OK) rc = map_do(&tmG, AB_BM);
   if (rc == FMC_OK && want_dkv) rc = map2d(&tmQb, Q, ldq, BQ, rows);
   if (rc == FMC_OK && want_dkv) rc = map_do(&tmGb, BQ);
@@ -621,8 +921,19 @@ static int attention_bwd_tc_launch(const void* Q, long long ldq, int q_col0, con
   }
   const int items = images * heads * p.blocks;
   const int grid = items < device_sm_count() ? items : device_sm_count();
-  launch_k(attn_bwd_dq_tc_kernel<D, QSTAGES>, dim3(grid), dim3(AB_THREADS), CfgQ::SMEM, stream, tmQ, tmK, tmV, tmG, p);
-  rc = check_launch("attn_bwd_dq_tc_kernel");
+  if constexpr (PP_STAGES > 0) {
+    if (ping_pong) {
+      using CfgP = AbpCfg<D, PP_STAGES>;
+      static unsigned long long pp_devs = 0;
+      if (first_use_on_this_device(&pp_devs))
+        FMC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_pp_kernel<D, PP_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         CfgP::SMEM));
+      launch_k(attn_bwd_dq_pp_kernel<D, PP_STAGES>, dim3(grid), dim3(ABP_THREADS), CfgP::SMEM, stream, tmQ, tmK64, tmV64, tmG, p);
+    }
+  }
+  if (!ping_pong)
+    launch_k(attn_bwd_dq_tc_kernel<D, QSTAGES>, dim3(grid), dim3(AB_THREADS), CfgQ::SMEM, stream, tmQ, tmK, tmV, tmG, p);
+  rc = check_launch("attn_bwd_dq kernel");
   if (rc != FMC_OK || !want_dkv) return rc;
   launch_k(attn_bwd_dkv_tc_kernel<D, BQ, KSTAGES>, dim3(grid), dim3(AB_THREADS), CfgK::SMEM, stream, tmQb, tmK, tmV, tmGb, p);
   return check_launch("attn_bwd_dkv_tc_kernel");
@@ -636,15 +947,15 @@ int attention_bwd_tc(int head_dim, const void* Q, long long ldq, int q_col0, con
                      long long lddv, int dv_col0, float* lse, float* dsum, int images, int heads, int n, int nk, int kv_div,
                      int kv_stride, float scale, cudaStream_t stream) {
   if (head_dim == 40)
-    return attention_bwd_tc_launch<40, 3, 128, 2>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
+    return attention_bwd_tc_launch<40, 3, 128, 2, 4>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
                                                   dQ, lddq, dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images,
                                                   heads, n, nk, kv_div, kv_stride, scale, stream);
   if (head_dim == 80)
-    return attention_bwd_tc_launch<80, 2, 64, 2>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
+    return attention_bwd_tc_launch<80, 2, 64, 2, 3>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
                                                  dQ, lddq, dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images,
                                                  heads, n, nk, kv_div, kv_stride, scale, stream);
   if (head_dim == 160)
-    return attention_bwd_tc_launch<160, 1, 64, 2>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
+    return attention_bwd_tc_launch<160, 1, 64, 2, 0>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
                                                   dQ, lddq, dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images,
                                                   heads, n, nk, kv_div, kv_stride, scale, stream);
   set_error("attention_bwd_tc: head_dim %d not in {40, 80, 160}", head_dim);
