@@ -527,11 +527,8 @@ attn_bwd_dq_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         ++n_tile;
         tc_fence_after_sync();
         float mx = -INFINITY;
-        uint32_t v[32];
-#pragma unroll 1
-        for (int c2 = 0; c2 < 2; ++c2) {
-          tmem_ld_x32(lane_addr + c2 * 32, v);
-          tmem_ld_wait();
+        uint32_t va[32], vb[32];
+        auto sweep1_chunk = [&](uint32_t (&v)[32], int c2) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float s = (c2 * 32 + i < valid) ? __uint_as_float(v[i]) * c : -INFINITY;
@@ -544,7 +541,13 @@ attn_bwd_dq_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           for (int i = 0; i < 32; ++i) sum += ab_exp2(__uint_as_float(v[i]) - m_new);
           l = l * ab_exp2(m - m_new) + sum;
           m = m_new;
-        }
+        };
+        tmem_ld_x32(lane_addr, va);
+        tmem_ld_wait();
+        tmem_ld_x32(lane_addr + 32, vb);  // in flight while the first chunk is reduced
+        sweep1_chunk(va, 0);
+        tmem_ld_wait();
+        sweep1_chunk(vb, 1);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[g]);
@@ -568,26 +571,39 @@ attn_bwd_dq_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_wait(&s_full[g], n_tile & 1u);
         ++n_tile;
         tc_fence_after_sync();
+        uint32_t sa[16], da[16], sb[16], db[16];
+        auto sweep2_chunk = [&](const uint32_t (&sv)[16], const uint32_t (&dv)[16], int c4) {
+          uint32_t pk[8];
 #pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          uint32_t sv[32], dv[32], pk[16];
-          tmem_ld_x32(lane_addr + c2 * 32, sv);
-          tmem_ld_x32(lane_addr + 64u + c2 * 32, dv);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const bool ok0 = c2 * 32 + i < valid, ok1 = c2 * 32 + i + 1 < valid;
+          for (int i = 0; i < 16; i += 2) {
+            const bool ok0 = c4 * 16 + i < valid, ok1 = c4 * 16 + i + 1 < valid;
             const float p0 = ok0 ? ab_exp2(fmaf(__uint_as_float(sv[i]), c, -L2)) : 0.f;
             const float p1 = ok1 ? ab_exp2(fmaf(__uint_as_float(sv[i + 1]), c, -L2)) : 0.f;
             const float d0 = ok0 ? p0 * (__uint_as_float(dv[i]) - dsum) * p.scale : 0.f;
             const float d1 = ok1 ? p1 * (__uint_as_float(dv[i + 1]) - dsum) * p.scale : 0.f;
             pk[i >> 1] = pack_bf16x2(d0, d1);
           }
-          if (c2 == 0) mbar_wait(&ds_free[g], (n_ds & 1u) ^ 1u);  // the dQ MMA of this group's previous tile has read dS
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            st_shared_v4(ab_piece_addr(my_ds, r, c2 * 4 + e), pk[4 * e], pk[4 * e + 1], pk[4 * e + 2], pk[4 * e + 3]);
-        }
+          if (c4 == 0) mbar_wait(&ds_free[g], (n_ds & 1u) ^ 1u);  // the dQ MMA of this group's previous tile has read dS
+          st_shared_v4(ab_piece_addr(my_ds, r, c4 * 2), pk[0], pk[1], pk[2], pk[3]);
+          st_shared_v4(ab_piece_addr(my_ds, r, c4 * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
+        };
+        // 16-column chunks; the loads of chunk k + 1 are in flight while chunk k is computed
+        tmem_ld_x16(lane_addr, sa);
+        tmem_ld_x16(lane_addr + 64u, da);
+        tmem_ld_wait();
+        tmem_ld_x16(lane_addr + 16, sb);
+        tmem_ld_x16(lane_addr + 64u + 16, db);
+        sweep2_chunk(sa, da, 0);
+        tmem_ld_wait();
+        tmem_ld_x16(lane_addr + 32, sa);
+        tmem_ld_x16(lane_addr + 64u + 32, da);
+        sweep2_chunk(sb, db, 1);
+        tmem_ld_wait();
+        tmem_ld_x16(lane_addr + 48, sb);
+        tmem_ld_x16(lane_addr + 64u + 48, db);
+        sweep2_chunk(sa, da, 2);
+        tmem_ld_wait();
+        sweep2_chunk(sb, db, 3);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[g]);
@@ -793,15 +809,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         ab_bar_sync(1, 128);
         mbar_wait(&s_full, t & 1u);
         tc_fence_after_sync();
+        uint32_t sa[16], da[16], sb[16], db[16];
+        auto chunk16 = [&](const uint32_t (&sv)[16], const uint32_t (&dv)[16], int k) {
+          uint32_t pp[8], pd[8];
 #pragma unroll
-        for (int c4 = 0; c4 < BQ / 32; ++c4) {
-          uint32_t sv[32], dv[32], pp[16], pd[16];
-          tmem_ld_x32(lane_addr + c4 * 32, sv);
-          tmem_ld_x32(lane_addr + Cfg::COL_DP + c4 * 32, dv);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const int col = c4 * 32 + e;
+          for (int e = 0; e < 16; e += 2) {
+            const int col = k * 16 + e;
             const float p0 = ab_exp2(fmaf(__uint_as_float(sv[e]), c, -vec_l[buf][col]));
             const float p1 = ab_exp2(fmaf(__uint_as_float(sv[e + 1]), c, -vec_l[buf][col + 1]));
             const float d0 = p0 * (__uint_as_float(dv[e]) - vec_d[buf][col]) * p.scale;
@@ -809,12 +822,29 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             pp[e >> 1] = pack_bf16x2(p0, p1);
             pd[e >> 1] = pack_bf16x2(d0, d1);
           }
-          if (c4 == 0) mbar_wait(&pds_free, (npd & 1u) ^ 1u);  // the accumulate MMAs of the previous tile have read P^T / dS^T
+          if (k == 0) mbar_wait(&pds_free, (npd & 1u) ^ 1u);  // the accumulate MMAs of the previous tile have read P^T / dS^T
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            st_shared_v4(ab_piece_addr(sP, r, c4 * 4 + g), pp[4 * g], pp[4 * g + 1], pp[4 * g + 2], pp[4 * g + 3]);
-            st_shared_v4(ab_piece_addr(sDS, r, c4 * 4 + g), pd[4 * g], pd[4 * g + 1], pd[4 * g + 2], pd[4 * g + 3]);
+          for (int h = 0; h < 2; ++h) {
+            st_shared_v4(ab_piece_addr(sP, r, k * 2 + h), pp[4 * h], pp[4 * h + 1], pp[4 * h + 2], pp[4 * h + 3]);
+            st_shared_v4(ab_piece_addr(sDS, r, k * 2 + h), pd[4 * h], pd[4 * h + 1], pd[4 * h + 2], pd[4 * h + 3]);
           }
+        };
+        // 16-column chunks; the TMEM loads of chunk k + 1 are in flight while chunk k is computed
+        tmem_ld_x16(lane_addr, sa);
+        tmem_ld_x16(lane_addr + Cfg::COL_DP, da);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < BQ / 16; k += 2) {
+          tmem_ld_x16(lane_addr + (k + 1) * 16, sb);
+          tmem_ld_x16(lane_addr + Cfg::COL_DP + (k + 1) * 16, db);
+          chunk16(sa, da, k);
+          tmem_ld_wait();
+          if (k + 2 < BQ / 16) {
+            tmem_ld_x16(lane_addr + (k + 2) * 16, sa);
+            tmem_ld_x16(lane_addr + Cfg::COL_DP + (k + 2) * 16, da);
+          }
+          chunk16(sb, db, k + 1);
+          if (k + 2 < BQ / 16) tmem_ld_wait();
         }
         tc_fence_before_sync();
         __syncwarp();
