@@ -59,3 +59,54 @@ def test_vae_gaussian_posterior():
     assert float(d.logvar.max()) <= 20.0 and float(d.logvar.min()) >= -30.0
     noise = torch.randn(1, 4, 3, 3, generator=torch.Generator().manual_seed(4))
     assert torch.equal(d.sample(noise=noise), d.mean + torch.exp(0.5 * d.logvar) * noise)
+
+
+def test_unet_diffusers_layer_restatement_matches_the_ldm_blocks():
+    """The diffusers layer UNDER the U-Net oracle (oracle/diffusers_restated.py: ResnetBlock2D, Attention, Upsample2D) has no
+    reference fixtures -- diffusers is not installed.  Where those blocks coincide with the CompVis/LDM blocks diffusers
+    ported them from (installed through torchtitan), they are held to them here: the residual block with the
+    time-embedding term switched off, single-head attention with biases (both restated processors: SDPA and the explicit
+    baddbmm / softmax / bmm path of fmc's AttnProcessor), and the nearest-2x upsampler."""
+    ae = pytest.importorskip("torchtitan.experiments.flux.model.autoencoder")
+    from oracle import diffusers_restated as dr
+    from oracle.attention_processor import AttnProcessor
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(1)
+
+    def jitter(m):
+        with torch.no_grad():
+            for p in m.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+        return m.eval()
+    for cin, cout in ((64, 64), (64, 128)):
+        ref = jitter(ae.ResnetBlock(cin, cout))
+        blk = dr.ResnetBlock2D(cin, cout, temb_channels=32, groups=32, eps=1e-6).eval()
+        state = {k.replace("nin_shortcut", "conv_shortcut"): v for k, v in ref.state_dict().items()}
+        state["time_emb_proj.weight"] = torch.zeros(cout, 32)   # no time embedding in the LDM block
+        state["time_emb_proj.bias"] = torch.zeros(cout)
+        blk.load_state_dict(state, strict=True)
+        x = torch.randn(2, cin, 12, 10, generator=g)
+        with torch.no_grad():
+            want, got = ref(x), blk(x, torch.randn(2, 32, generator=g))
+        assert float((got - want).abs().max()) < 1e-5 * max(1.0, float(want.abs().max()))
+    C = 64
+    ref = jitter(ae.AttnBlock(C))
+    x = torch.randn(2, C, 6, 5, generator=g)
+    for processor in (dr.AttnProcessorSDPA(), AttnProcessor()):
+        attn = dr.Attention(C, heads=1, dim_head=C, bias=True, processor=processor).eval()
+        sd = ref.state_dict()
+        attn.load_state_dict({"to_q.weight": sd["q.weight"][:, :, 0, 0], "to_q.bias": sd["q.bias"],
+                              "to_k.weight": sd["k.weight"][:, :, 0, 0], "to_k.bias": sd["k.bias"],
+                              "to_v.weight": sd["v.weight"][:, :, 0, 0], "to_v.bias": sd["v.bias"],
+                              "to_out.0.weight": sd["proj_out.weight"][:, :, 0, 0], "to_out.0.bias": sd["proj_out.bias"]},
+                             strict=True)
+        with torch.no_grad():
+            tokens = ref.norm(x).flatten(2).transpose(1, 2)                       # [b, h w, C]
+            got = x + attn(tokens).transpose(1, 2).reshape(x.shape)
+            want = ref(x)
+        assert float((got - want).abs().max()) < 1e-5 * max(1.0, float(want.abs().max())), type(processor).__name__
+    ref = jitter(ae.Upsample(C))
+    up = dr.Upsample2D(C).eval()
+    up.load_state_dict(ref.state_dict(), strict=True)
+    with torch.no_grad():
+        assert float((up(x) - ref(x)).abs().max()) < 1e-6
