@@ -80,11 +80,32 @@ class GradAllReduce:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
     def install_hooks(self):
-        """Launch a bucket's all-reduce from inside backward, when its last gradient has been accumulated."""
+        """Launch a bucket's all-reduce from inside backward, when its last gradient has been accumulated: through torch's
+        post-accumulate-grad hooks for gradients autograd delivers, and through the tape's early delivery
+        (train_engine.EARLY_GRAD_SINK) for the parameters of the B200 training path -- their gradients are complete long
+        before the tape's single autograd node returns, and only this way does the all-reduce overlap the backward."""
+        from . import train_engine
         self.reset()
+        index = {id(p): j for j, p in enumerate(self.flat.params)}
         for j, p in enumerate(self.flat.params):
             self.hooks.append(p.register_post_accumulate_grad_hook(lambda _p, j=j: self._ready(j)))
+
+        def early(param, grad):
+            j = index.get(id(param))
+            if j is None or param.grad is None:
+                return False
+            param.grad.add_(grad.to(param.grad.dtype))
+            self._ready(j)
+            return True
+        train_engine.EARLY_GRAD_SINK = early
         return self
+
+    def remove_hooks(self):
+        from . import train_engine
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
+        train_engine.EARLY_GRAD_SINK = None
 
     def reset(self):
         self.pending = [len(idxs) for _, _, idxs in self.buckets]

@@ -54,20 +54,42 @@ class Var:
             self.grad, self._owned = ops.add(a, b).view(self.grad.shape), True
 
 
+# Early gradient delivery (train.GradAllReduce.install_hooks sets it): `sink(param, grad) -> bool`, called from INSIDE the
+# tape's backward as soon as the last contribution to a parameter's gradient has been produced; True = the sink has added
+# the gradient to `param.grad` itself (and may have launched the bucket's all-reduce), so the autograd bridge returns
+# None for that parameter.  Without it every parameter gradient reaches autograd at the END of the tape's backward, and a
+# hook-launched all-reduce cannot overlap the backward pass.
+EARLY_GRAD_SINK = None
+
+
 class Tape:
     def __init__(self):
         self.nodes = []        # (outputs, backward closure)
-        self.param_grads = {}  # nn.Parameter -> fp32 gradient tensor
+        self.param_grads = {}  # nn.Parameter -> fp32 gradient tensor (None once delivered early)
+        self.parts = {}        # nn.Parameter -> contributions seen in this backward
 
     def record(self, outputs, backward):
         self.nodes.append((outputs, backward))
 
     def add_param_grad(self, param, g):
         g = g.reshape(param.shape)
-        if param in self.param_grads:
+        if self.param_grads.get(param) is not None:
             self.param_grads[param].add_(g)
         else:
             self.param_grads[param] = g.contiguous()
+        n = self.parts.get(param, 0) + 1
+        self.parts[param] = n
+        # the number of contributions per backward is learned in the first step (`_fmc_grad_parts`); from the second step
+        # on a gradient is handed over the moment it is complete
+        if EARLY_GRAD_SINK is not None and n == getattr(param, "_fmc_grad_parts", -1):
+            if EARLY_GRAD_SINK(param, self.param_grads[param]):
+                self.param_grads[param] = None
+
+    def finish_params(self):
+        """After the backward: remember how many contributions each parameter received (early delivery next time)."""
+        for param, n in self.parts.items():
+            param._fmc_grad_parts = n
+        self.parts = {}
 
     def backward(self):
         for outputs, fn in reversed(self.nodes):
@@ -731,6 +753,7 @@ class _Runner:
                 var.accumulate(cl.view(-1, cl.shape[-1]))
         with torch.no_grad():
             self.tape.backward()
+        self.tape.finish_params()
         grads = [self.tape.param_grads.get(p) for p in self.params]
         for var, shp in zip(self.in_vars, self.in_shapes):
             grads.append(ops.from_channels_last(var.grad.view(shp)) if var.grad is not None else None)

@@ -272,3 +272,50 @@ def test_graphed_training_step_matches_eager(cuda_device):
     assert l_e[0] > l_e[-1]                                   # it trains
     assert abs(l_e[-1] - l_g[-1]) < 3e-2 * abs(l_e[-1])       # the 4th step of both runs
     assert cos > 0.9 and 0.9 < ratio < 1.1
+
+
+@pytest.mark.timeout(900)
+def test_early_gradient_delivery_matches_end_of_backward_delivery(cuda_device):
+    """GradAllReduce.install_hooks: from the second step on the tape hands every parameter gradient to the reducer the
+    moment it is complete (so a bucket's all-reduce overlaps the rest of backward) instead of returning all of them through
+    its single autograd node at the end -- same gradients either way, every trainable parameter delivered early."""
+    from oracle.rays import to_plucker_embedding
+    from synfmc_b200 import synth, train_engine
+    from synfmc_b200.fmc.models.pose_adaptor import PoseAdaptor
+    from synfmc_b200.train import FlatParams, GradAllReduce
+    channels = (320, 640)
+    dev = cuda_device
+    unet = helpers.build_product_unet(helpers.build_oracle_unet(tiny=True), tiny=True, device=dev)
+    enc = helpers.build_product_pose_encoder(helpers.build_oracle_pose_encoder(channels), channels, device=dev)
+    _cmc_trainable(unet, enc)
+    wrapper = PoseAdaptor(unet, enc)
+    flat = FlatParams(list(enc.parameters()) + [p for p in unet.parameters() if p.requires_grad])
+    b, f, H, W = 1, 8, 64, 96
+    K, c2w = synth.synth_camera(b, f, H, W, seed=6)
+    plucker = to_plucker_embedding(c2w, K, (H, W)).permute(0, 2, 1, 3, 4).contiguous().to(dev)
+    latents, text = synth.synth_step_inputs(b, f, H // 8, W // 8, cfg=False, seed=6)
+    latents, text = latents.to(dev), text.to(dev)
+    target = torch.randn(latents.shape, generator=torch.Generator().manual_seed(9)).to(dev)
+    t = torch.tensor([441], device=dev)
+    red = GradAllReduce(flat, bucket_bytes=8 << 20).install_hooks()
+    launched, early = [], []
+    red._launch = lambda bkt: launched.append(bkt)       # world size 1: record the bucket order instead of a collective
+    sink = train_engine.EARLY_GRAD_SINK
+    train_engine.EARLY_GRAD_SINK = lambda p, g: early.append(id(p)) or sink(p, g)
+    try:
+        grads = []
+        for step in range(2):
+            flat.zero_grad()
+            red.reset()
+            del launched[:], early[:]
+            loss = torch.nn.functional.mse_loss(wrapper(latents, t, text, plucker).float(), target)
+            loss.backward()
+            assert sorted(launched) == list(range(len(red.buckets)))    # every bucket exactly once
+            assert len(early) == (0 if step == 0 else len(flat.params))
+            grads.append(flat.grads.clone())
+        assert float(grads[0].norm()) > 0
+        assert rel_l2(grads[1], grads[0]) < 1e-5
+        assert launched[0] != len(red.buckets) - 1                       # buckets go out DURING backward, not in flat order
+    finally:
+        red.remove_hooks()
+    assert train_engine.EARLY_GRAD_SINK is None
