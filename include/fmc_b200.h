@@ -329,6 +329,16 @@ int fmc_timestep_embedding_f32(const float* t, float* out, int B, int dim, void*
 int fmc_mask_modulate_f32(const float* x, const float* mask, const int* row_index, const int* col_index, float* out,
                           int N, int h, int w, int C, int H, int W, void* stream);
 
+/* Weight gradient of a linear layer y = x W^T: dW [M, N] fp32 (+)= dY^T X with dY [T, M], X [T, N] bf16 row-major (M, N and
+ * the row strides multiples of 8).  Both operands go to tcgen05 MN-major straight from the row-major tensors (no
+ * transposed copies), the token axis is split across CTAs, the fp32 partials are folded in a fixed order (deterministic).
+ * workspace: fmc_wgrad_workspace_floats(T, M, N) floats (may be NULL when that many splits is 1 and accumulate = 0).
+ * Replaces the parameter-gradient half of `scaler.scale(loss).backward()` for the trainable linears
+ * (train_cam_ctrl.py:648, train_cam_obj_ctrl.py:857). */
+long long fmc_wgrad_workspace_floats(long long T, int M, int N);
+int fmc_wgrad_bf16(const void* dY, long long lddy, const void* X, long long ldx, float* dW, long long lddw, float* workspace,
+                   long long T, int M, int N, int accumulate, void* stream);
+
 /* ---- pipeline edges: VAE decode / encode and the CLIP text encoder -----------------------------------
  * Their convolutions, linears, GroupNorm and LayerNorm run on the entry points above; these are the remaining pieces.
  * `is_f32` / `out_is_f32`: activation dtype of the call (0 = bf16, the product mode; 1 = fp32, reference-precision mode). */

@@ -45,6 +45,7 @@ SIGNATURES = {
     "fmc_transpose_bf16": [P, L, P, L, L, I, P],
     "fmc_colsum_f32": [P, L, I, P, P, L, I, I, P],
     "fmc_layernorm_bwd_bf16": [P, L, P, L, P, F, P, L, P, L, I, P],
+    "fmc_wgrad_bf16": [P, L, P, L, P, L, P, L, I, I, I, P],
     # relative poses (csrc/pose.cu)
     "fmc_pose_relative_to_first_f64": [P, L, P, I, I, D, P],
     "fmc_pose_absolute_from_relative_f64": [P, P, P, I, I, D, P],
@@ -107,6 +108,8 @@ def lib():
         handle.fmc_groupnorm_launches.argtypes = [c_int, c_int, c_int]
         handle.fmc_grad_norm_workspace_floats.restype = c_int
         handle.fmc_grad_norm_workspace_floats.argtypes = []
+        handle.fmc_wgrad_workspace_floats.restype = c_longlong
+        handle.fmc_wgrad_workspace_floats.argtypes = [c_longlong, c_int, c_int]
         handle.fmc_groupnorm_bwd_workspace_floats.restype = c_longlong
         handle.fmc_groupnorm_bwd_workspace_floats.argtypes = [c_int, c_int, c_int]
         handle.fmc_colsum_workspace_floats.restype = c_int
@@ -133,6 +136,9 @@ def _kernels_per_call(handle, name, args):
         return 2  # statistics + apply / partial sums + finalize
     if name == "fmc_groupnorm_bwd_bf16":
         return 3  # statistics, gradient means, dx
+    if name == "fmc_wgrad_bf16":  # T, M, N = args[7:10]; one direct kernel when the token axis is not split, else + the fold
+        splits = handle.fmc_wgrad_workspace_floats(args[7], args[8], args[9]) // (args[8] * args[9])
+        return 1 if splits == 1 and not args[10] else 2
     if name == "fmc_attention_bwd_bf16":
         if args[17] and args[-7] == 16 and args[-6] == 16:
             return 1  # 16-frame self-attention: one warp per sequence

@@ -146,6 +146,27 @@ def linear_dgrad(dy, w_t, residual=None):
     return ops.gemm(dy, w_t, residual=residual)
 
 
-def linear_wgrad(dy, x):
-    """dW [N_out, K_in] (fp32) = dY^T X on the tensor cores: both operands transposed into K-major form first."""
-    return ops.gemm(transpose(dy, 8), transpose(x, 8), out_f32=True)
+def linear_wgrad(dy, x, out=None, accumulate=False):
+    """dW [N_out, K_in] (fp32) (+)= dY^T X on the tensor cores, straight from the row-major dY [T, N_out] and X [T, K_in]
+    (fmc_wgrad_bf16: MN-major operands, token axis split across CTAs, deterministic fold)."""
+    _check_cuda(dy, x)
+    _rows2d(dy)
+    _rows2d(x)
+    T, M = dy.shape
+    N = x.shape[1]
+    assert x.shape[0] == T
+    if M % 8 or N % 8 or dy.stride(0) % 8 or x.stride(0) % 8:
+        # odd widths (not on the training path): K-major GEMM on transposed copies
+        dw = ops.gemm(transpose(dy, 8), transpose(x, 8), out_f32=True)
+        if out is None:
+            return dw
+        return out.add_(dw) if accumulate else out.copy_(dw)
+    if out is None:
+        assert not accumulate
+        out = torch.empty((M, N), device=dy.device, dtype=F32)
+    assert out.dtype == F32 and out.shape == (M, N) and out.stride(1) == 1
+    nws = 4 * M * N if ops.DRY_RUN else int(_cabi.lib().fmc_wgrad_workspace_floats(T, M, N))
+    ws = torch.empty(max(nws, 1), device=dy.device, dtype=F32)
+    _cabi.call("fmc_wgrad_bf16", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0),
+               ws.data_ptr(), T, M, N, 1 if accumulate else 0, _stream())
+    return out

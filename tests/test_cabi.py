@@ -17,7 +17,7 @@ def test_header_matches_binding_table():
     declared = set(_declared())
     bound = set(_cabi.SIGNATURES) | {"fmc_abi_version", "fmc_last_error_string", "fmc_groupnorm_launches",
                                      "fmc_grad_norm_workspace_floats", "fmc_colsum_workspace_floats",
-                                     "fmc_layernorm_bwd_blocks", "fmc_groupnorm_bwd_workspace_floats"}
+                                     "fmc_layernorm_bwd_blocks", "fmc_groupnorm_bwd_workspace_floats", "fmc_wgrad_workspace_floats"}
     assert declared == bound, (declared - bound, bound - declared)
 
 

@@ -56,6 +56,22 @@ def test_linear_dgrad_wgrad(B, cuda_device, M, N, K):
     assert dw.dtype == torch.float32 and rel(dw, dy.double().t() @ x.double()) < F32_TOL
 
 
+@pytest.mark.parametrize("T,M,N", [(40960, 320, 320), (10240, 640, 2560), (300, 1280, 320), (1000, 328, 72), (64, 128, 128),
+                                   (2560, 1280, 1280)])
+def test_wgrad_tn(B, cuda_device, T, M, N):
+    """fmc_wgrad_bf16: dW = dY^T X from the row-major operands (MN-major MMA operands, split token axis), plain and
+    accumulating, on row-strided inputs; twice the same result (deterministic fold)."""
+    dy_full, x_full = randn(T, M + 8, seed=1), randn(T, N + 16, seed=2)
+    dy, x = bf(dy_full).to(cuda_device)[:, :M], bf(x_full).to(cuda_device)[:, 8:8 + N]
+    want = bf(dy_full)[:, :M].double().t() @ bf(x_full)[:, 8:8 + N].double()
+    dw = B.linear_wgrad(dy, x)
+    assert dw.shape == (M, N) and dw.dtype == torch.float32 and rel(dw, want) < F32_TOL
+    assert torch.equal(dw, B.linear_wgrad(dy, x))
+    acc = torch.full((M, N), 2.0, device=cuda_device)
+    B.linear_wgrad(dy, x, out=acc, accumulate=True)
+    assert rel(acc, want + 2.0) < F32_TOL
+
+
 @pytest.mark.parametrize("rows,C", [(1000, 320), (333, 640), (200, 1280)])
 def test_layernorm_bwd(B, cuda_device, rows, C):
     x = randn(rows, C, seed=1, scale=2.0).requires_grad_(True)
