@@ -256,7 +256,7 @@ def test_training_tape_plumbing(recorder, stage):
     out.square().mean().backward()
     bnames = set(recorder.names())
     assert {"fmc_attention_bwd_bf16", "fmc_layernorm_bwd_bf16", "fmc_groupnorm_bwd_bf16", "fmc_geglu_bwd_bf16",
-            "fmc_transpose_bf16"} <= bnames
+            "fmc_wgrad_bf16"} <= bnames   # weight gradients straight from the row-major operands: no transposed copies
     trainable = [(n, p) for m in (unet, enc) + ((omcm,) if obj else ()) for n, p in m.named_parameters() if p.requires_grad]
     assert trainable
     for n, p in trainable:
