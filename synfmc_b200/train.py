@@ -18,6 +18,8 @@ train_cam_ctrl.py:647-665 / train_cam_obj_ctrl.py:843-862 -- DDP's gradient all-
 
 The gradients come from the backward kernels behind train_engine.py or from any other source (the
 tests also feed these classes torch-autograd gradients of small modules and compare with DDP-style mean + AdamW)."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -97,7 +99,8 @@ class GradAllReduce:
             param.grad.add_(grad.to(param.grad.dtype))
             self._ready(j)
             return True
-        train_engine.EARLY_GRAD_SINK = early
+        # FMC_NO_EARLY_GRADS=1: A/B switch -- every gradient reaches the reducer through autograd at the end of the tape
+        train_engine.EARLY_GRAD_SINK = None if os.environ.get("FMC_NO_EARLY_GRADS") == "1" else early
         return self
 
     def remove_hooks(self):
@@ -204,16 +207,19 @@ class GraphedStep:
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedStep captures a CUDA graph: no CUDA device (there is no CPU path)")
         cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
+        # warm-up and capture run on ONE side stream: autograd remembers the stream each AccumulateGrad node was created on
+        # (the first warm-up step) and synchronises with it in every later backward -- a capture on a different stream would
+        # then depend on uncaptured work (cudaErrorStreamCaptureIsolation)
+        self.stream = torch.cuda.Stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
             for _ in range(warmup):
                 fn()
-        cur.wait_stream(side)
+        cur.wait_stream(self.stream)
         torch.cuda.synchronize()
         self.warmup_steps = warmup
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=self.stream):
             self.out = fn()
 
     def __call__(self):
