@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, GPU call 18 (8 GPUs): BASELINE configs 3 / 4 as defined -- one clip per GPU x 8, the whole training step as a CUDA
 # graph with the NCCL gradient all-reduce inside it
-TAG=r02r
+TAG=r02w
 export PYTHONUNBUFFERED=1
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
