@@ -87,6 +87,9 @@ class GradAllReduce:
         (train_engine.EARLY_GRAD_SINK) for the parameters of the B200 training path -- their gradients are complete long
         before the tape's single autograd node returns, and only this way does the all-reduce overlap the backward."""
         from . import train_engine
+        if train_engine.EARLY_GRAD_SINK is not None and getattr(train_engine.EARLY_GRAD_SINK, "owner", None) is not self:
+            raise RuntimeError("another GradAllReduce has its hooks installed: call its remove_hooks() first (the tape "
+                               "hands gradients to one reducer)")
         self.reset()
         index = {id(p): j for j, p in enumerate(self.flat.params)}
         for j, p in enumerate(self.flat.params):
@@ -99,6 +102,7 @@ class GradAllReduce:
             param.grad.add_(grad.to(param.grad.dtype))
             self._ready(j)
             return True
+        early.owner = self
         # FMC_NO_EARLY_GRADS=1: A/B switch -- every gradient reaches the reducer through autograd at the end of the tape
         train_engine.EARLY_GRAD_SINK = None if os.environ.get("FMC_NO_EARLY_GRADS") == "1" else early
         return self

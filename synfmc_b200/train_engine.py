@@ -81,14 +81,14 @@ class Tape:
         self.parts[param] = n
         # the number of contributions per backward is learned in the first step (`_fmc_grad_parts`); from the second step
         # on a gradient is handed over the moment it is complete
-        if EARLY_GRAD_SINK is not None and n == getattr(param, "_fmc_grad_parts", -1):
+        if EARLY_GRAD_SINK is not None and (engine.STRUCTURE_EPOCH, n) == getattr(param, "_fmc_grad_parts", None):
             if EARLY_GRAD_SINK(param, self.param_grads[param]):
                 self.param_grads[param] = None
 
     def finish_params(self):
         """After the backward: remember how many contributions each parameter received (early delivery next time)."""
         for param, n in self.parts.items():
-            param._fmc_grad_parts = n
+            param._fmc_grad_parts = (engine.STRUCTURE_EPOCH, n)  # re-learned after a processor / structure change
         self.parts = {}
 
     def backward(self):

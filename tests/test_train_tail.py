@@ -125,3 +125,39 @@ def test_fused_adamw_skips_on_nonfinite_gradients(cuda_device):
     flat.grads[12345 % flat.numel] = 0.5
     opt.step(loss_scale=1024.0)
     assert not opt.found_inf() and not torch.equal(flat.values, before)
+
+
+def test_early_gradient_delivery_protocol_cpu():
+    """Host logic of the tape -> reducer hand-over (train_engine.EARLY_GRAD_SINK): contribution counts are learned in the
+    first backward, from the second one a gradient is added to `.grad` and its bucket released the moment its last
+    contribution arrives; a structure change invalidates the learned counts; a second reducer cannot steal the sink."""
+    from synfmc_b200 import engine, train_engine
+    from synfmc_b200.train import FlatParams, GradAllReduce
+    a, b = torch.nn.Parameter(torch.zeros(4, 8)), torch.nn.Parameter(torch.zeros(8))
+    flat = FlatParams([a, b])
+    red = GradAllReduce(flat, bucket_bytes=16).install_hooks()      # one bucket per parameter
+    launched = []
+    red._launch = lambda bkt: launched.append(bkt)
+    try:
+        with pytest.raises(RuntimeError):
+            GradAllReduce(flat).install_hooks()
+        for step in range(3):
+            if step == 2:
+                engine.structure_changed()                          # e.g. set_processor: counts must be re-learned
+            flat.zero_grad()
+            red.reset()
+            del launched[:]
+            tape = train_engine.Tape()
+            tape.add_param_grad(a, torch.ones(4, 8))                # `a` receives two contributions per backward
+            assert float(a.grad.sum()) == 0.0
+            tape.add_param_grad(b, torch.full((8,), 2.0))
+            tape.add_param_grad(a, torch.ones(32))
+            early = step == 1
+            assert (tape.param_grads[a] is None) == early and (tape.param_grads[b] is None) == early
+            assert float(a.grad.sum()) == (64.0 if early else 0.0) and float(b.grad.sum()) == (16.0 if early else 0.0)
+            assert sorted(launched) == ([0, 1] if early else [])
+            tape.finish_params()
+            assert a._fmc_grad_parts[1] == 2 and b._fmc_grad_parts[1] == 1
+    finally:
+        red.remove_hooks()
+    assert train_engine.EARLY_GRAD_SINK is None
