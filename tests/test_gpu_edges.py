@@ -148,3 +148,72 @@ def test_vae_decode_full_size_frame(cuda_device):
     e = rel_l2(got.cpu(), want)
     print(f"[parity] VAE decode 320x512 frame: rel-L2 {e:.3e}")
     assert e < VAE_TOL
+
+
+class _StubTokenizer:
+    """Stands in for transformers' CLIPTokenizer (its vocabulary files are not available offline): deterministic ids per
+    prompt string, padded to 77 with the end-of-text id -- the call signature the pipelines use."""
+    model_max_length = 77
+
+    def __call__(self, texts, padding=None, max_length=77, truncation=True, return_tensors="pt"):
+        texts = [texts] if isinstance(texts, str) else list(texts)
+        ids = torch.full((len(texts), max_length), 49407, dtype=torch.long)
+        for i, t in enumerate(texts):
+            g = torch.Generator().manual_seed(sum(map(ord, t)) + 1)
+            n = min(len(t.split()) + 2, max_length)
+            ids[i, :n] = torch.randint(0, 49000, (n,), generator=g)
+            ids[i, 0] = 49406
+        return type("Enc", (), {"input_ids": ids})()
+
+
+@pytest.mark.timeout(900)
+def test_sample_call_end_to_end_with_the_b200_text_encoder_and_vae(cuda_device):
+    """One whole `CameraCtrlPipeline.__call__` (fmc/pipelines/pipeline_animation.py:570-702): prompt + negative prompt ->
+    text encoder -> CameraEncoder -> 3 CFG denoising steps -> VAE decode -> `.videos` [b, 3, f, H, W] in [0, 1] on the CPU,
+    every stage on the library's kernels, against the composition of the CPU restatements."""
+    from oracle.clip_text import CLIPTextModel as OC
+    from oracle.diffusers_restated import DDIMScheduler as ODDIM
+    from oracle.pipeline import denoise as o_denoise
+    from oracle.rays import to_plucker_embedding
+    from oracle.vae import AutoencoderKL as OV
+    from oracle import harness as helpers
+    from synfmc_b200 import synth
+    from synfmc_b200.edge import AutoencoderKL, CLIPTextModel
+    from synfmc_b200.fmc._blocks import DDIMScheduler
+    from synfmc_b200.fmc.pipelines.pipeline_animation import CameraCtrlPipeline
+    from synfmc_b200.synth import synth_init_
+    dev = cuda_device
+    channels = (320, 640)
+    o_unet = helpers.build_oracle_unet(tiny=True)
+    p_unet = helpers.build_product_unet(o_unet, tiny=True, device=dev)
+    o_enc = helpers.build_oracle_pose_encoder(channels)
+    p_enc = helpers.build_product_pose_encoder(o_enc, channels, device=dev)
+    oc = OC(num_hidden_layers=2).eval().requires_grad_(False)              # SD1.5 width (768 = the U-Net's text width)
+    synth_init_(oc, seed=21)
+    pc = CLIPTextModel(num_hidden_layers=2)
+    pc.load_state_dict(oc.state_dict())
+    ov = OV(block_out_channels=(32, 64, 128, 128)).eval().requires_grad_(False)
+    synth_init_(ov, seed=22)
+    pv = AutoencoderKL(block_out_channels=(32, 64, 128, 128))
+    pv.load_state_dict(ov.state_dict())
+    tok = _StubTokenizer()
+    b, f, H, W = 1, 8, 64, 128
+    K, c2w = synth.synth_camera(b, f, H, W, seed=4)
+    plucker = to_plucker_embedding(c2w, K, (H, W)).permute(0, 2, 1, 3, 4).contiguous()
+    latents, _ = synth.synth_step_inputs(b, f, H // 8, W // 8, cfg=True, seed=4)
+    prompt, negative = "a red car drives through a forest", "blurry"
+    # restatement chain
+    text = torch.cat([oc(tok([negative]).input_ids)[0], oc(tok([prompt]).input_ids)[0]])
+    lat = o_denoise(o_unet, ODDIM(), o_enc, latents, text, plucker, f, num_inference_steps=25, guidance_scale=7.5, max_steps=3)
+    frames = (lat / 0.18215).permute(0, 2, 1, 3, 4).reshape(b * f, 4, H // 8, W // 8)
+    want = torch.cat([ov.decode(frames[i:i + 1]).sample for i in range(b * f)]).view(b, f, 3, H, W).permute(0, 2, 1, 3, 4)
+    want = (want / 2 + 0.5).clamp(0, 1)
+    # product
+    pipe = CameraCtrlPipeline(pv.to(dev), pc.to(dev), tok, p_unet, DDIMScheduler(), p_enc)
+    out = pipe(prompt, plucker.to(dev), f, height=H, width=W, num_inference_steps=25, guidance_scale=7.5,
+               negative_prompt=negative, latents=latents.to(dev), max_steps=3)
+    assert out.videos.shape == (b, 3, f, H, W) and out.videos.device.type == "cpu" and out.videos.dtype == torch.float32
+    assert float(out.videos.min()) >= 0.0 and float(out.videos.max()) <= 1.0
+    e_lat, e_vid = rel_l2(out.latents.cpu(), lat), rel_l2(out.videos, want)
+    print(f"[parity] sample call end to end (text encoder -> 3 CFG steps -> VAE): latents {e_lat:.3e}, video {e_vid:.3e}")
+    assert e_lat < 3e-2 and e_vid < 3e-2
