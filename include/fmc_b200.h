@@ -86,6 +86,12 @@ int fmc_spatial_attn_vf16(const void* Q, long long ldq, int q_col0, long long q_
                           int k_col0, const void* V, long long ldv, int v_col0, long long kv_rows, int head_stride,
                           void* O, long long ldo, int images, int heads, int head_dim, int nq, int nk, int kv_div,
                           int kv_stride, float scale, void* stream);
+/* fmc_spatial_attn_bf16 that also writes lse[q_row, head] = row log-sum-exp of the scaled scores in log2 units (fp32,
+ * [q_rows, heads]) for the training backward (fmc_attention_bwd_bf16 with lse_given = 1); always the generic flash kernel. */
+int fmc_spatial_attn_lse_bf16(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K, long long ldk,
+                              int k_col0, const void* V, long long ldv, int v_col0, long long kv_rows, int head_stride,
+                              void* O, long long ldo, float* lse, int images, int heads, int head_dim, int nq, int nk,
+                              int kv_div, int kv_stride, float scale, void* stream);
 
 /* Temporal self-attention core over the f frames of every latent position, directly on channels-last activations
  * (row of token (b, frame, hw) = (b*F + frame)*HW + hw; QKV row = [q | k | v] column blocks).
@@ -255,13 +261,16 @@ int fmc_avgpool2_bwd_bf16(const void* dy, void* dx, int N, int h, int w, int C, 
  * One entry point, three kernel families chosen by shape (same results within bf16 rounding; FMC_ATTN_BWD_SIMT=1 in the
  * environment forces the last one for A/B checks): tcgen05 kernels (csrc/attn_bwd_tc.cu) for inner = 1 at head_dim 40
  * (head_stride 48) / 80 / 160 -- self-attention and the dQ-only cross form; one warp per (sequence, head) for nq = nk = 16
- * self-attention (the temporal attentions; lse / dsum are not written there); CUDA-core kernels for everything else. */
+ * self-attention (the temporal attentions; lse / dsum are not written there); CUDA-core kernels for everything else.
+ * lse_given = 1: `lse` already holds the row log-sum-exp of the forward in log2 units (fmc_spatial_attn_lse_bf16); the
+ * tcgen05 self-attention path at head_dim 40 / 80 then skips its first sweep over the keys, every other path ignores it
+ * and recomputes. */
 int fmc_attention_bwd_bf16(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
                            const void* V, long long ldv, int v_col0, int head_stride, const void* O, long long ldo,
                            const void* dO, long long lddo, void* dQ, long long lddq, int dq_col0, void* dK, long long lddk,
-                           int dk_col0, void* dV, long long lddv, int dv_col0, float* lse, float* dsum, int images,
-                           int heads, int head_dim, int nq, int nk, int kv_div, int kv_stride, int inner, float scale,
-                           void* stream);
+                           int dk_col0, void* dV, long long lddv, int dv_col0, float* lse, float* dsum, int lse_given,
+                           int images, int heads, int head_dim, int nq, int nk, int kv_div, int kv_stride, int inner,
+                           float scale, void* stream);
 
 /* Training-step tail on flat fp32 buffers (train_cam_ctrl.py:647-665, train_cam_obj_ctrl.py:843-862: scaler.unscale_ ->
  * clip_grad_norm_ -> AdamW.step -- three passes over the trainable set in the reference), after the gradient all-reduce.

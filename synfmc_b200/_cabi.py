@@ -19,6 +19,7 @@ SIGNATURES = {
     "fmc_conv3x3_bf16": [P, P, P, P, P, I, I, I, I, I, I, I, P],
     "fmc_spatial_attn_bf16": [P, L, I, L, P, L, I, P, L, I, L, I, P, L, I, I, I, I, I, I, I, F, P],
     "fmc_spatial_attn_vf16": [P, L, I, L, P, L, I, P, L, I, L, I, P, L, I, I, I, I, I, I, I, F, P],
+    "fmc_spatial_attn_lse_bf16": [P, L, I, L, P, L, I, P, L, I, L, I, P, L, P, I, I, I, I, I, I, I, F, P],
     "fmc_temporal_attn_bf16": [P, L, I, I, I, I, P, L, I, I, I, I, I, F, P],
     "fmc_temporal_qkv_attn_bf16": [P, L, P, L, P, L, I, I, I, I, I, F, P],
     "fmc_debug_set_timeline": [P],
@@ -63,8 +64,7 @@ SIGNATURES = {
     "fmc_relu_bwd_bf16": [P, P, P, L, P],
     "fmc_resize_nearest_bwd_bf16": [P, P, I, I, I, I, I, I, P],
     "fmc_avgpool2_bwd_bf16": [P, P, I, I, I, I, P],
-    "fmc_attention_bwd_bf16": [P, L, I, P, L, I, P, L, I, I, P, L, P, L, P, L, I, P, L, I, P, L, I, P, P, I, I, I, I, I, I,
-                               I, I, F, P],
+    "fmc_attention_bwd_bf16": [P, L, I, P, L, I, P, L, I, I, P, L, P, L, P, L, I, P, L, I, P, L, I, P, P, I, I, I, I, I, I, I, I, I, F, P],
     "fmc_grad_norm_f32": [P, L, F, F, P, P, P],
     "fmc_adamw_step_f32": [P, P, P, P, L, F, F, F, F, F, I, P, P],
     # reference-precision mode (csrc/precise.cu)

@@ -125,17 +125,23 @@ def avgpool2_bwd(dy, h, w):
 
 
 def attention_bwd(q, q_col0, k, k_col0, v, v_col0, head_stride, o, do, dq, dq_col0, dk, dk_col0, dv, dv_col0, images, heads,
-                  head_dim, nq, nk, kv_div, kv_stride, inner, scale):
-    """Gradients written into dq (and dk, dv unless None) in the layouts of q / k / v."""
+                  head_dim, nq, nk, kv_div, kv_stride, inner, scale, lse=None):
+    """Gradients written into dq (and dk, dv unless None) in the layouts of q / k / v.  `lse`: the forward's row
+    log-sum-exp (ops.spatial_attn(..., lse=...)), fp32 [q rows, heads]; saves the tcgen05 path its first sweep."""
     _check_cuda(q, k, v, o, do, dq)
     for t in (q, k, v, o, do, dq) + ((dk, dv) if dk is not None else ()):
         _rows2d(t)
-    lse = torch.empty((q.shape[0], heads), device=q.device, dtype=F32)
+    lse_given = lse is not None
+    if lse_given:
+        assert lse.dtype == F32 and lse.shape == (q.shape[0], heads) and lse.is_contiguous()
+    else:
+        lse = torch.empty((q.shape[0], heads), device=q.device, dtype=F32)
     dsum = torch.empty((q.shape[0], heads), device=q.device, dtype=F32)
     _cabi.call("fmc_attention_bwd_bf16", q.data_ptr(), q.stride(0), q_col0, k.data_ptr(), k.stride(0), k_col0, v.data_ptr(),
                v.stride(0), v_col0, head_stride, o.data_ptr(), o.stride(0), do.data_ptr(), do.stride(0), dq.data_ptr(),
                dq.stride(0), dq_col0, _ptr(dk), dk.stride(0) if dk is not None else 0, dk_col0, _ptr(dv),
-               dv.stride(0) if dv is not None else 0, dv_col0, lse.data_ptr(), dsum.data_ptr(), images, heads, head_dim, nq, nk,
+               dv.stride(0) if dv is not None else 0, dv_col0, lse.data_ptr(), dsum.data_ptr(), 1 if lse_given else 0, images, heads,
+               head_dim, nq, nk,
                kv_div, kv_stride, inner, float(scale), _stream())
     return dq
 

@@ -35,6 +35,7 @@ constexpr int AB_PT = 2 * AB_BM * 128;      // [128 x 128] bf16 probability-type
 struct AbParams {
   int heads, n, images, blocks;  // n query tokens per image, blocks = ceil(n / 128)
   int nk, key_blocks, kv_div, kv_stride;  // keys per group; image i reads keys of group i / kv_div at row group * kv_stride
+  int have_lse;  // lse already holds the forward's row log-sum-exp (log2 units): the ping-pong dQ kernel skips its first sweep
   int head_stride, q_col0, k_col0, v_col0;
   float scale, scale_log2e;
   const __nv_bfloat16* O;
@@ -376,6 +377,7 @@ attn_bwd_dq_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = p.images * p.heads * p.blocks;
   const int T = (p.nk + ABP_BN - 1) / ABP_BN;  // 64-key tiles per sweep
+  const int U0 = p.have_lse ? T : 0;           // first step of an item: the log-sum-exp sweep is skipped when the forward supplied it
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmG);
@@ -413,7 +415,7 @@ attn_bwd_dq_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           tma_load_2d_a(sQ + ch * AB_TILE, &tmQ, &q_full, p.q_col0 + head * p.head_stride + ch * 64, row0 + qb * AB_BM);
           ab_tma_load_3d(sG + ch * AB_TILE, &tmG, &q_full, ch * 64, head, row0 + qb * AB_BM);
         }
-        for (int u = 0; u < 2 * T; ++u, ++t) {
+        for (int u = U0; u < 2 * T; ++u, ++t) {
           const int j = u < T ? u : u - T;
           const int st = t % STAGES;
           mbar_wait(&kv_empty[st], ((t / STAGES) & 1u) ^ 1u);
@@ -453,7 +455,7 @@ attn_bwd_dq_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_wait(&q_full, it & 1u);
         tc_fence_after_sync();
         int prev_st = -1, prev_g = 0;
-        for (int u = 0; u < 2 * T; ++u, ++t) {
+        for (int u = U0; u < 2 * T; ++u, ++t) {
           const int st = t % STAGES;
           const int g = u & 1;
           mbar_wait(&kv_full[st], (t / STAGES) & 1u);
@@ -521,7 +523,7 @@ attn_bwd_dq_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       float m = -INFINITY, l = 0.f;
       // ---- sweep 1 (this group's tiles): online row maximum / sum in log2 units
-      for (int u = g; u < T; u += 2) {
+      for (int u = g + U0; u < T; u += 2) {
         const int valid = p.nk - u * ABP_BN;
         mbar_wait(&s_full[g], n_tile & 1u);
         ++n_tile;
@@ -553,18 +555,24 @@ attn_bwd_dq_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (lane == 0) mbar_arrive(&s_free[g]);
       }
       // ---- fold (m, l) of the two groups (a group without a sweep-1 tile contributes (-inf, 0)); group 0 always has tile 0
-      fold_m[g][r] = m;
-      fold_l[g][r] = l;
-      ab_bar_sync(1, 256);
-      const float m0 = fold_m[0][r], m1 = fold_m[1][r];
-      const float mm = fmaxf(m0, m1);
-      const float lsum = fold_l[0][r] * ab_exp2(m0 - mm) + fold_l[1][r] * ab_exp2(m1 - mm);
-      const float L2 = mm + log2f(lsum);
-      if (g == 0 && row_ok) {
-        p.lse[row * p.heads + head] = L2;
-        p.dsum[row * p.heads + head] = dsum;
+      float L2;
+      if (p.have_lse) {  // uniform over the CTA: no fold barriers
+        L2 = row_ok ? p.lse[row * p.heads + head] : 0.f;
+        if (g == 0 && row_ok) p.dsum[row * p.heads + head] = dsum;
+      } else {
+        fold_m[g][r] = m;
+        fold_l[g][r] = l;
+        ab_bar_sync(1, 256);
+        const float m0 = fold_m[0][r], m1 = fold_m[1][r];
+        const float mm = fmaxf(m0, m1);
+        const float lsum = fold_l[0][r] * ab_exp2(m0 - mm) + fold_l[1][r] * ab_exp2(m1 - mm);
+        L2 = mm + log2f(lsum);
+        if (g == 0 && row_ok) {
+          p.lse[row * p.heads + head] = L2;
+          p.dsum[row * p.heads + head] = dsum;
+        }
+        ab_bar_sync(2, 256);  // fold_* are rewritten by the next item only after both groups have read them
       }
-      ab_bar_sync(2, 256);  // fold_* are rewritten by the next item only after both groups have read them
       // ---- sweep 2 (this group's tiles): dS = exp2(S c - L) (dP - D) scale  -> bf16 -> this group's smem tile
       for (int u = T + ((T & 1) == g ? 0 : 1); u < 2 * T; u += 2) {
         const int valid = p.nk - (u - T) * ABP_BN;
@@ -901,7 +909,7 @@ static int attention_bwd_tc_launch(const void* Q, long long ldq, int q_col0, con
                                    const void* dO, long long lddo, void* dQ, long long lddq, int dq_col0, void* dK,
                                    long long lddk, int dk_col0, void* dV, long long lddv, int dv_col0, float* lse, float* dsum,
                                    int images, int heads, int n, int nk, int kv_div, int kv_stride, float scale,
-                                   cudaStream_t stream) {
+                                   bool have_lse, cudaStream_t stream) {
   using CfgQ = AbqCfg<D, QSTAGES>;
   using CfgK = AbkCfg<D, BQ, KSTAGES>;
   const long long rows = static_cast<long long>(images) * n;
@@ -936,6 +944,7 @@ static int attention_bwd_tc_launch(const void* Q, long long ldq, int q_col0, con
   AbParams p{};
   p.heads = heads; p.n = n; p.images = images; p.blocks = ceil_div(n, AB_BM);
   p.nk = nk; p.key_blocks = ceil_div(nk, AB_BM); p.kv_div = kv_div; p.kv_stride = kv_stride;
+  p.have_lse = have_lse && ping_pong ? 1 : 0;  // only the ping-pong dQ kernel has the short form; the others recompute
   p.head_stride = head_stride; p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   p.O = static_cast<const __nv_bfloat16*>(O); p.dO = static_cast<const __nv_bfloat16*>(dO); p.ldo = ldo; p.lddo = lddo;
@@ -975,19 +984,19 @@ int attention_bwd_tc(int head_dim, const void* Q, long long ldq, int q_col0, con
                      const void* V, long long ldv, int v_col0, int head_stride, const void* O, long long ldo, const void* dO,
                      long long lddo, void* dQ, long long lddq, int dq_col0, void* dK, long long lddk, int dk_col0, void* dV,
                      long long lddv, int dv_col0, float* lse, float* dsum, int images, int heads, int n, int nk, int kv_div,
-                     int kv_stride, float scale, cudaStream_t stream) {
+                     int kv_stride, float scale, bool have_lse, cudaStream_t stream) {
   if (head_dim == 40)
     return attention_bwd_tc_launch<40, 3, 128, 2, 4>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
                                                   dQ, lddq, dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images,
-                                                  heads, n, nk, kv_div, kv_stride, scale, stream);
+                                                  heads, n, nk, kv_div, kv_stride, scale, have_lse, stream);
   if (head_dim == 80)
     return attention_bwd_tc_launch<80, 2, 64, 2, 3>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
                                                  dQ, lddq, dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images,
-                                                 heads, n, nk, kv_div, kv_stride, scale, stream);
+                                                 heads, n, nk, kv_div, kv_stride, scale, have_lse, stream);
   if (head_dim == 160)
     return attention_bwd_tc_launch<160, 1, 64, 2, 0>(Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo,
                                                   dQ, lddq, dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images,
-                                                  heads, n, nk, kv_div, kv_stride, scale, stream);
+                                                  heads, n, nk, kv_div, kv_stride, scale, have_lse, stream);
   set_error("attention_bwd_tc: head_dim %d not in {40, 80, 160}", head_dim);
   return FMC_ERR_SHAPE;
 }

@@ -42,6 +42,7 @@ struct FaParams {
   float scale_log2e;  // softmax scale * log2(e)
   __nv_bfloat16* O;
   long long ldo;
+  float* lse;         // optional [q_rows, heads]: row log-sum-exp in log2 units (m + log2 l), for the training backward
 };
 
 template <int D>
@@ -341,6 +342,8 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float inv = 1.0f / l;
       const int q_in_img = qb * FA_BM + r;
       const bool row_ok = q_in_img < p.nq;
+      if (p.lse != nullptr && row_ok)
+        p.lse[(static_cast<long long>(img) * p.nq + q_in_img) * p.heads + head] = m_used + log2f(l);
       __nv_bfloat16* orow = p.O + (static_cast<long long>(img) * p.nq + q_in_img) * p.ldo + head * D;
 #pragma unroll 1
       for (int cc = 0; cc < DK / 16; ++cc) {
@@ -709,6 +712,8 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float inv = 1.0f / l;
       const int q_in_img = qp * 2 * FA_BM + w * FA_BM + r;
       const bool row_ok = q_in_img < p.nq;
+      if (p.lse != nullptr && row_ok)
+        p.lse[(static_cast<long long>(img) * p.nq + q_in_img) * p.heads + head] = m_used + log2f(l);
       __nv_bfloat16* orow = p.O + (static_cast<long long>(img) * p.nq + q_in_img) * p.ldo + head * D;
 #pragma unroll 1
       for (int cc = 0; cc < DK / 16; ++cc) {
@@ -781,7 +786,7 @@ using namespace fmc;
 static int spatial_attn_impl(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K, long long ldk,
                              int k_col0, const void* V, long long ldv, int v_col0, long long kv_rows, int head_stride,
                              void* O, long long ldo, int images, int heads, int head_dim, int nq, int nk, int kv_div,
-                             int kv_stride, float scale, bool v_f16, void* stream_) {
+                             int kv_stride, float scale, bool v_f16, float* lse, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FMC_REQUIRE(Q && K && V && O, FMC_ERR_ARG, "fmc_spatial_attn_bf16: null operand");
   FMC_REQUIRE(head_dim == 40 || head_dim == 80 || head_dim == 160, FMC_ERR_SHAPE,
@@ -799,7 +804,7 @@ static int spatial_attn_impl(const void* Q, long long ldq, int q_col0, long long
   // short-key cross-attention (text: 77 keys): K / V stay resident per (kv group, head), the query tiles stream
   // (attn_cross.cu); FMC_CROSS_GENERIC=1 keeps the generic flash kernel
   static const bool cross_generic = getenv("FMC_CROSS_GENERIC") != nullptr;
-  if (!cross_generic && !v_f16 && nk <= 80 && kv_stride >= 80 && images % kv_div == 0 &&
+  if (!cross_generic && !v_f16 && lse == nullptr && nk <= 80 && kv_stride >= 80 && images % kv_div == 0 &&
       (images / kv_div) * static_cast<long long>(kv_stride) <= kv_rows)
     return cross_attention_short_keys(Q, ldq, q_col0, q_rows, K, ldk, k_col0, V, ldv, v_col0, kv_rows, head_stride, O, ldo,
                                       images, heads, head_dim, nq, nk, kv_div, kv_stride, scale, stream);
@@ -840,6 +845,7 @@ static int spatial_attn_impl(const void* Q, long long ldq, int q_col0, long long
   p.scale_log2e = scale * 1.4426950408889634f;
   p.O = static_cast<__nv_bfloat16*>(O);
   p.ldo = ldo;
+  p.lse = lse;
   FMC_REQUIRE(!v_f16 || head_dim == 40, FMC_ERR_SHAPE, "fp16 V is implemented for head_dim 40 only (got %d)", head_dim);
   switch (head_dim) {
     case 40: return v_f16 ? launch_fa2<40, true>(tmQ, tmK, tmV, p, stream) : launch_fa2<40, false>(tmQ, tmK, tmV, p, stream);
@@ -854,7 +860,7 @@ extern "C" int fmc_spatial_attn_bf16(const void* Q, long long ldq, int q_col0, l
                                      int head_dim, int nq, int nk, int kv_div, int kv_stride, float scale,
                                      void* stream_) {
   return spatial_attn_impl(Q, ldq, q_col0, q_rows, K, ldk, k_col0, V, ldv, v_col0, kv_rows, head_stride, O, ldo, images,
-                           heads, head_dim, nq, nk, kv_div, kv_stride, scale, false, stream_);
+                           heads, head_dim, nq, nk, kv_div, kv_stride, scale, false, nullptr, stream_);
 }
 
 extern "C" int fmc_spatial_attn_vf16(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K,
@@ -863,5 +869,15 @@ extern "C" int fmc_spatial_attn_vf16(const void* Q, long long ldq, int q_col0, l
                                      int head_dim, int nq, int nk, int kv_div, int kv_stride, float scale,
                                      void* stream_) {
   return spatial_attn_impl(Q, ldq, q_col0, q_rows, K, ldk, k_col0, V, ldv, v_col0, kv_rows, head_stride, O, ldo, images,
-                           heads, head_dim, nq, nk, kv_div, kv_stride, scale, true, stream_);
+                           heads, head_dim, nq, nk, kv_div, kv_stride, scale, true, nullptr, stream_);
+}
+
+extern "C" int fmc_spatial_attn_lse_bf16(const void* Q, long long ldq, int q_col0, long long q_rows, const void* K,
+                                         long long ldk, int k_col0, const void* V, long long ldv, int v_col0,
+                                         long long kv_rows, int head_stride, void* O, long long ldo, float* lse, int images,
+                                         int heads, int head_dim, int nq, int nk, int kv_div, int kv_stride, float scale,
+                                         void* stream_) {
+  FMC_REQUIRE(lse != nullptr, FMC_ERR_ARG, "fmc_spatial_attn_lse_bf16: null lse");
+  return spatial_attn_impl(Q, ldq, q_col0, q_rows, K, ldk, k_col0, V, ldv, v_col0, kv_rows, head_stride, O, ldo, images,
+                           heads, head_dim, nq, nk, kv_div, kv_stride, scale, false, lse, stream_);
 }

@@ -1189,14 +1189,14 @@ int attention_bwd_tc(int head_dim, const void* Q, long long ldq, int q_col0, con
                          long long ldv, int v_col0, int head_stride, const void* O, long long ldo, const void* dO,
                          long long lddo, void* dQ, long long lddq, int dq_col0, void* dK, long long lddk, int dk_col0,
                          void* dV, long long lddv, int dv_col0, float* lse, float* dsum, int images, int heads, int n, int nk,
-                         int kv_div, int kv_stride, float scale, cudaStream_t stream);
+                         int kv_div, int kv_stride, float scale, bool have_lse, cudaStream_t stream);
 }
 extern "C" int fmc_attention_bwd_bf16(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
                                       const void* V, long long ldv, int v_col0, int head_stride, const void* O,
                                       long long ldo, const void* dO, long long lddo, void* dQ, long long lddq, int dq_col0,
                                       void* dK, long long lddk, int dk_col0, void* dV, long long lddv, int dv_col0,
-                                      float* lse, float* dsum, int images, int heads, int head_dim, int nq, int nk,
-                                      int kv_div, int kv_stride, int inner, float scale, void* stream_) {
+                                      float* lse, float* dsum, int lse_given, int images, int heads, int head_dim, int nq,
+                                      int nk, int kv_div, int kv_stride, int inner, float scale, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FMC_REQUIRE(Q && K && V && O && dO && dQ && lse && dsum, FMC_ERR_ARG, "fmc_attention_bwd_bf16: null operand");
   FMC_REQUIRE((dK == nullptr) == (dV == nullptr), FMC_ERR_ARG, "fmc_attention_bwd_bf16: dK and dV go together");
@@ -1240,7 +1240,7 @@ extern "C" int fmc_attention_bwd_bf16(const void* Q, long long ldq, int q_col0, 
       static_cast<long long>(images) * nq < 0x7fffffffll)
     return attention_bwd_tc(head_dim, Q, ldq, q_col0, K, ldk, k_col0, V, ldv, v_col0, head_stride, O, ldo, dO, lddo, dQ, lddq,
                             dq_col0, dK, lddk, dk_col0, dV, lddv, dv_col0, lse, dsum, images, heads, nq, nk, kv_div, kv_stride,
-                            scale, stream);
+                            scale, lse_given != 0 && dK != nullptr, stream);
   switch (head_dim) {
     case 40: return launch_attention_bwd<40>(p, dK != nullptr, stream);
     case 80: return launch_attention_bwd<80>(p, dK != nullptr, stream);

@@ -163,16 +163,24 @@ def gemm(a, w, bias=None, residual=None, out=None, geglu=False, out_f32=False, r
 
 
 def spatial_attn(q, q_col0, k, k_col0, v, v_col0, head_stride, out, images, heads, head_dim, nq, nk, kv_div, kv_stride,
-                 scale, v_f16=False):
-    """`v_f16`: the V columns hold IEEE fp16 bit patterns (gemm(..., f16_from_col=v_col0)); head_dim 40 only."""
+                 scale, v_f16=False, lse=None):
+    """`v_f16`: the V columns hold IEEE fp16 bit patterns (gemm(..., f16_from_col=v_col0)); head_dim 40 only.
+    `lse`: fp32 [q rows, heads] receiving the row log-sum-exp in log2 units (training forward: the backward skips its
+    first sweep, fmc_attention_bwd_bf16 with lse_given)."""
     if _act(q) == F32:
-        assert not v_f16 and head_stride == head_dim
+        assert not v_f16 and head_stride == head_dim and lse is None
         return attention_f32(q, q_col0, k, k_col0, v, v_col0, out, images, heads, head_dim, nq, nk, kv_div, kv_stride, 1,
                              scale)
     _check_cuda(q, k, v, out)
     for t in (q, k, v, out):
         _rows2d(t)
     assert k.shape[0] == v.shape[0]
+    if lse is not None:
+        assert not v_f16 and lse.dtype == F32 and lse.shape == (q.shape[0], heads) and lse.is_contiguous()
+        _cabi.call("fmc_spatial_attn_lse_bf16", q.data_ptr(), q.stride(0), q_col0, q.shape[0], k.data_ptr(), k.stride(0), k_col0,
+                   v.data_ptr(), v.stride(0), v_col0, k.shape[0], head_stride, out.data_ptr(), out.stride(0), lse.data_ptr(),
+                   images, heads, head_dim, nq, nk, kv_div, kv_stride, float(scale), _stream())
+        return out
     _cabi.call("fmc_spatial_attn_vf16" if v_f16 else "fmc_spatial_attn_bf16", q.data_ptr(), q.stride(0), q_col0, q.shape[0], k.data_ptr(), k.stride(0), k_col0,
                v.data_ptr(), v.stride(0), v_col0, k.shape[0], head_stride, out.data_ptr(), out.stride(0), images, heads,
                head_dim, nq, nk, kv_div, kv_stride, float(scale), _stream())

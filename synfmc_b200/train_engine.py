@@ -424,9 +424,12 @@ class TrainAttention:
         n = frames)."""
         qkv = self.qkv(tape, x)
         ctx = torch.empty((x.t.shape[0], self.C), device=x.t.device, dtype=BF16)
+        lse = None
         if inner == 1:
+            # the forward hands its row log-sum-exp to the backward (which then skips its first sweep over the keys)
+            lse = torch.empty((x.t.shape[0], self.heads), device=x.t.device, dtype=torch.float32)
             ops.spatial_attn(qkv.t, 0, qkv.t, self.k0, qkv.t, self.v0, self.hs, ctx, images, self.heads, self.d, n, n, 1, n,
-                             self.scale)
+                             self.scale, lse=lse)
         else:
             ops.temporal_attn(qkv.t, 0, self.k0, self.v0, self.hs, ctx, images // inner, n, inner, self.heads, self.d, self.scale)
         out = Var(ctx)
@@ -434,7 +437,7 @@ class TrainAttention:
         def bwd(dctx):
             dqkv = torch.zeros_like(qkv.t)
             bwd_ops.attention_bwd(qkv.t, 0, qkv.t, self.k0, qkv.t, self.v0, self.hs, ctx, dctx.contiguous(), dqkv, 0, dqkv,
-                                  self.k0, dqkv, self.v0, images, self.heads, self.d, n, n, 1, n, inner, self.scale)
+                                  self.k0, dqkv, self.v0, images, self.heads, self.d, n, n, 1, n, inner, self.scale, lse=lse)
             qkv.accumulate(dqkv)
         tape.record([out], bwd)
         return out

@@ -202,6 +202,40 @@ def test_attention_bwd_tensor_core_matches_simt(B, cuda_device, monkeypatch, d, 
         assert float(out["0"][:, :v0].view(-1, 2 * heads, hs)[:, :, d:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("d,images,n", [(40, 2, 2560), (40, 3, 200), (80, 2, 640), (160, 2, 160)])
+def test_attention_bwd_with_the_forward_log_sum_exp(B, cuda_device, d, images, n):
+    """ops.spatial_attn(..., lse=) writes the row log-sum-exp (log2 units) the backward would recompute; given it, the
+    tcgen05 dQ kernel skips its first sweep -- same gradients; the lse itself against torch."""
+    from synfmc_b200 import ops
+    heads, hs = 8, (d + 15) // 16 * 16
+    rows = images * n
+    qkv = torch.zeros(rows, 2 * heads * hs + heads * d)
+    qkv[:, :heads * hs] = _pad_heads(randn(rows, heads * d, seed=1), heads, d, hs)
+    qkv[:, heads * hs:2 * heads * hs] = _pad_heads(randn(rows, heads * d, seed=2), heads, d, hs)
+    qkv[:, 2 * heads * hs:] = randn(rows, heads * d, seed=3)
+    dev_qkv = bf(qkv).to(cuda_device)
+    k0, v0 = heads * hs, 2 * heads * hs
+    o_plain = torch.empty(rows, heads * d, dtype=torch.bfloat16, device=cuda_device)
+    o_lse = torch.empty_like(o_plain)
+    lse = torch.empty(rows, heads, device=cuda_device)
+    ops.spatial_attn(dev_qkv, 0, dev_qkv, k0, dev_qkv, v0, hs, o_plain, images, heads, d, n, n, 1, n, d ** -0.5)
+    ops.spatial_attn(dev_qkv, 0, dev_qkv, k0, dev_qkv, v0, hs, o_lse, images, heads, d, n, n, 1, n, d ** -0.5, lse=lse)
+    assert torch.equal(o_plain, o_lse)
+    qf = bf(qkv)[:, :k0].view(images, n, heads, hs)[..., :d].transpose(1, 2).double()
+    kf = bf(qkv)[:, k0:v0].view(images, n, heads, hs)[..., :d].transpose(1, 2).double()
+    want_lse = torch.logsumexp(qf @ kf.transpose(-1, -2) * d ** -0.5, dim=-1) / torch.log(torch.tensor(2.0, dtype=torch.float64))
+    got_lse = lse.cpu().double().view(images, n, heads).transpose(1, 2)
+    assert float((got_lse - want_lse).abs().max()) < 2e-3
+    dev_do = bf(randn(rows, heads * d, seed=4)).to(cuda_device)
+    out = {}
+    for given in (False, True):
+        dqkv = torch.zeros_like(dev_qkv)
+        B.attention_bwd(dev_qkv, 0, dev_qkv, k0, dev_qkv, v0, hs, o_plain, dev_do, dqkv, 0, dqkv, k0, dqkv, v0, images, heads, d,
+                        n, n, 1, n, 1, d ** -0.5, lse=lse.clone() if given else None)
+        out[given] = dqkv.float().cpu()
+    assert rel(out[True], out[False]) < 2e-3
+
+
 @pytest.mark.parametrize("d,Bc,HW", [(40, 1, 300), (80, 2, 33), (160, 1, 9)])
 def test_attention_bwd_temporal16_matches_simt(B, cuda_device, monkeypatch, d, Bc, HW):
     """16-frame temporal self-attention: the one-warp-per-sequence kernel against the generic SIMT kernels."""
