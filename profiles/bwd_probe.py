@@ -3,7 +3,7 @@
 L2 flushed between calls) and the algorithmic rate.  `--once` runs every case exactly once (for ncu captures).
 
     python profiles/bwd_probe.py
-    ncu --set full --clock-control none -k regex:'attn_bwd|temporal16|groupnorm_bwd|layernorm_bwd' -o gpurun_out/bwd \
+    ncu --set full --clock-control none -k regex:'attn_bwd|temporal16|groupnorm_bwd|layernorm_bwd|wgrad' -o gpurun_out/bwd \
         python profiles/bwd_probe.py --once"""
 import argparse
 import json
@@ -65,6 +65,10 @@ def main():
         x, dy = rnd(rows, C), rnd(rows, C)
         gam = torch.ones(C, device=dev)
         cases.append((name, (lambda x=x, dy=dy, gam=gam: B.layernorm_bwd(x, dy, gam, 1e-5)), None, 3 * x.numel() * 2))
+    for name, T, M, N in (("wgrad 320x320 over 40960 tokens (split-token TN kernel)", 40960, 320, 320),
+                          ("wgrad 2560x320 over 40960 tokens", 40960, 2560, 320), ("wgrad 1280x1280 over 2560 tokens", 2560, 1280, 1280)):
+        dy, x = rnd(T, M), rnd(T, N)
+        cases.append((name, (lambda dy=dy, x=x: B.linear_wgrad(dy, x)), 2.0 * T * M * N, None))
     out = []
     for name, fn, flops, nbytes in cases:
         if args.once:
