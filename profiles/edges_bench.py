@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """SURVEY 8 f3 timing: the pipeline edges around the denoising loop at BASELINE configs[1] (1 clip 320x512x16f) --
 decode_latents (16 frames through the SD1.5 VAE decoder), vae.encode of the same clip (the trainers' first step) and the CLIP
-text encoder on a CFG pair of prompts -- on the B200 kernels, next to the CPU restatement on a bounded sample (1 frame /
-1 prompt pair).  CUDA events, warm-up first; one JSON line."""
+text encoder on a CFG pair of prompts -- on the B200 kernels.  CUDA events, warm-up first; one JSON line.  (The CPU time of
+the fp32 restatements on the same box is printed by tests/test_gpu_edges.py: oracle/ is test infrastructure and is not
+imported from here.)"""
 import argparse
 import json
 import os
 import sys
-import time
 
 import torch
 
@@ -32,7 +32,6 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--cpu", action="store_true", help="also time the CPU restatement (1 frame, 1 prompt pair)")
     ap.add_argument("--trace", action="store_true")
     args = ap.parse_args()
     from synfmc_b200 import _cabi
@@ -69,23 +68,6 @@ def main():
             d[1] += s0.elapsed_time(s1)
         for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             print(f"{ms:9.2f} ms {n:6d} calls  {name}", file=sys.stderr)
-    if args.cpu:
-        from oracle.clip_text import CLIPTextModel as OC
-        from oracle.vae import AutoencoderKL as OV
-        ov, oc = OV().eval().requires_grad_(False), OC().eval().requires_grad_(False)
-        ov.load_state_dict(vae.state_dict())
-        oc.load_state_dict(clip.state_dict())
-        with torch.no_grad():
-            z1 = (latents[:, :, 0] / 0.18215).cpu()
-            ov.decode(z1)
-            t0 = time.perf_counter()
-            ov.decode(z1)
-            out["cpu_decode_ms_per_frame"] = round((time.perf_counter() - t0) * 1e3, 1)
-            oc(ids.cpu())
-            t0 = time.perf_counter()
-            oc(ids.cpu())
-            out["cpu_clip_text_2x77_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
-            out["cpu_threads"] = torch.get_num_threads()
     print(json.dumps(out), flush=True)
 
 
