@@ -308,3 +308,28 @@ def test_edge_models_refuse_cpu_tensors_without_the_dry_run():
     with pytest.raises(Exception, match="CUDA"):
         CLIPTextModel(vocab_size=10, hidden_size=64, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64)(
             torch.zeros(1, 77, dtype=torch.long))
+
+
+def test_linear_wgrad_routes(recorder):
+    """bwd_ops.linear_wgrad: 16-byte-aligned widths go to fmc_wgrad_bf16 (row-major operands, no transposes); odd widths fall
+    back to transposed copies + the K-major GEMM with fp32 output."""
+    from synfmc_b200 import bwd_ops
+    dy, x = torch.zeros(300, 328, dtype=torch.bfloat16), torch.zeros(300, 72, dtype=torch.bfloat16)
+    dw = bwd_ops.linear_wgrad(dy, x)
+    assert dw.shape == (328, 72) and dw.dtype == torch.float32 and recorder.names() == ["fmc_wgrad_bf16"]
+    args = recorder.calls[0][1]
+    assert args[7:11] == (300, 328, 72, 0)                                  # T, M, N, accumulate
+    acc = torch.zeros(328, 72)
+    bwd_ops.linear_wgrad(dy, x, out=acc, accumulate=True)
+    assert recorder.calls[1][1][10] == 1
+    del recorder.calls[:]
+    dw = bwd_ops.linear_wgrad(torch.zeros(64, 20, dtype=torch.bfloat16), torch.zeros(64, 12, dtype=torch.bfloat16))
+    assert dw.shape == (20, 12) and recorder.names() == ["fmc_transpose_bf16", "fmc_transpose_bf16", "fmc_gemm_bf16"]
+
+
+def test_graphed_step_needs_a_gpu():
+    from synfmc_b200.train import GraphedStep
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GraphedStep(lambda: None)
