@@ -110,3 +110,22 @@ def test_unet_diffusers_layer_restatement_matches_the_ldm_blocks():
     up.load_state_dict(ref.state_dict(), strict=True)
     with torch.no_grad():
         assert float((up(x) - ref(x)).abs().max()) < 1e-6
+
+
+def test_timestep_embedding_restatement_matches_an_independent_implementation():
+    """diffusers `Timesteps(320, flip_sin_to_cos=True, downscale_freq_shift=0)` + `TimestepEmbedding` (unet.py:1090-1096) as
+    restated in oracle/diffusers_restated.py against the sinusoidal embedding + two-layer SiLU MLP of torchtitan's flux
+    model (the same published formula, written independently: [cos | sin] of t * 10000^(-i / half))."""
+    layers = pytest.importorskip("torchtitan.experiments.flux.model.layers")
+    from oracle import diffusers_restated as dr
+    t = torch.tensor([961.0, 41.0, 1.0, 500.0])
+    want = layers.timestep_embedding(t, 320, time_factor=1.0)
+    got = dr.Timesteps(320, flip_sin_to_cos=True, downscale_freq_shift=0)(t)
+    assert got.shape == (4, 320) and float((got - want).abs().max()) < 1e-6
+    torch.manual_seed(0)
+    ref = layers.MLPEmbedder(320, 1280).eval()
+    emb = dr.TimestepEmbedding(320, 1280).eval()
+    emb.load_state_dict({"linear_1.weight": ref.in_layer.weight, "linear_1.bias": ref.in_layer.bias,
+                         "linear_2.weight": ref.out_layer.weight, "linear_2.bias": ref.out_layer.bias}, strict=True)
+    with torch.no_grad():
+        assert float((emb(got) - ref(want)).abs().max()) < 1e-5
