@@ -18,6 +18,7 @@ train_cam_ctrl.py:647-665 / train_cam_obj_ctrl.py:843-862 -- DDP's gradient all-
 
 The gradients come from the backward kernels behind train_engine.py or from any other source (the
 tests also feed these classes torch-autograd gradients of small modules and compare with DDP-style mean + AdamW)."""
+import contextlib
 import os
 
 import torch
@@ -79,6 +80,7 @@ class GradAllReduce:
             for j in idxs:
                 self.bucket_of[j] = b
         self.pending, self.handles, self.hooks = [], [], []
+        self.sync = True  # False inside no_sync(): gradients accumulate locally, no bucket is released
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
     def install_hooks(self):
@@ -118,7 +120,19 @@ class GradAllReduce:
         self.pending = [len(idxs) for _, _, idxs in self.buckets]
         self.handles = []
 
+    @contextlib.contextmanager
+    def no_sync(self):
+        """DDP.no_sync for gradient accumulation: backward passes inside the block only accumulate into `.grad`; the
+        all-reduce happens in the first backward after it (call `reset()` before that one as usual)."""
+        self.sync = False
+        try:
+            yield self
+        finally:
+            self.sync = True
+
     def _ready(self, j):
+        if not self.sync:
+            return
         b = self.bucket_of[j]
         self.pending[b] -= 1
         if self.pending[b] == 0:

@@ -158,6 +158,20 @@ def test_early_gradient_delivery_protocol_cpu():
             assert sorted(launched) == ([0, 1] if early else [])
             tape.finish_params()
             assert a._fmc_grad_parts[1] == 2 and b._fmc_grad_parts[1] == 1
+        # gradient accumulation: inside no_sync() gradients are delivered (early) but no bucket goes out
+        flat.zero_grad()
+        red.reset()
+        del launched[:]
+        a._fmc_grad_parts = b._fmc_grad_parts = (engine.STRUCTURE_EPOCH, 1)
+        with red.no_sync():
+            tape = train_engine.Tape()
+            tape.add_param_grad(a, torch.ones(4, 8))
+            tape.add_param_grad(b, torch.ones(8))
+        assert launched == [] and float(a.grad.sum()) == 32.0
+        tape = train_engine.Tape()
+        tape.add_param_grad(a, torch.ones(4, 8))
+        tape.add_param_grad(b, torch.ones(8))
+        assert sorted(launched) == [0, 1] and float(a.grad.sum()) == 64.0 and float(b.grad.sum()) == 16.0
     finally:
         red.remove_hooks()
     assert train_engine.EARLY_GRAD_SINK is None
