@@ -333,3 +333,25 @@ def test_graphed_step_needs_a_gpu():
         pytest.skip("CPU-only check")
     with pytest.raises(RuntimeError, match="CUDA"):
         GraphedStep(lambda: None)
+
+
+def test_edge_model_plans_follow_the_weights(recorder):
+    """The VAE / text-encoder plans are rebuilt when a weight changes (load_state_dict after the first call), like the
+    U-Net's (engine.fingerprint)."""
+    from synfmc_b200.edge import AutoencoderKL, CLIPTextModel
+    vae = AutoencoderKL(block_out_channels=(32, 32, 32, 32))
+    vae.decode(torch.randn(1, 4, 4, 4))
+    first = vae._plans
+    vae.decode(torch.randn(1, 4, 4, 4))
+    assert vae._plans is first                                   # unchanged weights: plans reused
+    with torch.no_grad():
+        vae.decoder.conv_out.weight.add_(1.0)
+    vae.decode(torch.randn(1, 4, 4, 4))
+    assert vae._plans is not first
+    clip = CLIPTextModel(vocab_size=50, hidden_size=64, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64)
+    ids = torch.randint(0, 50, (1, 77))
+    clip(ids)
+    first = clip._plans
+    clip.load_state_dict({k: v + 0.01 for k, v in clip.state_dict().items()})
+    clip(ids)
+    assert clip._plans is not first
